@@ -1,0 +1,230 @@
+/* b2u.h — C-ABI of the B200-native U-Net hot path (libb2u.so).
+ *
+ * The reference (LUP-LuftbildUmweltPlanung/UNet) has no FFI of its own: its hot path is fastai/PyTorch module calls
+ * issued from train.py:98-160 (unet_learner_MS -> DynamicUnet), train.py:246-250 (fit_one_cycle -> fwd/bwd/step) and
+ * predict.py:191-337 (learn.predict per tile, numpy merge).  Each entry point below replaces the third-party ATen/cuDNN
+ * call those lines reach; the exact call each one stands in for is named on the declaration.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every buffer is owned by the caller (the Python host allocates through torch);
+ *   - every function enqueues work on `stream` (a cudaStream_t passed as void*) and returns without host sync;
+ *   - return 0 on success, a negative b2u_status otherwise; b2u_last_error() returns a thread-local message;
+ *   - activations are NHWC bf16 with a channel pitch that is a multiple of 8 ("Cp"), weights are bf16
+ *     [Cout][taps][CinP]; master parameters / gradients are fp32 in the torch layout [Cout][Cin][kh][kw].
+ */
+#ifndef B2U_H_
+#define B2U_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum b2u_status {
+  B2U_OK = 0,
+  B2U_ERR_ARG = -1,      /* bad descriptor / unsupported shape */
+  B2U_ERR_CUDA = -2,     /* a CUDA runtime/driver call failed  */
+  B2U_ERR_NO_DEVICE = -3 /* no sm_100 device                    */
+} b2u_status;
+
+const char* b2u_last_error(void);
+int b2u_version(void);
+/* 0 when the current device is sm_100 and the driver entry points resolve. */
+int b2u_device_check(void);
+
+/* A strided NHWC window onto a bf16 tensor: element (n,y,x,c) lives at ptr[n*sN + y*sH + x*sW + c].
+ * Plain tensors, channel slices of a concat buffer and stride-2 parity planes are all expressed this way. */
+typedef struct b2u_view {
+  void* ptr;
+  int32_t C, W, H, N;
+  int64_t sW, sH, sN; /* in elements; each must be a multiple of 8 (16-byte TMA stride rule) */
+} b2u_view;
+
+#define B2U_MAX_TAPS 16
+#define B2U_MAX_VIEWS 4
+
+enum {
+  B2U_EPI_RELU = 1,    /* max(v, 0) */
+  B2U_EPI_STATS = 2,   /* emit per-channel sum / sum-of-squares partials of the stored values */
+  B2U_EPI_OUT_F32 = 4  /* store fp32 to out_f32 (dense NHWC with pitch out_f32_ld) instead of bf16 through `out` */
+};
+
+/* Implicit-GEMM convolution:  out[n,y,x,co] = epi( sum_t sum_ci a[tap_a[t]][n, y+tap_dy[t], x+tap_dx[t], ci] * w[co][tap_w[t]][ci] ).
+ * Out-of-range reads are zero (the conv padding).  The same descriptor expresses
+ *   - fprop 3x3/1x1 stride 1          (F.conv2d reached from fastai ConvLayer, train.py:141 DynamicUnet),
+ *   - fprop stride 2 (taps address the four stride-2 parity planes of the input),
+ *   - AvgPool2d(2)+1x1 idpath conv     (four taps, one per parity plane, weights pre-scaled by 1/4),
+ *   - dgrad (conv of dY with the flipped/transposed filter; stride 2 = four launches writing parity planes of dX),
+ * i.e. cudnnConvolutionForward / cudnnConvolutionBackwardData in the reference stack.
+ * epilogue: v = acc*scale[co] + shift[co]; v += res (times (res_mask>0) if given); ReLU; v = (zmask>0) ? v : 0. */
+typedef struct b2u_conv_desc {
+  b2u_view a[B2U_MAX_VIEWS];
+  int32_t num_a;
+  b2u_view out;      /* geometry (N,H,W) defines the GEMM M space; C = Cout */
+  const void* w;     /* bf16 [w_rows][w_taps][w_cinp] */
+  int32_t w_rows, w_taps, w_cin, w_cinp;
+  int32_t num_taps;
+  int8_t tap_a[B2U_MAX_TAPS], tap_dy[B2U_MAX_TAPS], tap_dx[B2U_MAX_TAPS], tap_w[B2U_MAX_TAPS];
+  const float* scale; /* nullable, per output channel */
+  const float* shift; /* nullable, per output channel (bias, or folded BN shift) */
+  b2u_view res;       /* ptr NULL = none */
+  b2u_view res_mask;  /* ptr NULL = none */
+  b2u_view zmask;     /* ptr NULL = none */
+  uint32_t flags;
+  float* stats;       /* B2U_EPI_STATS: [4*m_tiles][2][stats_ld] fp32 partials */
+  int32_t stats_ld;
+  float* out_f32;     /* B2U_EPI_OUT_F32 */
+  int32_t out_f32_ld;
+} b2u_conv_desc;
+
+typedef struct b2u_conv_info {
+  int32_t m_tiles, n_tiles, block_n, tile_w, tile_h, tile_n, stages, k_chunks, grid;
+  int32_t stats_rows; /* = 4*m_tiles: rows of the stats partial buffer */
+} b2u_conv_info;
+
+typedef struct b2u_conv_plan b2u_conv_plan;
+int b2u_conv_query(const b2u_conv_desc* d, b2u_conv_info* info);
+int b2u_conv_plan_create(const b2u_conv_desc* d, b2u_conv_plan** plan);
+int b2u_conv_plan_info(const b2u_conv_plan* plan, b2u_conv_info* info);
+int b2u_conv_run(const b2u_conv_plan* plan, void* stream);
+void b2u_conv_plan_destroy(b2u_conv_plan* plan);
+
+/* Weight gradient: dw[co][t][ci] = sum_{n,y,x} dy[n,y,x,co] * a[tap_a[t]][n, y+tap_dy[t], x+tap_dx[t], ci]
+ * (cudnnConvolutionBackwardFilter in the reference stack), optionally with db[co] = sum dy[n,y,x,co].
+ * Partials over `splits` pixel ranges land in `partial` (fp32 [splits][taps][co_pad][ci_pad]); b2u_wgrad_reduce sums
+ * them in a fixed order (deterministic) into the torch-layout fp32 gradient. */
+typedef struct b2u_wgrad_desc {
+  b2u_view dy;
+  b2u_view a[B2U_MAX_VIEWS];
+  int32_t num_a;
+  int32_t num_taps;
+  int8_t tap_a[B2U_MAX_TAPS], tap_dy[B2U_MAX_TAPS], tap_dx[B2U_MAX_TAPS];
+  int32_t Cout, Cin;
+  int32_t want_bias;
+  float* partial;        /* workspace, size from b2u_wgrad_query */
+  size_t partial_bytes;
+} b2u_wgrad_desc;
+
+typedef struct b2u_wgrad_info {
+  int32_t splits, co_pad, ci_pad, taps_per_unit, units, grid, k_steps, block_n, stages;
+  size_t partial_bytes;
+} b2u_wgrad_info;
+
+typedef struct b2u_wgrad_plan b2u_wgrad_plan;
+int b2u_wgrad_query(const b2u_wgrad_desc* d, b2u_wgrad_info* info);
+int b2u_wgrad_plan_create(const b2u_wgrad_desc* d, b2u_wgrad_plan** plan);
+int b2u_wgrad_run(const b2u_wgrad_plan* plan, void* stream);
+void b2u_wgrad_plan_destroy(b2u_wgrad_plan* plan);
+
+/* Sum split partials into torch-layout gradients.  dw[co_map(co)][ci][tap_kidx[t]] (+)= alpha * sum_s partial[s][t][co][ci];
+ * several taps may map to the same kernel index (the fused AvgPool idpath: 4 taps -> 1 kernel element).
+ * row_perm (nullable, int32[Cout]) maps GEMM row -> torch output channel (PixelShuffle-friendly row order).
+ * db (nullable) receives the bias gradient. */
+int b2u_wgrad_reduce(const float* partial, int32_t splits, int32_t taps, int32_t co_pad, int32_t ci_pad, int32_t Cout,
+                     int32_t Cin, int32_t ksize /* kh*kw of the torch weight */, const int32_t* tap_kidx,
+                     const int32_t* row_perm, float alpha, float* dw, float* db, int32_t has_bias_cols, void* stream);
+
+/* ---- weight staging: fp32 master [Cout][Cin][kh*kw] -> bf16 GEMM layouts -------------------------------------- */
+/* fprop layout  wf[row(co)][t][ci]   = scale * w[co][ci][t]
+ * dgrad layout  wd[ci][kk-1-t][row(co)] = w[co][ci][t]   (flipped taps, transposed channels; only if wd != NULL)
+ * row(co) = row_of_co[co] if given (inverse of row_perm above), else co. */
+int b2u_stage_weights(const float* w, int32_t Cout, int32_t Cin, int32_t kk, float scale, const int32_t* row_of_co,
+                      void* wf, int32_t wf_cinp, void* wd, int32_t wd_coutp, void* stream);
+
+/* ---- BatchNorm (training): statistics finalize / apply / backward ------------------------------------------------
+ * nn.BatchNorm2d reached from fastai ConvLayer / BatchNorm (train.py:128 create_body, :141 DynamicUnet). */
+/* partial: [rows][2][ld] (sum, sumsq) -> mean/invstd, scale = g*invstd, shift = b - mean*scale; running stats updated
+ * with `momentum` (unbiased variance), as torch does. count = elements per channel. */
+int b2u_bn_finalize(const float* partial, int32_t rows, int32_t ld, int32_t C, double count, const float* gamma,
+                    const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                    float* mean, float* invstd, float* scale, float* shift, void* stream);
+/* eval-mode affine from running statistics */
+int b2u_bn_eval_affine(int32_t C, const float* gamma, const float* beta, const float* running_mean,
+                       const float* running_var, float eps, float* scale, float* shift, void* stream);
+/* standalone per-channel sum/sumsq partials of a bf16 NHWC tensor (the skip-connection BN of UnetBlock) */
+int b2u_bn_stats(const void* x, int64_t pixels, int32_t C, int32_t ld, float* partial, int32_t rows, int32_t part_ld,
+                 void* stream);
+/* y = act( x*scale+shift  [+ r*rscale+rshift | + r] )   all bf16 NHWC with pitch ld */
+int b2u_bn_apply(const void* x, const float* scale, const float* shift, const void* r, const float* rscale,
+                 const float* rshift, int32_t relu, void* y, int64_t pixels, int32_t C, int32_t ld, void* stream);
+/* backward reductions: g = dz * mask, mask = (y>0) if y given else (x*scale+shift>0) if relu else 1
+ * partial[row][0][c] = sum g, partial[row][1][c] = sum g*xhat  (xhat = (x-mean)*invstd) */
+int b2u_bn_bwd_reduce(const void* dz, const void* x, const void* y, const float* scale, const float* shift,
+                      const float* mean, const float* invstd, int32_t relu, int64_t pixels, int32_t C, int32_t ld,
+                      float* partial, int32_t rows, int32_t part_ld, void* stream);
+/* dgamma = sum g*xhat, dbeta = sum g; coefficients for the apply pass */
+int b2u_bn_bwd_finalize(const float* partial, int32_t rows, int32_t part_ld, int32_t C, double count,
+                        const float* gamma, const float* invstd, float* dgamma, float* dbeta, float* c_g, float* c_x,
+                        float* c_0, void* stream);
+/* dx = c_g*g + c_x*xhat_raw + c_0   (the closed form of the BN input gradient), optional accumulate into dx */
+int b2u_bn_bwd_apply(const void* dz, const void* x, const void* y, const float* scale, const float* shift,
+                     const float* mean, const float* invstd, const float* gamma, const float* sum_g,
+                     const float* sum_gx, double count, int32_t relu, int32_t accumulate, void* dx, int64_t pixels,
+                     int32_t C, int32_t ld, void* stream);
+
+/* ---- pooling ------------------------------------------------------------------------------------------------ */
+/* nn.MaxPool2d(3, stride 2, padding 1) (xresnet stem, body child 3); idx = argmax position 0..8 (uint8) */
+int b2u_maxpool_fwd(const void* x, void* y, uint8_t* idx, int32_t N, int32_t H, int32_t W, int32_t C, int32_t ld,
+                    void* stream);
+int b2u_maxpool_bwd(const void* dy, const uint8_t* idx, void* dx, int32_t accumulate, int32_t N, int32_t H, int32_t W,
+                    int32_t C, int32_t ld, void* stream);
+
+/* ---- decoder glue: PixelShuffle_ICNR (+blur) + skip BN + concat + ReLU (fastai UnetBlock.forward) ---------------
+ * u: conv1x1 output, bf16 [N,h,w,4*cu] with channel order (i,j,c) (rows permuted at weight staging);
+ * skip: bf16 [N,2h,2w,cs]; cat: bf16 [N,2h,2w,ldc], channels [0,cu) = blur(shuffle(u)), [cu,cu+cs) = relu(skip*s+b).
+ * blur=0 gives the plain PixelShuffle of the final layer; skip may be NULL; skip_f32_nchw (nullable) instead appends
+ * the raw fp32 NCHW network input (MergeLayer(dense=True)). */
+int b2u_shuffle_cat_fwd(const void* u, int32_t ldu, int32_t cu, int32_t blur, const void* skip, int32_t lds,
+                        int32_t cs, const float* sscale, const float* sshift, int32_t skip_relu, void* cat,
+                        int32_t ldc, int32_t N, int32_t h, int32_t w, void* stream);
+/* backward of the shuffle(+blur) part: du[n,h,w,(i,j,c)] = (u>0) * blur^T(dcat[..., 0:cu]) */
+int b2u_shuffle_bwd(const void* dcat, int32_t ldc, const void* u, void* du, int32_t ldu, int32_t cu, int32_t blur,
+                    int32_t N, int32_t h, int32_t w, void* stream);
+
+/* ---- layout casts at the API edge --------------------------------------------------------------------------- */
+/* x fp32 NCHW (already /255) or uint8 NCHW (divided by 255 here, data.py:24 + IntToFloatTensor) -> bf16 NHWC pitch ld */
+int b2u_nchw_to_nhwc(const void* x, int32_t x_is_u8, void* y, int32_t N, int32_t C, int32_t H, int32_t W, int32_t ld,
+                     int32_t ch_off, void* stream);
+/* bf16/f32 NHWC -> fp32 NCHW */
+int b2u_nhwc_to_nchw_f32(const void* x, int32_t x_is_f32, int32_t ld, float* y, int32_t N, int32_t C, int32_t H,
+                         int32_t W, void* stream);
+
+/* ---- loss: CrossEntropyLossFlat(axis=1) with class weights, mean reduction (train.py:195,211) ----------------- */
+/* logits fp32 [P][ld]; labels uint8 [P]; wsum = sum_p weight[label_p] (computed by b2u_ce_weight_sum first).
+ * Writes dlogits bf16 [P][ldg] = w[y]*(softmax - onehot)/wsum and block partials of sum w[y]*nll into loss_partial. */
+int b2u_ce_weight_sum(const uint8_t* labels, int64_t P, const float* weight, int32_t C, float* wsum_partial,
+                      int32_t rows, void* stream);
+int b2u_ce_fwd_bwd(const float* logits, int32_t ld, const uint8_t* labels, int64_t P, int32_t C, const float* weight,
+                   const float* wsum_partial, int32_t wsum_rows, void* dlogits, int32_t ldg, float* loss_partial,
+                   int32_t rows, float grad_scale, void* stream);
+/* loss = sum(loss_partial)/sum(wsum_partial) -> loss[0] */
+int b2u_ce_finalize(const float* loss_partial, int32_t rows, const float* wsum_partial, int32_t wsum_rows, float* loss,
+                    void* stream);
+
+/* ---- optimizer ------------------------------------------------------------------------------------------------ */
+/* p -= lr * g over one flat fp32 buffer (BASELINE config 1: plain SGD) */
+int b2u_sgd_step(float* p, const float* g, int64_t n, float lr, float grad_scale, void* stream);
+/* fastai Adam (train.py:218): decoupled wd, per-segment lr / wd via seg tables (seg_end exclusive prefix, sorted) */
+int b2u_adam_step(float* p, const float* g, float* m, float* v, int64_t n, const int64_t* seg_end, const float* seg_lr,
+                  const float* seg_wd, int32_t nseg, float mom, float sqr_mom, float eps, int32_t step,
+                  float grad_scale, void* stream);
+
+/* ---- prediction: softmax + overlap-tile accumulate, normalise + argmax (predict.py:284-334) ------------------- */
+/* logits fp32 [T][th][tw][ld] for T tiles; tile t is placed at (y0[t], x0[t]) of the raster; acc fp32 [C][Y][X],
+ * cnt uint8 [Y][X]; additions are atomic-free because the host issues non-overlapping tile sets per launch
+ * (4-colouring of the overlap grid) — results do not depend on scheduling. */
+int b2u_stitch_accumulate(const float* logits, int32_t ld, int32_t C, int32_t T, int32_t th, int32_t tw,
+                          const int32_t* y0, const int32_t* x0, float* acc, uint8_t* cnt, int64_t Y, int64_t X,
+                          int64_t y_off, int64_t x_off, void* stream);
+/* mask[y][x] = argmax_c acc[c][y][x]/cnt (first max wins, unplaced pixels -> 0), uint8 */
+int b2u_stitch_finalize(const float* acc, const uint8_t* cnt, int32_t C, int64_t Y, int64_t X, uint8_t* mask,
+                        void* stream);
+/* per-tile softmax probabilities (fp32 NCHW, what learn.predict returns, predict.py:193-203) and argmax */
+int b2u_softmax_nchw(const float* logits, int32_t ld, int32_t C, int64_t tiles, int32_t H, int32_t W, float* probs,
+                     uint8_t* argmax, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2U_H_ */

@@ -1,0 +1,240 @@
+"""GPU parity of the tcgen05 implicit-GEMM kernels (fprop / dgrad / wgrad) against torch fp32 convolutions computed on
+the same bf16-rounded operands.  Tolerance: max|a-b| / max|b| <= 1e-2 for bf16 outputs (north_star bf16 bar),
+<= 2e-3 for fp32 outputs (wgrad, fp32 logits) — inputs are bf16 so products are exact and only accumulation order differs.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b):
+    return ((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-20)).item()
+
+
+def to_nhwc(x_nchw, cp=None):
+    from unet_b200.ops import pad8
+    n, c, h, w = x_nchw.shape
+    cp = cp or pad8(c)
+    out = torch.zeros((n, h, w, cp), dtype=torch.bfloat16, device=x_nchw.device)
+    out[..., :c] = x_nchw.permute(0, 2, 3, 1).to(torch.bfloat16)
+    return out
+
+
+def gemm_weights(w):
+    """torch [Cout,Cin,kh,kw] fp32 -> bf16 [Cout][kh*kw][CinP]"""
+    from unet_b200.ops import pad8
+    co, ci, kh, kw = w.shape
+    out = torch.zeros((co, kh * kw, pad8(ci)), dtype=torch.bfloat16, device=w.device)
+    out[..., :ci] = w.permute(0, 2, 3, 1).reshape(co, kh * kw, ci).to(torch.bfloat16)
+    return out
+
+
+def dgrad_weights(w):
+    """torch [Cout,Cin,kh,kw] -> bf16 [Cin][kk (flipped)][CoutP]"""
+    from unet_b200.ops import pad8
+    co, ci, kh, kw = w.shape
+    out = torch.zeros((ci, kh * kw, pad8(co)), dtype=torch.bfloat16, device=w.device)
+    out[..., :co] = w.flip(2, 3).permute(1, 2, 3, 0).reshape(ci, kh * kw, co).to(torch.bfloat16)
+    return out
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, generator=g, device="cuda") * scale).to(torch.bfloat16).float()
+
+
+CONV_CASES = [
+    # N, Cin, Cout, H, W, ks
+    (2, 64, 64, 16, 16, 3),
+    (2, 64, 64, 64, 64, 3),
+    (3, 128, 128, 32, 32, 3),
+    (4, 256, 256, 16, 16, 3),
+    (4, 512, 512, 8, 8, 3),
+    (1, 100, 100, 128, 128, 3),
+    (1, 192, 96, 64, 64, 3),
+    (2, 32, 64, 128, 128, 3),
+    (2, 512, 1024, 8, 8, 3),
+    (2, 1024, 512, 8, 8, 3),
+    (2, 384, 768, 32, 32, 1),
+    (1, 96, 384, 64, 64, 1),
+    (2, 4, 32, 64, 64, 3),
+    (1, 64, 64, 25, 25, 3),     # ragged (the reference's default 400-px tiles reach 25x25)
+    (3, 48, 40, 13, 50, 3),     # ragged, odd channel counts
+]
+
+
+@pytest.mark.parametrize("N,Cin,Cout,H,W,ks", CONV_CASES)
+def test_conv_fprop_s1(N, Cin, Cout, H, W, ks):
+    from unet_b200 import ops
+    x = rnd(N, Cin, H, W, seed=1)
+    w = rnd(Cout, Cin, ks, ks, seed=2, scale=(Cin * ks * ks) ** -0.5)
+    b = rnd(Cout, seed=3)
+    ref = F.relu(F.conv2d(x, w, b, padding=(ks - 1) // 2))
+    xa = to_nhwc(x)
+    ya = torch.full((N, H, W, ops.pad8(Cout)), 7.0, dtype=torch.bfloat16, device="cuda")
+    plan = ops.ConvPlan([ops.view_nhwc(xa, Cin)], ops.view_nhwc(ya, Cout), gemm_weights(w), Cin, ops.taps_conv(ks),
+                        shift=b.contiguous(), relu=True)
+    plan.run()
+    torch.cuda.synchronize()
+    got = ya[..., :Cout].permute(0, 3, 1, 2).float()
+    e = rel_err(got, ref)
+    assert e <= 1e-2, f"rel err {e} info={[(n, getattr(plan.info, n)) for n, _ in plan.info._fields_]}"
+    if ops.pad8(Cout) != Cout:  # pad lanes are never written
+        assert (ya[..., Cout:] == 7.0).all()
+
+
+def test_conv_fprop_stats_and_residual():
+    from unet_b200 import ops
+    N, Cin, Cout, H, W = 2, 64, 128, 32, 32
+    x = rnd(N, Cin, H, W, seed=1)
+    w = rnd(Cout, Cin, 3, 3, seed=2, scale=(Cin * 9) ** -0.5)
+    r = rnd(N, Cout, H, W, seed=4)
+    m = rnd(N, Cout, H, W, seed=5)
+    z = rnd(N, Cout, H, W, seed=6)
+    sc = rnd(Cout, seed=7).abs() + 0.5
+    sh = rnd(Cout, seed=8)
+    ref = F.conv2d(x, w, None, padding=1) * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1)
+    ref = ref + r * (m > 0)
+    ref = F.relu(ref) * (z > 0)
+    xa, ra, ma, za = to_nhwc(x), to_nhwc(r), to_nhwc(m), to_nhwc(z)
+    ya = torch.zeros((N, H, W, Cout), dtype=torch.bfloat16, device="cuda")
+    plan = ops.ConvPlan([ops.view_nhwc(xa)], ops.view_nhwc(ya), gemm_weights(w), Cin, ops.taps_conv(3),
+                        scale=sc.contiguous(), shift=sh.contiguous(), res=ops.view_nhwc(ra),
+                        res_mask=ops.view_nhwc(ma), zmask=ops.view_nhwc(za), relu=True, stats=True)
+    plan.run()
+    torch.cuda.synchronize()
+    got = ya.permute(0, 3, 1, 2).float()
+    assert rel_err(got, ref) <= 1e-2
+    s = plan.stats.sum(0)  # [2, ld]
+    assert rel_err(s[0, :Cout], got.sum((0, 2, 3))) <= 1e-4
+    assert rel_err(s[1, :Cout], (got * got).sum((0, 2, 3))) <= 1e-4
+
+
+@pytest.mark.parametrize("N,Cin,Cout,H,W", [(2, 64, 128, 64, 64), (2, 4, 32, 64, 64), (1, 256, 512, 16, 16)])
+def test_conv_fprop_stride2(N, Cin, Cout, H, W):
+    from unet_b200 import ops
+    x = rnd(N, Cin, H, W, seed=1)
+    w = rnd(Cout, Cin, 3, 3, seed=2, scale=(Cin * 9) ** -0.5)
+    ref = F.conv2d(x, w, None, stride=2, padding=1)
+    xa = to_nhwc(x)
+    ya = torch.zeros((N, H // 2, W // 2, ops.pad8(Cout)), dtype=torch.bfloat16, device="cuda")
+    views = [ops.view_nhwc(xa, Cin, parity=(py, px)) for py in range(2) for px in range(2)]
+    plan = ops.ConvPlan(views, ops.view_nhwc(ya, Cout), gemm_weights(w), Cin, ops.taps_conv3_s2())
+    plan.run()
+    torch.cuda.synchronize()
+    assert rel_err(ya[..., :Cout].permute(0, 3, 1, 2), ref) <= 1e-2
+
+
+def test_avgpool_1x1_fused():
+    from unet_b200 import ops
+    N, Cin, Cout, H, W = 2, 64, 128, 32, 32
+    x = rnd(N, Cin, H, W, seed=1)
+    w = rnd(Cout, Cin, 1, 1, seed=2, scale=Cin ** -0.5)
+    ref = F.conv2d(F.avg_pool2d(x, 2, ceil_mode=True), w)
+    xa = to_nhwc(x)
+    ya = torch.zeros((N, H // 2, W // 2, Cout), dtype=torch.bfloat16, device="cuda")
+    views = [ops.view_nhwc(xa, Cin, parity=(py, px)) for py in range(2) for px in range(2)]
+    plan = ops.ConvPlan(views, ops.view_nhwc(ya), gemm_weights(w * 0.25), Cin, ops.taps_avgpool_1x1())
+    plan.run()
+    torch.cuda.synchronize()
+    assert rel_err(ya.permute(0, 3, 1, 2), ref) <= 1e-2
+
+
+@pytest.mark.parametrize("N,Cin,Cout,H,W,ks", [(2, 64, 64, 32, 32, 3), (1, 100, 100, 64, 64, 3), (2, 384, 768, 16, 16, 1)])
+def test_dgrad_s1(N, Cin, Cout, H, W, ks):
+    from unet_b200 import ops
+    w = rnd(Cout, Cin, ks, ks, seed=2, scale=(Cout * ks * ks) ** -0.5)
+    dy = rnd(N, Cout, H, W, seed=3)
+    ref = torch.nn.grad.conv2d_input((N, Cin, H, W), w, dy, padding=(ks - 1) // 2)
+    dya = to_nhwc(dy)
+    dxa = torch.zeros((N, H, W, ops.pad8(Cin)), dtype=torch.bfloat16, device="cuda")
+    plan = ops.ConvPlan([ops.view_nhwc(dya, Cout)], ops.view_nhwc(dxa, Cin), dgrad_weights(w), Cout, ops.taps_conv(ks))
+    plan.run()
+    torch.cuda.synchronize()
+    assert rel_err(dxa[..., :Cin].permute(0, 3, 1, 2), ref) <= 1e-2
+
+
+def test_dgrad_s2():
+    from unet_b200 import ops
+    N, Cin, Cout, H, W = 2, 64, 128, 32, 32
+    w = rnd(Cout, Cin, 3, 3, seed=2, scale=(Cout * 9) ** -0.5)
+    dy = rnd(N, Cout, H // 2, W // 2, seed=3)
+    ref = torch.nn.grad.conv2d_input((N, Cin, H, W), w, dy, stride=2, padding=1)
+    dya = to_nhwc(dy)
+    dxa = torch.zeros((N, H, W, Cin), dtype=torch.bfloat16, device="cuda")
+    wd = dgrad_weights(w)
+    for py in range(2):
+        for px in range(2):
+            plan = ops.ConvPlan([ops.view_nhwc(dya)], ops.view_nhwc(dxa, parity=(py, px)), wd, Cout,
+                                ops.taps_dgrad_s2(py, px))
+            plan.run()
+    torch.cuda.synchronize()
+    assert rel_err(dxa.permute(0, 3, 1, 2), ref) <= 1e-2
+
+
+def test_conv_out_f32_head():
+    from unet_b200 import ops
+    N, Cin, Cout, H, W = 2, 100, 2, 64, 64
+    x = rnd(N, Cin, H, W, seed=1)
+    w = rnd(Cout, Cin, 1, 1, seed=2, scale=Cin ** -0.5)
+    b = rnd(Cout, seed=3)
+    ref = F.conv2d(x, w, b)
+    xa = to_nhwc(x)
+    out = torch.zeros((N, H, W, 8), dtype=torch.float32, device="cuda")
+    ov = ops.view_nhwc(torch.zeros((N, H, W, 8), dtype=torch.bfloat16, device="cuda"), Cout)
+    plan = ops.ConvPlan([ops.view_nhwc(xa, Cin)], ov, gemm_weights(w), Cin, ops.taps_conv(1), shift=b.contiguous(),
+                        out_f32=out)
+    plan.run()
+    torch.cuda.synchronize()
+    assert rel_err(out[..., :Cout].permute(0, 3, 1, 2), ref) <= 2e-3
+
+
+WGRAD_CASES = [
+    # N, Cin, Cout, H, W, ks, bias
+    (2, 64, 64, 32, 32, 3, True),
+    (2, 100, 100, 64, 64, 3, True),
+    (4, 512, 512, 8, 8, 3, True),
+    (2, 128, 256, 16, 16, 3, False),
+    (2, 384, 768, 16, 16, 1, True),
+    (1, 100, 2, 64, 64, 1, True),
+    (2, 4, 32, 32, 32, 3, False),
+    (1, 48, 40, 13, 50, 3, True),
+]
+
+
+@pytest.mark.parametrize("N,Cin,Cout,H,W,ks,bias", WGRAD_CASES)
+def test_wgrad_s1(N, Cin, Cout, H, W, ks, bias):
+    from unet_b200 import ops
+    x = rnd(N, Cin, H, W, seed=1)
+    dy = rnd(N, Cout, H, W, seed=3)
+    ref = torch.nn.grad.conv2d_weight(x, (Cout, Cin, ks, ks), dy, padding=(ks - 1) // 2)
+    xa, dya = to_nhwc(x), to_nhwc(dy)
+    dw = torch.zeros((Cout, Cin, ks, ks), dtype=torch.float32, device="cuda")
+    db = torch.zeros(Cout, dtype=torch.float32, device="cuda") if bias else None
+    taps = ops.taps_conv(ks)
+    plan = ops.WgradPlan(ops.view_nhwc(dya, Cout), [ops.view_nhwc(xa, Cin)], taps, Cout, Cin, ks * ks,
+                         [t[3] for t in taps], dw, db)
+    plan.run()
+    torch.cuda.synchronize()
+    e = rel_err(dw, ref)
+    assert e <= 2e-3, f"rel err {e} info={[(n, getattr(plan.info, n)) for n, _ in plan.info._fields_]}"
+    if bias:
+        assert rel_err(db, dy.sum((0, 2, 3))) <= 2e-3
+
+
+def test_wgrad_s2():
+    from unet_b200 import ops
+    N, Cin, Cout, H, W = 2, 64, 128, 32, 32
+    x = rnd(N, Cin, H, W, seed=1)
+    dy = rnd(N, Cout, H // 2, W // 2, seed=3)
+    ref = torch.nn.grad.conv2d_weight(x, (Cout, Cin, 3, 3), dy, stride=2, padding=1)
+    xa, dya = to_nhwc(x), to_nhwc(dy)
+    dw = torch.zeros((Cout, Cin, 3, 3), dtype=torch.float32, device="cuda")
+    taps = ops.taps_conv3_s2()
+    views = [ops.view_nhwc(xa, Cin, parity=(py, px)) for py in range(2) for px in range(2)]
+    plan = ops.WgradPlan(ops.view_nhwc(dya), views, taps, Cout, Cin, 9, [t[3] for t in taps], dw)
+    plan.run()
+    torch.cuda.synchronize()
+    assert rel_err(dw, ref) <= 2e-3

@@ -1,0 +1,496 @@
+// Implicit-GEMM convolution for sm_100a: TMA (im2col-free, one 4-D box per filter tap) -> 128B-swizzled smem ->
+// tcgen05.mma (M=128 pixels x N<=256 channels, fp32 accumulators in TMEM, double buffered) -> fused epilogue ->
+// swizzled smem staging -> TMA store.  One persistent CTA per SM, warp-specialised:
+//   warp 0: TMA producer | warp 1: MMA issuer | warp 2: TMEM allocator | warps 4-7: epilogue (one TMEM lane quarter each)
+//
+// Replaces F.conv2d / cudnnConvolutionForward / cudnnConvolutionBackwardData as reached from fastai's ConvLayer,
+// ResBlock, UnetBlock and PixelShuffle_ICNR (reference train.py:128,141; SURVEY.md 8(a) layer table).
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace b2u {
+
+struct EpiView {
+  const __nv_bfloat16* ptr;
+  long long sW, sH, sN;
+};
+
+struct ConvParams {
+  CUtensorMap tm_a[B2U_MAX_VIEWS];
+  CUtensorMap tm_b;
+  CUtensorMap tm_out;
+  int num_taps, k_chunks, last_mmas;
+  int8_t tap_a[B2U_MAX_TAPS], tap_dy[B2U_MAX_TAPS], tap_dx[B2U_MAX_TAPS], tap_w[B2U_MAX_TAPS];
+  int tw, th, tn, tiles_x, tiles_y;
+  int m_tiles, n_tiles, BN, stages;
+  uint32_t idesc;
+  int N, Ho, Wo, Cout, CoutP8;
+  const float* scale;
+  const float* shift;
+  EpiView res, res_mask, zmask;
+  uint32_t flags;
+  float* stats;
+  int stats_ld;
+  float* out_f32;
+  int out_f32_ld;
+};
+
+static constexpr int kThreads = 256;
+static constexpr uint32_t kABytes = 128 * 128;       // 128 pixels x 64 bf16
+static constexpr uint32_t kStagingBytes = 128 * 128; // 128 pixels x 64 bf16, one output chunk
+static constexpr uint32_t kTmemCols = 512;
+static constexpr uint32_t kAccStride = 256;
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&o)[8]) {
+  uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  o[0] = bf16_lo(u.x); o[1] = bf16_hi(u.x); o[2] = bf16_lo(u.y); o[3] = bf16_hi(u.y);
+  o[4] = bf16_lo(u.z); o[5] = bf16_hi(u.z); o[6] = bf16_lo(u.w); o[7] = bf16_hi(u.w);
+}
+
+// Column sums across the 32 lanes of a warp for 32 per-lane values: afterwards lane l holds sum over lanes of v[l].
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      float keep = upper ? v[i + off] : v[i];
+      float send = upper ? v[i] : v[i + off];
+      float recv = __shfl_xor_sync(0xffffffffu, send, off);
+      v[i] = keep + recv;
+    }
+  }
+  return v[0];
+}
+
+__global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t b_bytes = (uint32_t)p.BN * 128u;
+  const uint32_t stage_bytes = kABytes + b_bytes;
+  const int S = p.stages;
+  const uint32_t stg_base = smem_base + (uint32_t)S * stage_bytes;
+  const uint32_t bar_base = stg_base + 2 * kStagingBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(S + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (uint32_t)(2 * S + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (uint32_t)(2 * S + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (uint32_t)(2 * S + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem + (size_t)S * stage_bytes + 2 * kStagingBytes + 8 * (2 * S + 4));
+
+  if (threadIdx.x == 0) {
+    if (smem_base & 1023u) {
+      printf("b2u: dynamic smem base 0x%x not 1024-byte aligned\n", smem_base);
+      __trap();
+    }
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < B2U_MAX_VIEWS; ++i) tma_prefetch_desc(&p.tm_a[i]);
+    tma_prefetch_desc(&p.tm_b);
+    tma_prefetch_desc(&p.tm_out);
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int tiles_xy = p.tiles_x * p.tiles_y;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // ------------------------------------------------------------ TMA producer
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m = tile / p.n_tiles, nt = tile - m * p.n_tiles;
+        const int bn = m / tiles_xy, rem = m - bn * tiles_xy;
+        const int by = rem / p.tiles_x, bx = rem - by * p.tiles_x;
+        const int x0 = bx * p.tw, y0 = by * p.th, n0 = bn * p.tn;
+        for (int t = 0; t < p.num_taps; ++t) {
+          const CUtensorMap* ma = &p.tm_a[p.tap_a[t]];
+          const int xx = x0 + p.tap_dx[t], yy = y0 + p.tap_dy[t], wt = p.tap_w[t];
+          for (int kc = 0; kc < p.k_chunks; ++kc) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t a_dst = smem_base + (uint32_t)stage * stage_bytes;
+            mbar_expect_tx(full_bar(stage), stage_bytes);
+            tma_load_4d(a_dst, ma, full_bar(stage), kc * 64, xx, yy, n0);
+            tma_load_3d(a_dst + kABytes, &p.tm_b, full_bar(stage), kc * 64, wt, nt * p.BN);
+            if (++stage == S) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      // ------------------------------------------------------------ MMA issuer (single thread)
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccStride;
+        uint32_t accumulate = 0;
+        for (int t = 0; t < p.num_taps; ++t) {
+          for (int kc = 0; kc < p.k_chunks; ++kc) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t a_addr = smem_base + (uint32_t)stage * stage_bytes;
+            const uint64_t a_desc = make_smem_desc(a_addr, 16, 1024);
+            const uint64_t b_desc = make_smem_desc(a_addr + kABytes, 16, 1024);
+            const int nm = (kc == p.k_chunks - 1) ? p.last_mmas : 4;
+            for (int k = 0; k < nm; ++k) {
+              // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in the (addr>>4) field
+              umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, accumulate);
+              accumulate = 1;
+            }
+            umma_commit(empty_bar(stage));
+            if (++stage == S) { stage = 0; phase ^= 1u; }
+          }
+        }
+        umma_commit(tfull_bar(acc));
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue: 128 threads, thread e <-> tile row e
+    const int e = threadIdx.x - 128;
+    const int ewarp = e >> 5;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint32_t chunk_ctr = 0;
+    const int n_groups = (p.BN + 31) >> 5;
+    const int twth = p.tw * p.th;
+    const bool out_f32 = (p.flags & B2U_EPI_OUT_F32) != 0;
+    const bool do_relu = (p.flags & B2U_EPI_RELU) != 0;
+    const bool do_stats = (p.flags & B2U_EPI_STATS) != 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m = tile / p.n_tiles, nt = tile - m * p.n_tiles;
+      const int bn = m / tiles_xy, rem = m - bn * tiles_xy;
+      const int by = rem / p.tiles_x, bx = rem - by * p.tiles_x;
+      const int x0 = bx * p.tw, y0 = by * p.th, n0 = bn * p.tn;
+      const int rn = e / twth, rr = e - rn * twth;
+      const int ry = rr / p.tw, rx = rr - ry * p.tw;
+      const int px = x0 + rx, py = y0 + ry, pn = n0 + rn;
+      const bool valid = (px < p.Wo) && (py < p.Ho) && (pn < p.N);
+
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)acc * kAccStride + ((uint32_t)(ewarp * 32) << 16);
+
+      for (int g = 0; g < n_groups; ++g) {
+        uint32_t r[32];
+        tmem_ld32(taddr + (uint32_t)(g * 32), r);
+        tmem_ld_wait();
+        if (g == n_groups - 1) {
+          // all TMEM reads of this accumulator are in registers: hand it back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(tempty_bar(acc));
+        }
+        const int c0 = nt * p.BN + g * 32;
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        if (p.scale) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c0 + i < p.Cout) v[i] *= __ldg(p.scale + c0 + i);
+        }
+        if (p.shift) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c0 + i < p.Cout) v[i] += __ldg(p.shift + c0 + i);
+        }
+        if (p.res.ptr && valid) {
+          const __nv_bfloat16* rp = p.res.ptr + pn * p.res.sN + py * p.res.sH + px * p.res.sW + c0;
+          const __nv_bfloat16* mp =
+              p.res_mask.ptr ? p.res_mask.ptr + pn * p.res_mask.sN + py * p.res_mask.sH + px * p.res_mask.sW + c0
+                             : nullptr;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (c0 + q * 8 < p.CoutP8) {
+              float rv[8];
+              load8(rp + q * 8, rv);
+              if (mp) {
+                float mv[8];
+                load8(mp + q * 8, mv);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[q * 8 + i] += (mv[i] > 0.f) ? rv[i] : 0.f;
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[q * 8 + i] += rv[i];
+              }
+            }
+          }
+        }
+        if (do_relu) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        if (p.zmask.ptr && valid) {
+          const __nv_bfloat16* zp = p.zmask.ptr + pn * p.zmask.sN + py * p.zmask.sH + px * p.zmask.sW + c0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (c0 + q * 8 < p.CoutP8) {
+              float zv[8];
+              load8(zp + q * 8, zv);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[q * 8 + i] = (zv[i] > 0.f) ? v[q * 8 + i] : 0.f;
+            }
+          }
+        }
+
+        if (out_f32) {
+          if (valid) {
+            float* op = p.out_f32 + ((long long)(pn * p.Ho + py) * p.Wo + px) * p.out_f32_ld + c0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c0 + i < p.Cout) op[i] = v[i];
+          }
+        } else {
+          // bf16 pack -> swizzled staging (SWIZZLE_128B: 16-byte chunk j of row e lands at chunk j ^ (e & 7))
+          const uint32_t buf = chunk_ctr & 1u;
+          if ((g & 1) == 0) {
+            if (e == 0) tma_store_wait_read<1>();  // the store issued two chunks ago has finished reading this buffer
+            named_bar_sync(1, 128);
+          }
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+          const uint32_t row_addr = stg_base + buf * kStagingBytes + (uint32_t)e * 128u;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t j = (uint32_t)((g & 1) * 4 + q);
+            const uint32_t addr = row_addr + ((j ^ ((uint32_t)e & 7u)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
+                         "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
+                         : "memory");
+          }
+          if (do_stats) {
+            // statistics of what is actually stored (bf16-rounded), so that BN forward/backward are self-consistent
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              v[2 * i] = bf16_lo(pk[i]);
+              v[2 * i + 1] = bf16_hi(pk[i]);
+            }
+          }
+          if ((g & 1) == 1 || g == n_groups - 1) {
+            fence_proxy_async_smem();
+            named_bar_sync(1, 128);
+            if (e == 0) {
+              tma_store_4d(&p.tm_out, stg_base + buf * kStagingBytes, nt * p.BN + (g >> 1) * 64, x0, y0, n0);
+              tma_store_commit();
+            }
+            ++chunk_ctr;
+          }
+        }
+        if (do_stats) {
+          float s1[32], s2[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float q = (valid && (c0 + i < p.Cout)) ? v[i] : 0.f;
+            s1[i] = q;
+            s2[i] = q * q;
+          }
+          const float sum = warp_transpose_reduce(s1, lane);
+          const float sq = warp_transpose_reduce(s2, lane);
+          const int c = c0 + lane;
+          if (c < p.stats_ld) {
+            float* sp = p.stats + (size_t)(m * 4 + ewarp) * 2 * p.stats_ld;
+            sp[c] = sum;
+            sp[p.stats_ld + c] = sq;
+          }
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+    if (e == 0 && !out_f32) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace b2u
+
+// ======================================================================================================= host side
+using namespace b2u;
+
+struct b2u_conv_plan {
+  ConvParams p;
+  b2u_conv_info info;
+  size_t smem_bytes;
+};
+
+static bool view_ok(const b2u_view& v, const char* name) {
+  if (!v.ptr) { set_error("%s: null pointer", name); return false; }
+  if (v.C <= 0 || v.W <= 0 || v.H <= 0 || v.N <= 0) { set_error("%s: non-positive extent", name); return false; }
+  if ((v.sW % 8) || (v.sH % 8) || (v.sN % 8)) { set_error("%s: strides must be multiples of 8 elements", name); return false; }
+  if (reinterpret_cast<uintptr_t>(v.ptr) & 15) { set_error("%s: pointer must be 16-byte aligned", name); return false; }
+  return true;
+}
+
+// Pick the 128-pixel M tile (tw x th x tn, powers of two) that wastes the fewest rows; ties prefer wide tiles.
+static void pick_m_tile(int N, int H, int W, int* tw, int* th, int* tn, int* tiles_x, int* tiles_y, int* tiles_n) {
+  long long best = -1;
+  for (int w = 128; w >= 1; w >>= 1) {
+    for (int h = 128 / w; h >= 1; h >>= 1) {
+      const int n = 128 / (w * h);
+      const long long tx = ceil_div(W, w), ty = ceil_div(H, h), tb = ceil_div(N, n);
+      const long long cost = tx * ty * tb;
+      if (best < 0 || cost < best) {
+        best = cost;
+        *tw = w; *th = h; *tn = n;
+        *tiles_x = (int)tx; *tiles_y = (int)ty; *tiles_n = (int)tb;
+      }
+    }
+  }
+}
+
+static int conv_plan_fill(const b2u_conv_desc* d, b2u_conv_plan* plan, bool encode) {
+  B2U_CHECK_ARG(d != nullptr, "conv: null descriptor");
+  B2U_CHECK_ARG(d->num_a >= 1 && d->num_a <= B2U_MAX_VIEWS, "conv: num_a=%d out of range", d->num_a);
+  B2U_CHECK_ARG(d->num_taps >= 1 && d->num_taps <= B2U_MAX_TAPS, "conv: num_taps=%d out of range", d->num_taps);
+  B2U_CHECK_ARG(d->w != nullptr && d->w_rows > 0 && d->w_taps > 0 && d->w_cin > 0, "conv: bad weight tensor");
+  B2U_CHECK_ARG(d->w_cinp % 8 == 0 && d->w_cinp >= d->w_cin, "conv: w_cinp=%d must be a multiple of 8 and >= w_cin", d->w_cinp);
+  const bool out_f32 = (d->flags & B2U_EPI_OUT_F32) != 0;
+  B2U_CHECK_ARG(d->out.C > 0 && d->out.W > 0 && d->out.H > 0 && d->out.N > 0, "conv: bad output geometry");
+  B2U_CHECK_ARG(d->out.C == d->w_rows, "conv: out.C=%d != w_rows=%d", d->out.C, d->w_rows);
+  if (!out_f32) { if (!view_ok(d->out, "conv.out")) return B2U_ERR_ARG; }
+  else B2U_CHECK_ARG(d->out_f32 != nullptr && d->out_f32_ld >= d->out.C, "conv: out_f32 / out_f32_ld invalid");
+  for (int i = 0; i < d->num_a; ++i) {
+    if (!view_ok(d->a[i], "conv.a")) return B2U_ERR_ARG;
+    B2U_CHECK_ARG(d->a[i].C == d->w_cin, "conv: a[%d].C=%d != w_cin=%d", i, d->a[i].C, d->w_cin);
+  }
+  for (int t = 0; t < d->num_taps; ++t) {
+    B2U_CHECK_ARG(d->tap_a[t] >= 0 && d->tap_a[t] < d->num_a, "conv: tap %d view index out of range", t);
+    B2U_CHECK_ARG(d->tap_w[t] >= 0 && d->tap_w[t] < d->w_taps, "conv: tap %d weight index out of range", t);
+  }
+  if (d->flags & B2U_EPI_STATS) B2U_CHECK_ARG(d->stats != nullptr && !out_f32, "conv: stats needs a buffer and bf16 output");
+
+  ConvParams& p = plan->p;
+  memset(&p, 0, sizeof(p));
+  const int Cout = d->out.C, Cin = d->w_cin;
+  // N tiling
+  int n_tiles, BN;
+  if (Cout <= 256) { n_tiles = 1; BN = round_up(Cout, 16); }
+  else { n_tiles = ceil_div(Cout, 256); BN = round_up(ceil_div(Cout, n_tiles), 64); n_tiles = ceil_div(Cout, BN); }
+  int tw, th, tn, tx, ty, tb;
+  pick_m_tile(d->out.N, d->out.H, d->out.W, &tw, &th, &tn, &tx, &ty, &tb);
+  p.tw = tw; p.th = th; p.tn = tn; p.tiles_x = tx; p.tiles_y = ty;
+  p.m_tiles = tx * ty * tb; p.n_tiles = n_tiles; p.BN = BN;
+  p.num_taps = d->num_taps;
+  p.k_chunks = ceil_div(Cin, 64);
+  p.last_mmas = ceil_div(Cin - 64 * (p.k_chunks - 1), 16);
+  for (int t = 0; t < d->num_taps; ++t) {
+    p.tap_a[t] = d->tap_a[t]; p.tap_dy[t] = d->tap_dy[t]; p.tap_dx[t] = d->tap_dx[t]; p.tap_w[t] = d->tap_w[t];
+  }
+  const uint32_t stage_bytes = kABytes + (uint32_t)BN * 128u;
+  const uint32_t fixed = 2 * kStagingBytes + 256;
+  int stages = (int)((232448u - fixed) / stage_bytes);
+  if (stages > 8) stages = 8;
+  B2U_CHECK_ARG(stages >= 2, "conv: not enough shared memory for 2 stages");
+  p.stages = stages;
+  plan->smem_bytes = (size_t)stages * stage_bytes + fixed;
+  // at least half of the SM's shared memory, so that exactly one CTA (and its 512 TMEM columns) lives on an SM
+  if (plan->smem_bytes < 120 * 1024) plan->smem_bytes = 120 * 1024;
+  p.idesc = make_idesc_bf16(128, BN, 0, 0);
+  p.N = d->out.N; p.Ho = d->out.H; p.Wo = d->out.W; p.Cout = Cout; p.CoutP8 = round_up(Cout, 8);
+  p.scale = d->scale; p.shift = d->shift;
+  auto ev = [](const b2u_view& v) { EpiView e; e.ptr = (const __nv_bfloat16*)v.ptr; e.sW = v.sW; e.sH = v.sH; e.sN = v.sN; return e; };
+  p.res = ev(d->res); p.res_mask = ev(d->res_mask); p.zmask = ev(d->zmask);
+  p.flags = d->flags; p.stats = d->stats; p.stats_ld = d->stats_ld;
+  p.out_f32 = d->out_f32; p.out_f32_ld = d->out_f32_ld;
+  if (d->flags & B2U_EPI_STATS) B2U_CHECK_ARG(d->stats_ld >= Cout, "conv: stats_ld=%d < Cout=%d", d->stats_ld, Cout);
+
+  b2u_conv_info& info = plan->info;
+  info.m_tiles = p.m_tiles; info.n_tiles = n_tiles; info.block_n = BN; info.tile_w = tw; info.tile_h = th; info.tile_n = tn;
+  info.stages = stages; info.k_chunks = p.k_chunks; info.stats_rows = 4 * p.m_tiles;
+  const int total = p.m_tiles * n_tiles;
+  const int sms = encode ? sm_count() : 148;
+  info.grid = total < sms ? total : sms;
+
+  if (encode) {
+    for (int i = 0; i < d->num_a; ++i) {
+      int rc = view_tmap(&p.tm_a[i], d->a[i], 64, (uint32_t)tw, (uint32_t)th, (uint32_t)tn);
+      if (rc) return rc;
+    }
+    for (int i = d->num_a; i < B2U_MAX_VIEWS; ++i) p.tm_a[i] = p.tm_a[0];
+    {
+      uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)d->w_taps, (uint64_t)d->w_rows};
+      uint64_t str[3] = {2, (uint64_t)d->w_cinp * 2, (uint64_t)d->w_cinp * 2 * (uint64_t)d->w_taps};
+      uint32_t box[3] = {64, 1, (uint32_t)BN};
+      int rc = encode_tmap_bf16(&p.tm_b, d->w, 3, dims, str, box);
+      if (rc) return rc;
+    }
+    if (!out_f32) {
+      int rc = view_tmap(&p.tm_out, d->out, 64, (uint32_t)tw, (uint32_t)th, (uint32_t)tn);
+      if (rc) return rc;
+    } else {
+      p.tm_out = p.tm_b;
+    }
+  }
+  return B2U_OK;
+}
+
+extern "C" int b2u_conv_query(const b2u_conv_desc* d, b2u_conv_info* info) {
+  b2u_conv_plan tmp;
+  int rc = conv_plan_fill(d, &tmp, false);
+  if (rc) return rc;
+  if (info) *info = tmp.info;
+  return B2U_OK;
+}
+
+extern "C" int b2u_conv_plan_create(const b2u_conv_desc* d, b2u_conv_plan** out) {
+  B2U_CHECK_ARG(out != nullptr, "conv_plan_create: null out");
+  b2u_conv_plan* plan = new b2u_conv_plan();
+  int rc = conv_plan_fill(d, plan, true);
+  if (rc) { delete plan; return rc; }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(conv_gemm_kernel): %s", cudaGetErrorString(e)); delete plan; return B2U_ERR_CUDA; }
+    attr_set = true;
+  }
+  *out = plan;
+  return B2U_OK;
+}
+
+extern "C" int b2u_conv_plan_info(const b2u_conv_plan* plan, b2u_conv_info* info) {
+  B2U_CHECK_ARG(plan && info, "conv_plan_info: null argument");
+  *info = plan->info;
+  return B2U_OK;
+}
+
+extern "C" int b2u_conv_run(const b2u_conv_plan* plan, void* stream) {
+  B2U_CHECK_ARG(plan != nullptr, "conv_run: null plan");
+  conv_gemm_kernel<<<plan->info.grid, kThreads, plan->smem_bytes, (cudaStream_t)stream>>>(plan->p);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" void b2u_conv_plan_destroy(b2u_conv_plan* plan) { delete plan; }

@@ -1,0 +1,408 @@
+// Weight-gradient GEMM for sm_100a:  dW[co][tap][ci] = sum_pixels dY[pixel][co] * X[pixel + tap offset][ci].
+// Both operands are read straight from NHWC activations with TMA (32-pixel boxes of 64 channels, 128B swizzle) and fed
+// to tcgen05.mma as MN-major matrices (the contraction index = pixels is the strided one), M = 128 output channels,
+// N <= 256 input channels, fp32 accumulators for up to 512/N filter taps live side by side in TMEM so that the dY tile
+// is fetched once for all of them.  The pixel range is split across CTAs; partial tiles go to an fp32 workspace that
+// b2u_wgrad_reduce sums in a fixed order (deterministic, no float atomics).  An optional all-ones B operand yields the
+// bias gradient (row sums of dY) from the same pass.
+//
+// Replaces cudnnConvolutionBackwardFilter as reached from loss.backward() in fastai's Learner (reference train.py:246-250).
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace b2u {
+
+static constexpr int kWgThreads = 256;
+static constexpr int kKP = 32;                   // pixels per pipeline stage
+static constexpr uint32_t kBoxBytes = kKP * 128; // one TMA box: 32 pixels x 64 bf16
+
+struct WgradParams {
+  CUtensorMap tm_dy;
+  CUtensorMap tm_a[B2U_MAX_VIEWS];
+  int num_taps;
+  int8_t tap_a[B2U_MAX_TAPS], tap_dy[B2U_MAX_TAPS], tap_dx[B2U_MAX_TAPS];
+  int Cout, Cin;
+  int BN, NB;            // ci tile width (multiple of 16) and its number of 64-channel boxes
+  int T;                 // taps per unit
+  int n_co, n_ci, n_tg;  // tiles over Cout (128), Cin (BN) and tap groups
+  int inner;             // units per (split, co tile) = n_ci*n_tg + want_bias
+  int want_bias;
+  int splits, k_steps, steps_per_split;
+  int tw, th, tn, tiles_x, tiles_y;
+  int stages;
+  uint32_t idesc, idesc_bias;
+  int co_pad, ci_pad, taps_total;  // partial layout [splits][taps_total][co_pad][ci_pad]
+  float* partial;
+  int units;
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_constant__ WgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5;
+  const uint32_t smem_base = smem_u32(smem);
+  const int S = p.stages;
+  const uint32_t stage_bytes = kBoxBytes * (uint32_t)(2 + p.T * p.NB);
+  const uint32_t ones_base = smem_base + (uint32_t)S * stage_bytes;  // 32 pixel rows x 128 B of bf16 1.0
+  const uint32_t bar_base = ones_base + kBoxBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(S + s); };
+  const uint32_t tfull_bar = bar_base + 8u * (uint32_t)(2 * S);
+  const uint32_t tempty_bar = bar_base + 8u * (uint32_t)(2 * S + 1);
+  const uint32_t tmem_slot = bar_base + 8u * (uint32_t)(2 * S + 2);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem + (size_t)S * stage_bytes + kBoxBytes + 8 * (2 * S + 2));
+
+  if (threadIdx.x == 0) {
+    if (smem_base & 1023u) {
+      printf("b2u: dynamic smem base 0x%x not 1024-byte aligned\n", smem_base);
+      __trap();
+    }
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tfull_bar, 1);
+    mbar_init(tempty_bar, 128);
+    fence_mbar_init();
+    tma_prefetch_desc(&p.tm_dy);
+    for (int i = 0; i < B2U_MAX_VIEWS; ++i) tma_prefetch_desc(&p.tm_a[i]);
+  }
+  {
+    // all-ones operand for the bias gradient; written through the generic proxy, read by the tensor core (async proxy)
+    uint32_t* ones = reinterpret_cast<uint32_t*>(smem + (size_t)S * stage_bytes);
+    for (int i = threadIdx.x; i < (int)(kBoxBytes / 4); i += kWgThreads) ones[i] = 0x3F803F80u;
+    fence_proxy_async_smem();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const int tiles_xy = p.tiles_x * p.tiles_y;
+
+  // unit -> (split, co tile, inner); inner < n_ci*n_tg: (ci tile, tap group); inner == n_ci*n_tg: bias unit
+  auto decode = [&](int u, int& split, int& co, int& ci, int& tg, bool& bias) {
+    const int per_split = p.n_co * p.inner;
+    split = u / per_split;
+    const int r = u - split * per_split;
+    co = r / p.inner;
+    const int in = r - co * p.inner;
+    bias = in >= p.n_ci * p.n_tg;
+    ci = bias ? 0 : in / p.n_tg;
+    tg = bias ? 0 : in - ci * p.n_tg;
+  };
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // ------------------------------------------------------------ TMA producer
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+        int split, co, ci, tg;
+        bool bias;
+        decode(u, split, co, ci, tg, bias);
+        const int t0 = tg * p.T;
+        const int nt = bias ? 0 : min(p.T, p.num_taps - t0);
+        const int k_begin = split * p.steps_per_split;
+        const int k_end = min(p.k_steps, k_begin + p.steps_per_split);
+        const uint32_t bytes = kBoxBytes * (uint32_t)(2 + nt * p.NB);
+        for (int ks = k_begin; ks < k_end; ++ks) {
+          const int bn = ks / tiles_xy, rem = ks - bn * tiles_xy;
+          const int by = rem / p.tiles_x, bx = rem - by * p.tiles_x;
+          const int x0 = bx * p.tw, y0 = by * p.th, n0 = bn * p.tn;
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t base = smem_base + (uint32_t)stage * stage_bytes;
+          mbar_expect_tx(full_bar(stage), bytes);
+          tma_load_4d(base, &p.tm_dy, full_bar(stage), co * 128, x0, y0, n0);
+          tma_load_4d(base + kBoxBytes, &p.tm_dy, full_bar(stage), co * 128 + 64, x0, y0, n0);
+          for (int j = 0; j < nt; ++j) {
+            const int t = t0 + j;
+            const CUtensorMap* ma = &p.tm_a[p.tap_a[t]];
+            for (int b = 0; b < p.NB; ++b)
+              tma_load_4d(base + kBoxBytes * (uint32_t)(2 + j * p.NB + b), ma, full_bar(stage), ci * p.BN + b * 64,
+                          x0 + p.tap_dx[t], y0 + p.tap_dy[t], n0);
+          }
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      // ------------------------------------------------------------ MMA issuer
+      int stage = 0;
+      uint32_t phase = 0, tphase = 0;
+      for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+        int split, co, ci, tg;
+        bool bias;
+        decode(u, split, co, ci, tg, bias);
+        const int t0 = tg * p.T;
+        const int nt = bias ? 0 : min(p.T, p.num_taps - t0);
+        const int k_begin = split * p.steps_per_split;
+        const int k_end = min(p.k_steps, k_begin + p.steps_per_split);
+        mbar_wait(tempty_bar, tphase ^ 1u);
+        tc_fence_after();
+        uint32_t accumulate = 0;
+        for (int ks = k_begin; ks < k_end; ++ks) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t base = smem_base + (uint32_t)stage * stage_bytes;
+#pragma unroll
+          for (int k = 0; k < kKP / 16; ++k) {
+            // MN-major, SW128: 64-channel groups are LBO = one box apart, 8-pixel groups are SBO = 1024 B apart;
+            // 16 pixels further along K = 16 rows x 128 B = 2048 B.
+            const uint64_t a_desc = make_smem_desc(base + (uint32_t)k * 2048u, kBoxBytes, 1024);
+            if (bias) {
+              const uint64_t b_desc = make_smem_desc(ones_base + (uint32_t)k * 2048u, kBoxBytes, 1024);
+              umma_bf16(tmem_base, a_desc, b_desc, p.idesc_bias, accumulate);
+            } else {
+              for (int j = 0; j < nt; ++j) {
+                const uint64_t b_desc =
+                    make_smem_desc(base + kBoxBytes * (uint32_t)(2 + j * p.NB) + (uint32_t)k * 2048u, kBoxBytes, 1024);
+                umma_bf16(tmem_base + (uint32_t)(j * p.BN), a_desc, b_desc, p.idesc, accumulate);
+              }
+            }
+            accumulate = 1;
+          }
+          umma_commit(empty_bar(stage));
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar);
+        tphase ^= 1u;
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue: TMEM -> fp32 partial tile in global
+    const int e = threadIdx.x - 128;
+    const int ewarp = e >> 5;
+    uint32_t tphase = 0;
+    for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+      int split, co, ci, tg;
+      bool bias;
+      decode(u, split, co, ci, tg, bias);
+      const int t0 = tg * p.T;
+      const int nt = bias ? 0 : min(p.T, p.num_taps - t0);
+      const int k_begin = split * p.steps_per_split;
+      const bool empty_range = k_begin >= p.k_steps;
+      mbar_wait(tfull_bar, tphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(ewarp * 32) << 16);
+      const int row = co * 128 + e;
+      if (bias) {
+        uint32_t r[16];
+        tmem_ld16(taddr, r);
+        tmem_ld_wait();
+        if (row < p.co_pad)
+          p.partial[(((size_t)split * p.taps_total + p.num_taps) * p.co_pad + row) * p.ci_pad] =
+              empty_range ? 0.f : __uint_as_float(r[0]);
+      } else {
+        const int n_groups = (p.BN + 31) >> 5;
+        for (int j = 0; j < nt; ++j) {
+          float* dst = p.partial + (((size_t)split * p.taps_total + (t0 + j)) * p.co_pad + row) * p.ci_pad + ci * p.BN;
+          for (int g = 0; g < n_groups; ++g) {
+            uint32_t r[32];
+            tmem_ld32(taddr + (uint32_t)(j * p.BN + g * 32), r);
+            tmem_ld_wait();
+            if (row < p.co_pad) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const int c = ci * p.BN + g * 32 + q * 4;
+                if (c < p.ci_pad && g * 32 + q * 4 < p.BN) {
+                  float4 o;
+                  o.x = empty_range ? 0.f : __uint_as_float(r[4 * q]);
+                  o.y = empty_range ? 0.f : __uint_as_float(r[4 * q + 1]);
+                  o.z = empty_range ? 0.f : __uint_as_float(r[4 * q + 2]);
+                  o.w = empty_range ? 0.f : __uint_as_float(r[4 * q + 3]);
+                  *reinterpret_cast<float4*>(dst + g * 32 + q * 4) = o;
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar);
+      tphase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// dw[perm(co)][ci][kidx] = alpha * sum_{t: tap_kidx[t]==kidx} sum_s partial[s][t][co][ci]
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int taps, int taps_total, int co_pad,
+                                    int ci_pad, int Cout, int Cin, int ksize, const int* __restrict__ tap_kidx,
+                                    const int* __restrict__ row_perm, float alpha, float* __restrict__ dw,
+                                    float* __restrict__ db) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)Cout * ksize * Cin;
+  if (idx < total) {
+    const int ci = (int)(idx % Cin);
+    const int kidx = (int)((idx / Cin) % ksize);
+    const int co = (int)(idx / ((long long)Cin * ksize));
+    float acc = 0.f;
+    for (int t = 0; t < taps; ++t) {
+      if (tap_kidx[t] != kidx) continue;
+      for (int s = 0; s < splits; ++s)
+        acc += partial[(((size_t)s * taps_total + t) * co_pad + co) * ci_pad + ci];
+    }
+    const int oc = row_perm ? row_perm[co] : co;
+    dw[((size_t)oc * Cin + ci) * ksize + kidx] = alpha * acc;
+  }
+  if (db && idx < Cout) {
+    const int co = (int)idx;
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += partial[(((size_t)s * taps_total + taps) * co_pad + co) * ci_pad];
+    const int oc = row_perm ? row_perm[co] : co;
+    db[oc] = acc;
+  }
+}
+
+}  // namespace b2u
+
+using namespace b2u;
+
+struct b2u_wgrad_plan {
+  WgradParams p;
+  b2u_wgrad_info info;
+  size_t smem_bytes;
+};
+
+static int wgrad_fill(const b2u_wgrad_desc* d, b2u_wgrad_plan* plan, bool encode) {
+  B2U_CHECK_ARG(d != nullptr, "wgrad: null descriptor");
+  B2U_CHECK_ARG(d->num_a >= 1 && d->num_a <= B2U_MAX_VIEWS, "wgrad: num_a out of range");
+  B2U_CHECK_ARG(d->num_taps >= 1 && d->num_taps <= B2U_MAX_TAPS, "wgrad: num_taps out of range");
+  B2U_CHECK_ARG(d->Cout > 0 && d->Cin > 0, "wgrad: bad channel counts");
+  B2U_CHECK_ARG(d->dy.C == d->Cout, "wgrad: dy.C=%d != Cout=%d", d->dy.C, d->Cout);
+  for (int i = 0; i < d->num_a; ++i) B2U_CHECK_ARG(d->a[i].C == d->Cin, "wgrad: a[%d].C != Cin", i);
+  WgradParams& p = plan->p;
+  memset(&p, 0, sizeof(p));
+  p.num_taps = d->num_taps;
+  for (int t = 0; t < d->num_taps; ++t) {
+    B2U_CHECK_ARG(d->tap_a[t] >= 0 && d->tap_a[t] < d->num_a, "wgrad: tap %d view index out of range", t);
+    p.tap_a[t] = d->tap_a[t]; p.tap_dy[t] = d->tap_dy[t]; p.tap_dx[t] = d->tap_dx[t];
+  }
+  p.Cout = d->Cout; p.Cin = d->Cin;
+  const int cin16 = round_up(d->Cin, 16);
+  p.n_ci = ceil_div(cin16, 256);
+  p.BN = round_up(ceil_div(cin16, p.n_ci), 16);
+  p.NB = ceil_div(p.BN, 64);
+  int tmax = 512 / p.BN;
+  if (tmax > d->num_taps) tmax = d->num_taps;
+  p.n_tg = ceil_div(d->num_taps, tmax);
+  p.T = ceil_div(d->num_taps, p.n_tg);
+  p.n_co = ceil_div(d->Cout, 128);
+  p.want_bias = d->want_bias ? 1 : 0;
+  p.inner = p.n_ci * p.n_tg + p.want_bias;
+  // pixel (K) tiling: 32-pixel boxes
+  {
+    long long best = -1;
+    for (int w = kKP; w >= 1; w >>= 1)
+      for (int h = kKP / w; h >= 1; h >>= 1) {
+        const int n = kKP / (w * h);
+        const long long c = (long long)ceil_div(d->dy.W, w) * ceil_div(d->dy.H, h) * ceil_div(d->dy.N, n);
+        if (best < 0 || c < best) {
+          best = c; p.tw = w; p.th = h; p.tn = n;
+          p.tiles_x = ceil_div(d->dy.W, w); p.tiles_y = ceil_div(d->dy.H, h);
+        }
+      }
+    p.k_steps = (int)best;
+  }
+  const int base_units = p.n_co * p.inner;
+  const int sms = encode ? sm_count() : 148;
+  int splits = (2 * sms) / base_units;
+  const int max_splits = p.k_steps / 16 > 0 ? p.k_steps / 16 : 1;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  p.steps_per_split = ceil_div(p.k_steps, splits);
+  splits = ceil_div(p.k_steps, p.steps_per_split);
+  p.splits = splits;
+  p.units = splits * base_units;
+  const uint32_t stage_bytes = kBoxBytes * (uint32_t)(2 + p.T * p.NB);
+  int stages = (int)((232448u - kBoxBytes - 256u) / stage_bytes);
+  if (stages > 8) stages = 8;
+  B2U_CHECK_ARG(stages >= 2, "wgrad: not enough shared memory");
+  p.stages = stages;
+  plan->smem_bytes = (size_t)stages * stage_bytes + kBoxBytes + 256;
+  if (plan->smem_bytes < 120 * 1024) plan->smem_bytes = 120 * 1024;
+  p.idesc = make_idesc_bf16(128, p.BN, 1, 1);
+  p.idesc_bias = make_idesc_bf16(128, 16, 1, 1);
+  p.co_pad = p.n_co * 128;
+  p.ci_pad = p.n_ci * p.BN;
+  p.taps_total = d->num_taps + p.want_bias;
+  p.partial = d->partial;
+
+  b2u_wgrad_info& info = plan->info;
+  info.splits = splits; info.co_pad = p.co_pad; info.ci_pad = p.ci_pad; info.taps_per_unit = p.T;
+  info.units = p.units; info.grid = p.units < sms ? p.units : sms; info.k_steps = p.k_steps;
+  info.block_n = p.BN; info.stages = stages;
+  info.partial_bytes = (size_t)splits * p.taps_total * p.co_pad * p.ci_pad * sizeof(float);
+
+  if (encode) {
+    B2U_CHECK_ARG(d->partial != nullptr && d->partial_bytes >= info.partial_bytes,
+                  "wgrad: partial workspace too small (%zu < %zu)", d->partial_bytes, info.partial_bytes);
+    int rc = view_tmap(&p.tm_dy, d->dy, 64, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.tn);
+    if (rc) return rc;
+    for (int i = 0; i < d->num_a; ++i) {
+      rc = view_tmap(&p.tm_a[i], d->a[i], 64, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.tn);
+      if (rc) return rc;
+    }
+    for (int i = d->num_a; i < B2U_MAX_VIEWS; ++i) p.tm_a[i] = p.tm_a[0];
+  }
+  return B2U_OK;
+}
+
+extern "C" int b2u_wgrad_query(const b2u_wgrad_desc* d, b2u_wgrad_info* info) {
+  b2u_wgrad_plan tmp;
+  int rc = wgrad_fill(d, &tmp, false);
+  if (rc) return rc;
+  if (info) *info = tmp.info;
+  return B2U_OK;
+}
+
+extern "C" int b2u_wgrad_plan_create(const b2u_wgrad_desc* d, b2u_wgrad_plan** out) {
+  B2U_CHECK_ARG(out != nullptr, "wgrad_plan_create: null out");
+  b2u_wgrad_plan* plan = new b2u_wgrad_plan();
+  int rc = wgrad_fill(d, plan, true);
+  if (rc) { delete plan; return rc; }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(wgrad_gemm_kernel): %s", cudaGetErrorString(e)); delete plan; return B2U_ERR_CUDA; }
+    attr_set = true;
+  }
+  *out = plan;
+  return B2U_OK;
+}
+
+extern "C" int b2u_wgrad_run(const b2u_wgrad_plan* plan, void* stream) {
+  B2U_CHECK_ARG(plan != nullptr, "wgrad_run: null plan");
+  wgrad_gemm_kernel<<<plan->info.grid, kWgThreads, plan->smem_bytes, (cudaStream_t)stream>>>(plan->p);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" void b2u_wgrad_plan_destroy(b2u_wgrad_plan* plan) { delete plan; }
+
+extern "C" int b2u_wgrad_reduce(const float* partial, int32_t splits, int32_t taps, int32_t co_pad, int32_t ci_pad,
+                                int32_t Cout, int32_t Cin, int32_t ksize, const int32_t* tap_kidx,
+                                const int32_t* row_perm, float alpha, float* dw, float* db, int32_t has_bias_cols,
+                                void* stream) {
+  B2U_CHECK_ARG(partial && dw && tap_kidx, "wgrad_reduce: null argument");
+  B2U_CHECK_ARG(!db || has_bias_cols, "wgrad_reduce: db requested but the partial buffer has no bias slot");
+  const long long total = (long long)Cout * ksize * Cin;
+  const int threads = 256;
+  const long long blocks = (total + threads - 1) / threads;
+  wgrad_reduce_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+      partial, splits, taps, taps + (has_bias_cols ? 1 : 0), co_pad, ci_pad, Cout, Cin, ksize, tap_kidx, row_perm,
+      alpha, dw, db);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}

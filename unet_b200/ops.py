@@ -1,0 +1,224 @@
+"""Host-side operator layer over the C-ABI: views, tap tables and plan objects for the implicit-GEMM kernels.
+
+Activations are torch bf16 tensors [N, H, W, Cp] (NHWC, channel pitch Cp a multiple of 8); torch only owns memory.
+All arithmetic happens in libb2u.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, ConvInfo, View, WgradDesc, WgradInfo
+
+
+def pad8(c: int) -> int:
+    return (c + 7) // 8 * 8
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def view_nhwc(t: torch.Tensor, C_: Optional[int] = None, c_off: int = 0,
+              parity: Optional[Tuple[int, int]] = None) -> View:
+    """A b2u_view over a contiguous NHWC bf16 tensor: a channel slice [c_off, c_off+C) and optionally one of the four
+    stride-2 parity planes (py, px): element (n, u, v, c) = t[n, 2u+py, 2v+px, c_off+c]."""
+    assert t.dtype == torch.bfloat16 and t.dim() == 4 and t.is_contiguous(), (t.dtype, t.shape, t.stride())
+    N, H, W, Cp = t.shape
+    assert Cp % 8 == 0 and c_off % 8 == 0
+    C_ = Cp - c_off if C_ is None else C_
+    assert 0 < C_ <= Cp - c_off
+    v = View()
+    if parity is None:
+        v.ptr = t.data_ptr() + 2 * c_off
+        v.C, v.W, v.H, v.N = C_, W, H, N
+        v.sW, v.sH, v.sN = Cp, W * Cp, H * W * Cp
+    else:
+        py, px = parity
+        v.ptr = t.data_ptr() + 2 * ((py * W + px) * Cp + c_off)
+        v.C, v.W, v.H, v.N = C_, (W - px + 1) // 2, (H - py + 1) // 2, N
+        v.sW, v.sH, v.sN = 2 * Cp, 2 * W * Cp, H * W * Cp
+    return v
+
+
+def null_view() -> View:
+    return View()
+
+
+Tap = Tuple[int, int, int, int]  # (view index, dy, dx, weight tap)
+
+
+def taps_conv(ks: int) -> List[Tap]:
+    """stride-1 'same' convolution: taps (r,s) read the single input view at offset (r-p, s-p)."""
+    p = (ks - 1) // 2
+    return [(0, r - p, s - p, r * ks + s) for r in range(ks) for s in range(ks)]
+
+
+_S2 = {0: (-1, 1), 1: (0, 0), 2: (0, 1)}  # filter row r -> (plane offset, plane parity) for stride 2, pad 1
+
+
+def taps_conv3_s2() -> List[Tap]:
+    """3x3 / stride 2 / pad 1 over the four parity planes (view index = 2*py+px) of the input."""
+    out = []
+    for r in range(3):
+        dy, py = _S2[r]
+        for s in range(3):
+            dx, px = _S2[s]
+            out.append((2 * py + px, dy, dx, r * 3 + s))
+    return out
+
+
+def taps_avgpool_1x1() -> List[Tap]:
+    """AvgPool2d(2) followed by a 1x1 conv == four taps (one per parity plane) sharing the 1x1 filter scaled by 1/4."""
+    return [(2 * py + px, 0, 0, 0) for py in range(2) for px in range(2)]
+
+
+def taps_dgrad_s2(py: int, px: int) -> List[Tap]:
+    """Input-gradient of the 3x3/stride-2/pad-1 conv for the (py,px) parity plane of dX: a stride-1 conv over dY using
+    the filter rows/cols of matching parity. Weight tap indices address the *flipped* dgrad layout (8 - t)."""
+    rows = [(1, 0)] if py == 0 else [(0, 1), (2, 0)]
+    cols = [(1, 0)] if px == 0 else [(0, 1), (2, 0)]
+    return [(0, di, dj, 8 - (r * 3 + s)) for (r, di) in rows for (s, dj) in cols]
+
+
+def _fill_taps(desc, taps: Sequence[Tap], with_w: bool = True):
+    desc.num_taps = len(taps)
+    for i, (a, dy, dx, w) in enumerate(taps):
+        desc.tap_a[i], desc.tap_dy[i], desc.tap_dx[i] = a, dy, dx
+        if with_w:
+            desc.tap_w[i] = w
+
+
+class ConvPlan:
+    """One launch of the implicit-GEMM kernel with its TMA descriptors pre-encoded (b2u_conv_plan)."""
+
+    def __init__(self, a_views: Sequence[View], out_view: View, w: torch.Tensor, w_cin: int, taps: Sequence[Tap],
+                 scale: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None,
+                 res: Optional[View] = None, res_mask: Optional[View] = None, zmask: Optional[View] = None,
+                 relu: bool = False, stats: bool = False, out_f32: Optional[torch.Tensor] = None,
+                 stats_ld: Optional[int] = None):
+        assert w.dtype == torch.bfloat16 and w.dim() == 3 and w.is_contiguous()
+        lib = _lib.load()
+        d = ConvDesc()
+        for i, v in enumerate(a_views):
+            d.a[i] = v
+        d.num_a = len(a_views)
+        d.out = out_view
+        d.w = w.data_ptr()
+        d.w_rows, d.w_taps, d.w_cinp = w.shape
+        d.w_cin = w_cin
+        _fill_taps(d, taps)
+        self._keep = [w, scale, shift, out_f32]
+        d.scale = scale.data_ptr() if scale is not None else None
+        d.shift = shift.data_ptr() if shift is not None else None
+        if res is not None:
+            d.res = res
+        if res_mask is not None:
+            d.res_mask = res_mask
+        if zmask is not None:
+            d.zmask = zmask
+        flags = 0
+        if relu:
+            flags |= _lib.EPI_RELU
+        if out_f32 is not None:
+            assert out_f32.dtype == torch.float32 and out_f32.is_contiguous()
+            flags |= _lib.EPI_OUT_F32
+            d.out_f32 = out_f32.data_ptr()
+            d.out_f32_ld = out_f32.shape[-1]
+        d.flags = flags
+        self.stats = None
+        if stats:
+            info = ConvInfo()
+            _lib.check(lib.b2u_conv_query(C.byref(d), C.byref(info)), "b2u_conv_query")
+            ld = stats_ld or pad8(out_view.C)
+            self.stats = torch.zeros((info.stats_rows, 2, ld), dtype=torch.float32, device=w.device)
+            d.flags = flags | _lib.EPI_STATS
+            d.stats = self.stats.data_ptr()
+            d.stats_ld = ld
+        self.desc = d
+        h = C.c_void_p()
+        _lib.check(lib.b2u_conv_plan_create(C.byref(d), C.byref(h)), "b2u_conv_plan_create")
+        self.handle = h
+        self.info = ConvInfo()
+        _lib.check(lib.b2u_conv_plan_info(h, C.byref(self.info)), "b2u_conv_plan_info")
+        self._lib = lib
+
+    def run(self, stream: Optional[int] = None):
+        _lib.check(self._lib.b2u_conv_run(self.handle, C.c_void_p(stream if stream is not None else stream_ptr())),
+                   "b2u_conv_run")
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h:
+            self._lib.b2u_conv_plan_destroy(h)
+            self.handle = None
+
+
+class WgradPlan:
+    """Weight-gradient GEMM + deterministic split reduction into a torch-layout fp32 gradient."""
+
+    def __init__(self, dy_view: View, a_views: Sequence[View], taps: Sequence[Tap], Cout: int, Cin: int,
+                 ksize: int, tap_kidx: Sequence[int], dw: torch.Tensor, db: Optional[torch.Tensor] = None,
+                 row_perm: Optional[torch.Tensor] = None, alpha: float = 1.0,
+                 workspace: Optional[torch.Tensor] = None):
+        lib = _lib.load()
+        d = WgradDesc()
+        d.dy = dy_view
+        for i, v in enumerate(a_views):
+            d.a[i] = v
+        d.num_a = len(a_views)
+        _fill_taps(d, taps, with_w=False)
+        d.Cout, d.Cin = Cout, Cin
+        d.want_bias = 1 if db is not None else 0
+        info = WgradInfo()
+        _lib.check(lib.b2u_wgrad_query(C.byref(d), C.byref(info)), "b2u_wgrad_query")
+        dev = dw.device
+        if workspace is None or workspace.numel() * 4 < info.partial_bytes:
+            workspace = torch.empty((info.partial_bytes + 3) // 4, dtype=torch.float32, device=dev)
+        self.workspace = workspace
+        d.partial = workspace.data_ptr()
+        d.partial_bytes = workspace.numel() * 4
+        h = C.c_void_p()
+        _lib.check(lib.b2u_wgrad_plan_create(C.byref(d), C.byref(h)), "b2u_wgrad_plan_create")
+        self.handle, self.info, self.desc = h, info, d
+        assert dw.dtype == torch.float32 and dw.is_contiguous() and dw.numel() == Cout * Cin * ksize
+        self.dw, self.db = dw, db
+        self.kidx = torch.tensor(list(tap_kidx), dtype=torch.int32, device=dev)
+        self.row_perm = row_perm
+        self.alpha, self.ksize, self.Cout, self.Cin, self.ntaps = alpha, ksize, Cout, Cin, len(taps)
+        self._lib = lib
+
+    @staticmethod
+    def query(dy_view: View, a_views: Sequence[View], taps: Sequence[Tap], Cout: int, Cin: int,
+              want_bias: bool) -> WgradInfo:
+        lib = _lib.load()
+        d = WgradDesc()
+        d.dy = dy_view
+        for i, v in enumerate(a_views):
+            d.a[i] = v
+        d.num_a = len(a_views)
+        _fill_taps(d, taps, with_w=False)
+        d.Cout, d.Cin, d.want_bias = Cout, Cin, int(want_bias)
+        info = WgradInfo()
+        _lib.check(lib.b2u_wgrad_query(C.byref(d), C.byref(info)), "b2u_wgrad_query")
+        return info
+
+    def run(self, stream: Optional[int] = None):
+        s = C.c_void_p(stream if stream is not None else stream_ptr())
+        _lib.check(self._lib.b2u_wgrad_run(self.handle, s), "b2u_wgrad_run")
+        _lib.check(self._lib.b2u_wgrad_reduce(
+            self.workspace.data_ptr(), self.info.splits, self.ntaps, self.info.co_pad, self.info.ci_pad, self.Cout,
+            self.Cin, self.ksize, self.kidx.data_ptr(),
+            self.row_perm.data_ptr() if self.row_perm is not None else None, self.alpha, self.dw.data_ptr(),
+            self.db.data_ptr() if self.db is not None else None, 1 if self.db is not None else 0, s),
+            "b2u_wgrad_reduce")
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h:
+            self._lib.b2u_wgrad_plan_destroy(h)
+            self.handle = None
