@@ -259,6 +259,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           }
         }
 
+        if (c0 + 32 > p.Cout) {
+          // lanes past Cout (channel padding up to the pitch) are stored as zeros, never as garbage
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c0 + i >= p.Cout) v[i] = 0.f;
+        }
+
         if (out_f32) {
           if (valid) {
             float* op = p.out_f32 + ((long long)(pn * p.Ho + py) * p.Wo + px) * p.out_f32_ld + c0;
