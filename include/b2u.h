@@ -125,56 +125,72 @@ int b2u_wgrad_reduce(const float* partial, int32_t splits, int32_t taps, int32_t
                      int32_t Cin, int32_t ksize /* kh*kw of the torch weight */, const int32_t* tap_kidx,
                      const int32_t* row_perm, float alpha, float* dw, float* db, int32_t has_bias_cols, void* stream);
 
-/* ---- weight staging: fp32 master [Cout][Cin][kh*kw] -> bf16 GEMM layouts -------------------------------------- */
-/* fprop layout  wf[row(co)][t][ci]   = scale * w[co][ci][t]
- * dgrad layout  wd[ci][kk-1-t][row(co)] = w[co][ci][t]   (flipped taps, transposed channels; only if wd != NULL)
- * row(co) = row_of_co[co] if given (inverse of row_perm above), else co. */
-int b2u_stage_weights(const float* w, int32_t Cout, int32_t Cin, int32_t kk, float scale, const int32_t* row_of_co,
-                      void* wf, int32_t wf_cinp, void* wd, int32_t wd_coutp, void* stream);
+/* ---- weight staging: fp32 master [Cout][Cin][kh*kw] -> bf16 GEMM layouts, all layers in ONE launch ------------- */
+/* fprop layout  wf[row(co)][t][ci]        = scale * w[co][ci][t]
+ * dgrad layout  wd[ci][kk-1-t][row(co)]   = scale * w[co][ci][t]   (flipped taps, transposed channels; if wd != NULL)
+ * bias_rows[row(co)] = bias[co]; row(co) = row_of_co[co] if given (PixelShuffle-friendly row order), else co.
+ * `items_dev` is a device array; block_start is the exclusive prefix sum of ceil(Cout*Cin*kk/256) over the items. */
+typedef struct b2u_wstage_item {
+  const float* w;
+  const float* bias;
+  const int32_t* row_of_co;
+  void* wf;
+  void* wd;
+  float* bias_rows;
+  int32_t Cout, Cin, kk, wf_cinp, wd_coutp;
+  float scale;
+  int32_t block_start;
+} b2u_wstage_item;
+int b2u_stage_weights(const b2u_wstage_item* items_dev, int32_t n_items, int32_t total_blocks, void* stream);
 
 /* ---- BatchNorm (training): statistics finalize / apply / backward ------------------------------------------------
- * nn.BatchNorm2d reached from fastai ConvLayer / BatchNorm (train.py:128 create_body, :141 DynamicUnet). */
-/* partial: [rows][2][ld] (sum, sumsq) -> mean/invstd, scale = g*invstd, shift = b - mean*scale; running stats updated
- * with `momentum` (unbiased variance), as torch does. count = elements per channel. */
+ * nn.BatchNorm2d reached from fastai ConvLayer / BatchNorm (train.py:128 create_body, :141 DynamicUnet).
+ * Every tensor carries its own channel pitch so that channel slices of a concat buffer can be used in place. */
+/* per-channel sum / sum-of-squares partial rows [rows][2][part_ld] of a bf16 NHWC tensor (one row per block) */
+int b2u_bn_stats(const void* x, int32_t ldx, int64_t pixels, int32_t C, float* partial, int32_t rows, int32_t part_ld,
+                 void* stream);
+/* partial rows -> mean/invstd, scale = g*invstd, shift = b - mean*scale; running stats updated with `momentum`
+ * (unbiased variance) as torch does. count = elements per channel. scratch: >= ceil(rows/128)*2*ld floats (+ one more
+ * level when rows > 16384); unused when rows <= 128. */
 int b2u_bn_finalize(const float* partial, int32_t rows, int32_t ld, int32_t C, double count, const float* gamma,
                     const float* beta, float eps, float momentum, float* running_mean, float* running_var,
-                    float* mean, float* invstd, float* scale, float* shift, void* stream);
+                    float* mean, float* invstd, float* scale, float* shift, float* scratch, size_t scratch_floats,
+                    void* stream);
 /* eval-mode affine from running statistics */
 int b2u_bn_eval_affine(int32_t C, const float* gamma, const float* beta, const float* running_mean,
                        const float* running_var, float eps, float* scale, float* shift, void* stream);
-/* standalone per-channel sum/sumsq partials of a bf16 NHWC tensor (the skip-connection BN of UnetBlock) */
-int b2u_bn_stats(const void* x, int64_t pixels, int32_t C, int32_t ld, float* partial, int32_t rows, int32_t part_ld,
-                 void* stream);
-/* y = act( x*scale+shift  [+ r*rscale+rshift | + r] )   all bf16 NHWC with pitch ld */
-int b2u_bn_apply(const void* x, const float* scale, const float* shift, const void* r, const float* rscale,
-                 const float* rshift, int32_t relu, void* y, int64_t pixels, int32_t C, int32_t ld, void* stream);
-/* backward reductions: g = dz * mask, mask = (y>0) if y given else (x*scale+shift>0) if relu else 1
+/* y = act( x*scale+shift  [+ r*rscale+rshift | + r] ) */
+int b2u_bn_apply(const void* x, int32_t ldx, const float* scale, const float* shift, const void* r, int32_t ldr,
+                 const float* rscale, const float* rshift, int32_t relu, void* y, int32_t ldy, int64_t pixels,
+                 int32_t C, void* stream);
+/* backward reductions: g = dz * mask, mask = (y>0) if y given, else (x*scale+shift>0) if relu, else 1
  * partial[row][0][c] = sum g, partial[row][1][c] = sum g*xhat  (xhat = (x-mean)*invstd) */
-int b2u_bn_bwd_reduce(const void* dz, const void* x, const void* y, const float* scale, const float* shift,
-                      const float* mean, const float* invstd, int32_t relu, int64_t pixels, int32_t C, int32_t ld,
-                      float* partial, int32_t rows, int32_t part_ld, void* stream);
-/* dgamma = sum g*xhat, dbeta = sum g; coefficients for the apply pass */
-int b2u_bn_bwd_finalize(const float* partial, int32_t rows, int32_t part_ld, int32_t C, double count,
-                        const float* gamma, const float* invstd, float* dgamma, float* dbeta, float* c_g, float* c_x,
-                        float* c_0, void* stream);
-/* dx = c_g*g + c_x*xhat_raw + c_0   (the closed form of the BN input gradient), optional accumulate into dx */
-int b2u_bn_bwd_apply(const void* dz, const void* x, const void* y, const float* scale, const float* shift,
-                     const float* mean, const float* invstd, const float* gamma, const float* sum_g,
-                     const float* sum_gx, double count, int32_t relu, int32_t accumulate, void* dx, int64_t pixels,
-                     int32_t C, int32_t ld, void* stream);
+int b2u_bn_bwd_reduce(const void* dz, int32_t lddz, const void* x, int32_t ldx, const void* y, int32_t ldy,
+                      const float* scale, const float* shift, const float* mean, const float* invstd, int32_t relu,
+                      int64_t pixels, int32_t C, float* partial, int32_t rows, int32_t part_ld, void* stream);
+/* dgamma = sum g*xhat, dbeta = sum g; mean_g / mean_gx feed the apply pass */
+int b2u_bn_bwd_finalize(const float* partial, int32_t rows, int32_t part_ld, int32_t C, double count, float* dgamma,
+                        float* dbeta, float* mean_g, float* mean_gx, float* scratch, size_t scratch_floats,
+                        void* stream);
+/* dx (+)= gamma*invstd*(g - mean_g - xhat*mean_gx) */
+int b2u_bn_bwd_apply(const void* dz, int32_t lddz, const void* x, int32_t ldx, const void* y, int32_t ldy,
+                     const float* scale, const float* shift, const float* mean, const float* invstd,
+                     const float* gamma, const float* mean_g, const float* mean_gx, int32_t relu, int32_t accumulate,
+                     void* dx, int32_t lddx, int64_t pixels, int32_t C, void* stream);
 
 /* ---- pooling ------------------------------------------------------------------------------------------------ */
-/* nn.MaxPool2d(3, stride 2, padding 1) (xresnet stem, body child 3); idx = argmax position 0..8 (uint8) */
+/* nn.MaxPool2d(3, stride 2, padding 1) (xresnet stem, body child 3); idx = argmax position 0..8 (uint8, pitch ld),
+ * first maximum wins as in ATen */
 int b2u_maxpool_fwd(const void* x, void* y, uint8_t* idx, int32_t N, int32_t H, int32_t W, int32_t C, int32_t ld,
                     void* stream);
 int b2u_maxpool_bwd(const void* dy, const uint8_t* idx, void* dx, int32_t accumulate, int32_t N, int32_t H, int32_t W,
                     int32_t C, int32_t ld, void* stream);
 
 /* ---- decoder glue: PixelShuffle_ICNR (+blur) + skip BN + concat + ReLU (fastai UnetBlock.forward) ---------------
- * u: conv1x1 output, bf16 [N,h,w,4*cu] with channel order (i,j,c) (rows permuted at weight staging);
- * skip: bf16 [N,2h,2w,cs]; cat: bf16 [N,2h,2w,ldc], channels [0,cu) = blur(shuffle(u)), [cu,cu+cs) = relu(skip*s+b).
- * blur=0 gives the plain PixelShuffle of the final layer; skip may be NULL; skip_f32_nchw (nullable) instead appends
- * the raw fp32 NCHW network input (MergeLayer(dense=True)). */
+ * u: conv1x1 output, bf16 [N,h,w,ldu>=4*cu] with channel order (i,j,c) (rows permuted at weight staging);
+ * skip: bf16 [N,2h,2w,lds]; cat: bf16 [N,2h,2w,ldc]: channels [0,cu) = blur(shuffle(u)) (blur=0: plain shuffle),
+ * [cu,cu+cs) = act(skip*sscale+sshift) (sscale NULL: copy, e.g. the network input of MergeLayer(dense=True)),
+ * remaining lanes zero.  cu must be a multiple of 8. */
 int b2u_shuffle_cat_fwd(const void* u, int32_t ldu, int32_t cu, int32_t blur, const void* skip, int32_t lds,
                         int32_t cs, const float* sscale, const float* sshift, int32_t skip_relu, void* cat,
                         int32_t ldc, int32_t N, int32_t h, int32_t w, void* stream);
@@ -183,41 +199,43 @@ int b2u_shuffle_bwd(const void* dcat, int32_t ldc, const void* u, void* du, int3
                     int32_t N, int32_t h, int32_t w, void* stream);
 
 /* ---- layout casts at the API edge --------------------------------------------------------------------------- */
-/* x fp32 NCHW (already /255) or uint8 NCHW (divided by 255 here, data.py:24 + IntToFloatTensor) -> bf16 NHWC pitch ld */
+/* x fp32 NCHW (already /255) or uint8 NCHW (divided by 255 here: data.py:24 + IntToFloatTensor) -> bf16 NHWC pitch ld,
+ * channels [ch_off, ch_off+write_c) written (lanes >= C zeroed) */
 int b2u_nchw_to_nhwc(const void* x, int32_t x_is_u8, void* y, int32_t N, int32_t C, int32_t H, int32_t W, int32_t ld,
-                     int32_t ch_off, void* stream);
+                     int32_t ch_off, int32_t write_c, void* stream);
 /* bf16/f32 NHWC -> fp32 NCHW */
 int b2u_nhwc_to_nchw_f32(const void* x, int32_t x_is_f32, int32_t ld, float* y, int32_t N, int32_t C, int32_t H,
                          int32_t W, void* stream);
 
 /* ---- loss: CrossEntropyLossFlat(axis=1) with class weights, mean reduction (train.py:195,211) ----------------- */
-/* logits fp32 [P][ld]; labels uint8 [P]; wsum = sum_p weight[label_p] (computed by b2u_ce_weight_sum first).
- * Writes dlogits bf16 [P][ldg] = w[y]*(softmax - onehot)/wsum and block partials of sum w[y]*nll into loss_partial. */
+/* logits fp32 [P][ld]; labels uint8 [P]; wsum = sum_p weight[label_p] (b2u_ce_weight_sum first, `rows` block partials).
+ * b2u_ce_fwd_bwd writes dlogits bf16 [P][ldg] = grad_scale*w[y]*(softmax - onehot)/wsum (NULL: loss only) and block
+ * partials of sum w[y]*nll; b2u_ce_finalize: loss = sum(loss_partial)/sum(wsum_partial). */
 int b2u_ce_weight_sum(const uint8_t* labels, int64_t P, const float* weight, int32_t C, float* wsum_partial,
                       int32_t rows, void* stream);
 int b2u_ce_fwd_bwd(const float* logits, int32_t ld, const uint8_t* labels, int64_t P, int32_t C, const float* weight,
                    const float* wsum_partial, int32_t wsum_rows, void* dlogits, int32_t ldg, float* loss_partial,
                    int32_t rows, float grad_scale, void* stream);
-/* loss = sum(loss_partial)/sum(wsum_partial) -> loss[0] */
 int b2u_ce_finalize(const float* loss_partial, int32_t rows, const float* wsum_partial, int32_t wsum_rows, float* loss,
                     void* stream);
 
 /* ---- optimizer ------------------------------------------------------------------------------------------------ */
-/* p -= lr * g over one flat fp32 buffer (BASELINE config 1: plain SGD) */
+/* p -= lr * grad_scale * g over one flat fp32 buffer (BASELINE config 1: plain SGD) */
 int b2u_sgd_step(float* p, const float* g, int64_t n, float lr, float grad_scale, void* stream);
-/* fastai Adam (train.py:218): decoupled wd, per-segment lr / wd via seg tables (seg_end exclusive prefix, sorted) */
+/* fastai Adam (train.py:218): decoupled wd, per-segment lr / wd via seg tables (seg_end = exclusive end offsets) */
 int b2u_adam_step(float* p, const float* g, float* m, float* v, int64_t n, const int64_t* seg_end, const float* seg_lr,
                   const float* seg_wd, int32_t nseg, float mom, float sqr_mom, float eps, int32_t step,
                   float grad_scale, void* stream);
 
 /* ---- prediction: softmax + overlap-tile accumulate, normalise + argmax (predict.py:284-334) ------------------- */
-/* logits fp32 [T][th][tw][ld] for T tiles; tile t is placed at (y0[t], x0[t]) of the raster; acc fp32 [C][Y][X],
- * cnt uint8 [Y][X]; additions are atomic-free because the host issues non-overlapping tile sets per launch
- * (4-colouring of the overlap grid) — results do not depend on scheduling. */
+/* logits fp32 [T][th][tw][ld]; tile t sits at (y0[t], x0[t]) of the full raster; acc fp32 [C][Y][X] and cnt uint8
+ * [Y][X] cover the raster window starting at (y_off, x_off).  `sel` (nullable, n_sel entries) lists the tiles of this
+ * launch; tiles within one launch must not overlap each other (the host colours the overlap graph), which makes the
+ * sums independent of scheduling without atomics. */
 int b2u_stitch_accumulate(const float* logits, int32_t ld, int32_t C, int32_t T, int32_t th, int32_t tw,
-                          const int32_t* y0, const int32_t* x0, float* acc, uint8_t* cnt, int64_t Y, int64_t X,
-                          int64_t y_off, int64_t x_off, void* stream);
-/* mask[y][x] = argmax_c acc[c][y][x]/cnt (first max wins, unplaced pixels -> 0), uint8 */
+                          const int32_t* y0, const int32_t* x0, const int32_t* sel, int32_t n_sel, float* acc,
+                          uint8_t* cnt, int64_t Y, int64_t X, int64_t y_off, int64_t x_off, void* stream);
+/* mask[y][x] = argmax_c acc[c][y][x]/cnt (first max wins like np.argmax, unplaced pixels -> 0), uint8 */
 int b2u_stitch_finalize(const float* acc, const uint8_t* cnt, int32_t C, int64_t Y, int64_t X, uint8_t* mask,
                         void* stream);
 /* per-tile softmax probabilities (fp32 NCHW, what learn.predict returns, predict.py:193-203) and argmax */

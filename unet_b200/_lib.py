@@ -54,6 +54,13 @@ class WgradDesc(C.Structure):
     ]
 
 
+class WStageItem(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("bias", C.c_void_p), ("row_of_co", C.c_void_p), ("wf", C.c_void_p),
+                ("wd", C.c_void_p), ("bias_rows", C.c_void_p), ("Cout", C.c_int32), ("Cin", C.c_int32),
+                ("kk", C.c_int32), ("wf_cinp", C.c_int32), ("wd_coutp", C.c_int32), ("scale", C.c_float),
+                ("block_start", C.c_int32)]
+
+
 class WgradInfo(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("splits", "co_pad", "ci_pad", "taps_per_unit", "units", "grid", "k_steps",
                                          "block_n", "stages")] + [("partial_bytes", C.c_size_t)]
@@ -97,26 +104,26 @@ def _declare(lib):
         "b2u_wgrad_plan_create": [C.POINTER(WgradDesc), C.POINTER(vp)],
         "b2u_wgrad_run": [vp, vp],
         "b2u_wgrad_reduce": [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, f32, vp, vp, i32, vp],
-        "b2u_stage_weights": [vp, i32, i32, i32, f32, vp, vp, i32, vp, i32, vp],
-        "b2u_bn_finalize": [vp, i32, i32, i32, f64, vp, vp, f32, f32, vp, vp, vp, vp, vp, vp, vp],
+        "b2u_stage_weights": [vp, i32, i32, vp],
+        "b2u_bn_stats": [vp, i32, i64, i32, vp, i32, i32, vp],
+        "b2u_bn_finalize": [vp, i32, i32, i32, f64, vp, vp, f32, f32, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp],
         "b2u_bn_eval_affine": [i32, vp, vp, vp, vp, f32, vp, vp, vp],
-        "b2u_bn_stats": [vp, i64, i32, i32, vp, i32, i32, vp],
-        "b2u_bn_apply": [vp, vp, vp, vp, vp, vp, i32, vp, i64, i32, i32, vp],
-        "b2u_bn_bwd_reduce": [vp, vp, vp, vp, vp, vp, vp, i32, i64, i32, i32, vp, i32, i32, vp],
-        "b2u_bn_bwd_finalize": [vp, i32, i32, i32, f64, vp, vp, vp, vp, vp, vp, vp, vp],
-        "b2u_bn_bwd_apply": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, f64, i32, i32, vp, i64, i32, i32, vp],
+        "b2u_bn_apply": [vp, i32, vp, vp, vp, i32, vp, vp, i32, vp, i32, i64, i32, vp],
+        "b2u_bn_bwd_reduce": [vp, i32, vp, i32, vp, i32, vp, vp, vp, vp, i32, i64, i32, vp, i32, i32, vp],
+        "b2u_bn_bwd_finalize": [vp, i32, i32, i32, f64, vp, vp, vp, vp, vp, C.c_size_t, vp],
+        "b2u_bn_bwd_apply": [vp, i32, vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, i32, i64, i32, vp],
         "b2u_maxpool_fwd": [vp, vp, u8p, i32, i32, i32, i32, i32, vp],
         "b2u_maxpool_bwd": [vp, u8p, vp, i32, i32, i32, i32, i32, i32, vp],
         "b2u_shuffle_cat_fwd": [vp, i32, i32, i32, vp, i32, i32, vp, vp, i32, vp, i32, i32, i32, i32, vp],
         "b2u_shuffle_bwd": [vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, vp],
-        "b2u_nchw_to_nhwc": [vp, i32, vp, i32, i32, i32, i32, i32, i32, vp],
+        "b2u_nchw_to_nhwc": [vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp],
         "b2u_nhwc_to_nchw_f32": [vp, i32, i32, vp, i32, i32, i32, i32, vp],
         "b2u_ce_weight_sum": [u8p, i64, vp, i32, vp, i32, vp],
         "b2u_ce_fwd_bwd": [vp, i32, u8p, i64, i32, vp, vp, i32, vp, i32, vp, i32, f32, vp],
         "b2u_ce_finalize": [vp, i32, vp, i32, vp, vp],
         "b2u_sgd_step": [vp, vp, i64, f32, f32, vp],
         "b2u_adam_step": [vp, vp, vp, vp, i64, vp, vp, vp, i32, f32, f32, f32, i32, f32, vp],
-        "b2u_stitch_accumulate": [vp, i32, i32, i32, i32, i32, vp, vp, vp, u8p, i64, i64, i64, i64, vp],
+        "b2u_stitch_accumulate": [vp, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp, u8p, i64, i64, i64, i64, vp],
         "b2u_stitch_finalize": [vp, u8p, i32, i64, i64, u8p, vp],
         "b2u_softmax_nchw": [vp, i32, i32, i64, i32, i32, vp, u8p, vp],
     }

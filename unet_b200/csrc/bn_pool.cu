@@ -1,0 +1,504 @@
+// Memory-bound kernels of the encoder: BatchNorm (training statistics, apply, backward) and MaxPool, NHWC bf16.
+// All are HBM-bound streaming passes: 16-byte vector accesses (8 bf16 channels per thread), fp32 math,
+// deterministic two-stage reductions (per-block partial rows -> fixed-order finalize), no float atomics.
+//
+// Replaces nn.BatchNorm2d / nn.MaxPool2d forward+backward (cudnnBatchNormalization*, ATen max_pool2d) as reached from
+// fastai's ConvLayer / XResNet / UnetBlock.bn (reference train.py:128,141).
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace b2u {
+
+struct f8 {
+  float v[8];
+};
+__device__ __forceinline__ f8 ld8(const __nv_bfloat16* p) {
+  uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  f8 o;
+  o.v[0] = bf16_lo(u.x); o.v[1] = bf16_hi(u.x); o.v[2] = bf16_lo(u.y); o.v[3] = bf16_hi(u.y);
+  o.v[4] = bf16_lo(u.z); o.v[5] = bf16_hi(u.z); o.v[6] = bf16_lo(u.w); o.v[7] = bf16_hi(u.w);
+  return o;
+}
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const f8& a) {
+  uint4 u;
+  u.x = pack_bf16x2(a.v[0], a.v[1]); u.y = pack_bf16x2(a.v[2], a.v[3]);
+  u.z = pack_bf16x2(a.v[4], a.v[5]); u.w = pack_bf16x2(a.v[6], a.v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ f8 ldc8(const float* p, int c, int C) {  // per-channel fp32 constants, guarded
+  f8 o;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o.v[i] = (c + i < C) ? __ldg(p + c + i) : 0.f;
+  return o;
+}
+
+// ------------------------------------------------------------------------------------------------ column reductions
+// Generic "sum K quantities per channel over many pixels": each block owns a contiguous pixel range and writes one
+// partial row [K][part_ld].  Thread layout: G = ceil(C/8) channel groups x PL pixel lanes (coalesced 16 B loads).
+template <int K, class F>
+__device__ __forceinline__ void block_column_sums(long long pixels, int C, float* partial, int part_ld, F f) {
+  extern __shared__ float red[];  // [PL][GP][K*8]
+  const int G = (C + 7) >> 3;
+  for (int g0 = 0; g0 < G; g0 += blockDim.x) {
+    const int GP = min(G - g0, (int)blockDim.x);
+    const int PL = blockDim.x / GP;
+    const int pl = threadIdx.x / GP, gi = threadIdx.x - pl * GP;
+    const int g = g0 + gi;
+    float acc[K][8];
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[k][i] = 0.f;
+    if (pl < PL) {
+      const long long per = (pixels + gridDim.x - 1) / gridDim.x;
+      const long long p0 = (long long)blockIdx.x * per;
+      const long long p1 = min(pixels, p0 + per);
+      for (long long p = p0 + pl; p < p1; p += PL) f(p, g * 8, acc);
+      float* dst = red + ((size_t)pl * GP + gi) * (K * 8);
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dst[k * 8 + i] = acc[k][i];
+    }
+    __syncthreads();
+    if (pl == 0) {
+      for (int q = 1; q < PL; ++q) {
+        const float* src = red + ((size_t)q * GP + gi) * (K * 8);
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[k][i] += src[k * 8 + i];
+      }
+      float* out = partial + (size_t)blockIdx.x * K * part_ld;
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (g * 8 + i < part_ld) out[(size_t)k * part_ld + g * 8 + i] = acc[k][i];
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void bn_stats_kernel(const __nv_bfloat16* __restrict__ x, int ldx, long long pixels, int C, float* partial,
+                                int part_ld) {
+  block_column_sums<2>(pixels, C, partial, part_ld, [&](long long p, int c, float (&acc)[2][8]) {
+    f8 a = ld8(x + p * ldx + c);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float q = (c + i < C) ? a.v[i] : 0.f;
+      acc[0][i] += q;
+      acc[1][i] += q * q;
+    }
+  });
+}
+
+// rows [rows][K][ld] -> [ceil(rows/128)][K][ld], fixed order
+__global__ void reduce_rows_kernel(const float* __restrict__ in, int rows, int width, float* __restrict__ out) {
+  const int r0 = blockIdx.x * 128, r1 = min(rows, r0 + 128);
+  for (int c = threadIdx.x; c < width; c += blockDim.x) {
+    float s = 0.f;
+    for (int r = r0; r < r1; ++r) s += in[(size_t)r * width + c];
+    out[(size_t)blockIdx.x * width + c] = s;
+  }
+}
+
+// final per-channel sums in double: block = 64 channels x 4 row lanes
+template <int K>
+__device__ __forceinline__ bool final_sums(const float* partial, int rows, int ld, int C, double (&out)[K], int& c) {
+  __shared__ double sh[4][64][K];
+  const int cl = threadIdx.x & 63, rl = threadIdx.x >> 6;
+  c = blockIdx.x * 64 + cl;
+  double s[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) s[k] = 0.0;
+  if (c < C)
+    for (int r = rl; r < rows; r += 4)
+#pragma unroll
+      for (int k = 0; k < K; ++k) s[k] += (double)partial[((size_t)r * K + k) * ld + c];
+#pragma unroll
+  for (int k = 0; k < K; ++k) sh[rl][cl][k] = s[k];
+  __syncthreads();
+  if (rl != 0 || c >= C) return false;
+#pragma unroll
+  for (int k = 0; k < K; ++k) out[k] = sh[0][cl][k] + sh[1][cl][k] + sh[2][cl][k] + sh[3][cl][k];
+  return true;
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ partial, int rows, int ld, int C, double count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   float momentum, float* running_mean, float* running_var, float* mean, float* invstd,
+                                   float* scale, float* shift) {
+  double s[2];
+  int c;
+  if (!final_sums<2>(partial, rows, ld, C, s, c)) return;
+  const double m = s[0] / count;
+  double var = s[1] / count - m * m;
+  if (var < 0) var = 0;
+  const double istd = 1.0 / sqrt(var + (double)eps);
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  mean[c] = (float)m;
+  invstd[c] = (float)istd;
+  scale[c] = (float)(g * istd);
+  shift[c] = (float)(b - m * g * istd);
+  if (running_mean) {
+    const double unbiased = count > 1 ? var * count / (count - 1) : var;
+    running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * m);
+    running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unbiased);
+  }
+}
+
+__global__ void bn_eval_affine_kernel(int C, const float* gamma, const float* beta, const float* rm, const float* rv,
+                                      float eps, float* scale, float* shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float istd = 1.f / sqrtf(rv[c] + eps);
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  scale[c] = g * istd;
+  shift[c] = b - rm[c] * g * istd;
+}
+
+// y = act(x*scale+shift [+ r*rscale+rshift | + r])
+__global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ scale,
+                                const float* __restrict__ shift, const __nv_bfloat16* __restrict__ r, int ldr,
+                                const float* __restrict__ rscale, const float* __restrict__ rshift, int relu,
+                                __nv_bfloat16* __restrict__ y, int ldy, long long pixels, int C) {
+  const int G = (C + 7) >> 3;
+  const long long total = pixels * G;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / G;
+    const int c = (int)(i - p * G) * 8;
+    f8 a = ld8(x + p * ldx + c);
+    const f8 sc = ldc8(scale, c, C), sh = ldc8(shift, c, C);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a.v[k] = a.v[k] * sc.v[k] + sh.v[k];
+    if (r) {
+      f8 b = ld8(r + p * ldr + c);
+      if (rscale) {
+        const f8 rs = ldc8(rscale, c, C), rh = ldc8(rshift, c, C);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) b.v[k] = b.v[k] * rs.v[k] + rh.v[k];
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a.v[k] += b.v[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (relu) a.v[k] = fmaxf(a.v[k], 0.f);
+      if (c + k >= C) a.v[k] = 0.f;
+    }
+    st8(y + p * ldy + c, a);
+  }
+}
+
+// backward: g = dz * mask; mask = (y > 0) if y else (x*scale+shift > 0) if relu else 1
+__device__ __forceinline__ void bn_bwd_gx(const __nv_bfloat16* dz, int lddz, const __nv_bfloat16* x, int ldx,
+                                          const __nv_bfloat16* y, int ldy, const float* scale, const float* shift,
+                                          const float* mean, const float* invstd, int relu, long long p, int c, int C,
+                                          f8& g, f8& xh) {
+  g = ld8(dz + p * lddz + c);
+  const f8 xv = ld8(x + p * ldx + c);
+  const f8 mu = ldc8(mean, c, C), is = ldc8(invstd, c, C);
+  if (y) {
+    const f8 yv = ld8(y + p * ldy + c);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g.v[k] = yv.v[k] > 0.f ? g.v[k] : 0.f;
+  } else if (relu) {
+    const f8 sc = ldc8(scale, c, C), sh = ldc8(shift, c, C);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g.v[k] = (xv.v[k] * sc.v[k] + sh.v[k]) > 0.f ? g.v[k] : 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    xh.v[k] = (xv.v[k] - mu.v[k]) * is.v[k];
+    if (c + k >= C) { g.v[k] = 0.f; xh.v[k] = 0.f; }
+  }
+}
+
+__global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dz, int lddz, const __nv_bfloat16* __restrict__ x,
+                                     int ldx, const __nv_bfloat16* __restrict__ y, int ldy, const float* scale,
+                                     const float* shift, const float* mean, const float* invstd, int relu,
+                                     long long pixels, int C, float* partial, int part_ld) {
+  block_column_sums<2>(pixels, C, partial, part_ld, [&](long long p, int c, float (&acc)[2][8]) {
+    f8 g, xh;
+    bn_bwd_gx(dz, lddz, x, ldx, y, ldy, scale, shift, mean, invstd, relu, p, c, C, g, xh);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      acc[0][i] += g.v[i];
+      acc[1][i] += g.v[i] * xh.v[i];
+    }
+  });
+}
+
+// sums -> dgamma/dbeta and the per-channel means used by the apply pass
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int rows, int ld, int C, double count,
+                                       float* dgamma, float* dbeta, float* mean_g, float* mean_gx) {
+  double s[2];
+  int c;
+  if (!final_sums<2>(partial, rows, ld, C, s, c)) return;
+  if (dbeta) dbeta[c] = (float)s[0];
+  if (dgamma) dgamma[c] = (float)s[1];
+  mean_g[c] = (float)(s[0] / count);
+  mean_gx[c] = (float)(s[1] / count);
+}
+
+// dx = gamma*invstd * (g - mean_g - xhat*mean_gx)
+__global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz, int lddz, const __nv_bfloat16* __restrict__ x,
+                                    int ldx, const __nv_bfloat16* __restrict__ y, int ldy, const float* scale,
+                                    const float* shift, const float* mean, const float* invstd, const float* gamma,
+                                    const float* mean_g, const float* mean_gx, int relu, int accumulate,
+                                    __nv_bfloat16* dx, int lddx, long long pixels, int C) {
+  const int G = (C + 7) >> 3;
+  const long long total = pixels * G;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / G;
+    const int c = (int)(i - p * G) * 8;
+    f8 g, xh;
+    bn_bwd_gx(dz, lddz, x, ldx, y, ldy, scale, shift, mean, invstd, relu, p, c, C, g, xh);
+    const f8 mg = ldc8(mean_g, c, C), mgx = ldc8(mean_gx, c, C), is = ldc8(invstd, c, C);
+    f8 ga;
+    if (gamma) ga = ldc8(gamma, c, C);
+    else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) ga.v[k] = 1.f;
+    }
+    f8 o;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o.v[k] = ga.v[k] * is.v[k] * (g.v[k] - mg.v[k] - xh.v[k] * mgx.v[k]);
+    if (accumulate) {
+      const f8 old = ld8(dx + p * lddx + c);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o.v[k] += old.v[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (c + k >= C) o.v[k] = 0.f;
+    st8(dx + p * lddx + c, o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ MaxPool 3x3 s2 p1
+__global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                   uint8_t* __restrict__ idx, int N, int H, int W, int C, int ld) {
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2, G = ld >> 3;
+  const long long total = (long long)N * Ho * Wo * G;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    long long t = i / G;
+    const int ox = (int)(t % Wo); t /= Wo;
+    const int oy = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    float best[8];
+    int bi[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { best[k] = -INFINITY; bi[k] = 0; }
+    bool first = true;
+    for (int r = 0; r < 3; ++r) {
+      const int yy = 2 * oy - 1 + r;
+      if (yy < 0 || yy >= H) continue;
+      for (int s = 0; s < 3; ++s) {
+        const int xx = 2 * ox - 1 + s;
+        if (xx < 0 || xx >= W) continue;
+        const f8 a = ld8(x + (((long long)n * H + yy) * W + xx) * ld + g * 8);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (first || a.v[k] > best[k]) { best[k] = a.v[k]; bi[k] = r * 3 + s; }
+        first = false;
+      }
+    }
+    f8 o;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o.v[k] = best[k];
+    const long long op = ((long long)n * Ho + oy) * Wo + ox;
+    st8(y + op * ld + g * 8, o);
+    if (idx) {
+      uint2 packed;
+      packed.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
+      packed.y = (uint32_t)bi[4] | ((uint32_t)bi[5] << 8) | ((uint32_t)bi[6] << 16) | ((uint32_t)bi[7] << 24);
+      *reinterpret_cast<uint2*>(idx + op * ld + g * 8) = packed;
+    }
+  }
+}
+
+__global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx,
+                                   __nv_bfloat16* dx, int accumulate, int N, int H, int W, int C, int ld) {
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2, G = ld >> 3;
+  const long long total = (long long)N * H * W * G;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    long long t = i / G;
+    const int xx = (int)(t % W); t /= W;
+    const int yy = (int)(t % H);
+    const int n = (int)(t / H);
+    f8 o;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o.v[k] = 0.f;
+    // windows containing row yy: even yy -> oy = yy/2 (r=1); odd yy -> oy = (yy-1)/2 (r=2) and (yy+1)/2 (r=0)
+    const int oys[2] = {yy >> 1, (yy + 1) >> 1};
+    const int rs[2] = {(yy & 1) ? 2 : 1, 0};
+    const int ny = (yy & 1) ? 2 : 1;
+    const int oxs[2] = {xx >> 1, (xx + 1) >> 1};
+    const int ss[2] = {(xx & 1) ? 2 : 1, 0};
+    const int nx = (xx & 1) ? 2 : 1;
+    for (int a = 0; a < ny; ++a) {
+      if (oys[a] >= Ho) continue;
+      for (int b = 0; b < nx; ++b) {
+        if (oxs[b] >= Wo) continue;
+        const long long op = ((long long)n * Ho + oys[a]) * Wo + oxs[b];
+        const uint2 pk = *reinterpret_cast<const uint2*>(idx + op * ld + g * 8);
+        const f8 d = ld8(dy + op * ld + g * 8);
+        const int want = rs[a] * 3 + ss[b];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t w = k < 4 ? pk.x : pk.y;
+          const int id = (w >> (8 * (k & 3))) & 0xFF;
+          if (id == want) o.v[k] += d.v[k];
+        }
+      }
+    }
+    __nv_bfloat16* dst = dx + (((long long)n * H + yy) * W + xx) * ld + g * 8;
+    if (accumulate) {
+      const f8 old = ld8(dst);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o.v[k] += old.v[k];
+    }
+    st8(dst, o);
+  }
+}
+
+static inline int grid_for(long long work_items, int threads, int per_sm = 8) {
+  long long b = (work_items + threads - 1) / threads;
+  const long long cap = (long long)sm_count() * per_sm;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace b2u
+
+using namespace b2u;
+typedef const __nv_bfloat16* cbf;
+typedef __nv_bfloat16* bf;
+
+extern "C" int b2u_bn_stats(const void* x, int32_t ldx, int64_t pixels, int32_t C, float* partial, int32_t rows,
+                            int32_t part_ld, void* stream) {
+  B2U_CHECK_ARG(x && partial && rows > 0 && C > 0 && ldx % 8 == 0 && part_ld >= C, "bn_stats: bad argument");
+  const int threads = 256;
+  const size_t smem = (size_t)threads * 16 * sizeof(float);
+  bn_stats_kernel<<<rows, threads, smem, (cudaStream_t)stream>>>((cbf)x, ldx, pixels, C, partial, part_ld);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+// Collapse many partial rows to <= 128 rows (in `scratch`) so that the finalize kernels stay short and parallel.
+static int collapse_rows(const float** partial, int* rows, int width, float* scratch, size_t scratch_floats,
+                         cudaStream_t st) {
+  float* dst = scratch;
+  size_t avail = scratch_floats;
+  while (*rows > 128) {
+    const int out_rows = ceil_div(*rows, 128);
+    const size_t need = (size_t)out_rows * width;
+    B2U_CHECK_ARG(dst && avail >= need, "bn finalize: scratch too small (%zu < %zu floats)", avail, need);
+    reduce_rows_kernel<<<out_rows, 256, 0, st>>>(*partial, *rows, width, dst);
+    *partial = dst;
+    *rows = out_rows;
+    dst += need;
+    avail -= need;
+  }
+  return B2U_OK;
+}
+
+extern "C" int b2u_bn_finalize(const float* partial, int32_t rows, int32_t ld, int32_t C, double count,
+                               const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
+                               float* running_var, float* mean, float* invstd, float* scale, float* shift,
+                               float* scratch, size_t scratch_floats, void* stream) {
+  B2U_CHECK_ARG(partial && rows > 0 && mean && invstd && scale && shift && count > 0, "bn_finalize: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = collapse_rows(&partial, &rows, 2 * ld, scratch, scratch_floats, st);
+  if (rc) return rc;
+  bn_finalize_kernel<<<ceil_div(C, 64), 256, 0, st>>>(partial, rows, ld, C, count, gamma, beta, eps, momentum,
+                                                      running_mean, running_var, mean, invstd, scale, shift);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" int b2u_bn_eval_affine(int32_t C, const float* gamma, const float* beta, const float* running_mean,
+                                  const float* running_var, float eps, float* scale, float* shift, void* stream) {
+  B2U_CHECK_ARG(C > 0 && running_mean && running_var && scale && shift, "bn_eval_affine: bad argument");
+  bn_eval_affine_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(C, gamma, beta, running_mean, running_var,
+                                                                          eps, scale, shift);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" int b2u_bn_apply(const void* x, int32_t ldx, const float* scale, const float* shift, const void* r,
+                            int32_t ldr, const float* rscale, const float* rshift, int32_t relu, void* y, int32_t ldy,
+                            int64_t pixels, int32_t C, void* stream) {
+  B2U_CHECK_ARG(x && y && scale && shift && C > 0 && ldx % 8 == 0 && ldy % 8 == 0 && (!r || ldr % 8 == 0),
+                "bn_apply: bad argument");
+  const long long items = pixels * ((C + 7) / 8);
+  bn_apply_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>((cbf)x, ldx, scale, shift, (cbf)r, ldr, rscale,
+                                                                        rshift, relu, (bf)y, ldy, pixels, C);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" int b2u_bn_bwd_reduce(const void* dz, int32_t lddz, const void* x, int32_t ldx, const void* y, int32_t ldy,
+                                 const float* scale, const float* shift, const float* mean, const float* invstd,
+                                 int32_t relu, int64_t pixels, int32_t C, float* partial, int32_t rows,
+                                 int32_t part_ld, void* stream) {
+  B2U_CHECK_ARG(dz && x && mean && invstd && partial && rows > 0 && part_ld >= C, "bn_bwd_reduce: bad argument");
+  B2U_CHECK_ARG(y || !relu || (scale && shift), "bn_bwd_reduce: relu mask needs scale/shift");
+  const int threads = 256;
+  const size_t smem = (size_t)threads * 16 * sizeof(float);
+  bn_bwd_reduce_kernel<<<rows, threads, smem, (cudaStream_t)stream>>>((cbf)dz, lddz, (cbf)x, ldx, (cbf)y, ldy, scale,
+                                                                     shift, mean, invstd, relu, pixels, C, partial,
+                                                                     part_ld);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" int b2u_bn_bwd_finalize(const float* partial, int32_t rows, int32_t part_ld, int32_t C, double count,
+                                   float* dgamma, float* dbeta, float* mean_g, float* mean_gx, float* scratch,
+                                   size_t scratch_floats, void* stream) {
+  B2U_CHECK_ARG(partial && rows > 0 && mean_g && mean_gx && count > 0, "bn_bwd_finalize: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = collapse_rows(&partial, &rows, 2 * part_ld, scratch, scratch_floats, st);
+  if (rc) return rc;
+  bn_bwd_finalize_kernel<<<ceil_div(C, 64), 256, 0, st>>>(partial, rows, part_ld, C, count, dgamma, dbeta, mean_g,
+                                                          mean_gx);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" int b2u_bn_bwd_apply(const void* dz, int32_t lddz, const void* x, int32_t ldx, const void* y, int32_t ldy,
+                                const float* scale, const float* shift, const float* mean, const float* invstd,
+                                const float* gamma, const float* mean_g, const float* mean_gx, int32_t relu,
+                                int32_t accumulate, void* dx, int32_t lddx, int64_t pixels, int32_t C, void* stream) {
+  B2U_CHECK_ARG(dz && x && dx && mean && invstd && mean_g && mean_gx, "bn_bwd_apply: bad argument");
+  const long long items = pixels * ((C + 7) / 8);
+  bn_bwd_apply_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>(
+      (cbf)dz, lddz, (cbf)x, ldx, (cbf)y, ldy, scale, shift, mean, invstd, gamma, mean_g, mean_gx, relu, accumulate,
+      (bf)dx, lddx, pixels, C);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" int b2u_maxpool_fwd(const void* x, void* y, uint8_t* idx, int32_t N, int32_t H, int32_t W, int32_t C,
+                               int32_t ld, void* stream) {
+  B2U_CHECK_ARG(x && y && ld % 8 == 0 && C <= ld, "maxpool_fwd: bad argument");
+  const long long items = (long long)N * ((H + 1) / 2) * ((W + 1) / 2) * (ld / 8);
+  maxpool_fwd_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>((cbf)x, (bf)y, idx, N, H, W, C, ld);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" int b2u_maxpool_bwd(const void* dy, const uint8_t* idx, void* dx, int32_t accumulate, int32_t N, int32_t H,
+                               int32_t W, int32_t C, int32_t ld, void* stream) {
+  B2U_CHECK_ARG(dy && idx && dx && ld % 8 == 0, "maxpool_bwd: bad argument");
+  const long long items = (long long)N * H * W * (ld / 8);
+  maxpool_bwd_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>((cbf)dy, idx, (bf)dx, accumulate, N, H, W,
+                                                                           C, ld);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}

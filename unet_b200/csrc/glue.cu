@@ -1,0 +1,573 @@
+// Memory-bound glue of the decoder, the loss, the optimizers, the layout casts at the API edge and the overlap-tile
+// stitching of prediction.  NHWC bf16 activations, 16-byte vector accesses, fp32 math, deterministic reductions.
+//
+// Replaces: PixelShuffle_ICNR (+ReplicationPad2d+AvgPool2d blur), torch.cat + ReLU of fastai UnetBlock/MergeLayer
+// (reference train.py:141 DynamicUnet), CrossEntropyLossFlat(axis=1) fwd+bwd (train.py:195,211), fastai Adam / SGD
+// (train.py:218), softmax + numpy sum/count/argmax merge (predict.py:193-203, 284-334).
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace b2u {
+
+struct f8 {
+  float v[8];
+};
+__device__ __forceinline__ f8 ld8(const __nv_bfloat16* p) {
+  uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  f8 o;
+  o.v[0] = bf16_lo(u.x); o.v[1] = bf16_hi(u.x); o.v[2] = bf16_lo(u.y); o.v[3] = bf16_hi(u.y);
+  o.v[4] = bf16_lo(u.z); o.v[5] = bf16_hi(u.z); o.v[6] = bf16_lo(u.w); o.v[7] = bf16_hi(u.w);
+  return o;
+}
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const f8& a) {
+  uint4 u;
+  u.x = pack_bf16x2(a.v[0], a.v[1]); u.y = pack_bf16x2(a.v[2], a.v[3]);
+  u.z = pack_bf16x2(a.v[4], a.v[5]); u.w = pack_bf16x2(a.v[6], a.v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+static inline int grid_for(long long work_items, int threads, int per_sm = 8) {
+  long long b = (work_items + threads - 1) / threads;
+  const long long cap = (long long)sm_count() * per_sm;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+// ------------------------------------------------------------------------------------------------ weight staging
+struct WStageItem {
+  const float* w;       // fp32 [Cout][Cin][kk]
+  const float* bias;    // fp32 [Cout] or null
+  const int* row_of_co; // null = identity
+  __nv_bfloat16* wf;    // [Cout rows][kk][wf_cinp]
+  __nv_bfloat16* wd;    // [Cin][kk][wd_coutp] (flipped taps) or null
+  float* bias_rows;     // fp32 [Cout] in GEMM row order, or null
+  int Cout, Cin, kk, wf_cinp, wd_coutp;
+  float scale;
+  int block_start;      // first block of this item in the batched launch
+};
+
+__global__ void stage_weights_kernel(const WStageItem* __restrict__ items, int n_items) {
+  // binary search for the item owning this block
+  int lo = 0, hi = n_items - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (items[mid].block_start <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const WStageItem it = items[lo];
+  const long long total = (long long)it.Cout * it.kk * it.Cin;
+  const long long i = (long long)(blockIdx.x - it.block_start) * blockDim.x + threadIdx.x;
+  if (i < total) {
+    const int ci = (int)(i % it.Cin);
+    const int t = (int)((i / it.Cin) % it.kk);
+    const int co = (int)(i / ((long long)it.Cin * it.kk));
+    const float v = it.w[((size_t)co * it.Cin + ci) * it.kk + t];
+    const int row = it.row_of_co ? it.row_of_co[co] : co;
+    it.wf[((size_t)row * it.kk + t) * it.wf_cinp + ci] = __float2bfloat16_rn(v * it.scale);
+    if (it.wd) it.wd[((size_t)ci * it.kk + (it.kk - 1 - t)) * it.wd_coutp + row] = __float2bfloat16_rn(v * it.scale);
+  }
+  if (it.bias && it.bias_rows && i < it.Cout) {
+    const int co = (int)i;
+    const int row = it.row_of_co ? it.row_of_co[co] : co;
+    it.bias_rows[row] = it.bias[co];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ decoder glue
+// cat[n,Y,X,0:cu]      = blur(PixelShuffle(u))       u: [N,h,w,4cu], channel order (i,j,c)
+// cat[n,Y,X,cu:cu+cs]  = act(skip*sscale+sshift)     (sscale null: plain copy)
+// cat[n,Y,X,cu+cs:ldc] = 0
+__global__ void shuffle_cat_fwd_kernel(const __nv_bfloat16* __restrict__ u, int ldu, int cu, int blur,
+                                       const __nv_bfloat16* __restrict__ skip, int lds, int cs,
+                                       const float* __restrict__ sscale, const float* __restrict__ sshift,
+                                       int skip_relu, __nv_bfloat16* __restrict__ cat, int ldc, int N, int h, int w) {
+  const int H = 2 * h, W = 2 * w, G = ldc >> 3;
+  const long long total = (long long)N * H * W * G;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    long long t = i / G;
+    const int X = (int)(t % W); t /= W;
+    const int Y = (int)(t % H);
+    const int n = (int)(t / H);
+    const int c = g * 8;
+    f8 o;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o.v[k] = 0.f;
+    if (c < cu) {
+      auto ps = [&](int yy, int xx) {
+        return ld8(u + (((long long)n * h + (yy >> 1)) * w + (xx >> 1)) * ldu + (((yy & 1) * 2 + (xx & 1)) * cu + c));
+      };
+      if (blur) {
+        const int y0 = Y > 0 ? Y - 1 : 0, x0 = X > 0 ? X - 1 : 0;
+        const f8 a = ps(y0, x0), b = ps(y0, X), d = ps(Y, x0), e = ps(Y, X);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o.v[k] = 0.25f * ((a.v[k] + b.v[k]) + (d.v[k] + e.v[k]));
+      } else {
+        o = ps(Y, X);
+      }
+    } else if (skip && c < cu + cs) {
+      const int sc0 = c - cu;
+      o = ld8(skip + (((long long)n * H + Y) * W + X) * lds + sc0);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (sc0 + k < cs) {
+          if (sscale) o.v[k] = o.v[k] * __ldg(sscale + sc0 + k) + __ldg(sshift + sc0 + k);
+          if (skip_relu) o.v[k] = fmaxf(o.v[k], 0.f);
+        } else {
+          o.v[k] = 0.f;
+        }
+      }
+    }
+    st8(cat + (((long long)n * H + Y) * W + X) * ldc + c, o);
+  }
+}
+
+// du[n,y,x,(i,j,c)] = (u>0) * blur^T(dcat[..., 0:cu])[n, 2y+i, 2x+j, c]
+__global__ void shuffle_bwd_kernel(const __nv_bfloat16* __restrict__ dcat, int ldc, const __nv_bfloat16* __restrict__ u,
+                                   __nv_bfloat16* __restrict__ du, int ldu, int cu, int blur, int N, int h, int w) {
+  const int H = 2 * h, W = 2 * w, G = (4 * cu) >> 3;
+  const long long total = (long long)N * h * w * G;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    long long t = i / G;
+    const int x = (int)(t % w); t /= w;
+    const int y = (int)(t % h);
+    const int n = (int)(t / h);
+    const int ch = g * 8;          // channel in (i,j,c) order
+    const int ij = ch / cu, c = ch - ij * cu;
+    const int Y = 2 * y + (ij >> 1), X = 2 * x + (ij & 1);
+    auto dc = [&](int yy, int xx) { return ld8(dcat + (((long long)n * H + yy) * W + xx) * ldc + c); };
+    f8 o;
+    if (blur) {
+      // PS[Y,X] feeds outputs (Y+a, X+b), a,b in {0,1}; the replicated first row/column counts twice
+      const float wy0 = (Y == 0) ? 2.f : 1.f, wx0 = (X == 0) ? 2.f : 1.f;
+      const bool hy = (Y + 1 < H), hx = (X + 1 < W);
+      const f8 a = dc(Y, X);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o.v[k] = wy0 * wx0 * a.v[k];
+      if (hx) {
+        const f8 b = dc(Y, X + 1);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o.v[k] += wy0 * b.v[k];
+      }
+      if (hy) {
+        const f8 d = dc(Y + 1, X);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o.v[k] += wx0 * d.v[k];
+        if (hx) {
+          const f8 e = dc(Y + 1, X + 1);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o.v[k] += e.v[k];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o.v[k] *= 0.25f;
+    } else {
+      o = dc(Y, X);
+    }
+    const long long up = (((long long)n * h + y) * w + x) * ldu + ch;
+    const f8 uv = ld8(u + up);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o.v[k] = uv.v[k] > 0.f ? o.v[k] : 0.f;
+    st8(du + up, o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ layout casts
+// NCHW (fp32, or uint8 divided by 255) -> NHWC bf16 with pitch ld at channel offset ch_off; remaining lanes of the
+// 8-channel group(s) touched are zeroed when zero_pad is set.
+__global__ void nchw_to_nhwc_kernel(const void* __restrict__ x, int is_u8, __nv_bfloat16* __restrict__ y, int N, int C,
+                                    int H, int W, int ld, int ch_off, int Cw) {
+  const long long HW = (long long)H * W;
+  const long long total = (long long)N * HW;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
+    const long long n = p / HW, hw = p - n * HW;
+    __nv_bfloat16* dst = y + p * ld + ch_off;
+    for (int c = 0; c < Cw; ++c) {
+      float v = 0.f;
+      if (c < C) {
+        const long long src = (n * C + c) * HW + hw;
+        v = is_u8 ? (float)reinterpret_cast<const uint8_t*>(x)[src] / 255.f : reinterpret_cast<const float*>(x)[src];
+      }
+      dst[c] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
+__global__ void nhwc_to_nchw_f32_kernel(const void* __restrict__ x, int is_f32, int ld, float* __restrict__ y, int N,
+                                        int C, int H, int W) {
+  const long long HW = (long long)H * W;
+  const long long total = (long long)N * C * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long hw = i % HW;
+    const int c = (int)((i / HW) % C);
+    const long long n = i / (HW * C);
+    const long long src = (n * HW + hw) * ld + c;
+    y[i] = is_f32 ? reinterpret_cast<const float*>(x)[src]
+                  : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[src]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ cross entropy
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  float r = 0.f;
+  if (threadIdx.x == 0)
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) r += sh[i];
+  __syncthreads();
+  return r;  // valid on thread 0
+}
+
+__global__ void ce_weight_sum_kernel(const uint8_t* __restrict__ labels, long long P, const float* __restrict__ weight,
+                                     int C, float* __restrict__ partial) {
+  __shared__ float sh[32];
+  float s = 0.f;
+  const long long per = (P + gridDim.x - 1) / gridDim.x;
+  const long long p0 = (long long)blockIdx.x * per, p1 = min(P, p0 + per);
+  for (long long p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
+    const int y = labels[p];
+    s += (y < C) ? (weight ? __ldg(weight + y) : 1.f) : 0.f;
+  }
+  const float r = block_sum(s, sh);
+  if (threadIdx.x == 0) partial[blockIdx.x] = r;
+}
+
+// loss partials + dlogits in one pass. dlogits[p][c] = grad_scale * w[y] * (softmax_c - [c==y]) / wsum
+template <int MAXC>
+__global__ void ce_fwd_bwd_kernel(const float* __restrict__ logits, int ld, const uint8_t* __restrict__ labels,
+                                  long long P, int C, const float* __restrict__ weight,
+                                  const float* __restrict__ wsum_partial, int wsum_rows,
+                                  __nv_bfloat16* __restrict__ dlogits, int ldg, float* __restrict__ loss_partial,
+                                  float grad_scale) {
+  __shared__ float sh[32];
+  __shared__ float s_wsum;
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < wsum_rows; ++i) t += wsum_partial[i];  // fixed order: every block derives the same value
+    s_wsum = t;
+  }
+  __syncthreads();
+  const float inv_wsum = s_wsum > 0.f ? 1.f / s_wsum : 0.f;
+  float acc = 0.f;
+  const long long per = (P + gridDim.x - 1) / gridDim.x;
+  const long long p0 = (long long)blockIdx.x * per, p1 = min(P, p0 + per);
+  for (long long p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
+    float z[MAXC];
+    float m = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      z[c] = (c < C) ? logits[p * ld + c] : -INFINITY;
+      m = fmaxf(m, z[c]);
+    }
+    float se = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      z[c] = (c < C) ? __expf(z[c] - m) : 0.f;
+      se += z[c];
+    }
+    const int y = labels[p];
+    const bool ok = y < C;
+    const float wy = ok ? (weight ? __ldg(weight + y) : 1.f) : 0.f;
+    const float inv = 1.f / se;
+    if (ok) {
+      float py = 0.f;
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) py = (c == y) ? z[c] * inv : py;
+      acc += -wy * __logf(fmaxf(py, 1e-37f));
+    }
+    if (dlogits) {
+      const float gs = grad_scale * wy * inv_wsum;
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c)
+        if (c < ldg) dlogits[p * ldg + c] = __float2bfloat16_rn(c < C ? gs * (z[c] * inv - (c == y ? 1.f : 0.f)) : 0.f);
+    }
+  }
+  const float r = block_sum(acc, sh);
+  if (threadIdx.x == 0) loss_partial[blockIdx.x] = r;
+}
+
+__global__ void ce_finalize_kernel(const float* loss_partial, int rows, const float* wsum_partial, int wsum_rows,
+                                   float* loss) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double l = 0, w = 0;
+    for (int i = 0; i < rows; ++i) l += loss_partial[i];
+    for (int i = 0; i < wsum_rows; ++i) w += wsum_partial[i];
+    loss[0] = w > 0 ? (float)(l / w) : 0.f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ optimizers
+__global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, long long n, float lr, float gs) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    p[i] -= lr * gs * g[i];
+}
+
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long long n, const long long* __restrict__ seg_end,
+                            const float* __restrict__ seg_lr, const float* __restrict__ seg_wd, int nseg, float mom,
+                            float sqr_mom, float eps, float debias1, float debias2, float gs) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int lo = 0, hi = nseg - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (i < seg_end[mid]) hi = mid; else lo = mid + 1;
+    }
+    const float lr = seg_lr[lo], wd = seg_wd[lo];
+    float pv = p[i];
+    const float gv = gs * g[i];
+    if (wd != 0.f) pv *= 1.f - lr * wd;
+    const float mv = mom * m[i] + (1.f - mom) * gv;
+    const float vv = sqr_mom * v[i] + (1.f - sqr_mom) * gv * gv;
+    m[i] = mv;
+    v[i] = vv;
+    pv -= (lr / debias1) * mv / (sqrtf(vv / debias2) + eps);
+    p[i] = pv;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ stitching
+// softmax of tile logits added into the raster accumulators; one launch handles tiles that do not overlap each other.
+template <int MAXC>
+__global__ void stitch_accumulate_kernel(const float* __restrict__ logits, int ld, int C, int T, int th, int tw,
+                                         const int* __restrict__ ty0, const int* __restrict__ tx0,
+                                         const int* __restrict__ sel, int n_sel, float* __restrict__ acc,
+                                         uint8_t* __restrict__ cnt, long long Y, long long X, long long y_off,
+                                         long long x_off) {
+  const long long per_tile = (long long)th * tw;
+  const int nt = sel ? n_sel : T;
+  const long long total = (long long)nt * per_tile;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i / per_tile);
+    const int t = sel ? sel[k] : k;
+    const long long r = i - (long long)k * per_tile;
+    const int yy = (int)(r / tw), xx = (int)(r - (long long)yy * tw);
+    const long long gy = (long long)ty0[t] + yy - y_off, gx = (long long)tx0[t] + xx - x_off;
+    if (gy < 0 || gy >= Y || gx < 0 || gx >= X) continue;
+    const float* z = logits + ((long long)t * per_tile + r) * ld;
+    float e[MAXC];
+    float m = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      e[c] = (c < C) ? z[c] : -INFINITY;
+      m = fmaxf(m, e[c]);
+    }
+    float se = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      e[c] = (c < C) ? expf(e[c] - m) : 0.f;
+      se += e[c];
+    }
+    const float inv = 1.f / se;
+    const long long o = gy * X + gx;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c)
+      if (c < C) acc[(long long)c * Y * X + o] += e[c] * inv;
+    cnt[o] += 1;
+  }
+}
+
+__global__ void stitch_finalize_kernel(const float* __restrict__ acc, const uint8_t* __restrict__ cnt, int C,
+                                       long long YX, uint8_t* __restrict__ mask) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < YX; i += (long long)gridDim.x * blockDim.x) {
+    const int n = cnt[i];
+    int best = 0;
+    if (n > 0) {
+      float bv = acc[i] / (float)n;
+      for (int c = 1; c < C; ++c) {
+        const float v = acc[(long long)c * YX + i] / (float)n;
+        if (v > bv) { bv = v; best = c; }
+      }
+    }
+    mask[i] = (uint8_t)best;
+  }
+}
+
+// per-tile probabilities (fp32 NCHW) and argmax — what learn.predict hands back per tile
+template <int MAXC>
+__global__ void softmax_nchw_kernel(const float* __restrict__ logits, int ld, int C, long long tiles, int H, int W,
+                                    float* __restrict__ probs, uint8_t* __restrict__ amax) {
+  const long long HW = (long long)H * W, total = tiles * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const float* z = logits + i * ld;
+    float e[MAXC];
+    float m = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      e[c] = (c < C) ? z[c] : -INFINITY;
+      m = fmaxf(m, e[c]);
+    }
+    float se = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      e[c] = (c < C) ? expf(e[c] - m) : 0.f;
+      se += e[c];
+    }
+    const float inv = 1.f / se;
+    const long long t = i / HW, hw = i - t * HW;
+    int best = 0;
+    float bv = -1.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      if (c < C) {
+        const float pr = e[c] * inv;
+        if (probs) probs[(t * C + c) * HW + hw] = pr;
+        if (pr > bv) { bv = pr; best = c; }
+      }
+    }
+    if (amax) amax[i] = (uint8_t)best;
+  }
+}
+
+}  // namespace b2u
+
+using namespace b2u;
+typedef const __nv_bfloat16* cbf;
+typedef __nv_bfloat16* bf;
+
+extern "C" int b2u_stage_weights(const b2u_wstage_item* items_dev, int32_t n_items, int32_t total_blocks,
+                                 void* stream) {
+  B2U_CHECK_ARG(items_dev && n_items > 0 && total_blocks > 0, "stage_weights: bad argument");
+  static_assert(sizeof(b2u_wstage_item) == sizeof(WStageItem), "b2u_wstage_item layout drifted");
+  stage_weights_kernel<<<total_blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const WStageItem*>(items_dev),
+                                                                      n_items);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" int b2u_shuffle_cat_fwd(const void* u, int32_t ldu, int32_t cu, int32_t blur, const void* skip, int32_t lds,
+                                   int32_t cs, const float* sscale, const float* sshift, int32_t skip_relu, void* cat,
+                                   int32_t ldc, int32_t N, int32_t h, int32_t w, void* stream) {
+  B2U_CHECK_ARG(u && cat && cu > 0 && cu % 8 == 0 && ldu % 8 == 0 && ldc % 8 == 0 && ldu >= 4 * cu,
+                "shuffle_cat_fwd: bad argument (cu must be a multiple of 8)");
+  B2U_CHECK_ARG(!skip || (lds % 8 == 0 && cs > 0 && cu + cs <= ldc), "shuffle_cat_fwd: bad skip");
+  B2U_CHECK_ARG(!sscale || sshift, "shuffle_cat_fwd: sscale without sshift");
+  const long long items = (long long)N * 4 * h * w * (ldc / 8);
+  shuffle_cat_fwd_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>(
+      (cbf)u, ldu, cu, blur, (cbf)skip, lds, cs, sscale, sshift, skip_relu, (bf)cat, ldc, N, h, w);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" int b2u_shuffle_bwd(const void* dcat, int32_t ldc, const void* u, void* du, int32_t ldu, int32_t cu,
+                               int32_t blur, int32_t N, int32_t h, int32_t w, void* stream) {
+  B2U_CHECK_ARG(dcat && u && du && cu % 8 == 0 && ldu % 8 == 0 && ldc % 8 == 0, "shuffle_bwd: bad argument");
+  const long long items = (long long)N * h * w * (4 * cu / 8);
+  shuffle_bwd_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>((cbf)dcat, ldc, (cbf)u, (bf)du, ldu, cu,
+                                                                           blur, N, h, w);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" int b2u_nchw_to_nhwc(const void* x, int32_t x_is_u8, void* y, int32_t N, int32_t C, int32_t H, int32_t W,
+                                int32_t ld, int32_t ch_off, int32_t write_c, void* stream) {
+  B2U_CHECK_ARG(x && y && C > 0 && write_c >= C && ch_off + write_c <= ld, "nchw_to_nhwc: bad argument");
+  const long long items = (long long)N * H * W;
+  nchw_to_nhwc_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>(x, x_is_u8, (bf)y, N, C, H, W, ld, ch_off,
+                                                                            write_c);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" int b2u_nhwc_to_nchw_f32(const void* x, int32_t x_is_f32, int32_t ld, float* y, int32_t N, int32_t C,
+                                    int32_t H, int32_t W, void* stream) {
+  B2U_CHECK_ARG(x && y && C > 0 && C <= ld, "nhwc_to_nchw_f32: bad argument");
+  const long long items = (long long)N * C * H * W;
+  nhwc_to_nchw_f32_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>(x, x_is_f32, ld, y, N, C, H, W);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" int b2u_ce_weight_sum(const uint8_t* labels, int64_t P, const float* weight, int32_t C, float* wsum_partial,
+                                 int32_t rows, void* stream) {
+  B2U_CHECK_ARG(labels && wsum_partial && rows > 0 && C > 0, "ce_weight_sum: bad argument");
+  ce_weight_sum_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(labels, P, weight, C, wsum_partial);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" int b2u_ce_fwd_bwd(const float* logits, int32_t ld, const uint8_t* labels, int64_t P, int32_t C,
+                              const float* weight, const float* wsum_partial, int32_t wsum_rows, void* dlogits,
+                              int32_t ldg, float* loss_partial, int32_t rows, float grad_scale, void* stream) {
+  B2U_CHECK_ARG(logits && labels && wsum_partial && loss_partial && rows > 0, "ce_fwd_bwd: bad argument");
+  B2U_CHECK_ARG(C >= 1 && C <= 32 && C <= ld && (!dlogits || (ldg >= C && ldg <= 32)), "ce_fwd_bwd: C=%d ld=%d ldg=%d unsupported", C, ld, ldg);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C <= 8 && ldg <= 8)
+    ce_fwd_bwd_kernel<8><<<rows, 256, 0, st>>>(logits, ld, labels, P, C, weight, wsum_partial, wsum_rows, (bf)dlogits,
+                                               ldg, loss_partial, grad_scale);
+  else
+    ce_fwd_bwd_kernel<32><<<rows, 256, 0, st>>>(logits, ld, labels, P, C, weight, wsum_partial, wsum_rows, (bf)dlogits,
+                                                ldg, loss_partial, grad_scale);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" int b2u_ce_finalize(const float* loss_partial, int32_t rows, const float* wsum_partial, int32_t wsum_rows,
+                               float* loss, void* stream) {
+  B2U_CHECK_ARG(loss_partial && wsum_partial && loss, "ce_finalize: bad argument");
+  ce_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(loss_partial, rows, wsum_partial, wsum_rows, loss);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" int b2u_sgd_step(float* p, const float* g, int64_t n, float lr, float grad_scale, void* stream) {
+  B2U_CHECK_ARG(p && g && n > 0, "sgd_step: bad argument");
+  sgd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, n, lr, grad_scale);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" int b2u_adam_step(float* p, const float* g, float* m, float* v, int64_t n, const int64_t* seg_end,
+                             const float* seg_lr, const float* seg_wd, int32_t nseg, float mom, float sqr_mom,
+                             float eps, int32_t step, float grad_scale, void* stream) {
+  B2U_CHECK_ARG(p && g && m && v && n > 0 && seg_end && seg_lr && seg_wd && nseg > 0 && step >= 1,
+                "adam_step: bad argument");
+  const float debias1 = 1.f - powf(mom, (float)step), debias2 = 1.f - powf(sqr_mom, (float)step);
+  adam_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, (const long long*)seg_end, seg_lr,
+                                                                  seg_wd, nseg, mom, sqr_mom, eps, debias1, debias2,
+                                                                  grad_scale);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" int b2u_stitch_accumulate(const float* logits, int32_t ld, int32_t C, int32_t T, int32_t th, int32_t tw,
+                                     const int32_t* y0, const int32_t* x0, const int32_t* sel, int32_t n_sel,
+                                     float* acc, uint8_t* cnt, int64_t Y, int64_t X, int64_t y_off, int64_t x_off,
+                                     void* stream) {
+  B2U_CHECK_ARG(logits && y0 && x0 && acc && cnt && C >= 1 && C <= 32 && C <= ld, "stitch_accumulate: bad argument");
+  const int nt = sel ? n_sel : T;
+  if (nt <= 0) return B2U_OK;
+  const long long items = (long long)nt * th * tw;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C <= 8)
+    stitch_accumulate_kernel<8><<<grid_for(items, 256), 256, 0, st>>>(logits, ld, C, T, th, tw, y0, x0, sel, n_sel,
+                                                                      acc, cnt, Y, X, y_off, x_off);
+  else
+    stitch_accumulate_kernel<32><<<grid_for(items, 256), 256, 0, st>>>(logits, ld, C, T, th, tw, y0, x0, sel, n_sel,
+                                                                       acc, cnt, Y, X, y_off, x_off);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" int b2u_stitch_finalize(const float* acc, const uint8_t* cnt, int32_t C, int64_t Y, int64_t X, uint8_t* mask,
+                                   void* stream) {
+  B2U_CHECK_ARG(acc && cnt && mask && C >= 1, "stitch_finalize: bad argument");
+  stitch_finalize_kernel<<<grid_for(Y * X, 256), 256, 0, (cudaStream_t)stream>>>(acc, cnt, C, Y * X, mask);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" int b2u_softmax_nchw(const float* logits, int32_t ld, int32_t C, int64_t tiles, int32_t H, int32_t W,
+                                float* probs, uint8_t* argmax, void* stream) {
+  B2U_CHECK_ARG(logits && C >= 1 && C <= 32 && C <= ld, "softmax_nchw: bad argument");
+  const long long items = tiles * H * W;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C <= 8)
+    softmax_nchw_kernel<8><<<grid_for(items, 256), 256, 0, st>>>(logits, ld, C, tiles, H, W, probs, argmax);
+  else
+    softmax_nchw_kernel<32><<<grid_for(items, 256), 256, 0, st>>>(logits, ld, C, tiles, H, W, probs, argmax);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}

@@ -1,0 +1,673 @@
+"""The xresnet-DynamicUnet as a static plan of libb2u.so launches (forward, backward, loss, optimizer).
+
+This is the B200-native replacement for `learn.model` + `loss.backward()` + `opt.step()` of the reference
+(train.py:141-154 model construction, train.py:246-250 fit loop -> fastai Learner._do_one_batch) and for the per-tile
+forward of `learn.predict` (predict.py:193).  torch is used for device memory, streams and NCCL only; every FLOP and
+every byte moved on the hot path is issued by a kernel in unet_b200/csrc.
+
+Data layout: activations NHWC bf16 with channel pitch pad8(C); parameters/gradients fp32 in ONE flat buffer each, in
+fastai's state_dict order and torch shapes (so reference weights load and the optimizer / NCCL all-reduce see a
+single contiguous range); bf16 GEMM copies of the weights are re-staged from the fp32 masters once per step by one
+batched kernel.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib, ops
+from .layout import ConvSpec, NetSpec, ParamLayout, build_spec, conv_flops, shuffle_row_of_co
+from .ops import ConvPlan, WgradPlan, pad8, view_nhwc
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+STATS_ROWS = 592  # block partial rows of the standalone reductions (4 per SM)
+
+
+class Act:
+    """An NHWC bf16 activation and (lazily) its gradient."""
+
+    def __init__(self, N: int, H: int, W: int, Cc: int, dev, name: str = "", zero: bool = False):
+        self.N, self.H, self.W, self.C, self.ld = N, H, W, Cc, pad8(Cc)
+        alloc = torch.zeros if (zero or self.ld != Cc) else torch.empty
+        self.t = alloc((N, H, W, self.ld), dtype=torch.bfloat16, device=dev)
+        self.name = name
+        self.grad: Optional[torch.Tensor] = None
+        self.grad_written = False
+        self.pre_relu_grad = False  # decoder tensors: the producer of the gradient applies the (t > 0) ReLU mask
+
+    @property
+    def pixels(self) -> int:
+        return self.N * self.H * self.W
+
+    def ensure_grad(self) -> torch.Tensor:
+        if self.grad is None:
+            self.grad = torch.zeros_like(self.t)
+        return self.grad
+
+
+class BNState:
+    def __init__(self, net: "UNetB200", prefix: str, Cc: int):
+        dev = net.device
+        self.C = Cc
+        self.gamma = net.param(prefix + ".weight")
+        self.beta = net.param(prefix + ".bias")
+        self.dgamma = net.grad(prefix + ".weight")
+        self.dbeta = net.grad(prefix + ".bias")
+        self.running_mean = net.buffers[prefix + ".running_mean"]
+        self.running_var = net.buffers[prefix + ".running_var"]
+        f = lambda: torch.zeros(Cc, dtype=torch.float32, device=dev)
+        self.mean, self.invstd, self.scale, self.shift = f(), f(), f(), f()
+        self.mean_g, self.mean_gx = f(), f()
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+class UNetB200:
+    """Static launch plan for one (arch, n_in, n_out, H, W, batch) configuration."""
+
+    def __init__(self, arch: str = "xresnet34", n_in: int = 4, n_out: int = 2, size: Tuple[int, int] = (256, 256),
+                 batch: int = 8, training: bool = True, device: Optional[torch.device] = None,
+                 class_weights: Optional[Sequence[float]] = None):
+        if not torch.cuda.is_available():
+            raise _lib.B2UError("UNetB200 needs a CUDA device (sm_100a); there is no CPU path")
+        self.lib = _lib.load()
+        _lib.check(self.lib.b2u_device_check(), "b2u_device_check")
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.spec: NetSpec = build_spec(arch, n_in, n_out)
+        self.layout = ParamLayout(self.spec)
+        self.N, (self.H, self.W) = batch, size
+        if self.H % 32 or self.W % 32:
+            raise ValueError("tile height/width must be multiples of 32 (five stride-2 stages, no interpolate branch)")
+        self.training = training
+        self.n_in, self.n_out = n_in, n_out
+        dev = self.device
+        self.params = torch.zeros(self.layout.total, dtype=torch.float32, device=dev)
+        self.grads = torch.zeros(self.layout.total, dtype=torch.float32, device=dev) if training else None
+        self.buffers: Dict[str, torch.Tensor] = {}
+        for prefix, c in self.layout.buffers:
+            self.buffers[prefix + ".running_mean"] = torch.zeros(c, dtype=torch.float32, device=dev)
+            self.buffers[prefix + ".running_var"] = torch.ones(c, dtype=torch.float32, device=dev)
+        cw = [1.0 / n_out] * n_out if class_weights is None else list(class_weights)  # "even" weights, train.py:338-339
+        self.class_weights = torch.tensor(cw, dtype=torch.float32, device=dev)
+        self.flops_fwd_per_tile = conv_flops(self.spec, self.H) if self.H == self.W else None
+
+        self._keep: List[object] = []
+        self.fwd_ops: List[Callable[[int], None]] = []
+        self.bwd_ops: List[Callable[[int], None]] = []
+        self._bwd_builders: List[Callable[[], None]] = []
+        self._wstage: List[_lib.WStageItem] = []
+        self._wgrad_specs: List[dict] = []
+        self.launches_fwd = 0
+        self.launches_bwd = 0
+        self._w: Dict[str, Dict[str, torch.Tensor]] = {}
+        self._bn: Dict[str, BNState] = {}
+        self._scratch = torch.zeros(1 << 20, dtype=torch.float32, device=dev)  # finalize scratch (4 MB)
+        self._build()
+
+    # ------------------------------------------------------------------------------------------------ parameters
+    def param(self, name: str) -> torch.Tensor:
+        e = self.layout.by_name[name]
+        return self.params[e.offset:e.offset + e.numel].view(e.shape)
+
+    def grad(self, name: str) -> Optional[torch.Tensor]:
+        if self.grads is None:
+            return None
+        e = self.layout.by_name[name]
+        return self.grads[e.offset:e.offset + e.numel].view(e.shape)
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
+        """Accepts a fastai/oracle state_dict (keys `layers.N....`). Missing keys raise."""
+        with torch.no_grad():
+            for e in self.layout.entries:
+                self.param(e.name).copy_(sd[e.name].to(self.device, torch.float32))
+            for k, b in self.buffers.items():
+                b.copy_(sd[k].to(self.device, torch.float32))
+        self.weights_changed()
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        out = {e.name: self.param(e.name).detach().clone() for e in self.layout.entries}
+        for k, b in self.buffers.items():
+            out[k] = b.detach().clone()
+            if k.endswith("running_var"):
+                out[k.replace("running_var", "num_batches_tracked")] = torch.tensor(0, dtype=torch.long)
+        return out
+
+    def weights_changed(self) -> None:
+        """Re-stage bf16 GEMM weights (and, in eval mode, the folded BN affines) from the fp32 masters."""
+        s = ops.stream_ptr()
+        self._stage_weights(s)
+        if not self.training:
+            for bn in self._bn.values():
+                _lib.check(self.lib.b2u_bn_eval_affine(bn.C, _p(bn.gamma), _p(bn.beta), _p(bn.running_mean),
+                                                       _p(bn.running_var), BN_EPS, _p(bn.scale), _p(bn.shift), s),
+                           "b2u_bn_eval_affine")
+
+    # ------------------------------------------------------------------------------------------------ build helpers
+    def _act(self, H: int, W: int, Cc: int, name: str = "", zero: bool = False) -> Act:
+        return Act(self.N, H, W, Cc, self.device, name, zero)
+
+    def _bn_state(self, prefix: str, Cc: int) -> BNState:
+        st = BNState(self, prefix, Cc)
+        self._bn[prefix] = st
+        return st
+
+    def _weights(self, cs: ConvSpec, need_dgrad: bool) -> Dict[str, torch.Tensor]:
+        """bf16 GEMM copies of one conv's weights + staging item for the batched cast kernel."""
+        dev = self.device
+        kk = cs.ks * cs.ks
+        wf = torch.zeros((cs.nf, kk, pad8(cs.ni)), dtype=torch.bfloat16, device=dev)
+        wd = torch.zeros((cs.ni, kk, pad8(cs.nf)), dtype=torch.bfloat16, device=dev) if need_dgrad else None
+        w = {"wf": wf, "wd": wd, "bias_rows": None, "row_of_co": None, "row_perm": None}
+        if cs.shuffle:
+            roc = shuffle_row_of_co(cs.nf)
+            w["row_of_co"] = torch.tensor(roc, dtype=torch.int32, device=dev)
+            perm = [0] * cs.nf
+            for co, r in enumerate(roc):
+                perm[r] = co
+            w["row_perm"] = torch.tensor(perm, dtype=torch.int32, device=dev)
+        if not cs.bn:
+            w["bias_rows"] = torch.zeros(cs.nf, dtype=torch.float32, device=dev)
+        it = _lib.WStageItem()
+        it.w = self.param(cs.wname).data_ptr()
+        it.bias = self.param(cs.bname).data_ptr() if cs.bname else None
+        it.row_of_co = _p(w["row_of_co"])
+        it.wf, it.wd, it.bias_rows = wf.data_ptr(), _p(wd), _p(w["bias_rows"])
+        it.Cout, it.Cin, it.kk, it.wf_cinp, it.wd_coutp = cs.nf, cs.ni, kk, pad8(cs.ni), pad8(cs.nf)
+        it.scale = 0.25 if cs.pool else 1.0
+        self._wstage.append(it)
+        self._w[cs.name] = w
+        return w
+
+    def _finish_wstage(self) -> None:
+        n = len(self._wstage)
+        arr = (_lib.WStageItem * n)()
+        blocks = 0
+        for i, it in enumerate(self._wstage):
+            it.block_start = blocks
+            blocks += (it.Cout * it.Cin * it.kk + 255) // 256
+            arr[i] = it
+        raw = bytes(arr)
+        host = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
+        self._wstage_dev = host.to(self.device)
+        self._wstage_n, self._wstage_blocks = n, blocks
+
+    def _stage_weights(self, s: int) -> None:
+        _lib.check(self.lib.b2u_stage_weights(self._wstage_dev.data_ptr(), self._wstage_n, self._wstage_blocks, s),
+                   "b2u_stage_weights")
+
+    @staticmethod
+    def _views_taps(cs: ConvSpec, x: Act):
+        """A-operand views and tap table for fprop / wgrad of conv `cs` reading activation x."""
+        if cs.pool:
+            views = [view_nhwc(x.t, x.C, parity=(py, px)) for py in range(2) for px in range(2)]
+            return views, ops.taps_avgpool_1x1()
+        if cs.stride == 2:
+            assert cs.ks == 3
+            views = [view_nhwc(x.t, x.C, parity=(py, px)) for py in range(2) for px in range(2)]
+            return views, ops.taps_conv3_s2()
+        return [view_nhwc(x.t, x.C)], ops.taps_conv(cs.ks)
+
+    def _fwd(self, fn: Callable[[int], None], n: int = 1) -> None:
+        self.fwd_ops.append(fn)
+        self.launches_fwd += n
+
+    def _bwd(self, fn: Callable[[int], None], n: int = 1) -> None:
+        self.bwd_ops.append(fn)
+        self.launches_bwd += n
+
+    def _conv_fwd(self, cs: ConvSpec, x: Act, y: Act, *, out_C: Optional[int] = None, scale=None, shift=None,
+                  relu=False, res: Optional[Act] = None, stats=False, out_f32: Optional[torch.Tensor] = None):
+        w = self._w[cs.name]
+        views, taps = self._views_taps(cs, x)
+        plan = ConvPlan(views, view_nhwc(y.t, out_C or cs.nf), w["wf"], cs.ni, taps, scale=scale, shift=shift,
+                        res=view_nhwc(res.t, cs.nf) if res is not None else None, relu=relu, stats=stats,
+                        out_f32=out_f32)
+        self._keep.append(plan)
+        self._fwd(plan.run)
+        return plan
+
+    def _bn_finalize_op(self, bn: BNState, partial: torch.Tensor, count: float, train_stats: bool = True):
+        rows, _, ld = partial.shape
+        lib, sc = self.lib, self._scratch
+
+        def run(s, bn=bn, partial=partial, rows=rows, ld=ld, count=count):
+            _lib.check(lib.b2u_bn_finalize(partial.data_ptr(), rows, ld, bn.C, float(count), _p(bn.gamma), _p(bn.beta),
+                                           BN_EPS, BN_MOMENTUM, _p(bn.running_mean), _p(bn.running_var), _p(bn.mean),
+                                           _p(bn.invstd), _p(bn.scale), _p(bn.shift), sc.data_ptr(), sc.numel(), s),
+                       "b2u_bn_finalize")
+        return run, (2 if rows > 128 else 1) + (1 if rows > 128 * 128 else 0)
+
+    def _bn_apply_op(self, x: torch.Tensor, ldx: int, bn: BNState, y: torch.Tensor, ldy: int, pixels: int, relu: bool,
+                     r: Optional[torch.Tensor] = None, ldr: int = 0, rbn: Optional[BNState] = None):
+        lib = self.lib
+
+        def run(s):
+            _lib.check(lib.b2u_bn_apply(x.data_ptr(), ldx, _p(bn.scale), _p(bn.shift), _p(r), ldr,
+                                        _p(rbn.scale) if rbn else None, _p(rbn.shift) if rbn else None, int(relu),
+                                        y.data_ptr(), ldy, pixels, bn.C, s), "b2u_bn_apply")
+        return run
+
+    def _stats_op(self, x: torch.Tensor, ldx: int, pixels: int, Cc: int):
+        rows = max(1, min(STATS_ROWS, pixels // 64))
+        partial = torch.zeros((rows, 2, pad8(Cc)), dtype=torch.float32, device=self.device)
+        lib = self.lib
+
+        def run(s):
+            _lib.check(lib.b2u_bn_stats(x.data_ptr(), ldx, pixels, Cc, partial.data_ptr(), rows, pad8(Cc), s),
+                       "b2u_bn_stats")
+        return run, partial
+
+    # ---- backward helpers ---------------------------------------------------------------------------------------
+    def _bn_bwd(self, bn: BNState, dz: torch.Tensor, lddz: int, x: torch.Tensor, ldx: int, y: Optional[torch.Tensor],
+                ldy: int, relu: bool, dx: torch.Tensor, lddx: int, pixels: int, accumulate: bool):
+        """reduce -> finalize -> apply; dgamma/dbeta land in the flat gradient buffer."""
+        rows = max(1, min(STATS_ROWS, pixels // 64))
+        partial = torch.zeros((rows, 2, pad8(bn.C)), dtype=torch.float32, device=self.device)
+        lib, sc = self.lib, self._scratch
+        ld = pad8(bn.C)
+
+        def run(s):
+            _lib.check(lib.b2u_bn_bwd_reduce(dz.data_ptr(), lddz, x.data_ptr(), ldx, _p(y), ldy, _p(bn.scale),
+                                             _p(bn.shift), _p(bn.mean), _p(bn.invstd), int(relu), pixels, bn.C,
+                                             partial.data_ptr(), rows, ld, s), "b2u_bn_bwd_reduce")
+            _lib.check(lib.b2u_bn_bwd_finalize(partial.data_ptr(), rows, ld, bn.C, float(pixels), _p(bn.dgamma),
+                                               _p(bn.dbeta), _p(bn.mean_g), _p(bn.mean_gx), sc.data_ptr(), sc.numel(),
+                                               s), "b2u_bn_bwd_finalize")
+            _lib.check(lib.b2u_bn_bwd_apply(dz.data_ptr(), lddz, x.data_ptr(), ldx, _p(y), ldy, _p(bn.scale),
+                                            _p(bn.shift), _p(bn.mean), _p(bn.invstd), _p(bn.gamma), _p(bn.mean_g),
+                                            _p(bn.mean_gx), int(relu), int(accumulate), dx.data_ptr(), lddx, pixels,
+                                            bn.C, s), "b2u_bn_bwd_apply")
+        self._keep.append(partial)
+        self._bwd(run, 3 + (1 if rows > 128 else 0))
+
+    def _wgrad(self, cs: ConvSpec, dy: torch.Tensor, x: Act):
+        """dW (and db) of conv `cs` from dy (bf16 NHWC tensor [N,Ho,Wo,pad8(nf)]) and its input activation x."""
+        w = self._w[cs.name]
+        views, taps = self._views_taps(cs, x)
+        kidx = [0] * len(taps) if cs.pool else [t[3] for t in taps]
+        spec = dict(cs=cs, dy_view=view_nhwc(dy, cs.nf), views=views, taps=taps, kidx=kidx,
+                    dw=self.grad(cs.wname), db=self.grad(cs.bname) if cs.bname else None, row_perm=w["row_perm"],
+                    alpha=0.25 if cs.pool else 1.0, keep=(dy, x))
+        info = WgradPlan.query(spec["dy_view"], views, taps, cs.nf, cs.ni, spec["db"] is not None)
+        spec["bytes"] = info.partial_bytes
+        self._wgrad_specs.append(spec)
+        slot = len(self._wgrad_specs) - 1
+
+        def run(s, slot=slot):
+            self._wgrad_plans[slot].run(s)
+        self._bwd(run, 2)
+
+    def _dgrad(self, cs: ConvSpec, dy: torch.Tensor, x: Act, *, zmask: bool = False, res: Optional[torch.Tensor] = None,
+               res_mask: Optional[torch.Tensor] = None, out_C: Optional[int] = None):
+        """dX of conv `cs` (accumulating if x.grad already holds a contribution)."""
+        w = self._w[cs.name]
+        dx = x.ensure_grad()
+        Cx = out_C or cs.ni
+        acc = x.grad_written
+        assert not (acc and res is not None), "dgrad: accumulate + extra residual not supported"
+        wd = w["wd"][:Cx] if Cx != cs.ni else w["wd"]
+        a = [view_nhwc(dy, cs.nf)]
+
+        def mk(out_view, taps, par):
+            r = out_view if acc else (view_nhwc(res, Cx, parity=par) if res is not None else None)
+            rm = view_nhwc(res_mask, Cx, parity=par) if (res_mask is not None and not acc) else None
+            zm = view_nhwc(x.t, Cx, parity=par) if zmask else None
+            plan = ConvPlan(a, out_view, wd, cs.nf, taps, res=r, res_mask=rm, zmask=zm)
+            self._keep.append(plan)
+            self._bwd(plan.run)
+
+        if cs.pool:
+            for py in range(2):
+                for px in range(2):
+                    mk(view_nhwc(dx, Cx, parity=(py, px)), [(0, 0, 0, 0)], (py, px))
+        elif cs.stride == 2:
+            for py in range(2):
+                for px in range(2):
+                    mk(view_nhwc(dx, Cx, parity=(py, px)), ops.taps_dgrad_s2(py, px), (py, px))
+        else:
+            mk(view_nhwc(dx, Cx), ops.taps_conv(cs.ks), None)
+        x.grad_written = True
+
+    # ------------------------------------------------------------------------------------------------ the network
+    def _build(self) -> None:
+        spec, N, H, W, dev, lib = self.spec, self.N, self.H, self.W, self.device, self.lib
+        train = self.training
+        # weights for every conv (first stem conv never needs a dgrad copy: the image has no gradient)
+        for i, cs in enumerate(spec.convs()):
+            self._weights(cs, need_dgrad=train and i != 0)
+        self._finish_wstage()
+
+        # ---- input
+        self.x_in = self._act(H, W, spec.n_in, "input", zero=True)
+        self.logits = torch.zeros((N, H, W, 8 if spec.n_out <= 8 else pad8(spec.n_out)), dtype=torch.float32, device=dev)
+        bwd_layers: List[Callable[[], None]] = []
+
+        # ---- encoder ConvLayer = conv -> BN -> [ReLU]
+        def conv_bn(cs: ConvSpec, x: Act, h: int, w_: int, apply: bool) -> Tuple[Act, Optional[Act], BNState]:
+            bn = self._bn_state(cs.bn_prefix, cs.nf)
+            if train:
+                R = self._act(h, w_, cs.nf, cs.name + ".raw")
+                plan = self._conv_fwd(cs, x, R, stats=True)
+                fin, nl = self._bn_finalize_op(bn, plan.stats, N * h * w_)
+                self._fwd(fin, nl)
+                Z = None
+                if apply:
+                    Z = self._act(h, w_, cs.nf, cs.name + ".out")
+                    self._fwd(self._bn_apply_op(R.t, R.ld, bn, Z.t, Z.ld, R.pixels, cs.act))
+                return R, Z, bn
+            Z = self._act(h, w_, cs.nf, cs.name + ".out")
+            if apply:
+                self._conv_fwd(cs, x, Z, scale=bn.scale, shift=bn.shift, relu=cs.act)
+            return Z, Z, bn  # (eval: when apply is False the caller fuses scale/shift itself)
+
+        def conv_bn_bwd(cs: ConvSpec, x: Act, R: Act, Z: Act, bn: BNState, need_dx: bool):
+            def build():
+                dR = torch.zeros_like(R.t)
+                self._keep.append(dR)
+                self._bn_bwd(bn, Z.grad, Z.ld, R.t, R.ld, None, 0, cs.act, dR, R.ld, R.pixels, False)
+                self._wgrad(cs, dR, x)
+                if need_dx:
+                    self._dgrad(cs, dR, x)
+            return build
+
+        x = self.x_in
+        h, w_ = H // 2, W // 2
+        feats: Dict[int, Act] = {}
+        for i, cs in enumerate(spec.stem):
+            R, Z, bn = conv_bn(cs, x, h, w_, apply=True)
+            if train:
+                bwd_layers.append(conv_bn_bwd(cs, x, R, Z, bn, need_dx=i != 0))
+            x = Z
+        feats[2] = x
+        # ---- maxpool
+        mp_in = x
+        h, w_ = h // 2, w_ // 2
+        mp = self._act(h, w_, mp_in.C, "maxpool")
+        idx = torch.zeros((N, h, w_, mp.ld), dtype=torch.uint8, device=dev) if train else None
+        self._fwd(lambda s, a=mp_in, b=mp, idx=idx: _lib.check(
+            lib.b2u_maxpool_fwd(a.t.data_ptr(), b.t.data_ptr(), _p(idx), N, a.H, a.W, a.C, a.ld, s), "b2u_maxpool_fwd"))
+        if train:
+            def mp_bwd():
+                g = mp_in.ensure_grad()
+                acc = int(mp_in.grad_written)
+                self._bwd(lambda s: _lib.check(lib.b2u_maxpool_bwd(mp.grad.data_ptr(), idx.data_ptr(), g.data_ptr(), acc,
+                                                                   N, mp_in.H, mp_in.W, mp_in.C, mp_in.ld, s),
+                                               "b2u_maxpool_bwd"))
+                mp_in.grad_written = True
+            bwd_layers.append(mp_bwd)
+        x = mp
+
+        # ---- residual stages
+        for si, blocks in enumerate(spec.stages):
+            for blk in blocks:
+                xin = x
+                ho, wo = h // blk.stride, w_ // blk.stride
+                cur, ch, cw = xin, h, w_
+                recs = []
+                for j, cs in enumerate(blk.convpath):
+                    ch, cw = ch // cs.stride, cw // cs.stride
+                    last = j == len(blk.convpath) - 1
+                    R, Z, bn = conv_bn(cs, cur, ch, cw, apply=not last)
+                    recs.append((cs, cur, R, Z, bn))
+                    cur = Z if not last else R
+                idrec = None
+                if blk.idconv is not None:
+                    Rid, _, bnid = conv_bn(blk.idconv, xin, ho, wo, apply=False)
+                    idrec = (blk.idconv, Rid, bnid)
+                out = self._act(ho, wo, blk.nf, blk.name + ".out")
+                csl, xl, Rl, _, bnl = recs[-1]
+                if train:
+                    if idrec is not None:
+                        self._fwd(self._bn_apply_op(Rl.t, Rl.ld, bnl, out.t, out.ld, out.pixels, True, idrec[1].t,
+                                                    idrec[1].ld, idrec[2]))
+                    else:
+                        self._fwd(self._bn_apply_op(Rl.t, Rl.ld, bnl, out.t, out.ld, out.pixels, True, xin.t, xin.ld))
+                else:
+                    # eval: BN folded into the conv epilogues; the block tail is one fused launch
+                    if idrec is not None:
+                        self._conv_fwd(idrec[0], xin, idrec[1], scale=idrec[2].scale, shift=idrec[2].shift)
+                        self._conv_fwd(csl, xl, out, scale=bnl.scale, shift=bnl.shift, relu=True, res=idrec[1])
+                    else:
+                        self._conv_fwd(csl, xl, out, scale=bnl.scale, shift=bnl.shift, relu=True, res=xin)
+
+                if train:
+                    def blk_bwd(blk=blk, xin=xin, out=out, recs=recs, idrec=idrec):
+                        dOut = out.grad
+                        assert dOut is not None and out.grad_written, blk.name
+                        # tail: BN of the last convpath conv, masked by the block output
+                        csl, xl, Rl, _, bnl = recs[-1]
+                        dRl = torch.zeros_like(Rl.t)
+                        self._keep.append(dRl)
+                        self._bn_bwd(bnl, dOut, out.ld, Rl.t, Rl.ld, out.t, out.ld, False, dRl, Rl.ld, Rl.pixels, False)
+                        if idrec is not None:
+                            csi, Rid, bnid = idrec
+                            dRid = torch.zeros_like(Rid.t)
+                            self._keep.append(dRid)
+                            self._bn_bwd(bnid, dOut, out.ld, Rid.t, Rid.ld, out.t, out.ld, False, dRid, Rid.ld,
+                                         Rid.pixels, False)
+                            self._wgrad(csi, dRid, xin)
+                            self._dgrad(csi, dRid, xin)
+                        dcur = dRl
+                        for j in range(len(recs) - 1, -1, -1):
+                            cs, xj, Rj, Zj, bnj = recs[j]
+                            self._wgrad(cs, dcur, xj)
+                            if j == 0:
+                                if idrec is None:
+                                    assert not xin.grad_written
+                                    self._dgrad(cs, dcur, xj, res=dOut, res_mask=out.t)  # identity path: + dOut*(out>0)
+                                else:
+                                    self._dgrad(cs, dcur, xj)
+                            else:
+                                self._dgrad(cs, dcur, xj)
+                                csp, xp, Rp, Zp, bnp = recs[j - 1]
+                                dRp = torch.zeros_like(Rp.t)
+                                self._keep.append(dRp)
+                                self._bn_bwd(bnp, Zp.grad, Zp.ld, Rp.t, Rp.ld, None, 0, True, dRp, Rp.ld, Rp.pixels, False)
+                                dcur = dRp
+                    bwd_layers.append(blk_bwd)
+                x, h, w_ = out, ho, wo
+            feats[4 + si] = x
+
+        # ---- layers.1/2: BatchNorm + ReLU on the encoder output
+        E = x
+        bnE = self._bn_state(spec.post_bn, E.C)
+        ZE = self._act(h, w_, E.C, "enc.bnrelu")
+        if train:
+            st, partial = self._stats_op(E.t, E.ld, E.pixels, E.C)
+            self._fwd(st)
+            fin, nl = self._bn_finalize_op(bnE, partial, E.pixels)
+            self._fwd(fin, nl)
+        self._fwd(self._bn_apply_op(E.t, E.ld, bnE, ZE.t, ZE.ld, E.pixels, True))
+        if train:
+            def post_bwd():
+                dE = E.ensure_grad()
+                self._bn_bwd(bnE, ZE.grad, ZE.ld, E.t, E.ld, None, 0, True, dE, E.ld, E.pixels, E.grad_written)
+                E.grad_written = True
+            bwd_layers.append(post_bwd)
+
+        # ---- decoder conv (+bias, ReLU fused): gradient buffers hold PRE-activation gradients
+        def conv_bias(cs: ConvSpec, xa: Act, hh: int, ww: int, res: Optional[Act] = None, relu: bool = True) -> Act:
+            y = self._act(hh, ww, cs.nf, cs.name + ".out")
+            y.pre_relu_grad = relu
+            self._conv_fwd(cs, xa, y, shift=self._w[cs.name]["bias_rows"], relu=relu, res=res)
+            return y
+
+        def conv_bias_bwd(cs: ConvSpec, xa: Act, y: Act, **dg):
+            def build():
+                assert y.grad is not None and y.grad_written, cs.name
+                self._wgrad(cs, y.grad, xa)
+                self._dgrad(cs, y.grad, xa, zmask=xa.pre_relu_grad, **dg)
+            return build
+
+        x = ZE
+        for cs in spec.middle:
+            y = conv_bias(cs, x, h, w_)
+            if train:
+                bwd_layers.append(conv_bias_bwd(cs, x, y))
+            x = y
+
+        # ---- UnetBlocks
+        for ub in spec.unet:
+            U, S = x, feats[ub.skip_child]
+            P = conv_bias(ub.shuf, U, h, w_)
+            bnS = self._bn_state(ub.bn_prefix, S.C)
+            if train:
+                st, partial = self._stats_op(S.t, S.ld, S.pixels, S.C)
+                self._fwd(st)
+                fin, nl = self._bn_finalize_op(bnS, partial, S.pixels)
+                self._fwd(fin, nl)
+            h, w_ = 2 * h, 2 * w_
+            assert (S.H, S.W) == (h, w_), "skip / upsample size mismatch (odd tile sizes are not supported yet)"
+            cat = self._act(h, w_, ub.cu + S.C, ub.name + ".cat")
+            cat.pre_relu_grad = True
+            self._fwd(lambda s, P=P, S=S, cat=cat, bnS=bnS, cu=ub.cu: _lib.check(
+                lib.b2u_shuffle_cat_fwd(P.t.data_ptr(), P.ld, cu, 1, S.t.data_ptr(), S.ld, S.C, _p(bnS.scale),
+                                        _p(bnS.shift), 1, cat.t.data_ptr(), cat.ld, N, P.H, P.W, s),
+                "b2u_shuffle_cat_fwd"))
+            c1 = conv_bias(ub.conv1, cat, h, w_)
+            c2 = conv_bias(ub.conv2, c1, h, w_)
+            if train:
+                def ub_bwd(ub=ub, U=U, S=S, P=P, cat=cat, c1=c1, c2=c2, bnS=bnS):
+                    conv_bias_bwd(ub.conv2, c1, c2)()
+                    conv_bias_bwd(ub.conv1, cat, c1)()
+                    dP = P.ensure_grad()
+                    dcat = cat.grad
+                    self._bwd(lambda s: _lib.check(lib.b2u_shuffle_bwd(dcat.data_ptr(), cat.ld, P.t.data_ptr(),
+                                                                       dP.data_ptr(), P.ld, ub.cu, 1, N, P.H, P.W, s),
+                                                   "b2u_shuffle_bwd"))
+                    P.grad_written = True
+                    dS = S.ensure_grad()
+                    self._bn_bwd(bnS, dcat[..., ub.cu:], cat.ld, S.t, S.ld, None, 0, False, dS, S.ld, S.pixels,
+                                 S.grad_written)
+                    S.grad_written = True
+                    conv_bias_bwd(ub.shuf, U, P)()
+                bwd_layers.append(ub_bwd)
+            x = c2
+
+        # ---- final PixelShuffle_ICNR (no blur) + MergeLayer(dense) + ResBlock(no norm) + head
+        U = x
+        fs = spec.final_shuf
+        P8 = conv_bias(fs, U, h, w_)
+        cu = fs.nf // 4
+        h, w_ = 2 * h, 2 * w_
+        assert (h, w_) == (H, W)
+        cat = self._act(h, w_, cu + spec.n_in, "layers.10.cat", zero=True)
+        xin = self.x_in
+        self._fwd(lambda s: _lib.check(
+            lib.b2u_shuffle_cat_fwd(P8.t.data_ptr(), P8.ld, cu, 0, xin.t.data_ptr(), xin.ld, xin.C, None, None, 0,
+                                    cat.t.data_ptr(), cat.ld, N, P8.H, P8.W, s), "b2u_shuffle_cat_fwd"))
+        ra, rb = spec.final_res
+        A1 = conv_bias(ra, cat, h, w_)
+        A2 = conv_bias(rb, A1, h, w_, res=cat, relu=True)  # relu(convpath(x) + x)
+        hd = spec.head
+        hv = self._act(h, w_, hd.nf, "head.geom")  # geometry carrier only; the head stores fp32 logits
+        self._conv_fwd(hd, A2, hv, shift=self._w[hd.name]["bias_rows"], out_f32=self.logits)
+        self.out_act = A2
+
+        if train:
+            # loss buffers
+            P_ = N * H * W
+            self.labels = torch.zeros((N, H, W), dtype=torch.uint8, device=dev)
+            self.dlogits = torch.zeros((N, H, W, 8 if spec.n_out <= 8 else pad8(spec.n_out)), dtype=torch.bfloat16, device=dev)
+            self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
+            self._ce_rows = 592
+            self._wsum_part = torch.zeros(self._ce_rows, dtype=torch.float32, device=dev)
+            self._loss_part = torch.zeros(self._ce_rows, dtype=torch.float32, device=dev)
+
+            def tail_bwd():
+                dL = self.dlogits
+                self._wgrad(hd, dL, A2)
+                self._dgrad(hd, dL, A2, zmask=True)
+                A2.grad_written = True
+                self._wgrad(rb, A2.grad, A1)
+                self._dgrad(rb, A2.grad, A1, zmask=True)
+                self._wgrad(ra, A1.grad, cat)
+                # only the shuffled channels need a gradient (the image does not): restrict dgrad to [0, cu)
+                self._dgrad(ra, A1.grad, cat, res=A2.grad, out_C=cu)
+                dP8 = P8.ensure_grad()
+                self._bwd(lambda s: _lib.check(lib.b2u_shuffle_bwd(cat.grad.data_ptr(), cat.ld, P8.t.data_ptr(),
+                                                                   dP8.data_ptr(), P8.ld, cu, 0, N, P8.H, P8.W, s),
+                                               "b2u_shuffle_bwd"))
+                P8.grad_written = True
+                conv_bias_bwd(fs, U, P8)()
+            bwd_layers.append(tail_bwd)
+
+            # build backward in true reverse order (gradient accumulation flags depend on it)
+            for b in reversed(bwd_layers):
+                b()
+            ws_bytes = max(sp["bytes"] for sp in self._wgrad_specs)
+            self._wgrad_ws = torch.zeros((ws_bytes + 3) // 4, dtype=torch.float32, device=dev)
+            self._wgrad_plans = []
+            for sp in self._wgrad_specs:
+                cs = sp["cs"]
+                self._wgrad_plans.append(WgradPlan(sp["dy_view"], sp["views"], sp["taps"], cs.nf, cs.ni, cs.ks * cs.ks,
+                                                   sp["kidx"], sp["dw"].reshape(-1), sp["db"], sp["row_perm"],
+                                                   sp["alpha"], self._wgrad_ws))
+        self.feats = feats
+
+    # ------------------------------------------------------------------------------------------------ execution
+    def set_input(self, x: torch.Tensor, stream: Optional[int] = None) -> None:
+        """x: [N, n_in, H, W] on the device — fp32 already scaled to [0,1] (the reference's x = raw/255, data.py:24 +
+        IntToFloatTensor) or raw uint8 (divided by 255 in the kernel)."""
+        assert x.is_cuda and x.is_contiguous() and tuple(x.shape) == (self.N, self.n_in, self.H, self.W), x.shape
+        assert x.dtype in (torch.float32, torch.uint8)
+        s = stream if stream is not None else ops.stream_ptr()
+        _lib.check(self.lib.b2u_nchw_to_nhwc(x.data_ptr(), int(x.dtype == torch.uint8), self.x_in.t.data_ptr(), self.N,
+                                             self.n_in, self.H, self.W, self.x_in.ld, 0, self.x_in.ld, s),
+                   "b2u_nchw_to_nhwc")
+
+    def set_labels(self, y: torch.Tensor) -> None:
+        assert self.training and tuple(y.shape) == (self.N, self.H, self.W)
+        self.labels.copy_(y.to(torch.uint8) if y.dtype != torch.uint8 else y, non_blocking=True)
+
+    def forward(self, stream: Optional[int] = None) -> torch.Tensor:
+        """Runs the forward plan; returns the fp32 NHWC logits buffer [N,H,W,ld] (first n_out lanes valid)."""
+        s = stream if stream is not None else ops.stream_ptr()
+        for op in self.fwd_ops:
+            op(s)
+        return self.logits
+
+    def loss_and_grad(self, stream: Optional[int] = None, grad_scale: float = 1.0) -> torch.Tensor:
+        s = stream if stream is not None else ops.stream_ptr()
+        lib, P_ = self.lib, self.N * self.H * self.W
+        ld = self.logits.shape[-1]
+        _lib.check(lib.b2u_ce_weight_sum(self.labels.data_ptr(), P_, _p(self.class_weights), self.n_out,
+                                         self._wsum_part.data_ptr(), self._ce_rows, s), "b2u_ce_weight_sum")
+        _lib.check(lib.b2u_ce_fwd_bwd(self.logits.data_ptr(), ld, self.labels.data_ptr(), P_, self.n_out,
+                                      _p(self.class_weights), self._wsum_part.data_ptr(), self._ce_rows,
+                                      self.dlogits.data_ptr(), self.dlogits.shape[-1], self._loss_part.data_ptr(),
+                                      self._ce_rows, grad_scale, s), "b2u_ce_fwd_bwd")
+        _lib.check(lib.b2u_ce_finalize(self._loss_part.data_ptr(), self._ce_rows, self._wsum_part.data_ptr(),
+                                       self._ce_rows, self.loss.data_ptr(), s), "b2u_ce_finalize")
+        return self.loss
+
+    def backward(self, stream: Optional[int] = None) -> None:
+        s = stream if stream is not None else ops.stream_ptr()
+        for op in self.bwd_ops:
+            op(s)
+
+    def sgd_step(self, lr: float, stream: Optional[int] = None) -> None:
+        s = stream if stream is not None else ops.stream_ptr()
+        _lib.check(self.lib.b2u_sgd_step(self.params.data_ptr(), self.grads.data_ptr(), self.layout.total, lr, 1.0, s),
+                   "b2u_sgd_step")
+        self._stage_weights(s)
+
+    def logits_nchw(self) -> torch.Tensor:
+        out = torch.empty((self.N, self.n_out, self.H, self.W), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.b2u_nhwc_to_nchw_f32(self.logits.data_ptr(), 1, self.logits.shape[-1], out.data_ptr(),
+                                                 self.N, self.n_out, self.H, self.W, ops.stream_ptr()),
+                   "b2u_nhwc_to_nchw_f32")
+        return out
+
+    def named_grads(self) -> Dict[str, torch.Tensor]:
+        return {e.name: self.grad(e.name) for e in self.layout.entries}
+
+    @property
+    def launches_per_train_step(self) -> int:
+        # forward + CE (3) + backward + optimizer (1) + weight staging (1)
+        return self.launches_fwd + 3 + self.launches_bwd + 2
