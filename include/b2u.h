@@ -222,10 +222,11 @@ int b2u_ce_finalize(const float* loss_partial, int32_t rows, const float* wsum_p
 /* ---- optimizer ------------------------------------------------------------------------------------------------ */
 /* p -= lr * grad_scale * g over one flat fp32 buffer (BASELINE config 1: plain SGD) */
 int b2u_sgd_step(float* p, const float* g, int64_t n, float lr, float grad_scale, void* stream);
-/* fastai Adam (train.py:218): decoupled wd, per-segment lr / wd via seg tables (seg_end = exclusive end offsets) */
+/* fastai Adam (train.py:218): decoupled wd, per-segment lr / wd via device tables (seg_end = exclusive end offsets);
+ * hyper (device, 6 floats) = {mom, sqr_mom, eps, 1-mom^step, 1-sqr_mom^step, grad_scale} so that the one-cycle
+ * schedule can change them between replays of a captured graph. */
 int b2u_adam_step(float* p, const float* g, float* m, float* v, int64_t n, const int64_t* seg_end, const float* seg_lr,
-                  const float* seg_wd, int32_t nseg, float mom, float sqr_mom, float eps, int32_t step,
-                  float grad_scale, void* stream);
+                  const float* seg_wd, int32_t nseg, const float* hyper, void* stream);
 
 /* ---- prediction: softmax + overlap-tile accumulate, normalise + argmax (predict.py:284-334) ------------------- */
 /* logits fp32 [T][th][tw][ld]; tile t sits at (y0[t], x0[t]) of the full raster; acc fp32 [C][Y][X] and cnt uint8

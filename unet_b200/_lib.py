@@ -122,7 +122,7 @@ def _declare(lib):
         "b2u_ce_fwd_bwd": [vp, i32, u8p, i64, i32, vp, vp, i32, vp, i32, vp, i32, f32, vp],
         "b2u_ce_finalize": [vp, i32, vp, i32, vp, vp],
         "b2u_sgd_step": [vp, vp, i64, f32, f32, vp],
-        "b2u_adam_step": [vp, vp, vp, vp, i64, vp, vp, vp, i32, f32, f32, f32, i32, f32, vp],
+        "b2u_adam_step": [vp, vp, vp, vp, i64, vp, vp, vp, i32, vp, vp],
         "b2u_stitch_accumulate": [vp, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp, u8p, i64, i64, i64, i64, vp],
         "b2u_stitch_finalize": [vp, u8p, i32, i64, i64, u8p, vp],
         "b2u_softmax_nchw": [vp, i32, i32, i64, i32, i32, vp, u8p, vp],

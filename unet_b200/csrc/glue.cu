@@ -307,8 +307,10 @@ __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, l
 
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long long n, const long long* __restrict__ seg_end,
-                            const float* __restrict__ seg_lr, const float* __restrict__ seg_wd, int nseg, float mom,
-                            float sqr_mom, float eps, float debias1, float debias2, float gs) {
+                            const float* __restrict__ seg_lr, const float* __restrict__ seg_wd, int nseg,
+                            const float* __restrict__ hyper) {
+  // hyper (device): {mom, sqr_mom, eps, debias1 = 1-mom^step, debias2 = 1-sqr_mom^step, grad_scale}
+  const float mom = hyper[0], sqr_mom = hyper[1], eps = hyper[2], debias1 = hyper[3], debias2 = hyper[4], gs = hyper[5];
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     int lo = 0, hi = nseg - 1;
     while (lo < hi) {
@@ -520,14 +522,12 @@ extern "C" int b2u_sgd_step(float* p, const float* g, int64_t n, float lr, float
 }
 
 extern "C" int b2u_adam_step(float* p, const float* g, float* m, float* v, int64_t n, const int64_t* seg_end,
-                             const float* seg_lr, const float* seg_wd, int32_t nseg, float mom, float sqr_mom,
-                             float eps, int32_t step, float grad_scale, void* stream) {
-  B2U_CHECK_ARG(p && g && m && v && n > 0 && seg_end && seg_lr && seg_wd && nseg > 0 && step >= 1,
+                             const float* seg_lr, const float* seg_wd, int32_t nseg, const float* hyper,
+                             void* stream) {
+  B2U_CHECK_ARG(p && g && m && v && n > 0 && seg_end && seg_lr && seg_wd && nseg > 0 && hyper,
                 "adam_step: bad argument");
-  const float debias1 = 1.f - powf(mom, (float)step), debias2 = 1.f - powf(sqr_mom, (float)step);
   adam_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, (const long long*)seg_end, seg_lr,
-                                                                  seg_wd, nseg, mom, sqr_mom, eps, debias1, debias2,
-                                                                  grad_scale);
+                                                                  seg_wd, nseg, hyper);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }

@@ -1,0 +1,159 @@
+"""Training engine: one data-parallel step = H2D tiles -> forward -> weighted CE (+grad) -> backward -> gradient
+all-reduce (NCCL over NVLink, N>1 only) -> optimizer -> bf16 weight re-staging; the whole device part is captured in
+ONE CUDA graph (≈700 kernel launches per step would otherwise be bounded by host launch latency).
+
+Mirrors what fastai's Learner does per batch for the reference (train.py:246-250 fit_one_cycle -> _do_one_batch:
+pred = model(xb); loss = loss_func(pred, yb); loss.backward(); opt.step(); opt.zero_grad()).
+"""
+from __future__ import annotations
+
+import math
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import _lib, ops
+from .network import UNetB200
+
+
+def one_cycle(pct: float, lr_max: float, div: float = 25.0, div_final: float = 1e5, pct_start: float = 0.25,
+              moms: Sequence[float] = (0.95, 0.85, 0.95)) -> Tuple[float, float]:
+    """fastai fit_one_cycle schedule (combined cosine for lr and momentum)."""
+    def cos(a, b, p):
+        return a + (1 + math.cos(math.pi * (1 - p))) * (b - a) / 2
+    if pct < pct_start:
+        q = pct / pct_start
+        return cos(lr_max / div, lr_max, q), cos(moms[0], moms[1], q)
+    q = (pct - pct_start) / (1 - pct_start)
+    return cos(lr_max, lr_max / div_final, q), cos(moms[1], moms[2], q)
+
+
+class Trainer:
+    def __init__(self, net: UNetB200, optimizer: str = "sgd", lr: float = 1e-3, wd: float = 0.01,
+                 encoder_factor: float = 10.0, use_graph: bool = True, bucket_mb: float = 32.0):
+        assert net.training
+        self.net, self.lr, self.optimizer = net, lr, optimizer.lower()
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.use_graph = use_graph
+        dev = net.device
+        N, C, H, W = net.N, net.n_in, net.H, net.W
+        self.x_static = torch.zeros((N, C, H, W), dtype=torch.uint8, device=dev)
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.step_count = 0
+        self.bucket_elems = int(bucket_mb * (1 << 20) / 4)
+        if self.optimizer == "adam":
+            L = net.layout
+            self.m = torch.zeros_like(net.params)
+            self.v = torch.zeros_like(net.params)
+            ends, self._seg_group, wds = [], [], []
+            for e in L.entries:
+                ends.append(e.offset + e.numel)
+                self._seg_group.append(e.group)
+                wds.append(wd if e.decay else 0.0)
+            ends[-1] = L.total
+            self.seg_end = torch.tensor(ends, dtype=torch.int64, device=dev)
+            self.seg_wd = torch.tensor(wds, dtype=torch.float32, device=dev)
+            self.seg_lr = torch.zeros(len(ends), dtype=torch.float32, device=dev)
+            self.hyper = torch.zeros(6, dtype=torch.float32, device=dev)
+            self.encoder_factor = encoder_factor
+            self.set_adam_hyper(lr, 0.9)
+        elif self.optimizer != "sgd":
+            raise ValueError("optimizer must be 'sgd' or 'adam'")
+
+    # fastai: lr_max = slice(lr/encoder_factor, lr) -> geometric spacing over the 3 parameter groups (train.py:246-250)
+    def set_adam_hyper(self, lr: float, mom: float, sqr_mom: float = 0.99, eps: float = 1e-5) -> None:
+        lo = lr / self.encoder_factor
+        group_lr = [lo, math.sqrt(lo * lr), lr]
+        self.seg_lr.copy_(torch.tensor([group_lr[g] for g in self._seg_group], dtype=torch.float32), non_blocking=True)
+        step = self.step_count + 1
+        self.hyper.copy_(torch.tensor([mom, sqr_mom, eps, 1 - mom ** step, 1 - sqr_mom ** step, 1.0 / self.world],
+                                      dtype=torch.float32), non_blocking=True)
+
+    # ------------------------------------------------------------------------------------------------ device step
+    def _allreduce(self) -> None:
+        if self.world == 1:
+            return
+        g = self.net.grads
+        n = g.numel()
+        # bucketed so that NCCL pipelines over NVLink; summed here, divided by world inside the optimizer kernel
+        for start in range(0, n, self.bucket_elems):
+            dist.all_reduce(g[start:min(n, start + self.bucket_elems)], op=dist.ReduceOp.SUM)
+
+    def _device_step(self) -> None:
+        net = self.net
+        s = ops.stream_ptr()
+        net.set_input(self.x_static, s)
+        net.forward(s)
+        net.loss_and_grad(s)
+        net.backward(s)
+        self._allreduce()
+        if self.optimizer == "sgd":
+            _lib.check(net.lib.b2u_sgd_step(net.params.data_ptr(), net.grads.data_ptr(), net.layout.total, self.lr,
+                                            1.0 / self.world, s), "b2u_sgd_step")
+        else:
+            _lib.check(net.lib.b2u_adam_step(net.params.data_ptr(), net.grads.data_ptr(), self.m.data_ptr(),
+                                             self.v.data_ptr(), net.layout.total, self.seg_end.data_ptr(),
+                                             self.seg_lr.data_ptr(), self.seg_wd.data_ptr(), self.seg_end.numel(),
+                                             self.hyper.data_ptr(), s), "b2u_adam_step")
+        net._stage_weights(s)
+
+    def capture(self) -> None:
+        """Warm up once eagerly on a side stream, then capture the device step into a CUDA graph."""
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            saved_p = self.net.params.clone()
+            saved_b = {k: v.clone() for k, v in self.net.buffers.items()}
+            if self.optimizer == "adam":
+                sm, sv = self.m.clone(), self.v.clone()
+            self._device_step()
+            # the warm-up step must not count: restore parameters, BN buffers and optimizer state
+            self.net.params.copy_(saved_p)
+            for k, v in saved_b.items():
+                self.net.buffers[k].copy_(v)
+            if self.optimizer == "adam":
+                self.m.copy_(sm)
+                self.v.copy_(sv)
+            self.net._stage_weights(ops.stream_ptr())
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._device_step()
+
+    def step(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        """x: uint8 [N,C,H,W] (host pinned or device), y: uint8/int64 [N,H,W]. Returns the device loss scalar of this
+        step (mean over the local batch, before the parameter update)."""
+        self.x_static.copy_(x, non_blocking=True)
+        self.net.labels.copy_(y if y.dtype == torch.uint8 else y.to(torch.uint8), non_blocking=True)
+        if self.use_graph:
+            if self.graph is None:
+                self.capture()
+                self.x_static.copy_(x, non_blocking=True)
+                self.net.labels.copy_(y if y.dtype == torch.uint8 else y.to(torch.uint8), non_blocking=True)
+            self.graph.replay()
+        else:
+            self._device_step()
+        self.step_count += 1
+        return self.net.loss
+
+
+def init_distributed() -> Tuple[int, int, int]:
+    """One process per GPU (torchrun env). Returns (rank, local_rank, world)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if torch.cuda.is_available():
+        torch.cuda.set_device(local)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo", rank=rank, world_size=world)
+    return rank, local, world
+
+
+def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced partition of n_items over ranks (first n_items % world ranks take one more)."""
+    base, rem = divmod(n_items, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)

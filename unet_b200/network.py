@@ -129,6 +129,37 @@ class UNetB200:
                 b.copy_(sd[k].to(self.device, torch.float32))
         self.weights_changed()
 
+    def init_parameters(self, seed: int = 0, randomize_bn: bool = True) -> None:
+        """Random initialisation on the device (no checkpoint is reachable offline): kaiming-normal conv weights as
+        fastai's init_cnn / apply_init do, biases 0.  With randomize_bn the BN affine parameters and running statistics
+        are drawn away from their defaults — stock fastai sets gamma = 0 on the last BN of every ResBlock, which would
+        switch the conv paths off and make throughput and parity measurements vacuous."""
+        g = torch.Generator(device=self.device).manual_seed(seed)
+        with torch.no_grad():
+            for e in self.layout.entries:
+                p = self.param(e.name)
+                if len(e.shape) == 4:
+                    fan_in = e.shape[1] * e.shape[2] * e.shape[3]
+                    p.copy_(torch.randn(e.shape, generator=g, device=self.device) * (2.0 / fan_in) ** 0.5)
+                elif e.name.endswith(".0.bias"):
+                    p.zero_()
+                elif e.name.endswith(".weight"):   # BN gamma
+                    if randomize_bn:
+                        p.copy_(torch.rand(e.shape, generator=g, device=self.device) + 0.5)
+                    else:
+                        p.fill_(1.0)
+                else:                              # BN beta
+                    if randomize_bn:
+                        p.copy_(torch.randn(e.shape, generator=g, device=self.device) * 0.1)
+                    else:
+                        p.fill_(1e-3)
+            for k, b in self.buffers.items():
+                if k.endswith("running_mean"):
+                    b.copy_(torch.randn(b.shape, generator=g, device=self.device) * 0.1 if randomize_bn else torch.zeros_like(b))
+                else:
+                    b.copy_(torch.rand(b.shape, generator=g, device=self.device) + 0.5 if randomize_bn else torch.ones_like(b))
+        self.weights_changed()
+
     def state_dict(self) -> Dict[str, torch.Tensor]:
         out = {e.name: self.param(e.name).detach().clone() for e in self.layout.entries}
         for k, b in self.buffers.items():

@@ -15,6 +15,23 @@ from . import _lib
 from ._lib import ConvDesc, ConvInfo, View, WgradDesc, WgradInfo
 
 
+# bench.py sets this to a list to time every GEMM launch with CUDA events on the launching stream (eager mode only):
+# entries are (kind, plan, start_event, end_event).
+PROFILE = None
+
+
+def _timed(kind, plan, fn):
+    if PROFILE is None:
+        fn()
+        return
+    st = torch.cuda.current_stream()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(st)
+    fn()
+    b.record(st)
+    PROFILE.append((kind, plan, a, b))
+
+
 def pad8(c: int) -> int:
     return (c + 7) // 8 * 8
 
@@ -148,8 +165,15 @@ class ConvPlan:
         self._lib = lib
 
     def run(self, stream: Optional[int] = None):
-        _lib.check(self._lib.b2u_conv_run(self.handle, C.c_void_p(stream if stream is not None else stream_ptr())),
-                   "b2u_conv_run")
+        _timed("conv", self, lambda: _lib.check(
+            self._lib.b2u_conv_run(self.handle, C.c_void_p(stream if stream is not None else stream_ptr())),
+            "b2u_conv_run"))
+
+    @property
+    def flops(self) -> int:
+        """algorithmic FLOPs of this launch: 2 * pixels * Cout * Cin * taps (unpadded channels)"""
+        d = self.desc
+        return 2 * d.out.N * d.out.H * d.out.W * d.out.C * d.w_cin * d.num_taps
 
     def __del__(self):
         h = getattr(self, "handle", None)
@@ -207,9 +231,14 @@ class WgradPlan:
         _lib.check(lib.b2u_wgrad_query(C.byref(d), C.byref(info)), "b2u_wgrad_query")
         return info
 
+    @property
+    def flops(self) -> int:
+        d = self.desc
+        return 2 * d.dy.N * d.dy.H * d.dy.W * d.Cout * d.Cin * d.num_taps
+
     def run(self, stream: Optional[int] = None):
         s = C.c_void_p(stream if stream is not None else stream_ptr())
-        _lib.check(self._lib.b2u_wgrad_run(self.handle, s), "b2u_wgrad_run")
+        _timed("wgrad", self, lambda: _lib.check(self._lib.b2u_wgrad_run(self.handle, s), "b2u_wgrad_run"))
         _lib.check(self._lib.b2u_wgrad_reduce(
             self.workspace.data_ptr(), self.info.splits, self.ntaps, self.info.co_pad, self.info.ci_pad, self.Cout,
             self.Cin, self.ksize, self.kidx.data_ptr(),
