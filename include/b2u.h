@@ -34,7 +34,10 @@ int b2u_version(void);
 int b2u_device_check(void);
 
 /* A strided NHWC window onto a bf16 tensor: element (n,y,x,c) lives at ptr[n*sN + y*sH + x*sW + c].
- * Plain tensors, channel slices of a concat buffer and stride-2 parity planes are all expressed this way. */
+ * Plain tensors, channel slices of a concat buffer and stride-2 parity planes are all expressed this way.
+ * Padding rule: the lanes from C up to round_up(C,16) (or round_up(C,8) when sW is smaller) of every pixel belong to
+ * the view; kernels read them as data (so they must hold zeros in GEMM operands) and write them as zeros.  This keeps
+ * every TMA row a whole number of 32-byte sectors — a row ending inside a sector halves TMA throughput. */
 typedef struct b2u_view {
   void* ptr;
   int32_t C, W, H, N;
@@ -66,8 +69,8 @@ typedef struct b2u_conv_desc {
   int32_t w_rows, w_taps, w_cin, w_cinp;
   int32_t num_taps;
   int8_t tap_a[B2U_MAX_TAPS], tap_dy[B2U_MAX_TAPS], tap_dx[B2U_MAX_TAPS], tap_w[B2U_MAX_TAPS];
-  const float* scale; /* nullable, per output channel */
-  const float* shift; /* nullable, per output channel (bias, or folded BN shift) */
+  const float* scale; /* nullable, per output channel; must be readable up to round_up(Cout,32) floats, 16B aligned */
+  const float* shift; /* nullable (bias, or folded BN shift); same padding rule */
   b2u_view res;       /* ptr NULL = none */
   b2u_view res_mask;  /* ptr NULL = none */
   b2u_view zmask;     /* ptr NULL = none */

@@ -14,9 +14,9 @@ def rel_err(a, b):
 
 
 def to_nhwc(x_nchw, cp=None):
-    from unet_b200.ops import pad8
+    from unet_b200.ops import padc
     n, c, h, w = x_nchw.shape
-    cp = cp or pad8(c)
+    cp = cp or padc(c)
     out = torch.zeros((n, h, w, cp), dtype=torch.bfloat16, device=x_nchw.device)
     out[..., :c] = x_nchw.permute(0, 2, 3, 1).to(torch.bfloat16)
     return out
@@ -24,19 +24,27 @@ def to_nhwc(x_nchw, cp=None):
 
 def gemm_weights(w):
     """torch [Cout,Cin,kh,kw] fp32 -> bf16 [Cout][kh*kw][CinP]"""
-    from unet_b200.ops import pad8
+    from unet_b200.ops import padc
     co, ci, kh, kw = w.shape
-    out = torch.zeros((co, kh * kw, pad8(ci)), dtype=torch.bfloat16, device=w.device)
+    out = torch.zeros((co, kh * kw, padc(ci)), dtype=torch.bfloat16, device=w.device)
     out[..., :ci] = w.permute(0, 2, 3, 1).reshape(co, kh * kw, ci).to(torch.bfloat16)
     return out
 
 
 def dgrad_weights(w):
     """torch [Cout,Cin,kh,kw] -> bf16 [Cin][kk (flipped)][CoutP]"""
-    from unet_b200.ops import pad8
+    from unet_b200.ops import padc
     co, ci, kh, kw = w.shape
-    out = torch.zeros((ci, kh * kw, pad8(co)), dtype=torch.bfloat16, device=w.device)
+    out = torch.zeros((ci, kh * kw, padc(co)), dtype=torch.bfloat16, device=w.device)
     out[..., :co] = w.flip(2, 3).permute(1, 2, 3, 0).reshape(ci, kh * kw, co).to(torch.bfloat16)
+    return out
+
+
+def padvec(v):
+    """per-channel epilogue vectors are read in whole 32-float groups"""
+    from unet_b200.ops import pad32
+    out = torch.zeros(pad32(v.numel()), dtype=torch.float32, device=v.device)
+    out[:v.numel()] = v
     return out
 
 
@@ -73,15 +81,15 @@ def test_conv_fprop_s1(N, Cin, Cout, H, W, ks):
     b = rnd(Cout, seed=3)
     ref = F.relu(F.conv2d(x, w, b, padding=(ks - 1) // 2))
     xa = to_nhwc(x)
-    ya = torch.full((N, H, W, ops.pad8(Cout)), 7.0, dtype=torch.bfloat16, device="cuda")
+    ya = torch.full((N, H, W, ops.padc(Cout)), 7.0, dtype=torch.bfloat16, device="cuda")
     plan = ops.ConvPlan([ops.view_nhwc(xa, Cin)], ops.view_nhwc(ya, Cout), gemm_weights(w), Cin, ops.taps_conv(ks),
-                        shift=b.contiguous(), relu=True)
+                        shift=padvec(b), relu=True)
     plan.run()
     torch.cuda.synchronize()
     got = ya[..., :Cout].permute(0, 3, 1, 2).float()
     e = rel_err(got, ref)
     assert e <= 1e-2, f"rel err {e} info={[(n, getattr(plan.info, n)) for n, _ in plan.info._fields_]}"
-    if ops.pad8(Cout) != Cout:  # pad lanes up to the 16-byte granule are written as zeros (TMA stores whole granules)
+    if ops.padc(Cout) != Cout:  # pad lanes up to the 16-byte granule are written as zeros (TMA stores whole granules)
         assert (ya[..., Cout:] == 0.0).all()
 
 
@@ -101,7 +109,7 @@ def test_conv_fprop_stats_and_residual():
     xa, ra, ma, za = to_nhwc(x), to_nhwc(r), to_nhwc(m), to_nhwc(z)
     ya = torch.zeros((N, H, W, Cout), dtype=torch.bfloat16, device="cuda")
     plan = ops.ConvPlan([ops.view_nhwc(xa)], ops.view_nhwc(ya), gemm_weights(w), Cin, ops.taps_conv(3),
-                        scale=sc.contiguous(), shift=sh.contiguous(), res=ops.view_nhwc(ra),
+                        scale=padvec(sc), shift=padvec(sh), res=ops.view_nhwc(ra),
                         res_mask=ops.view_nhwc(ma), zmask=ops.view_nhwc(za), relu=True, stats=True)
     plan.run()
     torch.cuda.synchronize()
@@ -119,7 +127,7 @@ def test_conv_fprop_stride2(N, Cin, Cout, H, W):
     w = rnd(Cout, Cin, 3, 3, seed=2, scale=(Cin * 9) ** -0.5)
     ref = F.conv2d(x, w, None, stride=2, padding=1)
     xa = to_nhwc(x)
-    ya = torch.zeros((N, H // 2, W // 2, ops.pad8(Cout)), dtype=torch.bfloat16, device="cuda")
+    ya = torch.zeros((N, H // 2, W // 2, ops.padc(Cout)), dtype=torch.bfloat16, device="cuda")
     views = [ops.view_nhwc(xa, Cin, parity=(py, px)) for py in range(2) for px in range(2)]
     plan = ops.ConvPlan(views, ops.view_nhwc(ya, Cout), gemm_weights(w), Cin, ops.taps_conv3_s2())
     plan.run()
@@ -149,7 +157,7 @@ def test_dgrad_s1(N, Cin, Cout, H, W, ks):
     dy = rnd(N, Cout, H, W, seed=3)
     ref = torch.nn.grad.conv2d_input((N, Cin, H, W), w, dy, padding=(ks - 1) // 2)
     dya = to_nhwc(dy)
-    dxa = torch.zeros((N, H, W, ops.pad8(Cin)), dtype=torch.bfloat16, device="cuda")
+    dxa = torch.zeros((N, H, W, ops.padc(Cin)), dtype=torch.bfloat16, device="cuda")
     plan = ops.ConvPlan([ops.view_nhwc(dya, Cout)], ops.view_nhwc(dxa, Cin), dgrad_weights(w), Cout, ops.taps_conv(ks))
     plan.run()
     torch.cuda.synchronize()
@@ -184,7 +192,7 @@ def test_conv_out_f32_head():
     xa = to_nhwc(x)
     out = torch.zeros((N, H, W, 8), dtype=torch.float32, device="cuda")
     ov = ops.view_nhwc(torch.zeros((N, H, W, 8), dtype=torch.bfloat16, device="cuda"), Cout)
-    plan = ops.ConvPlan([ops.view_nhwc(xa, Cin)], ov, gemm_weights(w), Cin, ops.taps_conv(1), shift=b.contiguous(),
+    plan = ops.ConvPlan([ops.view_nhwc(xa, Cin)], ov, gemm_weights(w), Cin, ops.taps_conv(1), shift=padvec(b),
                         out_f32=out)
     plan.run()
     torch.cuda.synchronize()

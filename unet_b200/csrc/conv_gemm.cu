@@ -19,6 +19,8 @@ struct ConvParams {
   CUtensorMap tm_a[B2U_MAX_VIEWS];
   CUtensorMap tm_b;
   CUtensorMap tm_out;
+  CUtensorMap tm_aux[3];  // residual, residual mask, output mask (same box as the output tile)
+  int n_aux;              // number of aux operands in use; slots are assigned in the order res, res_mask, zmask
   int num_taps, k_chunks, last_mmas;
   int8_t tap_a[B2U_MAX_TAPS], tap_dy[B2U_MAX_TAPS], tap_dx[B2U_MAX_TAPS], tap_w[B2U_MAX_TAPS];
   int tw, th, tn, tiles_x, tiles_y;
@@ -43,6 +45,19 @@ static constexpr uint32_t kAccStride = 256;
 
 __device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&o)[8]) {
   uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  o[0] = bf16_lo(u.x); o[1] = bf16_hi(u.x); o[2] = bf16_lo(u.y); o[3] = bf16_hi(u.y);
+  o[4] = bf16_lo(u.z); o[5] = bf16_hi(u.z); o[6] = bf16_lo(u.w); o[7] = bf16_hi(u.w);
+}
+
+struct Aux {
+  uint4 r[4], m[4], z[4];  // residual, residual mask, output mask: 32 channels (4 x 16 B) of this thread's pixel
+};
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&o)[8]) {
   o[0] = bf16_lo(u.x); o[1] = bf16_hi(u.x); o[2] = bf16_lo(u.y); o[3] = bf16_hi(u.y);
   o[4] = bf16_lo(u.z); o[5] = bf16_hi(u.z); o[6] = bf16_lo(u.w); o[7] = bf16_hi(u.w);
 }
@@ -72,14 +87,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   const uint32_t stage_bytes = kABytes + b_bytes;
   const int S = p.stages;
   const uint32_t stg_base = smem_base + (uint32_t)S * stage_bytes;
-  const uint32_t bar_base = stg_base + 2 * kStagingBytes;
+  const uint32_t aux_base = stg_base + 2 * kStagingBytes;  // n_aux x 2 x 16 KB, double buffered per output chunk
+  const uint32_t bar_base = aux_base + (uint32_t)p.n_aux * 2 * kStagingBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(S + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (uint32_t)(2 * S + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (uint32_t)(2 * S + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (uint32_t)(2 * S + 4);
-  volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem + (size_t)S * stage_bytes + 2 * kStagingBytes + 8 * (2 * S + 4));
+  auto aux_bar = [&](int b) { return bar_base + 8u * (uint32_t)(2 * S + 4 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (uint32_t)(2 * S + 6);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
+      smem + (size_t)S * stage_bytes + (size_t)(2 + 2 * p.n_aux) * kStagingBytes + 8 * (2 * S + 6));
 
   if (threadIdx.x == 0) {
     if (smem_base & 1023u) {
@@ -93,6 +110,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), 128);
+      mbar_init(aux_bar(a), 1);
     }
     fence_mbar_init();
   }
@@ -100,6 +118,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     for (int i = 0; i < B2U_MAX_VIEWS; ++i) tma_prefetch_desc(&p.tm_a[i]);
     tma_prefetch_desc(&p.tm_b);
     tma_prefetch_desc(&p.tm_out);
+    for (int i = 0; i < p.n_aux; ++i) tma_prefetch_desc(&p.tm_aux[i]);
   }
   if (warp == 2) {
     tmem_alloc(tmem_slot, kTmemCols);
@@ -183,6 +202,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const bool out_f32 = (p.flags & B2U_EPI_OUT_F32) != 0;
     const bool do_relu = (p.flags & B2U_EPI_RELU) != 0;
     const bool do_stats = (p.flags & B2U_EPI_STATS) != 0;
+    const bool has_res = p.res.ptr != nullptr, has_rm = p.res_mask.ptr != nullptr, has_zm = p.zmask.ptr != nullptr;
+    auto issue_aux = [&](int t, int chunk, uint32_t buf) {
+      const int m2 = t / p.n_tiles, nt2 = t - m2 * p.n_tiles;
+      const int bn2 = m2 / tiles_xy, rem2 = m2 - bn2 * tiles_xy;
+      const int by2 = rem2 / p.tiles_x, bx2 = rem2 - by2 * p.tiles_x;
+      mbar_expect_tx(aux_bar(buf), (uint32_t)p.n_aux * kStagingBytes);
+      for (int i = 0; i < p.n_aux; ++i)
+        tma_load_4d(aux_base + (uint32_t)i * 2 * kStagingBytes + buf * kStagingBytes, &p.tm_aux[i], aux_bar(buf),
+                    nt2 * p.BN + chunk * 64, bx2 * p.tw, by2 * p.th, bn2 * p.tn);
+    };
+    if (p.n_aux > 0 && e == 0 && (int)blockIdx.x < total_tiles) issue_aux(blockIdx.x, 0, 0);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m = tile / p.n_tiles, nt = tile - m * p.n_tiles;
       const int bn = m / tiles_xy, rem = m - bn * tiles_xy;
@@ -197,7 +227,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)acc * kAccStride + ((uint32_t)(ewarp * 32) << 16);
 
-      for (int g = 0; g < n_groups; ++g) {
+      auto process = [&](int g) {
+        if (p.n_aux > 0 && (g & 1) == 0) {
+          // residual / mask tiles arrive through TMA (coalesced, asynchronous), one 64-channel chunk ahead
+          if (e == 0) {
+            int t2 = tile, g2 = g + 2;
+            if (g2 >= n_groups) { t2 = tile + gridDim.x; g2 = 0; }
+            if (t2 < total_tiles) issue_aux(t2, g2 >> 1, (chunk_ctr + 1u) & 1u);
+          }
+          mbar_wait(aux_bar(chunk_ctr & 1u), (chunk_ctr >> 1) & 1u);
+        }
+        Aux ax;
+        {
+          const uint32_t abase = aux_base + (chunk_ctr & 1u) * kStagingBytes + (uint32_t)e * 128u;
+          int slot = 0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t off = (((uint32_t)((g & 1) * 4 + q)) ^ ((uint32_t)e & 7u)) << 4;
+            slot = 0;
+            if (has_res) { ax.r[q] = ld_shared_v4(abase + (uint32_t)slot * 2 * kStagingBytes + off); ++slot; }
+            if (has_rm) { ax.m[q] = ld_shared_v4(abase + (uint32_t)slot * 2 * kStagingBytes + off); ++slot; }
+            if (has_zm) { ax.z[q] = ld_shared_v4(abase + (uint32_t)slot * 2 * kStagingBytes + off); ++slot; }
+          }
+        }
         uint32_t r[32];
         tmem_ld32(taddr + (uint32_t)(g * 32), r);
         tmem_ld_wait();
@@ -210,35 +262,33 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        // per-channel scale / shift: arrays are padded to a multiple of 32 floats (see b2u.h), uniform 16-byte loads
         if (p.scale) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c0 + i < p.Cout) v[i] *= __ldg(p.scale + c0 + i);
+          for (int q = 0; q < 8; ++q) {
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + c0) + q);
+            v[4 * q] *= sc.x; v[4 * q + 1] *= sc.y; v[4 * q + 2] *= sc.z; v[4 * q + 3] *= sc.w;
+          }
         }
         if (p.shift) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c0 + i < p.Cout) v[i] += __ldg(p.shift + c0 + i);
+          for (int q = 0; q < 8; ++q) {
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + c0) + q);
+            v[4 * q] += sh.x; v[4 * q + 1] += sh.y; v[4 * q + 2] += sh.z; v[4 * q + 3] += sh.w;
+          }
         }
-        if (p.res.ptr && valid) {
-          const __nv_bfloat16* rp = p.res.ptr + pn * p.res.sN + py * p.res.sH + px * p.res.sW + c0;
-          const __nv_bfloat16* mp =
-              p.res_mask.ptr ? p.res_mask.ptr + pn * p.res_mask.sN + py * p.res_mask.sH + px * p.res_mask.sW + c0
-                             : nullptr;
+        if (has_res) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            if (c0 + q * 8 < p.CoutP8) {
-              float rv[8];
-              load8(rp + q * 8, rv);
-              if (mp) {
-                float mv[8];
-                load8(mp + q * 8, mv);
+            float rv[8], mv[8];
+            unpack8(ax.r[q], rv);
+            if (has_rm) {
+              unpack8(ax.m[q], mv);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[q * 8 + i] += (mv[i] > 0.f) ? rv[i] : 0.f;
-              } else {
+              for (int i = 0; i < 8; ++i) v[q * 8 + i] += (mv[i] > 0.f) ? rv[i] : 0.f;
+            } else {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[q * 8 + i] += rv[i];
-              }
+              for (int i = 0; i < 8; ++i) v[q * 8 + i] += rv[i];
             }
           }
         }
@@ -246,19 +296,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
         }
-        if (p.zmask.ptr && valid) {
-          const __nv_bfloat16* zp = p.zmask.ptr + pn * p.zmask.sN + py * p.zmask.sH + px * p.zmask.sW + c0;
+        if (has_zm) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            if (c0 + q * 8 < p.CoutP8) {
-              float zv[8];
-              load8(zp + q * 8, zv);
+            float zv[8];
+            unpack8(ax.z[q], zv);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[q * 8 + i] = (zv[i] > 0.f) ? v[q * 8 + i] : 0.f;
-            }
+            for (int i = 0; i < 8; ++i) v[q * 8 + i] = (zv[i] > 0.f) ? v[q * 8 + i] : 0.f;
           }
         }
-
         if (c0 + 32 > p.Cout) {
           // lanes past Cout (channel padding up to the pitch) are stored as zeros, never as garbage
 #pragma unroll
@@ -327,7 +373,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             sp[p.stats_ld + c] = sq;
           }
         }
-      }
+      };
+
+      for (int g = 0; g < n_groups; ++g) process(g);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
@@ -416,8 +464,12 @@ static int conv_plan_fill(const b2u_conv_desc* d, b2u_conv_plan* plan, bool enco
   for (int t = 0; t < d->num_taps; ++t) {
     p.tap_a[t] = d->tap_a[t]; p.tap_dy[t] = d->tap_dy[t]; p.tap_dx[t] = d->tap_dx[t]; p.tap_w[t] = d->tap_w[t];
   }
+  const int n_aux = (d->res.ptr ? 1 : 0) + (d->res_mask.ptr ? 1 : 0) + (d->zmask.ptr ? 1 : 0);
+  B2U_CHECK_ARG(n_aux == 0 || !out_f32, "conv: residual / mask operands need the bf16 output path");
+  B2U_CHECK_ARG(!d->res_mask.ptr || d->res.ptr, "conv: res_mask without res");
+  p.n_aux = n_aux;
   const uint32_t stage_bytes = kABytes + (uint32_t)BN * 128u;
-  const uint32_t fixed = 2 * kStagingBytes + 256;
+  const uint32_t fixed = (2 + 2 * (uint32_t)n_aux) * kStagingBytes + 256;
   int stages = (int)((232448u - fixed) / stage_bytes);
   if (stages > 8) stages = 8;
   B2U_CHECK_ARG(stages >= 2, "conv: not enough shared memory for 2 stages");
@@ -448,7 +500,8 @@ static int conv_plan_fill(const b2u_conv_desc* d, b2u_conv_plan* plan, bool enco
     }
     for (int i = d->num_a; i < B2U_MAX_VIEWS; ++i) p.tm_a[i] = p.tm_a[0];
     {
-      uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)d->w_taps, (uint64_t)d->w_rows};
+      const int cin_ext = round_up(Cin, 16) <= d->w_cinp ? round_up(Cin, 16) : (round_up(Cin, 8) <= d->w_cinp ? round_up(Cin, 8) : Cin);
+      uint64_t dims[3] = {(uint64_t)cin_ext, (uint64_t)d->w_taps, (uint64_t)d->w_rows};
       uint64_t str[3] = {2, (uint64_t)d->w_cinp * 2, (uint64_t)d->w_cinp * 2 * (uint64_t)d->w_taps};
       uint32_t box[3] = {64, 1, (uint32_t)BN};
       int rc = encode_tmap_bf16(&p.tm_b, d->w, 3, dims, str, box);
@@ -459,6 +512,19 @@ static int conv_plan_fill(const b2u_conv_desc* d, b2u_conv_plan* plan, bool enco
       if (rc) return rc;
     } else {
       p.tm_out = p.tm_b;
+    }
+    {
+      const b2u_view* aux[3] = {&d->res, &d->res_mask, &d->zmask};
+      int slot = 0;
+      for (int i = 0; i < 3; ++i) {
+        if (!aux[i]->ptr) continue;
+        if (!view_ok(*aux[i], "conv.aux")) return B2U_ERR_ARG;
+        B2U_CHECK_ARG(aux[i]->W == d->out.W && aux[i]->H == d->out.H && aux[i]->N == d->out.N,
+                      "conv: residual / mask geometry differs from the output");
+        int rc = view_tmap(&p.tm_aux[slot++], *aux[i], 64, (uint32_t)tw, (uint32_t)th, (uint32_t)tn);
+        if (rc) return rc;
+      }
+      for (; slot < 3; ++slot) p.tm_aux[slot] = p.tm_b;
     }
   }
   return B2U_OK;

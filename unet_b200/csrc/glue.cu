@@ -283,6 +283,7 @@ __global__ void ce_fwd_bwd_kernel(const float* __restrict__ logits, int ld, cons
 #pragma unroll
       for (int c = 0; c < MAXC; ++c)
         if (c < ldg) dlogits[p * ldg + c] = __float2bfloat16_rn(c < C ? gs * (z[c] * inv - (c == y ? 1.f : 0.f)) : 0.f);
+      for (int c = MAXC; c < ldg; ++c) dlogits[p * ldg + c] = __float2bfloat16_rn(0.f);
     }
   }
   const float r = block_sum(acc, sh);
@@ -494,9 +495,9 @@ extern "C" int b2u_ce_fwd_bwd(const float* logits, int32_t ld, const uint8_t* la
                               const float* weight, const float* wsum_partial, int32_t wsum_rows, void* dlogits,
                               int32_t ldg, float* loss_partial, int32_t rows, float grad_scale, void* stream) {
   B2U_CHECK_ARG(logits && labels && wsum_partial && loss_partial && rows > 0, "ce_fwd_bwd: bad argument");
-  B2U_CHECK_ARG(C >= 1 && C <= 32 && C <= ld && (!dlogits || (ldg >= C && ldg <= 32)), "ce_fwd_bwd: C=%d ld=%d ldg=%d unsupported", C, ld, ldg);
+  B2U_CHECK_ARG(C >= 1 && C <= 32 && C <= ld && (!dlogits || ldg >= C), "ce_fwd_bwd: C=%d ld=%d ldg=%d unsupported", C, ld, ldg);
   cudaStream_t st = (cudaStream_t)stream;
-  if (C <= 8 && ldg <= 8)
+  if (C <= 8)
     ce_fwd_bwd_kernel<8><<<rows, 256, 0, st>>>(logits, ld, labels, P, C, weight, wsum_partial, wsum_rows, (bf)dlogits,
                                                ldg, loss_partial, grad_scale);
   else

@@ -5,7 +5,7 @@ This is the B200-native replacement for `learn.model` + `loss.backward()` + `opt
 forward of `learn.predict` (predict.py:193).  torch is used for device memory, streams and NCCL only; every FLOP and
 every byte moved on the hot path is issued by a kernel in unet_b200/csrc.
 
-Data layout: activations NHWC bf16 with channel pitch pad8(C); parameters/gradients fp32 in ONE flat buffer each, in
+Data layout: activations NHWC bf16 with channel pitch padc(C); parameters/gradients fp32 in ONE flat buffer each, in
 fastai's state_dict order and torch shapes (so reference weights load and the optimizer / NCCL all-reduce see a
 single contiguous range); bf16 GEMM copies of the weights are re-staged from the fp32 masters once per step by one
 batched kernel.
@@ -19,7 +19,7 @@ import torch
 
 from . import _lib, ops
 from .layout import ConvSpec, NetSpec, ParamLayout, build_spec, conv_flops, shuffle_row_of_co
-from .ops import ConvPlan, WgradPlan, pad8, view_nhwc
+from .ops import ConvPlan, WgradPlan, padc, view_nhwc
 
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
@@ -30,7 +30,7 @@ class Act:
     """An NHWC bf16 activation and (lazily) its gradient."""
 
     def __init__(self, N: int, H: int, W: int, Cc: int, dev, name: str = "", zero: bool = False):
-        self.N, self.H, self.W, self.C, self.ld = N, H, W, Cc, pad8(Cc)
+        self.N, self.H, self.W, self.C, self.ld = N, H, W, Cc, padc(Cc)
         alloc = torch.zeros if (zero or self.ld != Cc) else torch.empty
         self.t = alloc((N, H, W, self.ld), dtype=torch.bfloat16, device=dev)
         self.name = name
@@ -58,7 +58,7 @@ class BNState:
         self.dbeta = net.grad(prefix + ".bias")
         self.running_mean = net.buffers[prefix + ".running_mean"]
         self.running_var = net.buffers[prefix + ".running_var"]
-        f = lambda: torch.zeros(Cc, dtype=torch.float32, device=dev)
+        f = lambda: torch.zeros(ops.pad32(Cc), dtype=torch.float32, device=dev)  # conv epilogue reads whole 32-float groups
         self.mean, self.invstd, self.scale, self.shift = f(), f(), f(), f()
         self.mean_g, self.mean_gx = f(), f()
 
@@ -191,8 +191,8 @@ class UNetB200:
         """bf16 GEMM copies of one conv's weights + staging item for the batched cast kernel."""
         dev = self.device
         kk = cs.ks * cs.ks
-        wf = torch.zeros((cs.nf, kk, pad8(cs.ni)), dtype=torch.bfloat16, device=dev)
-        wd = torch.zeros((cs.ni, kk, pad8(cs.nf)), dtype=torch.bfloat16, device=dev) if need_dgrad else None
+        wf = torch.zeros((cs.nf, kk, padc(cs.ni)), dtype=torch.bfloat16, device=dev)
+        wd = torch.zeros((cs.ni, kk, padc(cs.nf)), dtype=torch.bfloat16, device=dev) if need_dgrad else None
         w = {"wf": wf, "wd": wd, "bias_rows": None, "row_of_co": None, "row_perm": None}
         if cs.shuffle:
             roc = shuffle_row_of_co(cs.nf)
@@ -202,13 +202,13 @@ class UNetB200:
                 perm[r] = co
             w["row_perm"] = torch.tensor(perm, dtype=torch.int32, device=dev)
         if not cs.bn:
-            w["bias_rows"] = torch.zeros(cs.nf, dtype=torch.float32, device=dev)
+            w["bias_rows"] = torch.zeros(ops.pad32(cs.nf), dtype=torch.float32, device=dev)
         it = _lib.WStageItem()
         it.w = self.param(cs.wname).data_ptr()
         it.bias = self.param(cs.bname).data_ptr() if cs.bname else None
         it.row_of_co = _p(w["row_of_co"])
         it.wf, it.wd, it.bias_rows = wf.data_ptr(), _p(wd), _p(w["bias_rows"])
-        it.Cout, it.Cin, it.kk, it.wf_cinp, it.wd_coutp = cs.nf, cs.ni, kk, pad8(cs.ni), pad8(cs.nf)
+        it.Cout, it.Cin, it.kk, it.wf_cinp, it.wd_coutp = cs.nf, cs.ni, kk, padc(cs.ni), padc(cs.nf)
         it.scale = 0.25 if cs.pool else 1.0
         self._wstage.append(it)
         self._w[cs.name] = w
@@ -285,11 +285,11 @@ class UNetB200:
 
     def _stats_op(self, x: torch.Tensor, ldx: int, pixels: int, Cc: int):
         rows = max(1, min(STATS_ROWS, pixels // 64))
-        partial = torch.zeros((rows, 2, pad8(Cc)), dtype=torch.float32, device=self.device)
+        partial = torch.zeros((rows, 2, padc(Cc)), dtype=torch.float32, device=self.device)
         lib = self.lib
 
         def run(s):
-            _lib.check(lib.b2u_bn_stats(x.data_ptr(), ldx, pixels, Cc, partial.data_ptr(), rows, pad8(Cc), s),
+            _lib.check(lib.b2u_bn_stats(x.data_ptr(), ldx, pixels, Cc, partial.data_ptr(), rows, padc(Cc), s),
                        "b2u_bn_stats")
         return run, partial
 
@@ -298,9 +298,9 @@ class UNetB200:
                 ldy: int, relu: bool, dx: torch.Tensor, lddx: int, pixels: int, accumulate: bool):
         """reduce -> finalize -> apply; dgamma/dbeta land in the flat gradient buffer."""
         rows = max(1, min(STATS_ROWS, pixels // 64))
-        partial = torch.zeros((rows, 2, pad8(bn.C)), dtype=torch.float32, device=self.device)
+        partial = torch.zeros((rows, 2, padc(bn.C)), dtype=torch.float32, device=self.device)
         lib, sc = self.lib, self._scratch
-        ld = pad8(bn.C)
+        ld = padc(bn.C)
 
         def run(s):
             _lib.check(lib.b2u_bn_bwd_reduce(dz.data_ptr(), lddz, x.data_ptr(), ldx, _p(y), ldy, _p(bn.scale),
@@ -317,7 +317,7 @@ class UNetB200:
         self._bwd(run, 3 + (1 if rows > 128 else 0))
 
     def _wgrad(self, cs: ConvSpec, dy: torch.Tensor, x: Act):
-        """dW (and db) of conv `cs` from dy (bf16 NHWC tensor [N,Ho,Wo,pad8(nf)]) and its input activation x."""
+        """dW (and db) of conv `cs` from dy (bf16 NHWC tensor [N,Ho,Wo,padc(nf)]) and its input activation x."""
         w = self._w[cs.name]
         views, taps = self._views_taps(cs, x)
         kidx = [0] * len(taps) if cs.pool else [t[3] for t in taps]
@@ -375,7 +375,7 @@ class UNetB200:
 
         # ---- input
         self.x_in = self._act(H, W, spec.n_in, "input", zero=True)
-        self.logits = torch.zeros((N, H, W, 8 if spec.n_out <= 8 else pad8(spec.n_out)), dtype=torch.float32, device=dev)
+        self.logits = torch.zeros((N, H, W, 8 if spec.n_out <= 8 else padc(spec.n_out)), dtype=torch.float32, device=dev)
         bwd_layers: List[Callable[[], None]] = []
 
         # ---- encoder ConvLayer = conv -> BN -> [ReLU]
@@ -604,7 +604,7 @@ class UNetB200:
             # loss buffers
             P_ = N * H * W
             self.labels = torch.zeros((N, H, W), dtype=torch.uint8, device=dev)
-            self.dlogits = torch.zeros((N, H, W, 8 if spec.n_out <= 8 else pad8(spec.n_out)), dtype=torch.bfloat16, device=dev)
+            self.dlogits = torch.zeros((N, H, W, padc(spec.n_out)), dtype=torch.bfloat16, device=dev)
             self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
             self._ce_rows = 592
             self._wsum_part = torch.zeros(self._ce_rows, dtype=torch.float32, device=dev)
