@@ -206,6 +206,10 @@ int b2u_shuffle_bwd(const void* dcat, int32_t ldc, const void* u, void* du, int3
  * channels [ch_off, ch_off+write_c) written (lanes >= C zeroed) */
 int b2u_nchw_to_nhwc(const void* x, int32_t x_is_u8, void* y, int32_t N, int32_t C, int32_t H, int32_t W, int32_t ld,
                      int32_t ch_off, int32_t write_c, void* stream);
+/* tile t = raster[:, y0[t]:y0[t]+P, x0[t]:x0[t]+P] / 255 -> bf16 NHWC [T,P,P,ld]: the crop of create_tiles_unet.py:410 fused with
+ * the input contract of data.py:24 (+ fastai IntToFloatTensor) and the layout cast; raster is uint8 [C][Y][X] on the device */
+int b2u_crop_tiles(const uint8_t* raster, int32_t C, int64_t Y, int64_t X, const int32_t* y0, const int32_t* x0, int32_t T,
+                   int32_t P, void* out, int32_t ld, void* stream);
 /* bf16/f32 NHWC -> fp32 NCHW */
 int b2u_nhwc_to_nchw_f32(const void* x, int32_t x_is_f32, int32_t ld, float* y, int32_t N, int32_t C, int32_t H,
                          int32_t W, void* stream);

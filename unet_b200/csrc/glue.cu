@@ -194,6 +194,26 @@ __global__ void nchw_to_nhwc_kernel(const void* __restrict__ x, int is_u8, __nv_
   }
 }
 
+// tile t = raster[:, y0[t]:y0[t]+P, x0[t]:x0[t]+P] / 255 -> bf16 NHWC [T,P,P,ld] (crop + IntToFloatTensor + layout cast)
+__global__ void crop_tiles_kernel(const uint8_t* __restrict__ raster, int C, long long Y, long long X,
+                                  const int* __restrict__ ty0, const int* __restrict__ tx0, int T, int P,
+                                  __nv_bfloat16* __restrict__ out, int ld) {
+  const long long PP = (long long)P * P, total = (long long)T * PP;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i / PP);
+    const long long r = i - (long long)t * PP;
+    const int yy = (int)(r / P), xx = (int)(r - (long long)yy * P);
+    const long long gy = (long long)ty0[t] + yy, gx = (long long)tx0[t] + xx;
+    const bool inb = gy >= 0 && gy < Y && gx >= 0 && gx < X;
+    __nv_bfloat16* dst = out + i * ld;
+    for (int c = 0; c < ld; ++c) {
+      float v = 0.f;
+      if (c < C && inb) v = (float)raster[((long long)c * Y + gy) * X + gx] / 255.f;
+      dst[c] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
 __global__ void nhwc_to_nchw_f32_kernel(const void* __restrict__ x, int is_f32, int ld, float* __restrict__ y, int N,
                                         int C, int H, int W) {
   const long long HW = (long long)H * W;
@@ -470,6 +490,15 @@ extern "C" int b2u_nchw_to_nhwc(const void* x, int32_t x_is_u8, void* y, int32_t
   const long long items = (long long)N * H * W;
   nchw_to_nhwc_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>(x, x_is_u8, (bf)y, N, C, H, W, ld, ch_off,
                                                                             write_c);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" int b2u_crop_tiles(const uint8_t* raster, int32_t C, int64_t Y, int64_t X, const int32_t* y0,
+                              const int32_t* x0, int32_t T, int32_t P, void* out, int32_t ld, void* stream) {
+  B2U_CHECK_ARG(raster && y0 && x0 && out && C > 0 && C <= ld && T > 0 && P > 0, "crop_tiles: bad argument");
+  const long long items = (long long)T * P * P;
+  crop_tiles_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>(raster, C, Y, X, y0, x0, T, P, (bf)out, ld);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }

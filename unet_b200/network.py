@@ -97,6 +97,8 @@ class UNetB200:
         self.flops_fwd_per_tile = conv_flops(self.spec, self.H) if self.H == self.W else None
 
         self._keep: List[object] = []
+        self.acts: List[Act] = []
+        self.named_acts: Dict[str, Act] = {}
         self.fwd_ops: List[Callable[[int], None]] = []
         self.bwd_ops: List[Callable[[int], None]] = []
         self._bwd_builders: List[Callable[[], None]] = []
@@ -180,7 +182,13 @@ class UNetB200:
 
     # ------------------------------------------------------------------------------------------------ build helpers
     def _act(self, H: int, W: int, Cc: int, name: str = "", zero: bool = False) -> Act:
-        return Act(self.N, H, W, Cc, self.device, name, zero)
+        a = Act(self.N, H, W, Cc, self.device, name, zero)
+        # every activation stays referenced for the life of the plan: the launch plans hold raw device pointers, so a
+        # garbage-collected tensor would hand its memory to a later allocation while kernels still address it
+        self.acts.append(a)
+        if name:
+            self.named_acts[name] = a
+        return a
 
     def _bn_state(self, prefix: str, Cc: int) -> BNState:
         st = BNState(self, prefix, Cc)

@@ -1,0 +1,81 @@
+"""Tiled prediction of a large raster on the GPU: crop -> forward (BN folded) -> softmax -> overlap accumulate ->
+normalise + argmax, sharded over GPUs by output column strips.
+
+Replaces the reference's `save_predictions` hot loops (predict.py:191-254 per-tile `learn.predict`, predict.py:284-337
+numpy merge): the reference keeps every tile's probabilities in a host list and merges with numpy slicing; here tiles
+never leave HBM between the network and the stitch.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib, ops
+from .network import UNetB200
+from .tiling import Window, colour_classes, compute_windows, shard_windows_by_columns
+
+
+class TiledPredictor:
+    def __init__(self, net: UNetB200):
+        assert not net.training, "prediction uses the eval plan (running BN statistics folded into the convolutions)"
+        self.net, self.lib, self.dev = net, net.lib, net.device
+        self.B, self.P = net.N, net.H
+        assert net.H == net.W
+
+    def predict_raster(self, raster: torch.Tensor, patch_overlap: float, rank: int = 0, world: int = 1,
+                       return_probs: bool = False):
+        """raster: uint8 [C, Y, X] on the device. Returns (mask uint8 [Y, x_end-x_begin], x_begin, x_end) for the
+        column strip this rank owns (the whole raster when world == 1)."""
+        net, lib, dev, P, B = self.net, self.lib, self.dev, self.P, self.B
+        assert raster.is_cuda and raster.dtype == torch.uint8 and raster.dim() == 3 and raster.is_contiguous()
+        Cc, Y, X = raster.shape
+        assert Cc == net.n_in and Y >= P and X >= P, "raster smaller than one tile is not supported"
+        windows = compute_windows(Y, X, P, patch_overlap)
+        idx, xb, xe = shard_windows_by_columns(windows, X, rank, world)
+        SX = xe - xb
+        acc = torch.zeros((net.n_out, Y, SX), dtype=torch.float32, device=dev)
+        cnt = torch.zeros((Y, SX), dtype=torch.uint8, device=dev)
+        mask = torch.empty((Y, SX), dtype=torch.uint8, device=dev)
+        s = ops.stream_ptr()
+        ld = net.logits.shape[-1]
+        self.tiles_run = len(idx)
+        for b0 in range(0, len(idx), B):
+            chunk = idx[b0:b0 + B]
+            n = len(chunk)
+            wins = [windows[i] for i in chunk]
+            # pad the last batch by repeating its first tile; padded tiles are never selected for stitching
+            pad = wins + [wins[0]] * (B - n)
+            y0 = torch.tensor([w[1] for w in pad], dtype=torch.int32).to(dev, non_blocking=True)
+            x0 = torch.tensor([w[0] for w in pad], dtype=torch.int32).to(dev, non_blocking=True)
+            _lib.check(lib.b2u_crop_tiles(raster.data_ptr(), Cc, Y, X, y0.data_ptr(), x0.data_ptr(), B, P,
+                                          net.x_in.t.data_ptr(), net.x_in.ld, s), "b2u_crop_tiles")
+            net.forward(s)
+            for cls in colour_classes(wins):
+                sel = torch.tensor(cls, dtype=torch.int32).to(dev, non_blocking=True)
+                _lib.check(lib.b2u_stitch_accumulate(net.logits.data_ptr(), ld, net.n_out, B, P, P, y0.data_ptr(),
+                                                     x0.data_ptr(), sel.data_ptr(), len(cls), acc.data_ptr(),
+                                                     cnt.data_ptr(), Y, SX, 0, xb, s), "b2u_stitch_accumulate")
+                self._keep = (y0, x0, sel)
+        _lib.check(lib.b2u_stitch_finalize(acc.data_ptr(), cnt.data_ptr(), net.n_out, Y, SX, mask.data_ptr(), s),
+                   "b2u_stitch_finalize")
+        if return_probs:
+            return mask, xb, xe, acc, cnt
+        return mask, xb, xe
+
+    def predict_tiles(self, tiles_u8: torch.Tensor):
+        """what `learn.predict` returns per tile (predict.py:193-203): softmax probabilities [T,C,H,W] fp32 and the
+        argmax [T,H,W] uint8, for a batch of uint8 tiles [T<=B, C, P, P] on the device."""
+        net, lib = self.net, self.lib
+        T = tiles_u8.shape[0]
+        assert T <= self.B
+        x = tiles_u8
+        if T < self.B:
+            x = torch.cat([tiles_u8, tiles_u8[:1].expand(self.B - T, -1, -1, -1)], 0).contiguous()
+        net.set_input(x)
+        net.forward()
+        probs = torch.empty((self.B, net.n_out, self.P, self.P), dtype=torch.float32, device=self.dev)
+        amax = torch.empty((self.B, self.P, self.P), dtype=torch.uint8, device=self.dev)
+        _lib.check(lib.b2u_softmax_nchw(net.logits.data_ptr(), net.logits.shape[-1], net.n_out, self.B, self.P, self.P,
+                                        probs.data_ptr(), amax.data_ptr(), ops.stream_ptr()), "b2u_softmax_nchw")
+        return probs[:T], amax[:T]
