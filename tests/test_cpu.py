@@ -1,0 +1,261 @@
+"""CPU suite (`-m "not gpu"`): the oracle against the committed golden vectors, the host logic (tiling, sharding,
+parameter layout, schedules), the C-ABI surface (library loads and exports every symbol include/b2u.h declares — no
+compute calls without a GPU) and the data-parallel host logic on a world_size-2 gloo group."""
+import hashlib
+import json
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+# ------------------------------------------------------------------------------------------------ windows (bit-exact)
+def test_windows_oracle_and_product_match_golden():
+    from oracle import windows as ow
+    from unet_b200 import tiling
+    gold = json.load(open(os.path.join(GOLD, "windows.json")))
+    for g in gold:
+        args = (g["height"], g["width"], g["patch"], g["overlap"])
+        for impl in (ow.compute_windows, tiling.compute_windows):
+            ws = impl(*args)
+            assert len(ws) == g["count"]
+            assert [list(w) for w in ws[:3]] == g["first"] and [list(w) for w in ws[-3:]] == g["last"]
+            assert hashlib.sha256(json.dumps([list(w) for w in ws]).encode()).hexdigest() == g["sha256"]
+        assert tiling.axis_offsets(g["width"], g["patch"], g["overlap"])[0] == g["xs"]
+        assert tiling.axis_offsets(g["height"], g["patch"], g["overlap"])[0] == g["ys"]
+
+
+def test_windows_survey_facts():
+    """config 3 has 90 offsets per axis [0,224,...,19712,19744] -> 8100 tiles, x-outer order."""
+    from unet_b200.tiling import axis_offsets, compute_windows
+    xs, win = axis_offsets(20000, 256, 0.125)
+    assert win == 256 and len(xs) == 90 and xs[:3] == [0, 224, 448] and xs[-2:] == [19712, 19744]
+    ws = compute_windows(20000, 20000, 256, 0.125)
+    assert len(ws) == 8100 and ws[0] == (0, 0, 256, 256) and ws[1] == (0, 224, 256, 256) and ws[90] == (224, 0, 256, 256)
+    with pytest.raises(ValueError):
+        compute_windows(100, 100, 64, 1.5)
+    # raster smaller than the patch: a single window clipped to the raster
+    assert compute_windows(64, 64, 256, 0.2) == [(0, 0, 64, 64)]
+
+
+def test_coverage_counts_and_colour_classes():
+    from unet_b200.tiling import colour_classes, compute_windows, shard_windows_by_columns
+    for (h, w, p, ov) in [(2000, 2000, 256, 0.125), (257, 511, 256, 0.5), (300, 300, 256, 0.75), (700, 500, 128, 0.2)]:
+        ws = compute_windows(h, w, p, ov)
+        cov = np.zeros((h, w), np.int32)
+        for (x, y, ww, hh) in ws:
+            cov[y:y + hh, x:x + ww] += 1
+        assert cov.min() >= 1
+        if ov <= 0.125:
+            assert set(np.unique(cov)) <= {1, 2, 4}          # predict.py:287: "1, 2, or 4 tiles"
+        classes = colour_classes(ws)
+        assert sorted(i for c in classes for i in c) == list(range(len(ws)))
+        for c in classes:                                      # tiles of one class never overlap
+            m = np.zeros((h, w), np.int8)
+            for i in c:
+                x, y, ww, hh = ws[i]
+                assert m[y:y + hh, x:x + ww].max() == 0
+                m[y:y + hh, x:x + ww] = 1
+        # owner-computes sharding: strips partition the columns, and every tile touching a strip is assigned to it
+        for world in (2, 3, 8):
+            xs = []
+            for r in range(world):
+                idx, xb, xe = shard_windows_by_columns(ws, w, r, world)
+                xs.append((xb, xe))
+                need = [i for i, (x, y, ww, hh) in enumerate(ws) if x < xe and x + ww > xb]
+                assert idx == need
+            assert xs[0][0] == 0 and xs[-1][1] == w and all(xs[i][1] == xs[i + 1][0] for i in range(world - 1))
+
+
+# ------------------------------------------------------------------------------------------------ stitch oracle
+def test_stitch_oracle_matches_golden():
+    from oracle import stitch
+    g = np.load(os.path.join(GOLD, "stitch.npz"))
+    h, w, p, c = g["shape"]
+    ws = [tuple(int(v) for v in r) for r in g["windows"]]
+    probs = [stitch.softmax_probs(l) for l in g["logits"]]
+    merged = stitch.merge_pixel_windows(probs, ws, int(h), int(w))
+    assert np.array_equal(merged.astype(np.uint8), g["merged"])
+    gts = [[float(x), float(ww), 1.0, -float(y), float(hh), -1.0] for (x, y, ww, hh) in ws]
+    m8, _ = stitch.merge_tiles(probs, gts, large_file=True)
+    assert np.array_equal(m8.astype(np.uint8), g["merged_large_file"])
+    # placement arithmetic of predict.py:294-297 through real geotransforms (0.2 m pixels, UTM-like origin)
+    from unet_b200.tiling import placement_from_geotransform
+    gt = (382000.0, 0.2, 0.0, 5812000.0, 0.0, -0.2)
+    gts2 = [[gt[0] + x * gt[1], ww, gt[1], gt[3] + y * gt[5], hh, gt[5]] for (x, y, ww, hh) in ws]
+    merged2, origin = stitch.merge_tiles(probs, gts2)
+    assert np.array_equal(merged2, merged) and origin[0] == gt[0] and origin[2] == gt[3]
+    for (x, y, ww, hh), q in zip(ws, gts2):
+        assert placement_from_geotransform(q[0], q[1], q[2], q[3], q[4], q[5], gt[0], gt[3]) == (x, y, x + ww, y + hh)
+
+
+# ------------------------------------------------------------------------------------------------ model oracle
+def test_oracle_model_matches_golden_and_survey_counts():
+    from oracle.unet_oracle import count_conv_flops, make_oracle, weighted_ce
+    g = np.load(os.path.join(GOLD, "model_xresnet18_32.npz"))
+    torch.set_num_threads(4)
+    m = make_oracle("xresnet18", 3, 2, seed=0).train()
+    p = dict(m.named_parameters())
+    assert np.allclose(p["layers.0.0.0.weight"].detach().flatten()[:8].numpy(), g["weight_probe"][0], atol=1e-7)
+    x = torch.from_numpy(g["x_u8"]).float() / 255.0
+    y = torch.from_numpy(g["y"]).long()
+    logits = m(x)
+    loss = weighted_ce(logits, y, torch.full((2,), 0.5))
+    loss.backward()
+    assert np.allclose(logits.detach().numpy(), g["logits_train"], rtol=1e-4, atol=1e-4)
+    assert abs(loss.item() - g["loss"][0]) <= 1e-5
+    for k in g.files:
+        if k.startswith("grad::"):
+            assert np.allclose(p[k[6:]].grad.numpy(), g[k], rtol=1e-3, atol=1e-6), k
+    m.eval()
+    with torch.no_grad():
+        assert np.allclose(m(x).numpy(), g["logits_eval"], rtol=1e-4, atol=1e-4)
+    # parameter totals and forward conv FLOPs of the restated topology
+    m34 = make_oracle("xresnet34", 4, 2)
+    assert sum(q.numel() for q in m34.parameters()) == 41244274 and len(list(m34.parameters())) == 160
+    assert count_conv_flops(m34, 256) == 63922241536
+
+
+def test_bf16_emulation_tracks_oracle():
+    from oracle.bf16_emulation import emulated_forward
+    from oracle.unet_oracle import make_oracle
+    m = make_oracle("xresnet18", 3, 2).train()
+    x = torch.rand(2, 3, 32, 32, generator=torch.Generator().manual_seed(0))
+    a, b = m(x), emulated_forward(m, x, True)
+    assert ((a - b).abs().max() / a.abs().max()).item() < 5e-2
+    b.sum().backward()
+    assert all(q.grad is not None for q in m.parameters())
+
+
+# ------------------------------------------------------------------------------------------------ layout / host logic
+@pytest.mark.parametrize("arch,n_in,n_out,size,params,mflops", [
+    ("xresnet34", 4, 2, 256, 41244274, 63922.241536), ("xresnet18", 3, 2, 128, 31132240, 14652.801024),
+    ("xresnet50", 4, 8, 512, 339101776, 2515290.554368)])
+def test_param_layout_matches_oracle_names(arch, n_in, n_out, size, params, mflops):
+    from oracle.unet_oracle import make_oracle, param_groups
+    from unet_b200.layout import ParamLayout, build_spec, conv_flops
+    spec = build_spec(arch, n_in, n_out)
+    L = ParamLayout(spec)
+    m = make_oracle(arch, n_in, n_out)
+    assert [(e.name, e.shape) for e in L.entries] == [(n, tuple(p.shape)) for n, p in m.named_parameters()]
+    assert L.n_params() == params
+    assert abs(conv_flops(spec, size) / 1e6 - mflops) < 1e-3
+    groups = param_groups(m)
+    for e in L.entries:
+        assert e.name in groups[e.group]
+        assert e.offset % 4 == 0
+        assert e.decay == (len(e.shape) == 4)
+    buf = {k for k, _ in m.named_buffers() if not k.endswith("num_batches_tracked")}
+    assert {pfx + s for pfx, _ in L.buffers for s in (".running_mean", ".running_var")} == buf
+
+
+def test_shuffle_row_permutation():
+    from unet_b200.layout import shuffle_row_of_co
+    roc = shuffle_row_of_co(16)
+    assert sorted(roc) == list(range(16))
+    x = torch.arange(16.0).view(1, 16, 1, 1)
+    ps = torch.nn.functional.pixel_shuffle(x, 2)[0]                  # [4, 2, 2]
+    for co in range(16):
+        r = roc[co]
+        ij, c = divmod(r, 4)
+        assert ps[c, ij // 2, ij % 2].item() == co                    # row (i,j,c) holds torch channel 4c+2i+j
+
+
+def test_one_cycle_and_shard_range():
+    from oracle.unet_oracle import one_cycle_lr
+    from unet_b200.engine import one_cycle, shard_range
+    for pct in (0.0, 0.1, 0.25, 0.5, 0.99, 1.0):
+        assert one_cycle(pct, 1e-3) == pytest.approx(one_cycle_lr(pct, 1e-3))
+    assert one_cycle(0.0, 1e-3)[0] == pytest.approx(1e-3 / 25) and one_cycle(0.25, 1e-3)[0] == pytest.approx(1e-3)
+    for n, world in ((8100, 8), (10, 3), (5, 8)):
+        parts = [shard_range(n, r, world) for r in range(world)]
+        assert parts[0][0] == 0 and parts[-1][1] == n
+        assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+        assert max(b - a for a, b in parts) - min(b - a for a, b in parts) <= 1
+
+
+def test_synthetic_data_is_deterministic():
+    from unet_b200.synth import aerial_like_tiles, uniform_tiles
+    a, b = uniform_tiles(2, 4, 32, 32, 2), uniform_tiles(2, 4, 32, 32, 2)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and a[0].dtype == torch.uint8
+    x, y = aerial_like_tiles(2, 4, 32, 32, 3)
+    assert x.shape == (2, 4, 32, 32) and int(y.max()) <= 2
+
+
+# ------------------------------------------------------------------------------------------------ C-ABI surface
+def test_c_abi_exports_every_declared_symbol():
+    import ctypes
+    from unet_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "b2u.h")).read()
+    declared = set(re.findall(r"\b(b2u_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 35
+    lib = _lib.load()
+    missing = [n for n in sorted(declared) if not hasattr(lib, n)]
+    assert not missing, missing
+    assert lib.b2u_version() >= 1
+    # struct layouts mirrored in ctypes must match the C side (sizes are part of the ABI)
+    assert ctypes.sizeof(_lib.View) == 48 and ctypes.sizeof(_lib.WStageItem) == 80
+    assert ctypes.sizeof(_lib.ConvInfo) == 40
+
+
+def test_product_never_imports_the_oracle():
+    """the oracle is test infrastructure: unet_b200/ must not import it (bench.py may, in its CPU-baseline legs only)"""
+    pkg = os.path.join(ROOT, "unet_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), fn
+
+
+def test_network_requires_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from unet_b200 import _lib
+    from unet_b200.network import UNetB200
+    with pytest.raises(_lib.B2UError):
+        UNetB200("xresnet18", 3, 2, (64, 64), 1)
+
+
+# ------------------------------------------------------------------------------------------------ gloo, world_size 2
+def _ddp_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from unet_b200.engine import shard_range
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3, padding=1), torch.nn.ReLU(), torch.nn.Conv2d(4, 2, 1))
+    x = torch.randn(8, 3, 8, 8, generator=torch.Generator().manual_seed(1))
+    y = torch.randint(0, 2, (8, 8, 8), generator=torch.Generator().manual_seed(2))
+    a, b = shard_range(8, rank, world)
+    loss = torch.nn.functional.cross_entropy(model(x[a:b]), y[a:b])
+    loss.backward()
+    flat = torch.cat([p.grad.flatten() for p in model.parameters()])
+    # the engine's scheme: bucketed SUM all-reduce over one flat buffer, 1/world applied by the optimizer kernel
+    bucket = 37
+    for s in range(0, flat.numel(), bucket):
+        dist.all_reduce(flat[s:s + bucket], op=dist.ReduceOp.SUM)
+    flat /= world
+    if rank == 0:
+        torch.save(flat, out)
+    dist.destroy_process_group()
+
+
+def test_data_parallel_gradient_average_gloo(tmp_path):
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "g.pt")
+    port = 29500 + (os.getpid() % 500)
+    mp.spawn(_ddp_worker, args=(2, port, out), nprocs=2, join=True)
+    got = torch.load(out)
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3, padding=1), torch.nn.ReLU(), torch.nn.Conv2d(4, 2, 1))
+    x = torch.randn(8, 3, 8, 8, generator=torch.Generator().manual_seed(1))
+    y = torch.randint(0, 2, (8, 8, 8), generator=torch.Generator().manual_seed(2))
+    torch.nn.functional.cross_entropy(model(x), y).backward()
+    ref = torch.cat([p.grad.flatten() for p in model.parameters()])
+    assert torch.allclose(got, ref, atol=1e-6)       # equal shards: mean of shard means == full-batch mean

@@ -164,3 +164,22 @@ def test_predict_raster_matches_reference_merge():
         parts.append(m)
     torch.cuda.synchronize()
     assert torch.equal(torch.cat(parts, dim=1), mask)
+
+
+def test_against_committed_golden_fixture():
+    """tests/golden/model_xresnet18_32.npz (generated by tests/golden/make_golden.py from the oracle): logits of the
+    train-mode and eval-mode forward for fixed inputs; the CUDA plan must reproduce them within the bf16 tolerance."""
+    import numpy as np
+    from oracle.unet_oracle import make_oracle
+    from unet_b200.network import UNetB200
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "model_xresnet18_32.npz"))
+    oracle = make_oracle("xresnet18", 3, 2, seed=0)
+    x_u8 = torch.from_numpy(g["x_u8"]).cuda()
+    for training, key in ((True, "logits_train"), (False, "logits_eval")):
+        net = UNetB200("xresnet18", 3, 2, (32, 32), 2, training=training)
+        net.load_state_dict(oracle.state_dict())
+        net.set_input(x_u8)
+        net.forward()
+        torch.cuda.synchronize()
+        e = rel(net.logits_nchw().cpu(), torch.from_numpy(g[key]))
+        assert e <= 3e-2, (key, e)
