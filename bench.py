@@ -62,9 +62,9 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0: float = 0.0, t1: float = float("inf")):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -74,7 +74,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ts, ln in self.lines:
+            if ts < t0 or ts > t1 + 0.15:   # only samples taken DURING the timed region
+                continue
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 7:
                 continue
@@ -197,25 +199,27 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()   # started early (nvidia-smi needs ~1 s to produce its first sample); filtered by time below
     # ---- warm-up (includes graph capture)
     for i in range(args.warmup):
         trainer.step(dev_x[i % n_pool], dev_y[i % n_pool])
     barrier()
 
     # ---- kernel-only value: inputs resident in HBM, CUDA events on the launching stream, max over ranks
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     st = torch.cuda.current_stream()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_wall0 = time.time()
     e0.record(st)
     for i in range(args.steps):
         trainer.step(dev_x[i % n_pool], dev_y[i % n_pool])
     e1.record(st)
     barrier()
+    t_wall1 = time.time()
     dev_ms = max_over_ranks(e0.elapsed_time(e1))
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     loss_val = float(net.loss.item())
 
     # ---- e2e: public API with HOST buffers, H2D of the tiles and D2H of the loss every step inside the timed region
