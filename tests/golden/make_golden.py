@@ -56,15 +56,16 @@ def golden_model():
     g = torch.Generator().manual_seed(1234)
     x_u8 = torch.randint(0, 256, (batch, n_in, size, size), generator=g, dtype=torch.uint8)
     y = torch.randint(0, n_out, (batch, size, size), generator=torch.Generator().manual_seed(4321), dtype=torch.uint8)
+    m.eval()                      # eval logits first: the train-mode pass below updates the BN running statistics
+    with torch.no_grad():
+        logits_eval = m(x_u8.float() / 255.0)
+    m.train()
     logits = m(x_u8.float() / 255.0)
     loss = weighted_ce(logits, y.long(), torch.full((n_out,), 1.0 / n_out))
     loss.backward()
     names = ["layers.12.0.weight", "layers.12.0.bias", "layers.11.convpath.1.0.bias", "layers.8.0.0.bias",
              "layers.7.bn.weight", "layers.0.0.0.weight"]
     p = dict(m.named_parameters())
-    m.eval()
-    with torch.no_grad():
-        logits_eval = m(x_u8.float() / 255.0)
     np.savez_compressed(
         os.path.join(HERE, "model_xresnet18_32.npz"), x_u8=x_u8.numpy(), y=y.numpy(),
         logits_train=logits.detach().numpy(), loss=np.array([loss.item()]), logits_eval=logits_eval.numpy(),

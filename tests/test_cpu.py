@@ -105,6 +105,10 @@ def test_oracle_model_matches_golden_and_survey_counts():
     assert np.allclose(p["layers.0.0.0.weight"].detach().flatten()[:8].numpy(), g["weight_probe"][0], atol=1e-7)
     x = torch.from_numpy(g["x_u8"]).float() / 255.0
     y = torch.from_numpy(g["y"]).long()
+    m.eval()                      # eval first (fresh running statistics), exactly as the generator does
+    with torch.no_grad():
+        assert np.allclose(m(x).numpy(), g["logits_eval"], rtol=1e-4, atol=1e-4)
+    m.train()
     logits = m(x)
     loss = weighted_ce(logits, y, torch.full((2,), 0.5))
     loss.backward()
@@ -113,9 +117,6 @@ def test_oracle_model_matches_golden_and_survey_counts():
     for k in g.files:
         if k.startswith("grad::"):
             assert np.allclose(p[k[6:]].grad.numpy(), g[k], rtol=1e-3, atol=1e-6), k
-    m.eval()
-    with torch.no_grad():
-        assert np.allclose(m(x).numpy(), g["logits_eval"], rtol=1e-4, atol=1e-4)
     # parameter totals and forward conv FLOPs of the restated topology
     m34 = make_oracle("xresnet34", 4, 2)
     assert sum(q.numel() for q in m34.parameters()) == 41244274 and len(list(m34.parameters())) == 160

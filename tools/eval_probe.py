@@ -6,10 +6,11 @@ from unet_b200.network import UNetB200
 from unet_b200.synth import aerial_like_tiles
 torch.backends.cudnn.allow_tf32 = False
 def rel(a, b): return ((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-30)).item()
-oracle = make_oracle("xresnet34", 4, 2).cuda().eval()
-net = UNetB200("xresnet34", 4, 2, (256, 256), 2, training=False)
+ARCH, NIN, SZ = (sys.argv[1], int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else ("xresnet34", 4, 256)
+oracle = make_oracle(ARCH, NIN, 2).cuda().eval()
+net = UNetB200(ARCH, NIN, 2, (SZ, SZ), 2, training=False)
 net.load_state_dict(oracle.state_dict())
-x_u8, _ = aerial_like_tiles(2, 4, 256, 256, 2); x_u8 = x_u8.cuda()
+x_u8, _ = aerial_like_tiles(2, NIN, SZ, SZ, 2); x_u8 = x_u8.cuda()
 acts = {}
 enc = oracle.layers[0]
 for i, child in enumerate(enc):
@@ -29,4 +30,13 @@ for k, v in names.items():
         print(k, rel(a.t[..., :a.C].permute(0, 3, 1, 2), v))
 for k, a in net.feats.items():
     print("feat", k, rel(a.t[..., :a.C].permute(0, 3, 1, 2), acts[k]))
+dec = {}
+for i in range(4, 8):
+    oracle.layers[i].register_forward_hook(lambda m, inp, out, i=i: dec.__setitem__(f"layers.{i}.conv2.out", out))
+oracle.layers[3].register_forward_hook(lambda m, inp, out: dec.__setitem__("layers.3.1.out", out))
+oracle.layers[2].register_forward_hook(lambda m, inp, out: dec.__setitem__("enc.bnrelu", out))
+with torch.no_grad(): ref = oracle(x_u8.float() / 255)
+for k, v in dec.items():
+    a = net.named_acts[k]
+    print(k, rel(a.t[..., :a.C].permute(0, 3, 1, 2), v))
 print("logits", rel(net.logits_nchw(), ref))

@@ -25,10 +25,18 @@ __device__ __forceinline__ void st8(__nv_bfloat16* p, const f8& a) {
   u.z = pack_bf16x2(a.v[4], a.v[5]); u.w = pack_bf16x2(a.v[6], a.v[7]);
   *reinterpret_cast<uint4*>(p) = u;
 }
-__device__ __forceinline__ f8 ldc8(const float* p, int c, int C) {  // per-channel fp32 constants, guarded
+// per-channel fp32 constants: the arrays are padded to a multiple of 32 floats and 16-byte aligned (b2u.h), so a
+// group of 8 channels is two 16-byte loads; lanes >= C are zeroed
+__device__ __forceinline__ f8 ldc8(const float* p, int c, int C) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p + c));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p + c) + 1);
   f8 o;
+  o.v[0] = a.x; o.v[1] = a.y; o.v[2] = a.z; o.v[3] = a.w; o.v[4] = b.x; o.v[5] = b.y; o.v[6] = b.z; o.v[7] = b.w;
+  if (c + 8 > C) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) o.v[i] = (c + i < C) ? __ldg(p + c + i) : 0.f;
+    for (int i = 0; i < 8; ++i)
+      if (c + i >= C) o.v[i] = 0.f;
+  }
   return o;
 }
 
@@ -95,11 +103,19 @@ __global__ void bn_stats_kernel(const __nv_bfloat16* __restrict__ x, int ldx, lo
 
 // rows [rows][K][ld] -> [ceil(rows/128)][K][ld], fixed order
 __global__ void reduce_rows_kernel(const float* __restrict__ in, int rows, int width, float* __restrict__ out) {
+  // 256 threads = 64 columns x 4 row lanes; each lane sums every 4th row, lanes are combined in a fixed order
+  __shared__ float sh[4][64];
   const int r0 = blockIdx.x * 128, r1 = min(rows, r0 + 128);
-  for (int c = threadIdx.x; c < width; c += blockDim.x) {
+  const int cl = threadIdx.x & 63, rl = threadIdx.x >> 6;
+  for (int c0 = 0; c0 < width; c0 += 64) {
+    const int c = c0 + cl;
     float s = 0.f;
-    for (int r = r0; r < r1; ++r) s += in[(size_t)r * width + c];
-    out[(size_t)blockIdx.x * width + c] = s;
+    if (c < width)
+      for (int r = r0 + rl; r < r1; r += 4) s += in[(size_t)r * width + c];
+    sh[rl][cl] = s;
+    __syncthreads();
+    if (rl == 0 && c < width) out[(size_t)blockIdx.x * width + c] = (sh[0][cl] + sh[1][cl]) + (sh[2][cl] + sh[3][cl]);
+    __syncthreads();
   }
 }
 

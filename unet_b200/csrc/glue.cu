@@ -183,13 +183,26 @@ __global__ void nchw_to_nhwc_kernel(const void* __restrict__ x, int is_u8, __nv_
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
     const long long n = p / HW, hw = p - n * HW;
     __nv_bfloat16* dst = y + p * ld + ch_off;
-    for (int c = 0; c < Cw; ++c) {
-      float v = 0.f;
-      if (c < C) {
-        const long long src = (n * C + c) * HW + hw;
-        v = is_u8 ? (float)reinterpret_cast<const uint8_t*>(x)[src] / 255.f : reinterpret_cast<const float*>(x)[src];
+    for (int c0 = 0; c0 < Cw; c0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int c = c0 + k;
+        v[k] = 0.f;
+        if (c < C) {
+          const long long src = (n * C + c) * HW + hw;
+          v[k] = is_u8 ? (float)reinterpret_cast<const uint8_t*>(x)[src] / 255.f
+                       : reinterpret_cast<const float*>(x)[src];
+        }
       }
-      dst[c] = __float2bfloat16_rn(v);
+      if (c0 + 8 <= Cw && (((ch_off + c0) & 7) == 0)) {
+        uint4 u;
+        u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+        u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+        *reinterpret_cast<uint4*>(dst + c0) = u;
+      } else {
+        for (int k = 0; k < 8 && c0 + k < Cw; ++k) dst[c0 + k] = __float2bfloat16_rn(v[k]);
+      }
     }
   }
 }
@@ -300,10 +313,22 @@ __global__ void ce_fwd_bwd_kernel(const float* __restrict__ logits, int ld, cons
     }
     if (dlogits) {
       const float gs = grad_scale * wy * inv_wsum;
+      // ldg is a multiple of 8 (checked on the host): 16-byte stores, zeros beyond C
+      for (int c0 = 0; c0 < ldg; c0 += 8) {
+        float gv[8];
 #pragma unroll
-      for (int c = 0; c < MAXC; ++c)
-        if (c < ldg) dlogits[p * ldg + c] = __float2bfloat16_rn(c < C ? gs * (z[c] * inv - (c == y ? 1.f : 0.f)) : 0.f);
-      for (int c = MAXC; c < ldg; ++c) dlogits[p * ldg + c] = __float2bfloat16_rn(0.f);
+        for (int k = 0; k < 8; ++k) {
+          const int c = c0 + k;
+          float zc = 0.f;
+#pragma unroll
+          for (int q = 0; q < MAXC; ++q) zc = (q == c) ? z[q] : zc;
+          gv[k] = (c < C) ? gs * (zc * inv - (c == y ? 1.f : 0.f)) : 0.f;
+        }
+        uint4 u;
+        u.x = pack_bf16x2(gv[0], gv[1]); u.y = pack_bf16x2(gv[2], gv[3]);
+        u.z = pack_bf16x2(gv[4], gv[5]); u.w = pack_bf16x2(gv[6], gv[7]);
+        *reinterpret_cast<uint4*>(dlogits + p * ldg + c0) = u;
+      }
     }
   }
   const float r = block_sum(acc, sh);
@@ -524,7 +549,8 @@ extern "C" int b2u_ce_fwd_bwd(const float* logits, int32_t ld, const uint8_t* la
                               const float* weight, const float* wsum_partial, int32_t wsum_rows, void* dlogits,
                               int32_t ldg, float* loss_partial, int32_t rows, float grad_scale, void* stream) {
   B2U_CHECK_ARG(logits && labels && wsum_partial && loss_partial && rows > 0, "ce_fwd_bwd: bad argument");
-  B2U_CHECK_ARG(C >= 1 && C <= 32 && C <= ld && (!dlogits || ldg >= C), "ce_fwd_bwd: C=%d ld=%d ldg=%d unsupported", C, ld, ldg);
+  B2U_CHECK_ARG(C >= 1 && C <= 32 && C <= ld && (!dlogits || (ldg >= C && ldg % 8 == 0)),
+                "ce_fwd_bwd: C=%d ld=%d ldg=%d unsupported (ldg must be a multiple of 8)", C, ld, ldg);
   cudaStream_t st = (cudaStream_t)stream;
   if (C <= 8)
     ce_fwd_bwd_kernel<8><<<rows, 256, 0, st>>>(logits, ld, labels, P, C, weight, wsum_partial, wsum_rows, (bf)dlogits,

@@ -237,31 +237,49 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_
 }
 
 // dw[perm(co)][ci][kidx] = alpha * sum_{t: tap_kidx[t]==kidx} sum_s partial[s][t][co][ci]
+// block = 32 input channels x 8 split lanes; one block row per (co, kidx).  Each lane sums its splits in ascending order,
+// lanes are combined in ascending order: the result does not depend on scheduling.
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int taps, int taps_total, int co_pad,
                                     int ci_pad, int Cout, int Cin, int ksize, const int* __restrict__ tap_kidx,
                                     const int* __restrict__ row_perm, float alpha, float* __restrict__ dw,
                                     float* __restrict__ db) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)Cout * ksize * Cin;
-  if (idx < total) {
-    const int ci = (int)(idx % Cin);
-    const int kidx = (int)((idx / Cin) % ksize);
-    const int co = (int)(idx / ((long long)Cin * ksize));
-    float acc = 0.f;
+  __shared__ float sh[8][33];
+  const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int co = blockIdx.y / ksize, kidx = blockIdx.y - co * ksize;
+  const int ci = blockIdx.x * 32 + lane;
+  float acc = 0.f;
+  if (ci < Cin) {
     for (int t = 0; t < taps; ++t) {
       if (tap_kidx[t] != kidx) continue;
-      for (int s = 0; s < splits; ++s)
-        acc += partial[(((size_t)s * taps_total + t) * co_pad + co) * ci_pad + ci];
+      const float* src = partial + ((size_t)t * co_pad + co) * ci_pad + ci;
+      const size_t sstride = (size_t)taps_total * co_pad * ci_pad;
+      for (int s = sl; s < splits; s += 8) acc += src[(size_t)s * sstride];
     }
-    const int oc = row_perm ? row_perm[co] : co;
-    dw[((size_t)oc * Cin + ci) * ksize + kidx] = alpha * acc;
   }
-  if (db && idx < Cout) {
-    const int co = (int)idx;
-    float acc = 0.f;
-    for (int s = 0; s < splits; ++s) acc += partial[(((size_t)s * taps_total + taps) * co_pad + co) * ci_pad];
+  sh[sl][lane] = acc;
+  __syncthreads();
+  if (sl == 0 && ci < Cin) {
+    float r = sh[0][lane];
+#pragma unroll
+    for (int q = 1; q < 8; ++q) r += sh[q][lane];
     const int oc = row_perm ? row_perm[co] : co;
-    db[oc] = acc;
+    dw[((size_t)oc * Cin + ci) * ksize + kidx] = alpha * r;
+  }
+  // bias gradient: column 0 of the extra "tap" slot; handled by the (kidx == 0, first ci block) blocks
+  if (db && kidx == 0 && blockIdx.x == 0) {
+    __syncthreads();
+    float b = 0.f;
+    for (int s = threadIdx.x; s < splits; s += 256)
+      b += partial[(((size_t)s * taps_total + taps) * co_pad + co) * ci_pad];
+    // fixed-order tree over the 256 threads
+    __shared__ float shb[256];
+    shb[threadIdx.x] = b;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if ((int)threadIdx.x < o) shb[threadIdx.x] += shb[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) db[row_perm ? row_perm[co] : co] = shb[0];
   }
 }
 
@@ -397,10 +415,8 @@ extern "C" int b2u_wgrad_reduce(const float* partial, int32_t splits, int32_t ta
                                 void* stream) {
   B2U_CHECK_ARG(partial && dw && tap_kidx, "wgrad_reduce: null argument");
   B2U_CHECK_ARG(!db || has_bias_cols, "wgrad_reduce: db requested but the partial buffer has no bias slot");
-  const long long total = (long long)Cout * ksize * Cin;
-  const int threads = 256;
-  const long long blocks = (total + threads - 1) / threads;
-  wgrad_reduce_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+  dim3 grid((unsigned)ceil_div(Cin, 32), (unsigned)(Cout * ksize));
+  wgrad_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
       partial, splits, taps, taps + (has_bias_cols ? 1 : 0), co_pad, ci_pad, Cout, Cin, ksize, tap_kidx, row_perm,
       alpha, dw, db);
   B2U_LAUNCH_CHECK();
