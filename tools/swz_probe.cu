@@ -64,6 +64,34 @@ __global__ void __launch_bounds__(128, 1) probe(const __grid_constant__ CUtensor
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 64); }
 }
 
+// timing: cycles per MMA (M=128, N=n, K=16) for aligned / unaligned operand starts
+__global__ void __launch_bounds__(128, 1) bench_mma(long long* out, int a_mn, int b_mn, int a_r0, int b_r0, int n, int iters, int sbo_a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sA = smem_u32(smem), sB = sA + 65536;
+  const uint32_t bar2 = sB + 65536, slot = bar2 + 16;
+  volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + 131072 + 16);
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 131072 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3C003C00u;
+  fence_proxy_async_smem();
+  if (threadIdx.x == 0) { mbar_init(bar2, 1); fence_mbar_init(); }
+  if (warp == 0) { tmem_alloc(slot, 256); tmem_relinquish(); }
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  const uint32_t tmem = *slot_ptr;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = make_idesc_bf16(128, n, a_mn, b_mn);
+    const uint64_t da = a_mn ? make_smem_desc(sA + a_r0 * 128, 16384, 1024) : make_smem_desc(sA + a_r0 * 128, 16, sbo_a);
+    const uint64_t db = b_mn ? make_smem_desc(sB + b_r0 * 128, 16384, 1024) : make_smem_desc(sB + b_r0 * 128, 16, 1024);
+    long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) umma_bf16(tmem, da, db, idesc, 1);
+    umma_commit(bar2);
+    mbar_wait(bar2, 0);
+    long long t1 = clock64();
+    out[0] = t1 - t0;
+  }
+  tc_fence_before(); __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 256); }
+}
+
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -117,5 +145,30 @@ int main() {
           printf("mode %d (%s) sbo %4d base_off_field %d r0 %2d : %s (%d mismatches)\n", mode, mode == 0 ? "K-major M-offset" : "MN-major K-offset",
                  sbo, ub, r0, bad ? "WRONG" : "ok", bad);
         }
+  // ---- MMA issue-rate microbenchmark
+  long long* dT; cudaMalloc(&dT, 8);
+  cudaFuncSetAttribute(bench_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072 + 64);
+  const int iters = 4000;
+  struct Cfg { int a_mn, b_mn, a_r0, b_r0, n, sbo; const char* name; };
+  Cfg cfgs[] = {
+    {0, 0, 0, 0, 112, 1024, "K-major A, K-major B, aligned            N=112"},
+    {0, 0, 1, 0, 112, 1024, "K-major A start +1 row                   N=112"},
+    {0, 0, 11, 0, 112, 1280, "K-major A start +11 rows, SBO 1280       N=112"},
+    {0, 0, 0, 0, 256, 1024, "K-major A, K-major B, aligned            N=256"},
+    {0, 0, 3, 0, 256, 1024, "K-major A start +3 rows                  N=256"},
+    {1, 1, 0, 0, 112, 1024, "MN-major A, MN-major B, aligned          N=112"},
+    {1, 1, 0, 1, 112, 1024, "MN-major B start +1 row                  N=112"},
+    {1, 1, 0, 2, 112, 1024, "MN-major B start +2 rows                 N=112"},
+    {1, 1, 0, 0, 256, 1024, "MN-major A, MN-major B, aligned          N=256"},
+    {1, 1, 0, 1, 256, 1024, "MN-major B start +1 row                  N=256"},
+    {1, 0, 0, 0, 112, 1024, "MN-major A, K-major B, aligned           N=112"},
+    {0, 1, 0, 0, 112, 1024, "K-major A, MN-major B, aligned           N=112"},
+  };
+  for (auto& c : cfgs) {
+    bench_mma<<<1, 128, 131072 + 64>>>(dT, c.a_mn, c.b_mn, c.a_r0, c.b_r0, c.n, iters, c.sbo);
+    cudaError_t e = cudaDeviceSynchronize();
+    long long t = 0; cudaMemcpy(&t, dT, 8, cudaMemcpyDeviceToHost);
+    printf("mma %s : %.1f cycles/MMA (%s)\n", c.name, (double)t / iters, cudaGetErrorString(e));
+  }
   return 0;
 }

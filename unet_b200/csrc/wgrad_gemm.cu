@@ -7,13 +7,15 @@
 // bias gradient (row sums of dY) from the same pass.
 //
 // Replaces cudnnConvolutionBackwardFilter as reached from loss.backward() in fastai's Learner (reference train.py:246-250).
+#include <stdlib.h>
+
 #include "host_util.h"
 #include "ptx.cuh"
 
 namespace b2u {
 
 static constexpr int kWgThreads = 256;
-static constexpr int kKP = 32;                   // pixels per pipeline stage
+static constexpr int kKP = 64;                   // pixels per pipeline stage
 static constexpr uint32_t kBoxBytes = kKP * 128; // one TMA box: 32 pixels x 64 bf16
 
 struct WgradParams {
@@ -31,6 +33,12 @@ struct WgradParams {
   int tw, th, tn, tiles_x, tiles_y;
   int stages;
   uint32_t idesc, idesc_bias;
+  // x-halo mode (3x3 stride-1 convs): the three taps of one filter row share ONE TMA box that is tw+2 pixels wide;
+  // tap dx is the same smem tile read from row offset dx+1 (the UMMA swizzle phase follows the absolute smem address,
+  // profiles/r01_swizzle_offset_probe.txt), which cuts the X-operand traffic and the TMA instruction count by 3.
+  int halo, hw;
+  uint32_t b_box_bytes, b_box_tx;  // smem footprint (1024-aligned) and TMA byte count of one X box
+  CUtensorMap tm_ah[B2U_MAX_VIEWS];
   int co_pad, ci_pad, taps_total;  // partial layout [splits][taps_total][co_pad][ci_pad]
   float* partial;
   int units;
@@ -41,8 +49,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_
   const int warp = threadIdx.x >> 5;
   const uint32_t smem_base = smem_u32(smem);
   const int S = p.stages;
-  const uint32_t stage_bytes = kBoxBytes * (uint32_t)(2 + p.T * p.NB);
-  const uint32_t ones_base = smem_base + (uint32_t)S * stage_bytes;  // 32 pixel rows x 128 B of bf16 1.0
+  const uint32_t stage_bytes = p.halo ? (2 * kBoxBytes + (uint32_t)p.NB * p.b_box_bytes)
+                                     : kBoxBytes * (uint32_t)(2 + p.T * p.NB);
+  const uint32_t ones_base = smem_base + (uint32_t)S * stage_bytes;  // kKP pixel rows x 128 B of bf16 1.0
   const uint32_t bar_base = ones_base + kBoxBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(S + s); };
@@ -66,6 +75,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_
     fence_mbar_init();
     tma_prefetch_desc(&p.tm_dy);
     for (int i = 0; i < B2U_MAX_VIEWS; ++i) tma_prefetch_desc(&p.tm_a[i]);
+    if (p.halo) tma_prefetch_desc(&p.tm_ah[0]);
   }
   {
     // all-ones operand for the bias gradient; written through the generic proxy, read by the tensor core (async proxy)
@@ -83,16 +93,17 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_
   const uint32_t tmem_base = *tmem_slot_ptr;
   const int tiles_xy = p.tiles_x * p.tiles_y;
 
-  // unit -> (split, co tile, inner); inner < n_ci*n_tg: (ci tile, tap group); inner == n_ci*n_tg: bias unit
+  // unit -> (split, co tile, ci tile, tap group).  The bias gradient (row sums of dY = an MMA against an all-ones
+  // operand, 16 extra TMEM columns) rides along with the (ci tile 0, tap group 0) unit, so all units cost the same.
   auto decode = [&](int u, int& split, int& co, int& ci, int& tg, bool& bias) {
     const int per_split = p.n_co * p.inner;
     split = u / per_split;
     const int r = u - split * per_split;
     co = r / p.inner;
     const int in = r - co * p.inner;
-    bias = in >= p.n_ci * p.n_tg;
-    ci = bias ? 0 : in / p.n_tg;
-    tg = bias ? 0 : in - ci * p.n_tg;
+    ci = in / p.n_tg;
+    tg = in - ci * p.n_tg;
+    bias = p.want_bias && ci == 0 && tg == 0;
   };
 
   if (warp == 0) {
@@ -105,10 +116,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_
         bool bias;
         decode(u, split, co, ci, tg, bias);
         const int t0 = tg * p.T;
-        const int nt = bias ? 0 : min(p.T, p.num_taps - t0);
+        const int nt = min(p.T, p.num_taps - t0);
         const int k_begin = split * p.steps_per_split;
         const int k_end = min(p.k_steps, k_begin + p.steps_per_split);
-        const uint32_t bytes = kBoxBytes * (uint32_t)(2 + nt * p.NB);
+        const uint32_t bytes = p.halo ? (2 * kBoxBytes + (uint32_t)p.NB * p.b_box_tx)
+                                      : kBoxBytes * (uint32_t)(2 + nt * p.NB);
         for (int ks = k_begin; ks < k_end; ++ks) {
           const int bn = ks / tiles_xy, rem = ks - bn * tiles_xy;
           const int by = rem / p.tiles_x, bx = rem - by * p.tiles_x;
@@ -118,12 +130,19 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_
           mbar_expect_tx(full_bar(stage), bytes);
           tma_load_4d(base, &p.tm_dy, full_bar(stage), co * 128, x0, y0, n0);
           tma_load_4d(base + kBoxBytes, &p.tm_dy, full_bar(stage), co * 128 + 64, x0, y0, n0);
-          for (int j = 0; j < nt; ++j) {
-            const int t = t0 + j;
-            const CUtensorMap* ma = &p.tm_a[p.tap_a[t]];
+          if (p.halo) {
+            const CUtensorMap* ma = &p.tm_ah[p.tap_a[t0]];
             for (int b = 0; b < p.NB; ++b)
-              tma_load_4d(base + kBoxBytes * (uint32_t)(2 + j * p.NB + b), ma, full_bar(stage), ci * p.BN + b * 64,
-                          x0 + p.tap_dx[t], y0 + p.tap_dy[t], n0);
+              tma_load_4d(base + 2 * kBoxBytes + (uint32_t)b * p.b_box_bytes, ma, full_bar(stage),
+                          ci * p.BN + b * 64, x0 - 1, y0 + p.tap_dy[t0], n0);
+          } else {
+            for (int j = 0; j < nt; ++j) {
+              const int t = t0 + j;
+              const CUtensorMap* ma = &p.tm_a[p.tap_a[t]];
+              for (int b = 0; b < p.NB; ++b)
+                tma_load_4d(base + kBoxBytes * (uint32_t)(2 + j * p.NB + b), ma, full_bar(stage), ci * p.BN + b * 64,
+                            x0 + p.tap_dx[t], y0 + p.tap_dy[t], n0);
+            }
           }
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
@@ -134,34 +153,53 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_
       // ------------------------------------------------------------ MMA issuer
       int stage = 0;
       uint32_t phase = 0, tphase = 0;
+      const uint32_t desc_hi = (uint32_t)(make_smem_desc(0, 0, 1024) >> 32);   // SBO, version, swizzle mode
+      const uint32_t a_lo_const = ((kBoxBytes >> 4) & 0x3FFFu) << 16;           // LBO of the dY operand
+      uint32_t halo_row16[kKP / 16];
+#pragma unroll
+      for (int k = 0; k < kKP / 16; ++k) {
+        const int pix = k * 16;
+        halo_row16[k] = (uint32_t)((pix / p.tw) * p.hw + (pix % p.tw)) * 8u;    // smem row of pixel 16k, in 16-byte units
+      }
       for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
         int split, co, ci, tg;
         bool bias;
         decode(u, split, co, ci, tg, bias);
         const int t0 = tg * p.T;
-        const int nt = bias ? 0 : min(p.T, p.num_taps - t0);
+        const int nt = min(p.T, p.num_taps - t0);
         const int k_begin = split * p.steps_per_split;
         const int k_end = min(p.k_steps, k_begin + p.steps_per_split);
         mbar_wait(tempty_bar, tphase ^ 1u);
         tc_fence_after();
         uint32_t accumulate = 0;
+        // The single issuing thread must sustain one MMA per ~N/2 cycles, so the loop is kept to a few integer ops per
+        // MMA: descriptor high words are constants, the low word is (start >> 4) | (LBO >> 4) << 16.
+        const uint32_t b_lbo = p.halo ? p.b_box_bytes : kBoxBytes;
+        const uint32_t b_lo_const = ((b_lbo >> 4) & 0x3FFFu) << 16;
+        const uint32_t b_first = p.halo ? 2 * kBoxBytes : 2 * kBoxBytes;           // X boxes follow the two dY boxes
+        const uint32_t b_tap_stride16 = p.halo ? 8u : (kBoxBytes * (uint32_t)p.NB) >> 4;  // per tap, in 16-byte units
         for (int ks = k_begin; ks < k_end; ++ks) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t base = smem_base + (uint32_t)stage * stage_bytes;
+          const uint32_t base16 = (smem_base + (uint32_t)stage * stage_bytes) >> 4;
 #pragma unroll
           for (int k = 0; k < kKP / 16; ++k) {
-            // MN-major, SW128: 64-channel groups are LBO = one box apart, 8-pixel groups are SBO = 1024 B apart;
-            // 16 pixels further along K = 16 rows x 128 B = 2048 B.
-            const uint64_t a_desc = make_smem_desc(base + (uint32_t)k * 2048u, kBoxBytes, 1024);
+            // MN-major, SW128: 64-channel groups are LBO apart, 8-pixel groups are SBO = 1024 B apart;
+            // 16 pixels further along K = 16 rows x 128 B = 2048 B (128 x 16 B).
+            const uint64_t a_desc = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo_const | (base16 + (uint32_t)k * 128u));
             if (bias) {
-              const uint64_t b_desc = make_smem_desc(ones_base + (uint32_t)k * 2048u, kBoxBytes, 1024);
-              umma_bf16(tmem_base, a_desc, b_desc, p.idesc_bias, accumulate);
-            } else {
-              for (int j = 0; j < nt; ++j) {
-                const uint64_t b_desc =
-                    make_smem_desc(base + kBoxBytes * (uint32_t)(2 + j * p.NB) + (uint32_t)k * 2048u, kBoxBytes, 1024);
-                umma_bf16(tmem_base + (uint32_t)(j * p.BN), a_desc, b_desc, p.idesc, accumulate);
+              const uint64_t b_desc = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo_const | ((ones_base >> 4) + (uint32_t)k * 128u));
+              umma_bf16(tmem_base + (uint32_t)(p.T * p.BN), a_desc, b_desc, p.idesc_bias, accumulate);
+            }
+            {
+              // halo: pixel 16k of the step -> smem row halo_row16[k]/8 of the (tw+2)-wide box, tap dx adds one row
+              const uint32_t b0 = base16 + (b_first >> 4) + (p.halo ? halo_row16[k] : (uint32_t)k * 128u);
+              uint32_t b_lo = b_lo_const | b0, d_tmem = tmem_base;
+#pragma unroll 1
+              for (int j = 0; j < nt; ++j) {   // a real loop: a fully unrolled body thrashes the instruction cache
+                umma_bf16(d_tmem, a_desc, ((uint64_t)desc_hi << 32) | (uint64_t)b_lo, p.idesc, accumulate);
+                b_lo += b_tap_stride16;
+                d_tmem += (uint32_t)p.BN;
               }
             }
             accumulate = 1;
@@ -183,7 +221,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_
       bool bias;
       decode(u, split, co, ci, tg, bias);
       const int t0 = tg * p.T;
-      const int nt = bias ? 0 : min(p.T, p.num_taps - t0);
+      const int nt = min(p.T, p.num_taps - t0);
       const int k_begin = split * p.steps_per_split;
       const bool empty_range = k_begin >= p.k_steps;
       mbar_wait(tfull_bar, tphase);
@@ -192,12 +230,13 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_
       const int row = co * 128 + e;
       if (bias) {
         uint32_t r[16];
-        tmem_ld16(taddr, r);
+        tmem_ld16(taddr + (uint32_t)(p.T * p.BN), r);
         tmem_ld_wait();
         if (row < p.co_pad)
           p.partial[(((size_t)split * p.taps_total + p.num_taps) * p.co_pad + row) * p.ci_pad] =
               empty_range ? 0.f : __uint_as_float(r[0]);
-      } else {
+      }
+      {
         const int n_groups = (p.BN + 31) >> 5;
         for (int j = 0; j < nt; ++j) {
           float* dst = p.partial + (((size_t)split * p.taps_total + (t0 + j)) * p.co_pad + row) * p.ci_pad + ci * p.BN;
@@ -309,21 +348,39 @@ static int wgrad_fill(const b2u_wgrad_desc* d, b2u_wgrad_plan* plan, bool encode
   }
   p.Cout = d->Cout; p.Cin = d->Cin;
   const int cin16 = round_up(d->Cin, 16);
-  p.n_ci = ceil_div(cin16, 256);
-  p.BN = round_up(ceil_div(cin16, p.n_ci), 16);
-  p.NB = ceil_div(p.BN, 64);
-  int tmax = 512 / p.BN;
-  if (tmax > d->num_taps) tmax = d->num_taps;
-  p.n_tg = ceil_div(d->num_taps, tmax);
-  p.T = ceil_div(d->num_taps, p.n_tg);
+  // x-halo eligibility: a 3x3 stride-1 tap table (t = 3r+s reads view 0 at (r-1, s-1)) over rows at least 16 wide
+  static const bool halo_disabled = getenv("B2U_WGRAD_NO_HALO") != nullptr;  // A/B switch for profiling
+  bool halo = !halo_disabled && d->num_taps == 9 && d->dy.W >= 16;
+  for (int t = 0; halo && t < 9; ++t)
+    halo = d->tap_a[t] == d->tap_a[0] && d->tap_dy[t] == t / 3 - 1 && d->tap_dx[t] == t % 3 - 1;
+  p.halo = halo ? 1 : 0;
+  if (halo) {
+    // three taps (one filter row) accumulate side by side: 3*BN <= 512 TMEM columns
+    p.n_ci = ceil_div(cin16, 160);
+    p.BN = round_up(ceil_div(cin16, p.n_ci), 16);
+    p.NB = ceil_div(p.BN, 64);
+    p.n_tg = 3;
+    p.T = 3;
+  } else {
+    p.n_ci = ceil_div(cin16, 256);
+    p.BN = round_up(ceil_div(cin16, p.n_ci), 16);
+    p.NB = ceil_div(p.BN, 64);
+    int tmax = (512 - (d->want_bias ? 16 : 0)) / p.BN;   // 16 TMEM columns are kept for the bias accumulator
+    if (tmax < 1) tmax = 1;
+    if (tmax > d->num_taps) tmax = d->num_taps;
+    p.n_tg = ceil_div(d->num_taps, tmax);
+    p.T = ceil_div(d->num_taps, p.n_tg);
+  }
   p.n_co = ceil_div(d->Cout, 128);
   p.want_bias = d->want_bias ? 1 : 0;
-  p.inner = p.n_ci * p.n_tg + p.want_bias;
-  // pixel (K) tiling: 32-pixel boxes
+  p.inner = p.n_ci * p.n_tg;
+  B2U_CHECK_ARG(p.T * p.BN + (p.want_bias ? 16 : 0) <= 512, "wgrad: TMEM budget exceeded (T=%d BN=%d)", p.T, p.BN);
+  // pixel (K) tiling: kKP-pixel boxes (x fastest); halo mode needs whole 16-pixel runs inside one image row
   {
     long long best = -1;
     for (int w = kKP; w >= 1; w >>= 1)
       for (int h = kKP / w; h >= 1; h >>= 1) {
+        if (halo && w < 16) continue;
         const int n = kKP / (w * h);
         const long long c = (long long)ceil_div(d->dy.W, w) * ceil_div(d->dy.H, h) * ceil_div(d->dy.N, n);
         if (best < 0 || c < best) {
@@ -333,6 +390,9 @@ static int wgrad_fill(const b2u_wgrad_desc* d, b2u_wgrad_plan* plan, bool encode
       }
     p.k_steps = (int)best;
   }
+  p.hw = p.tw + 2;
+  p.b_box_tx = (uint32_t)(p.hw * p.th * p.tn) * 128u;
+  p.b_box_bytes = (p.b_box_tx + 1023u) & ~1023u;
   const int base_units = p.n_co * p.inner;
   const int sms = encode ? sm_count() : 148;
   int splits = (2 * sms) / base_units;
@@ -343,7 +403,8 @@ static int wgrad_fill(const b2u_wgrad_desc* d, b2u_wgrad_plan* plan, bool encode
   splits = ceil_div(p.k_steps, p.steps_per_split);
   p.splits = splits;
   p.units = splits * base_units;
-  const uint32_t stage_bytes = kBoxBytes * (uint32_t)(2 + p.T * p.NB);
+  const uint32_t stage_bytes = halo ? (2 * kBoxBytes + (uint32_t)p.NB * p.b_box_bytes)
+                                    : kBoxBytes * (uint32_t)(2 + p.T * p.NB);
   int stages = (int)((232448u - kBoxBytes - 256u) / stage_bytes);
   if (stages > 8) stages = 8;
   B2U_CHECK_ARG(stages >= 2, "wgrad: not enough shared memory");
@@ -373,6 +434,13 @@ static int wgrad_fill(const b2u_wgrad_desc* d, b2u_wgrad_plan* plan, bool encode
       if (rc) return rc;
     }
     for (int i = d->num_a; i < B2U_MAX_VIEWS; ++i) p.tm_a[i] = p.tm_a[0];
+    for (int i = 0; i < B2U_MAX_VIEWS; ++i) p.tm_ah[i] = p.tm_a[i];
+    if (p.halo) {
+      for (int i = 0; i < d->num_a; ++i) {
+        rc = view_tmap(&p.tm_ah[i], d->a[i], 64, (uint32_t)p.hw, (uint32_t)p.th, (uint32_t)p.tn);
+        if (rc) return rc;
+      }
+    }
   }
   return B2U_OK;
 }
