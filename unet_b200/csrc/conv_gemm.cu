@@ -5,6 +5,8 @@
 //
 // Replaces F.conv2d / cudnnConvolutionForward / cudnnConvolutionBackwardData as reached from fastai's ConvLayer,
 // ResBlock, UnetBlock and PixelShuffle_ICNR (reference train.py:128,141; SURVEY.md 8(a) layer table).
+#include <stdlib.h>
+
 #include "host_util.h"
 #include "ptx.cuh"
 
@@ -25,6 +27,13 @@ struct ConvParams {
   int8_t tap_a[B2U_MAX_TAPS], tap_dy[B2U_MAX_TAPS], tap_dx[B2U_MAX_TAPS], tap_w[B2U_MAX_TAPS];
   int tw, th, tn, tiles_x, tiles_y;
   int m_tiles, n_tiles, BN, stages;
+  // halo mode (3x3 stride-1): ONE TMA box of (tw+2) x (th+2) pixels per (tile, 64-channel chunk) serves all nine taps;
+  // tap (dy,dx) is the same smem tile addressed from row (dy+1)*(tw+2) + dx+1 with SBO = (tw+2)*128 (tiles are 8 wide, so
+  // every 8-row group of the M dimension is one image row).  The UMMA swizzle phase follows the absolute smem address
+  // (profiles/r01_swizzle_offset_probe.txt).  A and B have separate rings: SA halo stages, SB weight stages.
+  int halo, SA, SB, hw;
+  uint32_t a_stage_bytes, a_tx_bytes;
+  CUtensorMap tm_ah;
   uint32_t idesc;
   int N, Ho, Wo, Cout, CoutP8;
   const float* scale;
@@ -86,27 +95,31 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   const uint32_t b_bytes = (uint32_t)p.BN * 128u;
   const uint32_t stage_bytes = kABytes + b_bytes;
   const int S = p.stages;
-  const uint32_t stg_base = smem_base + (uint32_t)S * stage_bytes;
+  const uint32_t ring_bytes = p.halo ? ((uint32_t)p.SA * p.a_stage_bytes + (uint32_t)p.SB * b_bytes) : (uint32_t)S * stage_bytes;
+  const int n_ring_bars = p.halo ? 2 * (p.SA + p.SB) : 2 * S;
+  const uint32_t stg_base = smem_base + ring_bytes;
   const uint32_t aux_base = stg_base + 2 * kStagingBytes;  // n_aux x 2 x 16 KB, double buffered per output chunk
   const uint32_t bar_base = aux_base + (uint32_t)p.n_aux * 2 * kStagingBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(S + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (uint32_t)(2 * S + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (uint32_t)(2 * S + 2 + a); };
-  auto aux_bar = [&](int b) { return bar_base + 8u * (uint32_t)(2 * S + 4 + b); };
-  const uint32_t tmem_slot = bar_base + 8u * (uint32_t)(2 * S + 6);
+  // halo-mode ring barriers: fullA[SA] emptyA[SA] fullB[SB] emptyB[SB]
+  auto fullA = [&](int s) { return bar_base + 8u * (uint32_t)s; };
+  auto emptyA = [&](int s) { return bar_base + 8u * (uint32_t)(p.SA + s); };
+  auto fullB = [&](int s) { return bar_base + 8u * (uint32_t)(2 * p.SA + s); };
+  auto emptyB = [&](int s) { return bar_base + 8u * (uint32_t)(2 * p.SA + p.SB + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (uint32_t)(n_ring_bars + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (uint32_t)(n_ring_bars + 2 + a); };
+  auto aux_bar = [&](int b) { return bar_base + 8u * (uint32_t)(n_ring_bars + 4 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (uint32_t)(n_ring_bars + 6);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
-      smem + (size_t)S * stage_bytes + (size_t)(2 + 2 * p.n_aux) * kStagingBytes + 8 * (2 * S + 6));
+      smem + (size_t)ring_bytes + (size_t)(2 + 2 * p.n_aux) * kStagingBytes + 8 * (n_ring_bars + 6));
 
   if (threadIdx.x == 0) {
     if (smem_base & 1023u) {
       printf("b2u: dynamic smem base 0x%x not 1024-byte aligned\n", smem_base);
       __trap();
     }
-    for (int s = 0; s < S; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
-    }
+    for (int s = 0; s < n_ring_bars; ++s) mbar_init(bar_base + 8u * (uint32_t)s, 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), 128);
@@ -119,6 +132,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     tma_prefetch_desc(&p.tm_b);
     tma_prefetch_desc(&p.tm_out);
     for (int i = 0; i < p.n_aux; ++i) tma_prefetch_desc(&p.tm_aux[i]);
+    if (p.halo) tma_prefetch_desc(&p.tm_ah);
   }
   if (warp == 2) {
     tmem_alloc(tmem_slot, kTmemCols);
@@ -133,7 +147,31 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   const int tiles_xy = p.tiles_x * p.tiles_y;
 
   if (warp == 0) {
-    if (elect_one()) {
+    const bool elected = elect_one();
+    if (elected && p.halo) {
+      // ------------------------------------------------------------ TMA producer, halo mode
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      const uint32_t b_ring = smem_base + (uint32_t)p.SA * p.a_stage_bytes;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m = tile / p.n_tiles, nt = tile - m * p.n_tiles;
+        const int bn = m / tiles_xy, rem = m - bn * tiles_xy;
+        const int by = rem / p.tiles_x, bx = rem - by * p.tiles_x;
+        const int x0 = bx * p.tw, y0 = by * p.th, n0 = bn * p.tn;
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          mbar_wait(emptyA(sa), pa ^ 1u);
+          mbar_expect_tx(fullA(sa), p.a_tx_bytes);
+          tma_load_4d(smem_base + (uint32_t)sa * p.a_stage_bytes, &p.tm_ah, fullA(sa), kc * 64, x0 - 1, y0 - 1, n0);
+          if (++sa == p.SA) { sa = 0; pa ^= 1u; }
+          for (int t = 0; t < p.num_taps; ++t) {
+            mbar_wait(emptyB(sb), pb ^ 1u);
+            mbar_expect_tx(fullB(sb), b_bytes);
+            tma_load_3d(b_ring + (uint32_t)sb * b_bytes, &p.tm_b, fullB(sb), kc * 64, p.tap_w[t], nt * p.BN);
+            if (++sb == p.SB) { sb = 0; pb ^= 1u; }
+          }
+        }
+      }
+    } else if (elected) {
       // ------------------------------------------------------------ TMA producer
       int stage = 0;
       uint32_t phase = 0;
@@ -157,7 +195,50 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       }
     }
   } else if (warp == 1) {
-    if (elect_one()) {
+    const bool elected = elect_one();
+    if (elected && p.halo) {
+      // ------------------------------------------------------------ MMA issuer, halo mode (single thread)
+      int sa = 0, sb = 0, acc = 0;
+      uint32_t pa = 0, pb = 0, acc_phase = 0;
+      const uint32_t b_ring = smem_base + (uint32_t)p.SA * p.a_stage_bytes;
+      const uint32_t hiA = (uint32_t)(make_smem_desc(0, 0, (uint32_t)p.hw * 128u) >> 32);  // SBO = one halo row
+      const uint32_t hiB = (uint32_t)(make_smem_desc(0, 0, 1024) >> 32);
+      const uint32_t lo_const = 1u << 16;  // LBO field (unused for K-major swizzled operands)
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccStride;
+        uint32_t accumulate = 0;
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          mbar_wait(fullA(sa), pa);
+          tc_fence_after();
+          const uint32_t a16 = (smem_base + (uint32_t)sa * p.a_stage_bytes) >> 4;
+          const int nm = (kc == p.k_chunks - 1) ? p.last_mmas : 4;
+#pragma unroll 1
+          for (int t = 0; t < p.num_taps; ++t) {
+            mbar_wait(fullB(sb), pb);
+            tc_fence_after();
+            // tap (dy,dx): the halo tile read from pixel row (dy+1)*(tw+2) + (dx+1); 8 x 16-byte units per 128-byte row
+            uint32_t a_lo = lo_const | (a16 + (uint32_t)((p.tap_dy[t] + 1) * p.hw + p.tap_dx[t] + 1) * 8u);
+            uint32_t b_lo = lo_const | ((b_ring + (uint32_t)sb * b_bytes) >> 4);
+#pragma unroll 1
+            for (int k = 0; k < nm; ++k) {
+              umma_bf16(d_tmem, ((uint64_t)hiA << 32) | a_lo, ((uint64_t)hiB << 32) | b_lo, p.idesc, accumulate);
+              accumulate = 1;
+              a_lo += 2;  // 16 bf16 = 32 bytes along K inside the swizzle atom
+              b_lo += 2;
+            }
+            umma_commit(emptyB(sb));
+            if (++sb == p.SB) { sb = 0; pb ^= 1u; }
+          }
+          umma_commit(emptyA(sa));
+          if (++sa == p.SA) { sa = 0; pa ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    } else if (elected) {
       // ------------------------------------------------------------ MMA issuer (single thread)
       int stage = 0;
       uint32_t phase = 0;
@@ -456,6 +537,16 @@ static int conv_plan_fill(const b2u_conv_desc* d, b2u_conv_plan* plan, bool enco
   else { n_tiles = ceil_div(Cout, 256); BN = round_up(ceil_div(Cout, n_tiles), 64); n_tiles = ceil_div(Cout, BN); }
   int tw, th, tn, tx, ty, tb;
   pick_m_tile(d->out.N, d->out.H, d->out.W, &tw, &th, &tn, &tx, &ty, &tb);
+  // halo mode: 3x3 stride-1 tap table over a single view (fprop and dgrad of the 3x3 convolutions), images >= 16 x 8
+  static const bool halo_disabled = getenv("B2U_CONV_NO_HALO") != nullptr;  // A/B switch for profiling
+  bool halo = !halo_disabled && d->num_taps == 9 && d->num_a == 1 && d->out.H >= 16 && d->out.W >= 8;
+  for (int t = 0; halo && t < 9; ++t) halo = d->tap_a[t] == 0 && d->tap_dy[t] == t / 3 - 1 && d->tap_dx[t] == t % 3 - 1;
+  if (halo) {
+    tw = 8; th = 16; tn = 1;
+    tx = ceil_div(d->out.W, tw); ty = ceil_div(d->out.H, th); tb = d->out.N;
+  }
+  p.halo = halo ? 1 : 0;
+  p.hw = tw + 2;
   p.tw = tw; p.th = th; p.tn = tn; p.tiles_x = tx; p.tiles_y = ty;
   p.m_tiles = tx * ty * tb; p.n_tiles = n_tiles; p.BN = BN;
   p.num_taps = d->num_taps;
@@ -469,12 +560,28 @@ static int conv_plan_fill(const b2u_conv_desc* d, b2u_conv_plan* plan, bool enco
   B2U_CHECK_ARG(!d->res_mask.ptr || d->res.ptr, "conv: res_mask without res");
   p.n_aux = n_aux;
   const uint32_t stage_bytes = kABytes + (uint32_t)BN * 128u;
-  const uint32_t fixed = (2 + 2 * (uint32_t)n_aux) * kStagingBytes + 256;
-  int stages = (int)((232448u - fixed) / stage_bytes);
-  if (stages > 8) stages = 8;
-  B2U_CHECK_ARG(stages >= 2, "conv: not enough shared memory for 2 stages");
+  const uint32_t fixed = (2 + 2 * (uint32_t)n_aux) * kStagingBytes + 512;
+  int stages;
+  if (halo) {
+    p.a_tx_bytes = (uint32_t)((tw + 2) * (th + 2)) * 128u;
+    p.a_stage_bytes = (p.a_tx_bytes + 1023u) & ~1023u;
+    const uint32_t bb = (uint32_t)BN * 128u;
+    const uint32_t avail = 232448u - fixed;
+    p.SA = 3;
+    int sb = (int)((avail - (uint32_t)p.SA * p.a_stage_bytes) / bb);
+    if (sb < 4) { p.SA = 2; sb = (int)((avail - (uint32_t)p.SA * p.a_stage_bytes) / bb); }
+    if (sb > 10) sb = 10;
+    B2U_CHECK_ARG(sb >= 2, "conv(halo): not enough shared memory");
+    p.SB = sb;
+    stages = sb;
+    plan->smem_bytes = (size_t)p.SA * p.a_stage_bytes + (size_t)sb * bb + fixed;
+  } else {
+    stages = (int)((232448u - fixed) / stage_bytes);
+    if (stages > 8) stages = 8;
+    B2U_CHECK_ARG(stages >= 2, "conv: not enough shared memory for 2 stages");
+    plan->smem_bytes = (size_t)stages * stage_bytes + fixed;
+  }
   p.stages = stages;
-  plan->smem_bytes = (size_t)stages * stage_bytes + fixed;
   // at least half of the SM's shared memory, so that exactly one CTA (and its 512 TMEM columns) lives on an SM
   if (plan->smem_bytes < 120 * 1024) plan->smem_bytes = 120 * 1024;
   p.idesc = make_idesc_bf16(128, BN, 0, 0);
@@ -499,6 +606,11 @@ static int conv_plan_fill(const b2u_conv_desc* d, b2u_conv_plan* plan, bool enco
       if (rc) return rc;
     }
     for (int i = d->num_a; i < B2U_MAX_VIEWS; ++i) p.tm_a[i] = p.tm_a[0];
+    p.tm_ah = p.tm_a[0];
+    if (halo) {
+      int rc = view_tmap(&p.tm_ah, d->a[0], 64, (uint32_t)(tw + 2), (uint32_t)(th + 2), 1);
+      if (rc) return rc;
+    }
     {
       const int cin_ext = round_up(Cin, 16) <= d->w_cinp ? round_up(Cin, 16) : (round_up(Cin, 8) <= d->w_cinp ? round_up(Cin, 8) : Cin);
       uint64_t dims[3] = {(uint64_t)cin_ext, (uint64_t)d->w_taps, (uint64_t)d->w_rows};
