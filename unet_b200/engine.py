@@ -82,13 +82,21 @@ class Trainer:
             dist.all_reduce(g[start:min(n, start + self.bucket_elems)], op=dist.ReduceOp.SUM)
 
     def _device_step(self) -> None:
+        self._fwd_bwd()
+        self._allreduce()
+        self._update()
+
+    def _fwd_bwd(self) -> None:
         net = self.net
         s = ops.stream_ptr()
         net.set_input(self.x_static, s)
         net.forward(s)
         net.loss_and_grad(s)
         net.backward(s)
-        self._allreduce()
+
+    def _update(self) -> None:
+        net = self.net
+        s = ops.stream_ptr()
         if self.optimizer == "sgd":
             _lib.check(net.lib.b2u_sgd_step(net.params.data_ptr(), net.grads.data_ptr(), net.layout.total, self.lr,
                                             1.0 / self.world, s), "b2u_sgd_step")
@@ -119,9 +127,18 @@ class Trainer:
             self.net._stage_weights(ops.stream_ptr())
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        # NCCL stays OUT of the graphs (an eager collective after a captured one dead-locked on this stack): with
+        # N > 1 the step is graph(fwd+loss+bwd) -> eager bucketed all-reduce -> graph(optimizer + weight staging)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self._device_step()
+        if self.world == 1:
+            with torch.cuda.graph(self.graph):
+                self._device_step()
+        else:
+            with torch.cuda.graph(self.graph):
+                self._fwd_bwd()
+            self.graph_update = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_update, pool=self.graph.pool()):
+                self._update()
 
     def step(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
         """x: uint8 [N,C,H,W] (host pinned or device), y: uint8/int64 [N,H,W]. Returns the device loss scalar of this
@@ -134,6 +151,9 @@ class Trainer:
                 self.x_static.copy_(x, non_blocking=True)
                 self.net.labels.copy_(y if y.dtype == torch.uint8 else y.to(torch.uint8), non_blocking=True)
             self.graph.replay()
+            if self.world > 1:
+                self._allreduce()
+                self.graph_update.replay()
         else:
             self._device_step()
         self.step_count += 1
