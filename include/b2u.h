@@ -75,7 +75,7 @@ typedef struct b2u_conv_desc {
   b2u_view res_mask;  /* ptr NULL = none */
   b2u_view zmask;     /* ptr NULL = none */
   uint32_t flags;
-  float* stats;       /* B2U_EPI_STATS: [4*m_tiles][2][stats_ld] fp32 partials */
+  float* stats;       /* B2U_EPI_STATS: [info.stats_rows][2][stats_ld] fp32 partials (zero-initialised by the caller) */
   int32_t stats_ld;
   float* out_f32;     /* B2U_EPI_OUT_F32 */
   int32_t out_f32_ld;
@@ -83,7 +83,7 @@ typedef struct b2u_conv_desc {
 
 typedef struct b2u_conv_info {
   int32_t m_tiles, n_tiles, block_n, tile_w, tile_h, tile_n, stages, k_chunks, grid;
-  int32_t stats_rows; /* = 4*m_tiles: rows of the stats partial buffer */
+  int32_t stats_rows; /* rows of the stats partial buffer: 4 per CTA (on-chip accumulation) or 4 per M tile */
 } b2u_conv_info;
 
 typedef struct b2u_conv_plan b2u_conv_plan;

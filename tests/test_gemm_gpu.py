@@ -246,3 +246,28 @@ def test_wgrad_s2():
     plan.run()
     torch.cuda.synchronize()
     assert rel_err(dw, ref) <= 2e-3
+
+
+@pytest.mark.parametrize("N,Cin,Cout,H,W,stride", [(8, 64, 128, 64, 64, 1), (6, 32, 64, 128, 128, 1), (8, 64, 128, 64, 64, 2),
+                                                    (4, 256, 512, 32, 32, 2)])
+def test_conv_stats_many_tiles_per_cta(N, Cin, Cout, H, W, stride):
+    """BN partial sums accumulated on chip over all tiles of a persistent CTA (more tiles than SMs), one and two N tiles."""
+    from unet_b200 import ops
+    x = rnd(N, Cin, H, W, seed=1)
+    w = rnd(Cout, Cin, 3, 3, seed=2, scale=(Cin * 9) ** -0.5)
+    ref = F.conv2d(x, w, None, stride=stride, padding=1)
+    xa = to_nhwc(x)
+    ya = torch.zeros((N, H // stride, W // stride, ops.padc(Cout)), dtype=torch.bfloat16, device="cuda")
+    if stride == 1:
+        views, taps = [ops.view_nhwc(xa, Cin)], ops.taps_conv(3)
+    else:
+        views, taps = [ops.view_nhwc(xa, Cin, parity=(py, px)) for py in range(2) for px in range(2)], ops.taps_conv3_s2()
+    plan = ops.ConvPlan(views, ops.view_nhwc(ya, Cout), gemm_weights(w), Cin, taps, stats=True)
+    plan.run()
+    plan.run()     # a second launch must not accumulate onto the first
+    torch.cuda.synchronize()
+    got = ya[..., :Cout].permute(0, 3, 1, 2).float()
+    assert rel_err(got, ref) <= 1e-2
+    s = plan.stats.double().sum(0)
+    assert rel_err(s[0, :Cout].float(), got.double().sum((0, 2, 3)).float()) <= 1e-4, plan.stats.shape
+    assert rel_err(s[1, :Cout].float(), (got.double() ** 2).sum((0, 2, 3)).float()) <= 1e-4

@@ -31,6 +31,7 @@ struct ConvParams {
   // tap (dy,dx) is the same smem tile addressed from row (dy+1)*(tw+2) + dx+1 with SBO = (tw+2)*128 (tiles are 8 wide, so
   // every 8-row group of the M dimension is one image row).  The UMMA swizzle phase follows the absolute smem address
   // (profiles/r01_swizzle_offset_probe.txt).  A and B have separate rings: SA halo stages, SB weight stages.
+  int stats_cols;  // > 0: BN partial sums are accumulated per warp in smem over all tiles of the CTA (4*grid rows)
   int halo, SA, SB, hw;
   uint32_t a_stage_bytes, a_tx_bytes;
   CUtensorMap tm_ah;
@@ -114,6 +115,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
       smem + (size_t)ring_bytes + (size_t)(2 + 2 * p.n_aux) * kStagingBytes + 8 * (n_ring_bars + 6));
 
+  float* s_stats = reinterpret_cast<float*>(smem + (size_t)ring_bytes + (size_t)(2 + 2 * p.n_aux) * kStagingBytes + 512);
+  for (int i = threadIdx.x; i < 8 * p.stats_cols; i += kThreads) s_stats[i] = 0.f;
   if (threadIdx.x == 0) {
     if (smem_base & 1023u) {
       printf("b2u: dynamic smem base 0x%x not 1024-byte aligned\n", smem_base);
@@ -448,7 +451,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           const float sum = warp_transpose_reduce(s1, lane);
           const float sq = warp_transpose_reduce(s2, lane);
           const int c = c0 + lane;
-          if (c < p.stats_ld) {
+          if (p.stats_cols > 0) {
+            if (c < p.stats_cols) {   // this warp's private accumulators: no race, fixed (tile) order
+              s_stats[(ewarp * 2 + 0) * p.stats_cols + c] += sum;
+              s_stats[(ewarp * 2 + 1) * p.stats_cols + c] += sq;
+            }
+          } else if (c < p.stats_ld) {
             float* sp = p.stats + (size_t)(m * 4 + ewarp) * 2 * p.stats_ld;
             sp[c] = sum;
             sp[p.stats_ld + c] = sq;
@@ -461,6 +469,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       if (acc == 0) acc_phase ^= 1u;
     }
     if (e == 0 && !out_f32) tma_store_wait_all<0>();
+    if (do_stats && p.stats_cols > 0) {
+      float* sp = p.stats + (size_t)(blockIdx.x * 4 + ewarp) * 2 * p.stats_ld;
+      for (int c = lane; c < p.stats_cols && c < p.stats_ld; c += 32) {
+        sp[c] = s_stats[(ewarp * 2 + 0) * p.stats_cols + c];
+        sp[p.stats_ld + c] = s_stats[(ewarp * 2 + 1) * p.stats_cols + c];
+      }
+    }
   }
 
   tc_fence_before();
@@ -526,7 +541,7 @@ static int conv_plan_fill(const b2u_conv_desc* d, b2u_conv_plan* plan, bool enco
     B2U_CHECK_ARG(d->tap_a[t] >= 0 && d->tap_a[t] < d->num_a, "conv: tap %d view index out of range", t);
     B2U_CHECK_ARG(d->tap_w[t] >= 0 && d->tap_w[t] < d->w_taps, "conv: tap %d weight index out of range", t);
   }
-  if (d->flags & B2U_EPI_STATS) B2U_CHECK_ARG(d->stats != nullptr && !out_f32, "conv: stats needs a buffer and bf16 output");
+  if (d->flags & B2U_EPI_STATS) B2U_CHECK_ARG((d->stats != nullptr || !encode) && !out_f32, "conv: stats needs a buffer and bf16 output");
 
   ConvParams& p = plan->p;
   memset(&p, 0, sizeof(p));
@@ -560,7 +575,8 @@ static int conv_plan_fill(const b2u_conv_desc* d, b2u_conv_plan* plan, bool enco
   B2U_CHECK_ARG(!d->res_mask.ptr || d->res.ptr, "conv: res_mask without res");
   p.n_aux = n_aux;
   const uint32_t stage_bytes = kABytes + (uint32_t)BN * 128u;
-  const uint32_t fixed = (2 + 2 * (uint32_t)n_aux) * kStagingBytes + 512;
+  p.stats_cols = ((d->flags & B2U_EPI_STATS) && n_tiles * BN <= 512) ? n_tiles * BN : 0;
+  const uint32_t fixed = (2 + 2 * (uint32_t)n_aux) * kStagingBytes + 512 + (uint32_t)p.stats_cols * 32u;
   int stages;
   if (halo) {
     p.a_tx_bytes = (uint32_t)((tw + 2) * (th + 2)) * 128u;
@@ -591,14 +607,16 @@ static int conv_plan_fill(const b2u_conv_desc* d, b2u_conv_plan* plan, bool enco
   p.res = ev(d->res); p.res_mask = ev(d->res_mask); p.zmask = ev(d->zmask);
   p.flags = d->flags; p.stats = d->stats; p.stats_ld = d->stats_ld;
   p.out_f32 = d->out_f32; p.out_f32_ld = d->out_f32_ld;
-  if (d->flags & B2U_EPI_STATS) B2U_CHECK_ARG(d->stats_ld >= Cout, "conv: stats_ld=%d < Cout=%d", d->stats_ld, Cout);
+  if ((d->flags & B2U_EPI_STATS) && encode) B2U_CHECK_ARG(d->stats_ld >= Cout, "conv: stats_ld=%d < Cout=%d", d->stats_ld, Cout);
 
   b2u_conv_info& info = plan->info;
   info.m_tiles = p.m_tiles; info.n_tiles = n_tiles; info.block_n = BN; info.tile_w = tw; info.tile_h = th; info.tile_n = tn;
-  info.stages = stages; info.k_chunks = p.k_chunks; info.stats_rows = 4 * p.m_tiles;
+  info.stages = stages; info.k_chunks = p.k_chunks;
   const int total = p.m_tiles * n_tiles;
   const int sms = encode ? sm_count() : 148;
   info.grid = total < sms ? total : sms;
+  // rows of the statistics partial buffer: one per (CTA, epilogue warp) when accumulated on chip, else per (tile, warp)
+  info.stats_rows = p.stats_cols > 0 ? 4 * (total < 148 ? total : 148) : 4 * p.m_tiles;
 
   if (encode) {
     for (int i = 0; i < d->num_a; ++i) {

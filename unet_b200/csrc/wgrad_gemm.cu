@@ -276,45 +276,45 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_
 }
 
 // dw[perm(co)][ci][kidx] = alpha * sum_{t: tap_kidx[t]==kidx} sum_s partial[s][t][co][ci]
-// block = 32 input channels x 8 split lanes; one block row per (co, kidx).  Each lane sums its splits in ascending order,
-// lanes are combined in ascending order: the result does not depend on scheduling.
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int taps, int taps_total, int co_pad,
-                                    int ci_pad, int Cout, int Cin, int ksize, const int* __restrict__ tap_kidx,
-                                    const int* __restrict__ row_perm, float alpha, float* __restrict__ dw,
-                                    float* __restrict__ db) {
-  __shared__ float sh[8][33];
-  const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
+// block = 32 input channels x 32 split lanes (1024 threads); one block per (co, kidx, 32-channel group).  Each lane sums
+// its splits in ascending order and the lanes are combined by a fixed tree: the result does not depend on scheduling.
+__global__ void __launch_bounds__(1024) wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int taps,
+                                                            int taps_total, int co_pad, int ci_pad, int Cout, int Cin,
+                                                            int ksize, const int* __restrict__ tap_kidx,
+                                                            const int* __restrict__ row_perm, float alpha,
+                                                            float* __restrict__ dw, float* __restrict__ db) {
+  __shared__ float sh[32][33];
+  const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5, L = blockDim.x >> 5;  // L split lanes (power of two)
   const int co = blockIdx.y / ksize, kidx = blockIdx.y - co * ksize;
   const int ci = blockIdx.x * 32 + lane;
+  const size_t sstride = (size_t)taps_total * co_pad * ci_pad;
   float acc = 0.f;
   if (ci < Cin) {
     for (int t = 0; t < taps; ++t) {
       if (tap_kidx[t] != kidx) continue;
       const float* src = partial + ((size_t)t * co_pad + co) * ci_pad + ci;
-      const size_t sstride = (size_t)taps_total * co_pad * ci_pad;
-      for (int s = sl; s < splits; s += 8) acc += src[(size_t)s * sstride];
+      for (int s = sl; s < splits; s += L) acc += src[(size_t)s * sstride];
     }
   }
   sh[sl][lane] = acc;
   __syncthreads();
+  for (int o = L >> 1; o > 0; o >>= 1) {
+    if (sl < o) sh[sl][lane] += sh[sl + o][lane];
+    __syncthreads();
+  }
   if (sl == 0 && ci < Cin) {
-    float r = sh[0][lane];
-#pragma unroll
-    for (int q = 1; q < 8; ++q) r += sh[q][lane];
     const int oc = row_perm ? row_perm[co] : co;
-    dw[((size_t)oc * Cin + ci) * ksize + kidx] = alpha * r;
+    dw[((size_t)oc * Cin + ci) * ksize + kidx] = alpha * sh[0][lane];
   }
   // bias gradient: column 0 of the extra "tap" slot; handled by the (kidx == 0, first ci block) blocks
   if (db && kidx == 0 && blockIdx.x == 0) {
-    __syncthreads();
+    __shared__ float shb[1024];
     float b = 0.f;
-    for (int s = threadIdx.x; s < splits; s += 256)
-      b += partial[(((size_t)s * taps_total + taps) * co_pad + co) * ci_pad];
-    // fixed-order tree over the 256 threads
-    __shared__ float shb[256];
+    for (int s = threadIdx.x; s < splits; s += blockDim.x)
+      b += partial[((size_t)s * taps_total + taps) * co_pad * ci_pad + (size_t)co * ci_pad];
     shb[threadIdx.x] = b;
     __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
+    for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
       if ((int)threadIdx.x < o) shb[threadIdx.x] += shb[threadIdx.x + o];
       __syncthreads();
     }
@@ -484,7 +484,9 @@ extern "C" int b2u_wgrad_reduce(const float* partial, int32_t splits, int32_t ta
   B2U_CHECK_ARG(partial && dw && tap_kidx, "wgrad_reduce: null argument");
   B2U_CHECK_ARG(!db || has_bias_cols, "wgrad_reduce: db requested but the partial buffer has no bias slot");
   dim3 grid((unsigned)ceil_div(Cin, 32), (unsigned)(Cout * ksize));
-  wgrad_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+  int lanes = 1;
+  while (lanes < 32 && lanes * 4 < splits) lanes <<= 1;   // ~4 sequential loads per lane
+  wgrad_reduce_kernel<<<grid, 32 * lanes, 0, (cudaStream_t)stream>>>(
       partial, splits, taps, taps + (has_bias_cols ? 1 : 0), co_pad, ci_pad, Cout, Cin, ksize, tap_kidx, row_perm,
       alpha, dw, db);
   B2U_LAUNCH_CHECK();

@@ -160,6 +160,7 @@ class ConvPlan:
         self.stats = None
         if stats:
             info = ConvInfo()
+            d.flags = flags | _lib.EPI_STATS   # the partial-row count depends on the statistics mode: query WITH the flag
             _lib.check(lib.b2u_conv_query(C.byref(d), C.byref(info)), "b2u_conv_query")
             ld = stats_ld or padc(out_view.C)
             self.stats = torch.zeros((info.stats_rows, 2, ld), dtype=torch.float32, device=w.device)
