@@ -198,78 +198,81 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       }
     }
   } else if (warp == 1) {
-    const bool elected = elect_one();
-    if (elected && p.halo) {
-      // ------------------------------------------------------------ MMA issuer, halo mode (single thread)
-      int sa = 0, sb = 0, acc = 0;
-      uint32_t pa = 0, pb = 0, acc_phase = 0;
+    // ------------------------------------------------------------ MMA issuer
+    // The whole warp runs the loop convergently (waits included); only the leader lane's tcgen05 instructions execute.
+    const uint32_t leader = elect_one() ? 1u : 0u;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const uint32_t lo_const = 1u << 16;  // LBO field (unused for K-major swizzled operands)
+    const uint32_t hiB = (uint32_t)(make_smem_desc(0, 0, 1024) >> 32);
+    if (p.halo) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
       const uint32_t b_ring = smem_base + (uint32_t)p.SA * p.a_stage_bytes;
       const uint32_t hiA = (uint32_t)(make_smem_desc(0, 0, (uint32_t)p.hw * 128u) >> 32);  // SBO = one halo row
-      const uint32_t hiB = (uint32_t)(make_smem_desc(0, 0, 1024) >> 32);
-      const uint32_t lo_const = 1u << 16;  // LBO field (unused for K-major swizzled operands)
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        mbar_wait_warp(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccStride;
         uint32_t accumulate = 0;
         for (int kc = 0; kc < p.k_chunks; ++kc) {
-          mbar_wait(fullA(sa), pa);
-          tc_fence_after();
+          mbar_wait_warp(fullA(sa), pa);
           const uint32_t a16 = (smem_base + (uint32_t)sa * p.a_stage_bytes) >> 4;
           const int nm = (kc == p.k_chunks - 1) ? p.last_mmas : 4;
 #pragma unroll 1
           for (int t = 0; t < p.num_taps; ++t) {
-            mbar_wait(fullB(sb), pb);
+            mbar_wait_warp(fullB(sb), pb);
             tc_fence_after();
             // tap (dy,dx): the halo tile read from pixel row (dy+1)*(tw+2) + (dx+1); 8 x 16-byte units per 128-byte row
-            uint32_t a_lo = lo_const | (a16 + (uint32_t)((p.tap_dy[t] + 1) * p.hw + p.tap_dx[t] + 1) * 8u);
-            uint32_t b_lo = lo_const | ((b_ring + (uint32_t)sb * b_bytes) >> 4);
-#pragma unroll 1
-            for (int k = 0; k < nm; ++k) {
-              umma_bf16(d_tmem, ((uint64_t)hiA << 32) | a_lo, ((uint64_t)hiB << 32) | b_lo, p.idesc, accumulate);
-              accumulate = 1;
-              a_lo += 2;  // 16 bf16 = 32 bytes along K inside the swizzle atom
-              b_lo += 2;
+            const uint32_t a_lo = lo_const | (a16 + (uint32_t)((p.tap_dy[t] + 1) * p.hw + p.tap_dx[t] + 1) * 8u);
+            const uint32_t b_lo = lo_const | ((b_ring + (uint32_t)sb * b_bytes) >> 4);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (k < nm) {
+                // 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+                umma_bf16_if(leader, d_tmem, ((uint64_t)hiA << 32) | (a_lo + 2u * k), ((uint64_t)hiB << 32) | (b_lo + 2u * k),
+                             p.idesc, accumulate);
+                accumulate = 1;
+              }
             }
-            umma_commit(emptyB(sb));
+            umma_commit_if(leader, emptyB(sb));
             if (++sb == p.SB) { sb = 0; pb ^= 1u; }
           }
-          umma_commit(emptyA(sa));
+          umma_commit_if(leader, emptyA(sa));
           if (++sa == p.SA) { sa = 0; pa ^= 1u; }
         }
-        umma_commit(tfull_bar(acc));
+        umma_commit_if(leader, tfull_bar(acc));
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
-    } else if (elected) {
-      // ------------------------------------------------------------ MMA issuer (single thread)
+    } else {
       int stage = 0;
       uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        mbar_wait_warp(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccStride;
         uint32_t accumulate = 0;
         for (int t = 0; t < p.num_taps; ++t) {
           for (int kc = 0; kc < p.k_chunks; ++kc) {
-            mbar_wait(full_bar(stage), phase);
+            mbar_wait_warp(full_bar(stage), phase);
             tc_fence_after();
             const uint32_t a_addr = smem_base + (uint32_t)stage * stage_bytes;
-            const uint64_t a_desc = make_smem_desc(a_addr, 16, 1024);
-            const uint64_t b_desc = make_smem_desc(a_addr + kABytes, 16, 1024);
+            const uint32_t a_lo = lo_const | (a_addr >> 4), b_lo = lo_const | ((a_addr + kABytes) >> 4);
             const int nm = (kc == p.k_chunks - 1) ? p.last_mmas : 4;
-            for (int k = 0; k < nm; ++k) {
-              // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in the (addr>>4) field
-              umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, accumulate);
-              accumulate = 1;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (k < nm) {
+                umma_bf16_if(leader, d_tmem, ((uint64_t)hiB << 32) | (a_lo + 2u * k), ((uint64_t)hiB << 32) | (b_lo + 2u * k),
+                             p.idesc, accumulate);
+                accumulate = 1;
+              }
             }
-            umma_commit(empty_bar(stage));
+            umma_commit_if(leader, empty_bar(stage));
             if (++stage == S) { stage = 0; phase ^= 1u; }
           }
         }
-        umma_commit(tfull_bar(acc));
+        umma_commit_if(leader, tfull_bar(acc));
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
