@@ -61,7 +61,12 @@ __device__ __forceinline__ void block_column_sums(long long pixels, int C, float
       const long long per = (pixels + gridDim.x - 1) / gridDim.x;
       const long long p0 = (long long)blockIdx.x * per;
       const long long p1 = min(pixels, p0 + per);
-      for (long long p = p0 + pl; p < p1; p += PL) f(p, g * 8, acc);
+      long long p = p0 + pl;
+      for (; p + PL < p1; p += 2 * PL) {   // two independent pixels per iteration (memory-level parallelism)
+        f(p, g * 8, acc);
+        f(p + PL, g * 8, acc);
+      }
+      if (p < p1) f(p, g * 8, acc);
       float* dst = red + ((size_t)pl * GP + gi) * (K * 8);
 #pragma unroll
       for (int k = 0; k < K; ++k)
@@ -174,60 +179,86 @@ __global__ void bn_eval_affine_kernel(int C, const float* gamma, const float* be
   shift[c] = b - rm[c] * g * istd;
 }
 
+// Streaming iteration used by the elementwise kernels: every block owns a contiguous pixel range and every thread a
+// FIXED 8-channel group, so per-channel constants are loaded once per thread and the loop has no integer division.
+template <class Init, class Body>
+__device__ __forceinline__ void for_each_pixel_group(int pixels, int C, Init init, Body body) {
+  const int G = (C + 7) >> 3;
+  const int per = (pixels + gridDim.x - 1) / gridDim.x;
+  const int p0 = blockIdx.x * per, p1 = min(pixels, p0 + per);
+  for (int g0 = 0; g0 < G; g0 += blockDim.x) {
+    const int GP = min(G - g0, (int)blockDim.x);
+    const int PL = blockDim.x / GP;
+    const int pl = threadIdx.x / GP, g = g0 + (threadIdx.x - pl * GP);
+    if (pl < PL) {
+      auto consts = init(g * 8);
+      int p = p0 + pl;
+      // two independent pixels per iteration: twice the bytes in flight per thread (inputs are __restrict__)
+      for (; p + PL < p1; p += 2 * PL) {
+        body(p, g * 8, consts);
+        body(p + PL, g * 8, consts);
+      }
+      if (p < p1) body(p, g * 8, consts);
+    }
+  }
+}
+
+struct ApplyConsts { f8 sc, sh, rs, rh; };
+
 // y = act(x*scale+shift [+ r*rscale+rshift | + r])
 __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ scale,
                                 const float* __restrict__ shift, const __nv_bfloat16* __restrict__ r, int ldr,
                                 const float* __restrict__ rscale, const float* __restrict__ rshift, int relu,
-                                __nv_bfloat16* __restrict__ y, int ldy, long long pixels, int C) {
-  const int G = (C + 7) >> 3;
-  const long long total = pixels * G;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long p = i / G;
-    const int c = (int)(i - p * G) * 8;
-    f8 a = ld8(x + p * ldx + c);
-    const f8 sc = ldc8(scale, c, C), sh = ldc8(shift, c, C);
+                                __nv_bfloat16* __restrict__ y, int ldy, int pixels, int C) {
+  for_each_pixel_group(pixels, C,
+      [&](int c) {
+        ApplyConsts k;
+        k.sc = ldc8(scale, c, C); k.sh = ldc8(shift, c, C);
+        if (rscale) { k.rs = ldc8(rscale, c, C); k.rh = ldc8(rshift, c, C); }
+        return k;
+      },
+      [&](int p, int c, const ApplyConsts& k) {
+        f8 a = ld8(x + (long long)p * ldx + c);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) a.v[k] = a.v[k] * sc.v[k] + sh.v[k];
-    if (r) {
-      f8 b = ld8(r + p * ldr + c);
-      if (rscale) {
-        const f8 rs = ldc8(rscale, c, C), rh = ldc8(rshift, c, C);
+        for (int i = 0; i < 8; ++i) a.v[i] = a.v[i] * k.sc.v[i] + k.sh.v[i];
+        if (r) {
+          f8 b = ld8(r + (long long)p * ldr + c);
+          if (rscale) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) b.v[k] = b.v[k] * rs.v[k] + rh.v[k];
-      }
+            for (int i = 0; i < 8; ++i) b.v[i] = b.v[i] * k.rs.v[i] + k.rh.v[i];
+          }
 #pragma unroll
-      for (int k = 0; k < 8; ++k) a.v[k] += b.v[k];
-    }
+          for (int i = 0; i < 8; ++i) a.v[i] += b.v[i];
+        }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      if (relu) a.v[k] = fmaxf(a.v[k], 0.f);
-      if (c + k >= C) a.v[k] = 0.f;
-    }
-    st8(y + p * ldy + c, a);
-  }
+        for (int i = 0; i < 8; ++i) {
+          if (relu) a.v[i] = fmaxf(a.v[i], 0.f);
+          if (c + i >= C) a.v[i] = 0.f;
+        }
+        st8(y + (long long)p * ldy + c, a);
+      });
 }
 
 // backward: g = dz * mask; mask = (y > 0) if y else (x*scale+shift > 0) if relu else 1
+struct BwdConsts { f8 sc, sh, mu, is, a, mg, mgx; };
+
 __device__ __forceinline__ void bn_bwd_gx(const __nv_bfloat16* dz, int lddz, const __nv_bfloat16* x, int ldx,
-                                          const __nv_bfloat16* y, int ldy, const float* scale, const float* shift,
-                                          const float* mean, const float* invstd, int relu, long long p, int c, int C,
-                                          f8& g, f8& xh) {
-  g = ld8(dz + p * lddz + c);
-  const f8 xv = ld8(x + p * ldx + c);
-  const f8 mu = ldc8(mean, c, C), is = ldc8(invstd, c, C);
+                                          const __nv_bfloat16* y, int ldy, int relu, int p, int c, int C,
+                                          const BwdConsts& k, f8& g, f8& xh) {
+  g = ld8(dz + (long long)p * lddz + c);
+  const f8 xv = ld8(x + (long long)p * ldx + c);
   if (y) {
-    const f8 yv = ld8(y + p * ldy + c);
+    const f8 yv = ld8(y + (long long)p * ldy + c);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) g.v[k] = yv.v[k] > 0.f ? g.v[k] : 0.f;
+    for (int i = 0; i < 8; ++i) g.v[i] = yv.v[i] > 0.f ? g.v[i] : 0.f;
   } else if (relu) {
-    const f8 sc = ldc8(scale, c, C), sh = ldc8(shift, c, C);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) g.v[k] = (xv.v[k] * sc.v[k] + sh.v[k]) > 0.f ? g.v[k] : 0.f;
+    for (int i = 0; i < 8; ++i) g.v[i] = (xv.v[i] * k.sc.v[i] + k.sh.v[i]) > 0.f ? g.v[i] : 0.f;
   }
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    xh.v[k] = (xv.v[k] - mu.v[k]) * is.v[k];
-    if (c + k >= C) { g.v[k] = 0.f; xh.v[k] = 0.f; }
+  for (int i = 0; i < 8; ++i) {
+    xh.v[i] = (xv.v[i] - k.mu.v[i]) * k.is.v[i];
+    if (c + i >= C) { g.v[i] = 0.f; xh.v[i] = 0.f; }
   }
 }
 
@@ -235,9 +266,17 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dz, int l
                                      int ldx, const __nv_bfloat16* __restrict__ y, int ldy, const float* scale,
                                      const float* shift, const float* mean, const float* invstd, int relu,
                                      long long pixels, int C, float* partial, int part_ld) {
+  // block_column_sums gives every thread a fixed channel group per outer iteration: cache the constants per group
+  int cached_c = -1;
+  BwdConsts k;
   block_column_sums<2>(pixels, C, partial, part_ld, [&](long long p, int c, float (&acc)[2][8]) {
+    if (c != cached_c) {
+      cached_c = c;
+      k.mu = ldc8(mean, c, C); k.is = ldc8(invstd, c, C);
+      if (!y && relu) { k.sc = ldc8(scale, c, C); k.sh = ldc8(shift, c, C); }
+    }
     f8 g, xh;
-    bn_bwd_gx(dz, lddz, x, ldx, y, ldy, scale, shift, mean, invstd, relu, p, c, C, g, xh);
+    bn_bwd_gx(dz, lddz, x, ldx, y, ldy, relu, (int)p, c, C, k, g, xh);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       acc[0][i] += g.v[i];
@@ -263,34 +302,39 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz, int ld
                                     int ldx, const __nv_bfloat16* __restrict__ y, int ldy, const float* scale,
                                     const float* shift, const float* mean, const float* invstd, const float* gamma,
                                     const float* mean_g, const float* mean_gx, int relu, int accumulate,
-                                    __nv_bfloat16* dx, int lddx, long long pixels, int C) {
-  const int G = (C + 7) >> 3;
-  const long long total = pixels * G;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long p = i / G;
-    const int c = (int)(i - p * G) * 8;
-    f8 g, xh;
-    bn_bwd_gx(dz, lddz, x, ldx, y, ldy, scale, shift, mean, invstd, relu, p, c, C, g, xh);
-    const f8 mg = ldc8(mean_g, c, C), mgx = ldc8(mean_gx, c, C), is = ldc8(invstd, c, C);
-    f8 ga;
-    if (gamma) ga = ldc8(gamma, c, C);
-    else {
+                                    __nv_bfloat16* __restrict__ dx, int lddx, int pixels, int C) {
+  for_each_pixel_group(pixels, C,
+      [&](int c) {
+        BwdConsts k;
+        k.mu = ldc8(mean, c, C); k.is = ldc8(invstd, c, C);
+        if (!y && relu) { k.sc = ldc8(scale, c, C); k.sh = ldc8(shift, c, C); }
+        k.mg = ldc8(mean_g, c, C); k.mgx = ldc8(mean_gx, c, C);
+        if (gamma) k.a = ldc8(gamma, c, C);
+        else {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) ga.v[k] = 1.f;
-    }
-    f8 o;
+          for (int i = 0; i < 8; ++i) k.a.v[i] = 1.f;
+        }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) o.v[k] = ga.v[k] * is.v[k] * (g.v[k] - mg.v[k] - xh.v[k] * mgx.v[k]);
-    if (accumulate) {
-      const f8 old = ld8(dx + p * lddx + c);
+        for (int i = 0; i < 8; ++i) k.a.v[i] *= k.is.v[i];   // gamma * invstd
+        return k;
+      },
+      [&](int p, int c, const BwdConsts& k) {
+        f8 g, xh;
+        bn_bwd_gx(dz, lddz, x, ldx, y, ldy, relu, p, c, C, k, g, xh);
+        f8 o;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) o.v[k] += old.v[k];
-    }
+        for (int i = 0; i < 8; ++i) o.v[i] = k.a.v[i] * (g.v[i] - k.mg.v[i] - xh.v[i] * k.mgx.v[i]);
+        __nv_bfloat16* dst = dx + (long long)p * lddx + c;
+        if (accumulate) {
+          const f8 old = ld8(dst);
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
-      if (c + k >= C) o.v[k] = 0.f;
-    st8(dx + p * lddx + c, o);
-  }
+          for (int i = 0; i < 8; ++i) o.v[i] += old.v[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (c + i >= C) o.v[i] = 0.f;
+        st8(dst, o);
+      });
 }
 
 // ------------------------------------------------------------------------------------------------ MaxPool 3x3 s2 p1
@@ -452,9 +496,10 @@ extern "C" int b2u_bn_apply(const void* x, int32_t ldx, const float* scale, cons
                             int64_t pixels, int32_t C, void* stream) {
   B2U_CHECK_ARG(x && y && scale && shift && C > 0 && ldx % 8 == 0 && ldy % 8 == 0 && (!r || ldr % 8 == 0),
                 "bn_apply: bad argument");
+  B2U_CHECK_ARG(pixels < (1ll << 31), "bn_apply: too many pixels");
   const long long items = pixels * ((C + 7) / 8);
   bn_apply_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>((cbf)x, ldx, scale, shift, (cbf)r, ldr, rscale,
-                                                                        rshift, relu, (bf)y, ldy, pixels, C);
+                                                                        rshift, relu, (bf)y, ldy, (int)pixels, C);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }
@@ -492,10 +537,11 @@ extern "C" int b2u_bn_bwd_apply(const void* dz, int32_t lddz, const void* x, int
                                 const float* gamma, const float* mean_g, const float* mean_gx, int32_t relu,
                                 int32_t accumulate, void* dx, int32_t lddx, int64_t pixels, int32_t C, void* stream) {
   B2U_CHECK_ARG(dz && x && dx && mean && invstd && mean_g && mean_gx, "bn_bwd_apply: bad argument");
+  B2U_CHECK_ARG(pixels < (1ll << 31), "bn_bwd_apply: too many pixels");
   const long long items = pixels * ((C + 7) / 8);
   bn_bwd_apply_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>(
       (cbf)dz, lddz, (cbf)x, ldx, (cbf)y, ldy, scale, shift, mean, invstd, gamma, mean_g, mean_gx, relu, accumulate,
-      (bf)dx, lddx, pixels, C);
+      (bf)dx, lddx, (int)pixels, C);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }

@@ -217,26 +217,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         uint32_t accumulate = 0;
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           mbar_wait_warp(fullA(sa), pa);
-          const uint32_t a16 = (smem_base + (uint32_t)sa * p.a_stage_bytes) >> 4;
+          const uint32_t a16 = lo_const | ((smem_base + (uint32_t)sa * p.a_stage_bytes) >> 4);
           const int nm = (kc == p.k_chunks - 1) ? p.last_mmas : 4;
+          // halo mode is always the 3x3 pattern: tap (r,s) reads the halo tile from pixel row r*(tw+2) + s
+          // (8 x 16-byte units per 128-byte pixel row): plain adds, no table lookups on the issue path
+          uint32_t a_row = a16;
 #pragma unroll 1
-          for (int t = 0; t < p.num_taps; ++t) {
-            mbar_wait_warp(fullB(sb), pb);
-            tc_fence_after();
-            // tap (dy,dx): the halo tile read from pixel row (dy+1)*(tw+2) + (dx+1); 8 x 16-byte units per 128-byte row
-            const uint32_t a_lo = lo_const | (a16 + (uint32_t)((p.tap_dy[t] + 1) * p.hw + p.tap_dx[t] + 1) * 8u);
-            const uint32_t b_lo = lo_const | ((b_ring + (uint32_t)sb * b_bytes) >> 4);
+          for (int r = 0; r < 3; ++r) {
+            uint32_t a_lo = a_row;
+#pragma unroll 1
+            for (int sx = 0; sx < 3; ++sx) {
+              mbar_wait_warp(fullB(sb), pb);
+              tc_fence_after();
+              const uint32_t b_lo = lo_const | ((b_ring + (uint32_t)sb * b_bytes) >> 4);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (k < nm) {
-                // 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-                umma_bf16_if(leader, d_tmem, ((uint64_t)hiA << 32) | (a_lo + 2u * k), ((uint64_t)hiB << 32) | (b_lo + 2u * k),
-                             p.idesc, accumulate);
-                accumulate = 1;
+              for (int k = 0; k < 4; ++k) {
+                if (k < nm) {
+                  // 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+                  umma_bf16_lohi_if(leader, d_tmem, a_lo + 2u * k, hiA, b_lo + 2u * k, hiB, p.idesc, accumulate);
+                  accumulate = 1;
+                }
               }
+              umma_commit_if(leader, emptyB(sb));
+              if (++sb == p.SB) { sb = 0; pb ^= 1u; }
+              a_lo += 8u;
             }
-            umma_commit_if(leader, emptyB(sb));
-            if (++sb == p.SB) { sb = 0; pb ^= 1u; }
+            a_row += (uint32_t)p.hw * 8u;
           }
           umma_commit_if(leader, emptyA(sa));
           if (++sa == p.SA) { sa = 0; pa ^= 1u; }

@@ -74,6 +74,32 @@ __global__ void stage_weights_kernel(const WStageItem* __restrict__ items, int n
 }
 
 // ------------------------------------------------------------------------------------------------ decoder glue
+// Streaming iteration over (pixel, 8-channel group) with block-contiguous pixel ranges, a fixed channel group per thread
+// and incrementally maintained (n, y, x) coordinates: no integer division inside the loop.
+template <class Body>
+__device__ __forceinline__ void for_each_pixel_group_xy(int N, int H, int W, int G, Body body) {
+  const int pixels = N * H * W;
+  const int per = (pixels + gridDim.x - 1) / gridDim.x;
+  const int p0 = blockIdx.x * per, p1 = min(pixels, p0 + per);
+  for (int g0 = 0; g0 < G; g0 += blockDim.x) {
+    const int GP = min(G - g0, (int)blockDim.x);
+    const int PL = blockDim.x / GP;
+    const int pl = threadIdx.x / GP, g = g0 + (threadIdx.x - pl * GP);
+    if (pl >= PL) continue;
+    int p = p0 + pl;
+    if (p >= p1) continue;
+    int n = p / (H * W), rem = p - n * H * W;
+    int y = rem / W, x = rem - y * W;
+    const int dy = PL / W, dx = PL - dy * W;    // step of PL pixels in (y, x)
+    for (; p < p1; p += PL) {
+      body(p, n, y, x, g * 8);
+      x += dx; y += dy;
+      if (x >= W) { x -= W; ++y; }
+      while (y >= H) { y -= H; ++n; }
+    }
+  }
+}
+
 // cat[n,Y,X,0:cu]      = blur(PixelShuffle(u))       u: [N,h,w,4cu], channel order (i,j,c)
 // cat[n,Y,X,cu:cu+cs]  = act(skip*sscale+sshift)     (sscale null: plain copy)
 // cat[n,Y,X,cu+cs:ldc] = 0
@@ -81,21 +107,14 @@ __global__ void shuffle_cat_fwd_kernel(const __nv_bfloat16* __restrict__ u, int 
                                        const __nv_bfloat16* __restrict__ skip, int lds, int cs,
                                        const float* __restrict__ sscale, const float* __restrict__ sshift,
                                        int skip_relu, __nv_bfloat16* __restrict__ cat, int ldc, int N, int h, int w) {
-  const int H = 2 * h, W = 2 * w, G = ldc >> 3;
-  const long long total = (long long)N * H * W * G;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(i % G);
-    long long t = i / G;
-    const int X = (int)(t % W); t /= W;
-    const int Y = (int)(t % H);
-    const int n = (int)(t / H);
-    const int c = g * 8;
+  const int H = 2 * h, W = 2 * w;
+  for_each_pixel_group_xy(N, H, W, ldc >> 3, [&](int p, int n, int Y, int X, int c) {
     f8 o;
 #pragma unroll
     for (int k = 0; k < 8; ++k) o.v[k] = 0.f;
     if (c < cu) {
       auto ps = [&](int yy, int xx) {
-        return ld8(u + (((long long)n * h + (yy >> 1)) * w + (xx >> 1)) * ldu + (((yy & 1) * 2 + (xx & 1)) * cu + c));
+        return ld8(u + ((long long)(n * h + (yy >> 1)) * w + (xx >> 1)) * ldu + (((yy & 1) * 2 + (xx & 1)) * cu + c));
       };
       if (blur) {
         const int y0 = Y > 0 ? Y - 1 : 0, x0 = X > 0 ? X - 1 : 0;
@@ -107,7 +126,7 @@ __global__ void shuffle_cat_fwd_kernel(const __nv_bfloat16* __restrict__ u, int 
       }
     } else if (skip && c < cu + cs) {
       const int sc0 = c - cu;
-      o = ld8(skip + (((long long)n * H + Y) * W + X) * lds + sc0);
+      o = ld8(skip + (long long)p * lds + sc0);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         if (sc0 + k < cs) {
@@ -118,25 +137,19 @@ __global__ void shuffle_cat_fwd_kernel(const __nv_bfloat16* __restrict__ u, int 
         }
       }
     }
-    st8(cat + (((long long)n * H + Y) * W + X) * ldc + c, o);
-  }
+    st8(cat + (long long)p * ldc + c, o);
+  });
 }
 
 // du[n,y,x,(i,j,c)] = (u>0) * blur^T(dcat[..., 0:cu])[n, 2y+i, 2x+j, c]
 __global__ void shuffle_bwd_kernel(const __nv_bfloat16* __restrict__ dcat, int ldc, const __nv_bfloat16* __restrict__ u,
                                    __nv_bfloat16* __restrict__ du, int ldu, int cu, int blur, int N, int h, int w) {
-  const int H = 2 * h, W = 2 * w, G = (4 * cu) >> 3;
-  const long long total = (long long)N * h * w * G;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(i % G);
-    long long t = i / G;
-    const int x = (int)(t % w); t /= w;
-    const int y = (int)(t % h);
-    const int n = (int)(t / h);
-    const int ch = g * 8;          // channel in (i,j,c) order
-    const int ij = ch / cu, c = ch - ij * cu;
+  const int H = 2 * h, W = 2 * w;
+  const int gpc = cu >> 3;   // 8-channel groups per (i,j) phase
+  for_each_pixel_group_xy(N, h, w, (4 * cu) >> 3, [&](int p, int n, int y, int x, int ch) {
+    const int ij = (ch >> 3) / gpc, c = ch - ij * cu;
     const int Y = 2 * y + (ij >> 1), X = 2 * x + (ij & 1);
-    auto dc = [&](int yy, int xx) { return ld8(dcat + (((long long)n * H + yy) * W + xx) * ldc + c); };
+    auto dc = [&](int yy, int xx) { return ld8(dcat + ((long long)(n * H + yy) * W + xx) * ldc + c); };
     f8 o;
     if (blur) {
       // PS[Y,X] feeds outputs (Y+a, X+b), a,b in {0,1}; the replicated first row/column counts twice
@@ -165,12 +178,12 @@ __global__ void shuffle_bwd_kernel(const __nv_bfloat16* __restrict__ dcat, int l
     } else {
       o = dc(Y, X);
     }
-    const long long up = (((long long)n * h + y) * w + x) * ldu + ch;
+    const long long up = (long long)p * ldu + ch;
     const f8 uv = ld8(u + up);
 #pragma unroll
     for (int k = 0; k < 8; ++k) o.v[k] = uv.v[k] > 0.f ? o.v[k] : 0.f;
     st8(du + up, o);
-  }
+  });
 }
 
 // ------------------------------------------------------------------------------------------------ layout casts

@@ -141,6 +141,20 @@ __device__ __forceinline__ void umma_bf16_if(uint32_t leader, uint32_t d_tmem, u
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(leader)
       : "memory");
 }
+// Same, taking the descriptors as (low word, high word) pairs: the high words are loop constants, so the issue loop only
+// updates two 32-bit values per MMA.
+__device__ __forceinline__ void umma_bf16_lohi_if(uint32_t leader, uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi,
+                                                  uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "setp.ne.b32 q, %7, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_if(uint32_t leader, uint32_t bar) {
   asm volatile(
       "{\n\t.reg .pred q;\n\t"

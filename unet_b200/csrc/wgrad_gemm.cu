@@ -276,38 +276,51 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_
 }
 
 // dw[perm(co)][ci][kidx] = alpha * sum_{t: tap_kidx[t]==kidx} sum_s partial[s][t][co][ci]
-// block = 32 input channels x 32 split lanes (1024 threads); one block per (co, kidx, 32-channel group).  Each lane sums
-// its splits in ascending order and the lanes are combined by a fixed tree: the result does not depend on scheduling.
+// One block per (output channel, 32 input channels): 32 ci lanes x L split lanes.  Every thread accumulates all KS kernel
+// positions of its (ci, split lane); lanes are combined by a fixed tree, and the block writes the 32*KS results as ONE
+// contiguous run of the torch-layout gradient.  Summation order is fixed: results do not depend on scheduling.
+template <int KS>
 __global__ void __launch_bounds__(1024) wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int taps,
                                                             int taps_total, int co_pad, int ci_pad, int Cout, int Cin,
-                                                            int ksize, const int* __restrict__ tap_kidx,
+                                                            const int* __restrict__ tap_kidx,
                                                             const int* __restrict__ row_perm, float alpha,
                                                             float* __restrict__ dw, float* __restrict__ db) {
-  __shared__ float sh[32][33];
+  __shared__ float sh[KS == 9 ? 8 : 32][KS][33];
   const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5, L = blockDim.x >> 5;  // L split lanes (power of two)
-  const int co = blockIdx.y / ksize, kidx = blockIdx.y - co * ksize;
-  const int ci = blockIdx.x * 32 + lane;
+  const int co = blockIdx.y;
+  const int ci0 = blockIdx.x * 32, ci = ci0 + lane;
   const size_t sstride = (size_t)taps_total * co_pad * ci_pad;
-  float acc = 0.f;
+  float acc[KS];
+#pragma unroll
+  for (int k = 0; k < KS; ++k) acc[k] = 0.f;
   if (ci < Cin) {
     for (int t = 0; t < taps; ++t) {
-      if (tap_kidx[t] != kidx) continue;
+      const int kidx = tap_kidx[t];
       const float* src = partial + ((size_t)t * co_pad + co) * ci_pad + ci;
-      for (int s = sl; s < splits; s += L) acc += src[(size_t)s * sstride];
+      float a = 0.f;
+      for (int s = sl; s < splits; s += L) a += src[(size_t)s * sstride];
+#pragma unroll
+      for (int k = 0; k < KS; ++k) acc[k] += (k == kidx) ? a : 0.f;
     }
   }
-  sh[sl][lane] = acc;
+#pragma unroll
+  for (int k = 0; k < KS; ++k) sh[sl][k][lane] = acc[k];
   __syncthreads();
   for (int o = L >> 1; o > 0; o >>= 1) {
-    if (sl < o) sh[sl][lane] += sh[sl + o][lane];
+    if (sl < o) {
+#pragma unroll
+      for (int k = 0; k < KS; ++k) sh[sl][k][lane] += sh[sl + o][k][lane];
+    }
     __syncthreads();
   }
-  if (sl == 0 && ci < Cin) {
-    const int oc = row_perm ? row_perm[co] : co;
-    dw[((size_t)oc * Cin + ci) * ksize + kidx] = alpha * sh[0][lane];
+  const int oc = row_perm ? row_perm[co] : co;
+  const int n_ci = min(32, Cin - ci0);
+  for (int j = threadIdx.x; j < n_ci * KS; j += blockDim.x) {
+    const int cl = j / KS, k = j - cl * KS;
+    dw[((size_t)oc * Cin + ci0) * KS + j] = alpha * sh[0][k][cl];
   }
-  // bias gradient: column 0 of the extra "tap" slot; handled by the (kidx == 0, first ci block) blocks
-  if (db && kidx == 0 && blockIdx.x == 0) {
+  // bias gradient: column 0 of the extra "tap" slot; handled by the first ci block of every output channel
+  if (db && blockIdx.x == 0) {
     __shared__ float shb[1024];
     float b = 0.f;
     for (int s = threadIdx.x; s < splits; s += blockDim.x)
@@ -318,7 +331,7 @@ __global__ void __launch_bounds__(1024) wgrad_reduce_kernel(const float* __restr
       if ((int)threadIdx.x < o) shb[threadIdx.x] += shb[threadIdx.x + o];
       __syncthreads();
     }
-    if (threadIdx.x == 0) db[row_perm ? row_perm[co] : co] = shb[0];
+    if (threadIdx.x == 0) db[oc] = shb[0];
   }
 }
 
@@ -483,12 +496,18 @@ extern "C" int b2u_wgrad_reduce(const float* partial, int32_t splits, int32_t ta
                                 void* stream) {
   B2U_CHECK_ARG(partial && dw && tap_kidx, "wgrad_reduce: null argument");
   B2U_CHECK_ARG(!db || has_bias_cols, "wgrad_reduce: db requested but the partial buffer has no bias slot");
-  dim3 grid((unsigned)ceil_div(Cin, 32), (unsigned)(Cout * ksize));
+  B2U_CHECK_ARG(ksize == 1 || ksize == 9, "wgrad_reduce: kernel size %d not supported (1x1 and 3x3 only)", ksize);
+  dim3 grid((unsigned)ceil_div(Cin, 32), (unsigned)Cout);
   int lanes = 1;
-  while (lanes < 32 && lanes * 4 < splits) lanes <<= 1;   // ~4 sequential loads per lane
-  wgrad_reduce_kernel<<<grid, 32 * lanes, 0, (cudaStream_t)stream>>>(
-      partial, splits, taps, taps + (has_bias_cols ? 1 : 0), co_pad, ci_pad, Cout, Cin, ksize, tap_kidx, row_perm,
-      alpha, dw, db);
+  const int lane_cap = ksize == 9 ? 8 : 32;               // shared-memory budget: 32*KS*33 floats per 32 lanes
+  while (lanes < lane_cap && lanes * 4 < splits) lanes <<= 1;   // ~4 sequential loads per lane and tap
+  const int tt = taps + (has_bias_cols ? 1 : 0);
+  if (ksize == 9)
+    wgrad_reduce_kernel<9><<<grid, 32 * lanes, 0, (cudaStream_t)stream>>>(partial, splits, taps, tt, co_pad, ci_pad, Cout,
+                                                                         Cin, tap_kidx, row_perm, alpha, dw, db);
+  else
+    wgrad_reduce_kernel<1><<<grid, 32 * lanes, 0, (cudaStream_t)stream>>>(partial, splits, taps, tt, co_pad, ci_pad, Cout,
+                                                                         Cin, tap_kidx, row_perm, alpha, dw, db);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }

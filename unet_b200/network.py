@@ -13,6 +13,7 @@ batched kernel.
 from __future__ import annotations
 
 import ctypes as C
+import sys
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -98,6 +99,7 @@ class UNetB200:
 
         self._keep: List[object] = []
         self.acts: List[Act] = []
+        self.op_tags: List[Tuple[str, str, int]] = []   # (phase, builder function, source line) per op, for profiling
         self.named_acts: Dict[str, Act] = {}
         self.fwd_ops: List[Callable[[int], None]] = []
         self.bwd_ops: List[Callable[[int], None]] = []
@@ -253,10 +255,12 @@ class UNetB200:
 
     def _fwd(self, fn: Callable[[int], None], n: int = 1) -> None:
         self.fwd_ops.append(fn)
+        self.op_tags.append(("fwd", sys._getframe(1).f_code.co_name, sys._getframe(1).f_lineno))
         self.launches_fwd += n
 
     def _bwd(self, fn: Callable[[int], None], n: int = 1) -> None:
         self.bwd_ops.append(fn)
+        self.op_tags.append(("bwd", sys._getframe(1).f_code.co_name, sys._getframe(1).f_lineno))
         self.launches_bwd += n
 
     def _conv_fwd(self, cs: ConvSpec, x: Act, y: Act, *, out_C: Optional[int] = None, scale=None, shift=None,
