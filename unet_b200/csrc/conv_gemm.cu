@@ -33,6 +33,9 @@ struct ConvParams {
   // (profiles/r01_swizzle_offset_probe.txt).  A and B have separate rings: SA halo stages, SB weight stages.
   int stats_cols;  // > 0: BN partial sums are accumulated per warp in smem over all tiles of the CTA (4*grid rows)
   int halo, SA, SB, hw;
+  int rowmode;       // halo mode with one weight stage per FILTER ROW (3 taps, one barrier): amortises the issue-side cost
+  int stg_bufs;      // output staging buffers (2, or 1 in row mode to make room for the larger weight stages)
+  CUtensorMap tm_b3; // weights viewed as (Cin, Cout, tap): a box of 3 taps lands as [3][BN][64] in smem
   uint32_t a_stage_bytes, a_tx_bytes;
   CUtensorMap tm_ah;
   uint32_t idesc;
@@ -96,10 +99,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   const uint32_t b_bytes = (uint32_t)p.BN * 128u;
   const uint32_t stage_bytes = kABytes + b_bytes;
   const int S = p.stages;
-  const uint32_t ring_bytes = p.halo ? ((uint32_t)p.SA * p.a_stage_bytes + (uint32_t)p.SB * b_bytes) : (uint32_t)S * stage_bytes;
+  const uint32_t bs_bytes = p.rowmode ? 3u * b_bytes : b_bytes;   // one weight stage
+  const uint32_t ring_bytes = p.halo ? ((uint32_t)p.SA * p.a_stage_bytes + (uint32_t)p.SB * bs_bytes) : (uint32_t)S * stage_bytes;
   const int n_ring_bars = p.halo ? 2 * (p.SA + p.SB) : 2 * S;
   const uint32_t stg_base = smem_base + ring_bytes;
-  const uint32_t aux_base = stg_base + 2 * kStagingBytes;  // n_aux x 2 x 16 KB, double buffered per output chunk
+  const uint32_t aux_base = stg_base + (uint32_t)p.stg_bufs * kStagingBytes;  // n_aux x 2 x 16 KB, double buffered per output chunk
   const uint32_t bar_base = aux_base + (uint32_t)p.n_aux * 2 * kStagingBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(S + s); };
@@ -113,9 +117,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   auto aux_bar = [&](int b) { return bar_base + 8u * (uint32_t)(n_ring_bars + 4 + b); };
   const uint32_t tmem_slot = bar_base + 8u * (uint32_t)(n_ring_bars + 6);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
-      smem + (size_t)ring_bytes + (size_t)(2 + 2 * p.n_aux) * kStagingBytes + 8 * (n_ring_bars + 6));
+      smem + (size_t)ring_bytes + (size_t)(p.stg_bufs + 2 * p.n_aux) * kStagingBytes + 8 * (n_ring_bars + 6));
 
-  float* s_stats = reinterpret_cast<float*>(smem + (size_t)ring_bytes + (size_t)(2 + 2 * p.n_aux) * kStagingBytes + 512);
+  float* s_stats = reinterpret_cast<float*>(smem + (size_t)ring_bytes + (size_t)(p.stg_bufs + 2 * p.n_aux) * kStagingBytes + 512);
   for (int i = threadIdx.x; i < 8 * p.stats_cols; i += kThreads) s_stats[i] = 0.f;
   if (threadIdx.x == 0) {
     if (smem_base & 1023u) {
@@ -136,6 +140,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     tma_prefetch_desc(&p.tm_out);
     for (int i = 0; i < p.n_aux; ++i) tma_prefetch_desc(&p.tm_aux[i]);
     if (p.halo) tma_prefetch_desc(&p.tm_ah);
+    if (p.rowmode) tma_prefetch_desc(&p.tm_b3);
   }
   if (warp == 2) {
     tmem_alloc(tmem_slot, kTmemCols);
@@ -166,11 +171,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           mbar_expect_tx(fullA(sa), p.a_tx_bytes);
           tma_load_4d(smem_base + (uint32_t)sa * p.a_stage_bytes, &p.tm_ah, fullA(sa), kc * 64, x0 - 1, y0 - 1, n0);
           if (++sa == p.SA) { sa = 0; pa ^= 1u; }
-          for (int t = 0; t < p.num_taps; ++t) {
-            mbar_wait(emptyB(sb), pb ^ 1u);
-            mbar_expect_tx(fullB(sb), b_bytes);
-            tma_load_3d(b_ring + (uint32_t)sb * b_bytes, &p.tm_b, fullB(sb), kc * 64, p.tap_w[t], nt * p.BN);
-            if (++sb == p.SB) { sb = 0; pb ^= 1u; }
+          if (p.rowmode) {
+            for (int r = 0; r < 3; ++r) {
+              mbar_wait(emptyB(sb), pb ^ 1u);
+              mbar_expect_tx(fullB(sb), bs_bytes);
+              tma_load_3d(b_ring + (uint32_t)sb * bs_bytes, &p.tm_b3, fullB(sb), kc * 64, nt * p.BN, 3 * r);
+              if (++sb == p.SB) { sb = 0; pb ^= 1u; }
+            }
+          } else {
+            for (int t = 0; t < p.num_taps; ++t) {
+              mbar_wait(emptyB(sb), pb ^ 1u);
+              mbar_expect_tx(fullB(sb), b_bytes);
+              tma_load_3d(b_ring + (uint32_t)sb * b_bytes, &p.tm_b, fullB(sb), kc * 64, p.tap_w[t], nt * p.BN);
+              if (++sb == p.SB) { sb = 0; pb ^= 1u; }
+            }
           }
         }
       }
@@ -225,6 +239,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 #pragma unroll 1
           for (int r = 0; r < 3; ++r) {
             uint32_t a_lo = a_row;
+            if (p.rowmode) {
+              // one barrier per filter row: 3 taps x nm MMAs between a wait and a commit
+              mbar_wait_warp(fullB(sb), pb);
+              tc_fence_after();
+              uint32_t b_lo = lo_const | ((b_ring + (uint32_t)sb * bs_bytes) >> 4);
+#pragma unroll 1
+              for (int sx = 0; sx < 3; ++sx) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  if (k < nm) {
+                    umma_bf16_lohi_if(leader, d_tmem, a_lo + 2u * k, hiA, b_lo + 2u * k, hiB, p.idesc, accumulate);
+                    accumulate = 1;
+                  }
+                }
+                a_lo += 8u;
+                b_lo += b_bytes >> 4;
+              }
+              umma_commit_if(leader, emptyB(sb));
+              if (++sb == p.SB) { sb = 0; pb ^= 1u; }
+              a_row += (uint32_t)p.hw * 8u;
+              continue;
+            }
 #pragma unroll 1
             for (int sx = 0; sx < 3; ++sx) {
               mbar_wait_warp(fullB(sb), pb);
@@ -414,9 +450,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           }
         } else {
           // bf16 pack -> swizzled staging (SWIZZLE_128B: 16-byte chunk j of row e lands at chunk j ^ (e & 7))
-          const uint32_t buf = chunk_ctr & 1u;
+          const uint32_t buf = p.stg_bufs == 2 ? (chunk_ctr & 1u) : 0u;
           if ((g & 1) == 0) {
-            if (e == 0) tma_store_wait_read<1>();  // the store issued two chunks ago has finished reading this buffer
+            // the store that last used this staging buffer has finished reading it
+            if (e == 0) { if (p.stg_bufs == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
             named_bar_sync(1, 128);
           }
           uint32_t pk[16];
@@ -585,21 +622,40 @@ static int conv_plan_fill(const b2u_conv_desc* d, b2u_conv_plan* plan, bool enco
   p.n_aux = n_aux;
   const uint32_t stage_bytes = kABytes + (uint32_t)BN * 128u;
   p.stats_cols = ((d->flags & B2U_EPI_STATS) && n_tiles * BN <= 512) ? n_tiles * BN : 0;
-  const uint32_t fixed = (2 + 2 * (uint32_t)n_aux) * kStagingBytes + 512 + (uint32_t)p.stats_cols * 32u;
+  p.stg_bufs = 2;
+  p.rowmode = 0;
+  uint32_t fixed = (2 + 2 * (uint32_t)n_aux) * kStagingBytes + 512 + (uint32_t)p.stats_cols * 32u;
   int stages;
   if (halo) {
     p.a_tx_bytes = (uint32_t)((tw + 2) * (th + 2)) * 128u;
     p.a_stage_bytes = (p.a_tx_bytes + 1023u) & ~1023u;
-    const uint32_t bb = (uint32_t)BN * 128u;
-    const uint32_t avail = 232448u - fixed;
-    p.SA = 3;
-    int sb = (int)((avail - (uint32_t)p.SA * p.a_stage_bytes) / bb);
-    if (sb < 4) { p.SA = 2; sb = (int)((avail - (uint32_t)p.SA * p.a_stage_bytes) / bb); }
-    if (sb > 10) sb = 10;
-    B2U_CHECK_ARG(sb >= 2, "conv(halo): not enough shared memory");
-    p.SB = sb;
-    stages = sb;
-    plan->smem_bytes = (size_t)p.SA * p.a_stage_bytes + (size_t)sb * bb + fixed;
+    uint32_t bb = (uint32_t)BN * 128u;
+    // row mode (one weight stage = one filter row = 3 taps): the single issuing thread pays its wait/commit cost once per
+    // 3 taps.  Used for N <= 128 (the wide tiles are MMA-bound already) when >= 3 such stages fit next to 2 halo
+    // stages; the output staging drops to a single buffer to make room.
+    static const bool row_disabled = getenv("B2U_CONV_NO_ROWMODE") != nullptr;
+    bool tapw_ok = true;
+    for (int t = 0; t < 9; ++t) tapw_ok = tapw_ok && d->tap_w[t] == t;
+    // (measured: a partial last K chunk, e.g. Cin = 100, makes row mode slower than per-tap stages, so it is excluded)
+    if (!row_disabled && BN <= 128 && tapw_ok && d->w_taps == 9 && Cin % 64 == 0) {
+      const uint32_t fixed1 = fixed - kStagingBytes;
+      const int sb3 = (int)((232448u - fixed1 - 2u * p.a_stage_bytes) / (3u * bb));
+      if (sb3 >= 3) {
+        p.rowmode = 1; p.stg_bufs = 1; fixed = fixed1; p.SA = 2; p.SB = sb3 > 4 ? 4 : sb3;
+        bb *= 3;
+      }
+    }
+    if (!p.rowmode) {
+      const uint32_t avail = 232448u - fixed;
+      p.SA = 3;
+      int sb = (int)((avail - (uint32_t)p.SA * p.a_stage_bytes) / bb);
+      if (sb < 4) { p.SA = 2; sb = (int)((avail - (uint32_t)p.SA * p.a_stage_bytes) / bb); }
+      if (sb > 10) sb = 10;
+      B2U_CHECK_ARG(sb >= 2, "conv(halo): not enough shared memory");
+      p.SB = sb;
+    }
+    stages = p.SB;
+    plan->smem_bytes = (size_t)p.SA * p.a_stage_bytes + (size_t)p.SB * bb + fixed;
   } else {
     stages = (int)((232448u - fixed) / stage_bytes);
     if (stages > 8) stages = 8;
@@ -644,6 +700,15 @@ static int conv_plan_fill(const b2u_conv_desc* d, b2u_conv_plan* plan, bool enco
       uint64_t str[3] = {2, (uint64_t)d->w_cinp * 2, (uint64_t)d->w_cinp * 2 * (uint64_t)d->w_taps};
       uint32_t box[3] = {64, 1, (uint32_t)BN};
       int rc = encode_tmap_bf16(&p.tm_b, d->w, 3, dims, str, box);
+      if (rc) return rc;
+    }
+    p.tm_b3 = p.tm_b;
+    if (p.rowmode) {
+      const int cin_ext = round_up(Cin, 16) <= d->w_cinp ? round_up(Cin, 16) : (round_up(Cin, 8) <= d->w_cinp ? round_up(Cin, 8) : Cin);
+      uint64_t dims[3] = {(uint64_t)cin_ext, (uint64_t)d->w_rows, (uint64_t)d->w_taps};
+      uint64_t str[3] = {2, (uint64_t)d->w_cinp * 2 * (uint64_t)d->w_taps, (uint64_t)d->w_cinp * 2};
+      uint32_t box[3] = {64, (uint32_t)BN, 3};
+      int rc = encode_tmap_bf16(&p.tm_b3, d->w, 3, dims, str, box);
       if (rc) return rc;
     }
     if (!out_f32) {
