@@ -468,6 +468,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                          "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
                          : "memory");
           }
+          if ((g & 1) == 0 && g == n_groups - 1) {
+            // odd number of 32-channel groups: the upper half of this 64-channel staging chunk has no accumulator
+            // columns behind it; it is stored as zeros (those lanes are channel padding of the output view)
+#pragma unroll
+            for (int q = 4; q < 8; ++q) {
+              const uint32_t addr = row_addr + (((uint32_t)q ^ ((uint32_t)e & 7u)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0u) : "memory");
+            }
+          }
           if (do_stats) {
             // statistics of what is actually stored (bf16-rounded), so that BN forward/backward are self-consistent
 #pragma unroll
@@ -591,7 +600,16 @@ static int conv_plan_fill(const b2u_conv_desc* d, b2u_conv_plan* plan, bool enco
 
   ConvParams& p = plan->p;
   memset(&p, 0, sizeof(p));
-  const int Cout = d->out.C, Cin = d->w_cin;
+  const int Cout = d->out.C;
+  // K extent: when both the activation pitch and the weight pitch cover the next multiple of 64 channels, the K loop
+  // runs over whole 64-channel chunks (pad lanes are zeros by the view contract), otherwise over the true Cin.
+  int Cin = d->w_cin;
+  {
+    const int c64 = round_up(Cin, 64);
+    bool ok = d->w_cinp >= c64;
+    for (int i = 0; i < d->num_a; ++i) ok = ok && d->a[i].sW >= c64;
+    if (ok) Cin = c64;
+  }
   // N tiling
   int n_tiles, BN;
   if (Cout <= 256) { n_tiles = 1; BN = round_up(Cout, 16); }

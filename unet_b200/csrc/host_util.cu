@@ -78,7 +78,8 @@ int view_tmap(CUtensorMap* out, const b2u_view& v, uint32_t box_c, uint32_t box_
   // granules): lanes [C, extent) are padding that belongs to the tensor (read as data - they hold zeros - and written
   // as zeros).  An extent that ends inside a sector (C=100 or 104) halves the TMA unit's throughput
   // (measured on B200: 3.1 ms vs 1.25 ms for the same 100->100 3x3 launch with extent 104 vs 112).
-  int ext = round_up(v.C, 16);
+  int ext = round_up(v.C, 64);                      // whole K chunks when the pitch covers them (pad lanes are zeros)
+  if ((int64_t)ext > v.sW) ext = round_up(v.C, 16);
   if ((int64_t)ext > v.sW) ext = round_up(v.C, 8);
   uint64_t dims[4] = {(uint64_t)ext, (uint64_t)v.W, (uint64_t)v.H, (uint64_t)v.N};
   uint64_t str[4] = {2, (uint64_t)v.sW * 2, (uint64_t)v.sH * 2, (uint64_t)v.sN * 2};
