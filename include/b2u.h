@@ -201,6 +201,12 @@ int b2u_shuffle_cat_fwd(const void* u, int32_t ldu, int32_t cu, int32_t blur, co
 int b2u_shuffle_bwd(const void* dcat, int32_t ldc, const void* u, void* du, int32_t ldu, int32_t cu, int32_t blur,
                     int32_t N, int32_t h, int32_t w, void* stream);
 
+/* out[p,c] = (z[p,c] > 0 ? 1 : 0) * sum_{k<K} a[p,k] * w[c][k], K <= 8, all bf16 (z nullable): the input gradient of the 1x1
+ * head conv (GEMM K = number of classes), i.e. cudnnConvolutionBackwardData for layers.12 of the DynamicUnet.  w is the
+ * dgrad weight layout [C][ldw] produced by b2u_stage_weights. */
+int b2u_pointwise_smallk(const void* a, int32_t lda, int32_t K, const void* w, int32_t ldw, const void* z, int32_t ldz,
+                         void* out, int32_t ldo, int64_t pixels, int32_t C, void* stream);
+
 /* ---- layout casts at the API edge --------------------------------------------------------------------------- */
 /* x fp32 NCHW (already /255) or uint8 NCHW (divided by 255 here: data.py:24 + IntToFloatTensor) -> bf16 NHWC pitch ld,
  * channels [ch_off, ch_off+write_c) written (lanes >= C zeroed) */

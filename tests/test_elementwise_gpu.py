@@ -335,3 +335,22 @@ def test_stitch_against_numpy_merge(H, W, P, ov, Cc):
     assert np.array_equal(cnt.cpu().numpy().astype(np.int64), cov)
     agree = (mask.cpu().numpy() == ref).mean()
     assert agree >= 0.9999, agree
+
+
+def test_pointwise_smallk_head_dgrad():
+    L, _lib = lib()
+    from unet_b200.ops import padc
+    P, Cc, K = 5000, 100, 2
+    dl = rnd(P, K, seed=1)
+    w = rnd(K, Cc, seed=2)                     # torch head weight [n_out][C]
+    zz = rnd(P, Cc, seed=3)
+    ref = (dl @ w) * (zz > 0)
+    a = torch.zeros((P, 16), dtype=torch.bfloat16, device="cuda"); a[:, :K] = dl.to(torch.bfloat16)
+    wd = torch.zeros((Cc, 16), dtype=torch.bfloat16, device="cuda"); wd[:, :K] = w.t().to(torch.bfloat16)
+    ld = padc(Cc)
+    z = torch.zeros((P, ld), dtype=torch.bfloat16, device="cuda"); z[:, :Cc] = zz.to(torch.bfloat16)
+    out = torch.full((P, ld), 3.0, dtype=torch.bfloat16, device="cuda")
+    _lib.check(L.b2u_pointwise_smallk(p(a), 16, K, p(wd), 16, p(z), ld, p(out), ld, P, Cc, S()))
+    torch.cuda.synchronize()
+    assert rel(out[:, :Cc], ref) <= 1e-2
+    assert (out[:, Cc:] == 0).all()

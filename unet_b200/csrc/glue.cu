@@ -186,6 +186,57 @@ __global__ void shuffle_bwd_kernel(const __nv_bfloat16* __restrict__ dcat, int l
   });
 }
 
+// ------------------------------------------------------------------------------------------------ small-K pointwise
+// out[p, c] = mask(z[p, c]) * sum_{k < K} a[p, k] * w[c][k]     (K <= 8: the input gradient of the 1x1 head, whose GEMM
+// K is the number of classes).  Pure streaming: a tensor-core tile would be >99 % padding, so this stays on CUDA cores.
+template <int KT>
+__global__ void pointwise_smallk_kernel(const __nv_bfloat16* __restrict__ a, int lda, int K,
+                                        const __nv_bfloat16* __restrict__ w, int ldw,
+                                        const __nv_bfloat16* __restrict__ z, int ldz, __nv_bfloat16* __restrict__ out,
+                                        int ldo, int pixels, int C) {
+  const int G = ldo >> 3;   // every lane of the output pitch is written (zeros beyond C)
+  const int per = (pixels + gridDim.x - 1) / gridDim.x;
+  const int p0 = blockIdx.x * per, p1 = min(pixels, p0 + per);
+  for (int g0 = 0; g0 < G; g0 += blockDim.x) {
+    const int GP = min(G - g0, (int)blockDim.x);
+    const int PL = blockDim.x / GP;
+    const int pl = threadIdx.x / GP, g = g0 + (threadIdx.x - pl * GP);
+    if (pl >= PL) continue;
+    const int c = g * 8;
+    float wk[KT][8];   // [k][lane]
+#pragma unroll
+    for (int k = 0; k < KT; ++k)
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        wk[k][i] = (k < K && c + i < C) ? __bfloat162float(w[(size_t)(c + i) * ldw + k]) : 0.f;
+    auto one = [&](int p, const f8& av, const f8& zv) {
+      f8 o;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < KT; ++k) s += av.v[k] * wk[k][i];
+        o.v[i] = (!z || zv.v[i] > 0.f) ? s : 0.f;
+      }
+      st8(out + (long long)p * ldo + c, o);
+    };
+    int p = p0 + pl;
+    for (; p + PL < p1; p += 2 * PL) {   // two pixels in flight per thread
+      const f8 a0 = ld8(a + (long long)p * lda), a1 = ld8(a + (long long)(p + PL) * lda);
+      f8 z0 = a0, z1 = a1;
+      if (z) { z0 = ld8(z + (long long)p * ldz + c); z1 = ld8(z + (long long)(p + PL) * ldz + c); }
+      one(p, a0, z0);
+      one(p + PL, a1, z1);
+    }
+    if (p < p1) {
+      const f8 a0 = ld8(a + (long long)p * lda);
+      f8 z0 = a0;
+      if (z) z0 = ld8(z + (long long)p * ldz + c);
+      one(p, a0, z0);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ layout casts
 // NCHW (fp32, or uint8 divided by 255) -> NHWC bf16 with pitch ld at channel offset ch_off; remaining lanes of the
 // 8-channel group(s) touched are zeroed when zero_pad is set.
@@ -518,6 +569,24 @@ extern "C" int b2u_shuffle_bwd(const void* dcat, int32_t ldc, const void* u, voi
   const long long items = (long long)N * h * w * (4 * cu / 8);
   shuffle_bwd_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>((cbf)dcat, ldc, (cbf)u, (bf)du, ldu, cu,
                                                                            blur, N, h, w);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" int b2u_pointwise_smallk(const void* a, int32_t lda, int32_t K, const void* w, int32_t ldw, const void* z,
+                                    int32_t ldz, void* out, int32_t ldo, int64_t pixels, int32_t C, void* stream) {
+  B2U_CHECK_ARG(a && w && out && K >= 1 && K <= 8 && lda >= 8 && lda % 8 == 0 && ldo % 8 == 0 && C <= ldo &&
+                    (!z || ldz % 8 == 0) && pixels < (1ll << 31),
+                "pointwise_smallk: bad argument (K must be <= 8)");
+  const long long items = pixels * (ldo / 8);
+  const int grid = grid_for(items, 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (K <= 2)
+    pointwise_smallk_kernel<2><<<grid, 256, 0, st>>>((cbf)a, lda, K, (cbf)w, ldw, (cbf)z, ldz, (bf)out, ldo, (int)pixels, C);
+  else if (K <= 4)
+    pointwise_smallk_kernel<4><<<grid, 256, 0, st>>>((cbf)a, lda, K, (cbf)w, ldw, (cbf)z, ldz, (bf)out, ldo, (int)pixels, C);
+  else
+    pointwise_smallk_kernel<8><<<grid, 256, 0, st>>>((cbf)a, lda, K, (cbf)w, ldw, (cbf)z, ldz, (bf)out, ldo, (int)pixels, C);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }

@@ -625,7 +625,15 @@ class UNetB200:
             def tail_bwd():
                 dL = self.dlogits
                 self._wgrad(hd, dL, A2)
-                self._dgrad(hd, dL, A2, zmask=True)
+                if hd.nf <= 8:
+                    # GEMM K = number of classes: a tensor-core tile would be almost all padding -> streaming kernel
+                    dA2 = A2.ensure_grad()
+                    wd = self._w[hd.name]["wd"]
+                    self._bwd(lambda s: _lib.check(lib.b2u_pointwise_smallk(
+                        dL.data_ptr(), dL.shape[-1], hd.nf, wd.data_ptr(), wd.shape[-1], A2.t.data_ptr(), A2.ld,
+                        dA2.data_ptr(), A2.ld, A2.pixels, A2.C, s), "b2u_pointwise_smallk"))
+                else:
+                    self._dgrad(hd, dL, A2, zmask=True)
                 A2.grad_written = True
                 self._wgrad(rb, A2.grad, A1)
                 self._dgrad(rb, A2.grad, A1, zmask=True)
