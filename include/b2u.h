@@ -53,6 +53,26 @@ enum {
   B2U_EPI_OUT_F32 = 4  /* store fp32 to out_f32 (dense NHWC with pitch out_f32_ld) instead of bf16 through `out` */
 };
 
+/* Optional fused BatchNorm finalize of a B2U_EPI_STATS convolution (training-mode nn.BatchNorm2d statistics, what
+ * b2u_bn_finalize computes in a launch of its own): the LAST CTA of the launch to retire sums the per-CTA partial rows
+ * in a fixed order (double accumulation) and writes mean / invstd / scale = gamma*invstd / shift = beta - mean*scale and
+ * the running statistics.  Enabled when `counter` is non-NULL: a zero-initialised uint32 owned by the caller (one per
+ * plan), which the kernel leaves at zero again.  Only honoured when the partials are accumulated on chip
+ * (info.fused_finalize == 1: Cout <= 512 and stats_ld <= 512); otherwise the caller runs b2u_bn_finalize. */
+typedef struct b2u_bn_fin {
+  uint32_t* counter;
+  double count;       /* elements per channel = N*H*W of the output */
+  const float* gamma; /* nullable (1) */
+  const float* beta;  /* nullable (0) */
+  float eps, momentum;
+  float* running_mean; /* nullable */
+  float* running_var;
+  float* mean;
+  float* invstd;
+  float* scale;
+  float* shift;
+} b2u_bn_fin;
+
 /* Implicit-GEMM convolution:  out[n,y,x,co] = epi( sum_t sum_ci a[tap_a[t]][n, y+tap_dy[t], x+tap_dx[t], ci] * w[co][tap_w[t]][ci] ).
  * Out-of-range reads are zero (the conv padding).  The same descriptor expresses
  *   - fprop 3x3/1x1 stride 1          (F.conv2d reached from fastai ConvLayer, train.py:141 DynamicUnet),
@@ -79,11 +99,13 @@ typedef struct b2u_conv_desc {
   int32_t stats_ld;
   float* out_f32;     /* B2U_EPI_OUT_F32 */
   int32_t out_f32_ld;
+  b2u_bn_fin fin;     /* counter NULL = no fused finalize */
 } b2u_conv_desc;
 
 typedef struct b2u_conv_info {
   int32_t m_tiles, n_tiles, block_n, tile_w, tile_h, tile_n, stages, k_chunks, grid;
-  int32_t stats_rows; /* rows of the stats partial buffer: 4 per CTA (on-chip accumulation) or 4 per M tile */
+  int32_t stats_rows; /* rows of the stats partial buffer: 1 per CTA (on-chip accumulation) or 4 per M tile */
+  int32_t fused_finalize; /* 1: this plan runs the BatchNorm finalize itself (desc.fin honoured) */
 } b2u_conv_info;
 
 typedef struct b2u_conv_plan b2u_conv_plan;
@@ -132,7 +154,8 @@ int b2u_wgrad_reduce(const float* partial, int32_t splits, int32_t taps, int32_t
 /* fprop layout  wf[row(co)][t][ci]        = scale * w[co][ci][t]
  * dgrad layout  wd[ci][kk-1-t][row(co)]   = scale * w[co][ci][t]   (flipped taps, transposed channels; if wd != NULL)
  * bias_rows[row(co)] = bias[co]; row(co) = row_of_co[co] if given (PixelShuffle-friendly row order), else co.
- * `items_dev` is a device array; block_start is the exclusive prefix sum of ceil(Cout*Cin*kk/256) over the items. */
+ * `items_dev` is a device array; block_start is the exclusive prefix sum of ceil(Cout/32)*ceil(Cin/32) over the items
+ * (one 256-thread block per 32x32 channel tile, all taps; kk <= 9). */
 typedef struct b2u_wstage_item {
   const float* w;
   const float* bias;
@@ -180,6 +203,15 @@ int b2u_bn_bwd_apply(const void* dz, int32_t lddz, const void* x, int32_t ldx, c
                      const float* scale, const float* shift, const float* mean, const float* invstd,
                      const float* gamma, const float* mean_g, const float* mean_gx, int32_t relu, int32_t accumulate,
                      void* dx, int32_t lddx, int64_t pixels, int32_t C, void* stream);
+
+/* b2u_bn_bwd_reduce + b2u_bn_bwd_finalize + b2u_bn_bwd_apply in ONE launch (an in-kernel grid barrier separates the two
+ * passes; the second pass re-reads dz/x from L2 when they fit).  partial: [rows][2][part_ld] scratch; sync: two
+ * zero-initialised uint32 owned by the caller (arrive counter, generation), reusable across launches on one stream. */
+int b2u_bn_bwd_fused(const void* dz, int32_t lddz, const void* x, int32_t ldx, const void* y, int32_t ldy,
+                     const float* scale, const float* shift, const float* mean, const float* invstd,
+                     const float* gamma, int32_t relu, int32_t accumulate, void* dx, int32_t lddx, int64_t pixels,
+                     int32_t C, float* partial, int32_t rows, int32_t part_ld, double count, float* dgamma,
+                     float* dbeta, float* mean_g, float* mean_gx, uint32_t* sync, void* stream);
 
 /* ---- pooling ------------------------------------------------------------------------------------------------ */
 /* nn.MaxPool2d(3, stride 2, padding 1) (xresnet stem, body child 3); idx = argmax position 0..8 (uint8, pitch ld),
@@ -255,6 +287,10 @@ int b2u_stitch_finalize(const float* acc, const uint8_t* cnt, int32_t C, int64_t
 /* per-tile softmax probabilities (fp32 NCHW, what learn.predict returns, predict.py:193-203) and argmax */
 int b2u_softmax_nchw(const float* logits, int32_t ld, int32_t C, int64_t tiles, int32_t H, int32_t W, float* probs,
                      uint8_t* argmax, void* stream);
+
+/* sizeof() of the ABI structs as this library was compiled, for bindings to verify their mirrors:
+ * which = 0 b2u_view, 1 b2u_conv_desc, 2 b2u_conv_info, 3 b2u_wgrad_desc, 4 b2u_wgrad_info, 5 b2u_wstage_item, 6 b2u_bn_fin */
+int b2u_abi_sizeof(int which);
 
 #ifdef __cplusplus
 }

@@ -100,6 +100,22 @@ def test_bn_train_forward_backward(N, Cc, H, W):
     assert rel(dgamma, g_.grad) <= 1e-3
     assert rel(dbeta, b_.grad) <= 1e-3
     assert rel(nchw(dxa, Cc), xr.grad) <= 1e-2
+    # the single-launch variant (grid barrier inside) against torch and against the three-launch path; run twice to
+    # check that the barrier words are left reusable
+    sync = torch.zeros(2, dtype=torch.int32, device="cuda")
+    for _ in range(2):
+        dg2, db2, mg2, mgx2 = f32(Cc), f32(Cc), f32(pad32(Cc)), f32(pad32(Cc))
+        dxf = torch.zeros_like(xa)
+        part3 = torch.zeros((592, 2, ld), dtype=torch.float32, device="cuda")
+        _lib.check(L.b2u_bn_bwd_fused(p(dza), ld, p(xa), ld, p(ya), ld, p(scale), p(shift), p(mean), p(invstd),
+                                      p(gamma), 0, 0, p(dxf), ld, pix, Cc, p(part3), 592, ld, float(pix), p(dg2),
+                                      p(db2), p(mg2), p(mgx2), p(sync), S()))
+        torch.cuda.synchronize()
+        assert rel(dg2, g_.grad) <= 1e-3 and rel(db2, b_.grad) <= 1e-3
+        assert rel(dg2, dgamma) <= 1e-5 and rel(db2, dbeta) <= 1e-5
+        assert rel(nchw(dxf, Cc), xr.grad) <= 1e-2
+        assert rel(dxf, dxa) <= 1e-2 and (dxf[..., Cc:] == 0).all()
+        assert sync[0].item() == 0
 
 
 def test_bn_relu_mask_from_scale_shift_and_large_row_count():
@@ -133,6 +149,18 @@ def test_bn_relu_mask_from_scale_shift_and_large_row_count():
                                   p(mg), p(mgx), 1, 0, p(dxa), ld, pix, Cc, S()))
     torch.cuda.synchronize()
     assert rel(nchw(dxa, Cc), xr.grad) <= 1e-2
+    # fused single launch, accumulate mode (dx += ...), ReLU mask recomputed from scale/shift
+    sync = torch.zeros(2, dtype=torch.int32, device="cuda")
+    base = rnd(N, Cc, H, W, seed=9)
+    dxf = nhwc(base)
+    mg2, mgx2 = f32(pad32(Cc)), f32(pad32(Cc))
+    part3 = torch.zeros((592, 2, ld), dtype=torch.float32, device="cuda")
+    _lib.check(L.b2u_bn_bwd_fused(p(dza), ld, p(xa), ld, None, 0, p(scale), p(shift), p(mean), p(invstd), p(gamma),
+                                  1, 1, p(dxf), ld, pix, Cc, p(part3), 592, ld, float(pix), None, None, p(mg2), p(mgx2),
+                                  p(sync), S()))
+    torch.cuda.synchronize()
+    assert rel(nchw(dxf, Cc), xr.grad + base) <= 1e-2
+    assert rel(mg2, mg) <= 1e-5 and rel(mgx2, mgx) <= 1e-5
 
 
 @pytest.mark.parametrize("N,Cc,H,W", [(2, 64, 32, 32), (1, 24, 13, 9)])
@@ -277,28 +305,29 @@ def test_layout_casts_and_crop():
         assert torch.equal(out[t, ..., :Cc].permute(2, 0, 1), ref)
 
 
-def test_stage_weights():
+@pytest.mark.parametrize("Cout,Cin,ks", [(16, 12, 3), (100, 100, 3), (384, 96, 1), (40, 4, 3)])
+def test_stage_weights(Cout, Cin, ks):
     L, _lib = lib()
     from unet_b200.layout import shuffle_row_of_co
     from unet_b200.ops import padc, pad32
-    Cout, Cin, ks = 16, 12, 3
+    kk = ks * ks
     w = torch.randn(Cout, Cin, ks, ks, device="cuda")
     b = torch.randn(Cout, device="cuda")
     roc = torch.tensor(shuffle_row_of_co(Cout), dtype=torch.int32, device="cuda")
-    wf = torch.zeros((Cout, 9, padc(Cin)), dtype=torch.bfloat16, device="cuda")
-    wd = torch.zeros((Cin, 9, padc(Cout)), dtype=torch.bfloat16, device="cuda")
+    wf = torch.zeros((Cout, kk, padc(Cin)), dtype=torch.bfloat16, device="cuda")
+    wd = torch.zeros((Cin, kk, padc(Cout)), dtype=torch.bfloat16, device="cuda")
     br = f32(pad32(Cout))
     it = _lib.WStageItem()
     it.w, it.bias, it.row_of_co, it.wf, it.wd, it.bias_rows = p(w), p(b), p(roc), p(wf), p(wd), p(br)
-    it.Cout, it.Cin, it.kk, it.wf_cinp, it.wd_coutp, it.scale, it.block_start = Cout, Cin, 9, padc(Cin), padc(Cout), 0.25, 0
+    it.Cout, it.Cin, it.kk, it.wf_cinp, it.wd_coutp, it.scale, it.block_start = Cout, Cin, kk, padc(Cin), padc(Cout), 0.25, 0
     dev_items = torch.frombuffer(bytearray(bytes(it)), dtype=torch.uint8).cuda()
-    _lib.check(L.b2u_stage_weights(p(dev_items), 1, (Cout * Cin * 9 + 255) // 256, S()))
+    _lib.check(L.b2u_stage_weights(p(dev_items), 1, ((Cout + 31) // 32) * ((Cin + 31) // 32), S()))
     torch.cuda.synchronize()
     ws = (w * 0.25).to(torch.bfloat16)
     ref_f = torch.zeros_like(wf)
-    ref_f[roc.long(), :, :Cin] = ws.permute(0, 2, 3, 1).reshape(Cout, 9, Cin)
+    ref_f[roc.long(), :, :Cin] = ws.permute(0, 2, 3, 1).reshape(Cout, kk, Cin)
     ref_d = torch.zeros_like(wd)
-    ref_d[:, :, roc.long()] = ws.flip(2, 3).permute(1, 2, 3, 0).reshape(Cin, 9, Cout)
+    ref_d[:, :, roc.long()] = ws.flip(2, 3).permute(1, 2, 3, 0).reshape(Cin, kk, Cout)
     assert torch.equal(wf, ref_f) and torch.equal(wd, ref_d)
     ref_b = torch.zeros_like(br)
     ref_b[roc.long()] = b

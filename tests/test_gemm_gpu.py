@@ -271,3 +271,41 @@ def test_conv_stats_many_tiles_per_cta(N, Cin, Cout, H, W, stride):
     s = plan.stats.double().sum(0)
     assert rel_err(s[0, :Cout].float(), got.double().sum((0, 2, 3)).float()) <= 1e-4, plan.stats.shape
     assert rel_err(s[1, :Cout].float(), (got.double() ** 2).sum((0, 2, 3)).float()) <= 1e-4
+
+
+@pytest.mark.parametrize("N,Cin,Cout,H,W", [(8, 64, 64, 64, 64), (4, 256, 512, 8, 8), (2, 32, 100, 40, 24)])
+def test_conv_fused_bn_finalize(N, Cin, Cout, H, W):
+    """The conv kernel's last CTA finalizes the BatchNorm batch statistics (b2u_bn_fin): mean / invstd / scale / shift and
+    the running statistics must equal torch's training-mode batch_norm on the stored (bf16) conv output."""
+    from unet_b200 import ops
+    x = rnd(N, Cin, H, W, seed=1)
+    w = rnd(Cout, Cin, 3, 3, seed=2, scale=(Cin * 9) ** -0.5)
+    xa = to_nhwc(x)
+    ya = torch.zeros((N, H, W, ops.padc(Cout)), dtype=torch.bfloat16, device="cuda")
+    f = lambda fill=0.0: torch.full((ops.pad32(Cout),), fill, dtype=torch.float32, device="cuda")
+    gamma, beta = torch.rand(Cout, device="cuda") + 0.5, torch.randn(Cout, device="cuda") * 0.1
+    rm0, rv0 = torch.randn(Cout, device="cuda") * 0.1, torch.rand(Cout, device="cuda") + 0.5
+    rm, rv = rm0.clone(), rv0.clone()
+    mean, invstd, scale, shift = f(), f(), f(), f()
+    plan = ops.ConvPlan([ops.view_nhwc(xa, Cin)], ops.view_nhwc(ya, Cout), gemm_weights(w), Cin, ops.taps_conv(3), stats=True,
+                        fin=dict(count=N * H * W, gamma=gamma, beta=beta, eps=1e-5, momentum=0.1, running_mean=rm,
+                                 running_var=rv, mean=mean, invstd=invstd, scale=scale, shift=shift))
+    assert plan.fused_finalize
+    plan.run()
+    torch.cuda.synchronize()
+    got = ya[..., :Cout].permute(0, 3, 1, 2).float()
+    rm_ref, rv_ref = rm0.clone(), rv0.clone()
+    y_ref = F.batch_norm(got, rm_ref, rv_ref, gamma, beta, True, 0.1, 1e-5)
+    m = got.double().mean((0, 2, 3))
+    v = got.double().var((0, 2, 3), unbiased=False)
+    assert rel_err(mean[:Cout], m.float()) <= 1e-4
+    assert rel_err(invstd[:Cout], (1.0 / torch.sqrt(v + 1e-5)).float()) <= 1e-4
+    assert rel_err(rm, rm_ref) <= 1e-4 and rel_err(rv, rv_ref) <= 1e-4
+    y = got * scale[:Cout].view(1, -1, 1, 1) + shift[:Cout].view(1, -1, 1, 1)
+    assert rel_err(y, y_ref) <= 1e-4
+    # a second launch restarts from a clean counter and applies the momentum update once more
+    plan.run()
+    torch.cuda.synchronize()
+    F.batch_norm(got, rm_ref, rv_ref, gamma, beta, True, 0.1, 1e-5)
+    assert rel_err(rm, rm_ref) <= 1e-4 and rel_err(rv, rv_ref) <= 1e-4
+    assert plan._fin_counter.item() == 0

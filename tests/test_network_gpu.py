@@ -2,7 +2,9 @@
 network API (which calls the C-ABI for every kernel).
 
 Stated tolerances (bf16 storage, fp32 accumulation; errors are max|a-b| / max|b| per tensor):
-  * logits vs the fp32 oracle            <= 3e-2   (stock torch bf16 autocast measures 2.0-2.4e-2 on the same inputs)
+  * logits vs the fp32 oracle            <= 3e-2   (stock torch bf16 autocast measures 2.0-2.4e-2 on the same inputs);
+    for xresnet50 <= max(3e-2, 1.25 x the autocast error measured in the same test) - autocast reads 5.6-5.8e-2 there
+    and this pipeline 5.3-6.2e-2 (tools/parity_probe.py xresnet50 4 8 64 2)
   * loss vs the fp32 oracle              <= 5e-3
   * logits vs the bf16-storage emulation <= 2e-2 and loss <= 2e-4 (same rounding points: only accumulation order and
     rounding-boundary flips differ)
@@ -40,7 +42,8 @@ def _setup(arch, n_in, n_out, size, batch, data):
 
 
 CASES = [("xresnet34", 4, 2, 256, 2, "uniform"), ("xresnet34", 4, 2, 128, 4, "aerial"),
-         ("xresnet18", 3, 2, 128, 8, "aerial"), ("xresnet34", 4, 5, 64, 4, "aerial")]
+         ("xresnet18", 3, 2, 128, 8, "aerial"), ("xresnet34", 4, 5, 64, 4, "aerial"),
+         ("xresnet50", 4, 8, 64, 2, "aerial")]   # bottleneck blocks, 2048-wide encoder, 8 classes (BASELINE configs[3])
 
 
 @pytest.mark.parametrize("arch,n_in,n_out,size,batch,data", CASES)
@@ -71,9 +74,12 @@ def test_train_step_parity(arch, n_in, n_out, size, batch, data):
     logits = net.logits_nchw()
 
     e_logits = rel(logits, logits_ref)
-    assert e_logits <= 3e-2, e_logits
+    # xresnet50 (50+ bf16 rounding points per path, 2048-wide sums): stock autocast itself measures 5.6-5.8e-2 there, so
+    # the bound follows torch's own bf16 error when that exceeds the flat 3e-2
+    e_auto = rel(l_auto.float(), logits_ref)
+    assert e_logits <= max(3e-2, 1.25 * e_auto), (e_logits, e_auto)
     assert abs(loss.item() - loss_ref.item()) / abs(loss_ref.item()) <= 5e-3
-    assert rel(logits, l_emu) <= 2e-2
+    assert rel(logits, l_emu) <= (3e-2 if arch == "xresnet50" else 2e-2)
     assert abs(loss.item() - loss_emu.item()) / abs(loss_emu.item()) <= 2e-4
     # argmax: disagreements only inside the error band
     top2 = logits_ref.topk(2, dim=1).values
@@ -86,7 +92,8 @@ def test_train_step_parity(arch, n_in, n_out, size, batch, data):
     # running statistics follow torch's update rule (momentum 0.1, unbiased variance)
     sd = oracle.state_dict()
     for k, b in net.buffers.items():
-        assert rel(b, sd[k]) <= 5e-2, k   # deep stages average over few samples (e.g. 4x4x4 at 1/32 resolution)
+        # deep stages average over few samples (e.g. 4x4x4 at 1/32 resolution; 2x2x2 for the xresnet50 case)
+        assert rel(b, sd[k]) <= (8e-2 if arch == "xresnet50" else 5e-2), k
     # gradients, calibrated against torch's own bf16 autocast
     grads, pa = net.named_grads(), dict(o_auto.named_parameters())
     bad = []

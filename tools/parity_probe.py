@@ -54,6 +54,10 @@ def run(arch, n_in, n_out, size, batch, data='uniform'):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1:   # parity_probe.py arch n_in n_out size batch [data]
+        a = sys.argv
+        run(a[1], int(a[2]), int(a[3]), int(a[4]), int(a[5]), a[6] if len(a) > 6 else 'aerial')
+        sys.exit(0)
     for cfg in [("xresnet34", 4, 2, 64, 2, 'uniform'), ("xresnet34", 4, 2, 256, 2, 'uniform'), ("xresnet34", 4, 2, 256, 4, 'aerial'),
                 ("xresnet18", 3, 2, 128, 8, 'aerial')]:
         run(*cfg)

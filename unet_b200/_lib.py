@@ -26,6 +26,13 @@ class View(C.Structure):
                 ("sW", C.c_int64), ("sH", C.c_int64), ("sN", C.c_int64)]
 
 
+class BNFin(C.Structure):
+    _fields_ = [("counter", C.c_void_p), ("count", C.c_double), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+                ("eps", C.c_float), ("momentum", C.c_float), ("running_mean", C.c_void_p),
+                ("running_var", C.c_void_p), ("mean", C.c_void_p), ("invstd", C.c_void_p), ("scale", C.c_void_p),
+                ("shift", C.c_void_p)]
+
+
 class ConvDesc(C.Structure):
     _fields_ = [
         ("a", View * MAX_VIEWS), ("num_a", C.c_int32), ("out", View),
@@ -37,12 +44,13 @@ class ConvDesc(C.Structure):
         ("res", View), ("res_mask", View), ("zmask", View),
         ("flags", C.c_uint32), ("stats", C.c_void_p), ("stats_ld", C.c_int32),
         ("out_f32", C.c_void_p), ("out_f32_ld", C.c_int32),
+        ("fin", BNFin),
     ]
 
 
 class ConvInfo(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("m_tiles", "n_tiles", "block_n", "tile_w", "tile_h", "tile_n", "stages",
-                                         "k_chunks", "grid", "stats_rows")]
+                                         "k_chunks", "grid", "stats_rows", "fused_finalize")]
 
 
 class WgradDesc(C.Structure):
@@ -112,6 +120,8 @@ def _declare(lib):
         "b2u_bn_bwd_reduce": [vp, i32, vp, i32, vp, i32, vp, vp, vp, vp, i32, i64, i32, vp, i32, i32, vp],
         "b2u_bn_bwd_finalize": [vp, i32, i32, i32, f64, vp, vp, vp, vp, vp, C.c_size_t, vp],
         "b2u_bn_bwd_apply": [vp, i32, vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, i32, i64, i32, vp],
+        "b2u_bn_bwd_fused": [vp, i32, vp, i32, vp, i32, vp, vp, vp, vp, vp, i32, i32, vp, i32, i64, i32, vp, i32, i32, f64,
+                             vp, vp, vp, vp, vp, vp],
         "b2u_maxpool_fwd": [vp, vp, u8p, i32, i32, i32, i32, i32, vp],
         "b2u_maxpool_bwd": [vp, u8p, vp, i32, i32, i32, i32, i32, i32, vp],
         "b2u_shuffle_cat_fwd": [vp, i32, i32, i32, vp, i32, i32, vp, vp, i32, vp, i32, i32, i32, i32, vp],

@@ -62,11 +62,13 @@ __device__ __forceinline__ void block_column_sums(long long pixels, int C, float
       const long long p0 = (long long)blockIdx.x * per;
       const long long p1 = min(pixels, p0 + per);
       long long p = p0 + pl;
-      for (; p + PL < p1; p += 2 * PL) {   // two independent pixels per iteration (memory-level parallelism)
+      for (; p + 3 * PL < p1; p += 4 * PL) {   // four independent pixels per iteration (memory-level parallelism)
         f(p, g * 8, acc);
         f(p + PL, g * 8, acc);
+        f(p + 2 * PL, g * 8, acc);
+        f(p + 3 * PL, g * 8, acc);
       }
-      if (p < p1) f(p, g * 8, acc);
+      for (; p < p1; p += PL) f(p, g * 8, acc);
       float* dst = red + ((size_t)pl * GP + gi) * (K * 8);
 #pragma unroll
       for (int k = 0; k < K; ++k)
@@ -74,20 +76,14 @@ __device__ __forceinline__ void block_column_sums(long long pixels, int C, float
         for (int i = 0; i < 8; ++i) dst[k * 8 + i] = acc[k][i];
     }
     __syncthreads();
-    if (pl == 0) {
-      for (int q = 1; q < PL; ++q) {
-        const float* src = red + ((size_t)q * GP + gi) * (K * 8);
-#pragma unroll
-        for (int k = 0; k < K; ++k)
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc[k][i] += src[k * 8 + i];
-      }
-      float* out = partial + (size_t)blockIdx.x * K * part_ld;
-#pragma unroll
-      for (int k = 0; k < K; ++k)
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (g * 8 + i < part_ld) out[(size_t)k * part_ld + g * 8 + i] = acc[k][i];
+    // all threads combine the PL pixel lanes: one (channel group, quantity, channel) element per thread and trip,
+    // lanes summed in ascending order (fixed order -> deterministic)
+    for (int e = threadIdx.x; e < GP * K * 8; e += blockDim.x) {
+      float s = 0.f;
+      for (int q = 0; q < PL; ++q) s += red[(size_t)q * GP * (K * 8) + e];
+      const int ge = e / (K * 8), r = e - ge * (K * 8);
+      const int k = r >> 3, c = (g0 + ge) * 8 + (r & 7);
+      if (c < part_ld) partial[((size_t)blockIdx.x * K + k) * part_ld + c] = s;
     }
     __syncthreads();
   }
@@ -337,6 +333,161 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz, int ld
       });
 }
 
+// ------------------------------------------------------------------------------------------------ fused BN backward
+// reduce -> finalize -> apply in ONE launch.  Phase 1 is bn_bwd_reduce (one partial row per block); the blocks then meet
+// at a grid barrier whose last arriver finalizes the sums in a fixed order (double accumulation, as bn_bwd_finalize)
+// and releases the others; phase 2 is bn_bwd_apply over the SAME per-block pixel ranges walked backwards, so the lines
+// read last in phase 1 are re-read first (they are still in the 126 MB L2 for all but the largest tensors).
+// The grid must be co-resident (the host caps it with the occupancy API); `sync` = {arrive counter, generation}.
+__device__ __forceinline__ f8 ldc8_cg(const float* p, int c, int C) {
+  const float4 a = __ldcg(reinterpret_cast<const float4*>(p + c));
+  const float4 b = __ldcg(reinterpret_cast<const float4*>(p + c) + 1);
+  f8 o;
+  o.v[0] = a.x; o.v[1] = a.y; o.v[2] = a.z; o.v[3] = a.w; o.v[4] = b.x; o.v[5] = b.y; o.v[6] = b.z; o.v[7] = b.w;
+  if (c + 8 > C) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (c + i >= C) o.v[i] = 0.f;
+  }
+  return o;
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_fused_kernel(
+    const __nv_bfloat16* __restrict__ dz, int lddz, const __nv_bfloat16* __restrict__ x, int ldx,
+    const __nv_bfloat16* __restrict__ y, int ldy, const float* scale, const float* shift, const float* mean,
+    const float* invstd, const float* gamma, int relu, int accumulate, __nv_bfloat16* __restrict__ dx, int lddx,
+    int pixels, int C, float* partial, int part_ld, double count, float* dgamma, float* dbeta, float* mean_g,
+    float* mean_gx, unsigned int* sync) {
+  extern __shared__ float red[];
+  __shared__ unsigned int s_gen;
+  __shared__ int s_last;
+  volatile unsigned int* vsync = sync;
+  if (threadIdx.x == 0) s_gen = vsync[1];
+  // ---- phase 1: partial sums of g and g*xhat over this block's pixel range
+  {
+    int cached_c = -1;
+    BwdConsts k;
+    block_column_sums<2>(pixels, C, partial, part_ld, [&](long long p, int c, float (&acc)[2][8]) {
+      if (c != cached_c) {
+        cached_c = c;
+        k.mu = ldc8(mean, c, C); k.is = ldc8(invstd, c, C);
+        if (!y && relu) { k.sc = ldc8(scale, c, C); k.sh = ldc8(shift, c, C); }
+      }
+      f8 g, xh;
+      bn_bwd_gx(dz, lddz, x, ldx, y, ldy, relu, (int)p, c, C, k, g, xh);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[0][i] += g.v[i];
+        acc[1][i] += g.v[i] * xh.v[i];
+      }
+    });
+  }
+  // ---- grid barrier; the last block to arrive finalizes
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int ticket = atomicAdd(&sync[0], 1u);
+    s_last = (ticket == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    double* sh = reinterpret_cast<double*>(red);   // 256 x 4 doubles = 8 KB of the 16 KB dynamic buffer
+    const int rows = (int)gridDim.x;
+    const int ncol4 = part_ld >> 1;                // float4 columns of one partial row [2][part_ld]
+    for (int cb = 0; cb < ncol4; cb += 256) {
+      const int nc = min(256, ncol4 - cb);
+      const int RL = 256 / nc;
+      const int rl = (int)threadIdx.x / nc, c4 = (int)threadIdx.x - rl * nc;
+      if (rl < RL) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        const float4* src = reinterpret_cast<const float4*>(partial) + cb + c4;
+#pragma unroll 8
+        for (int r = rl; r < rows; r += RL) {
+          const float4 v = __ldcg(src + (size_t)r * ncol4);
+          a0 += (double)v.x; a1 += (double)v.y; a2 += (double)v.z; a3 += (double)v.w;
+        }
+        double* d = sh + ((size_t)rl * nc + c4) * 4;
+        d[0] = a0; d[1] = a1; d[2] = a2; d[3] = a3;
+      }
+      __syncthreads();
+      for (int j = threadIdx.x; j < nc * 4; j += 256) {
+        double t = 0.0;
+        for (int q = 0; q < RL; ++q) t += sh[(size_t)q * nc * 4 + j];
+        const int col = cb * 4 + j;                // position inside [2][part_ld]
+        const int kk = col >= part_ld ? 1 : 0, c = col - kk * part_ld;
+        if (c < C) {
+          if (kk == 0) { if (dbeta) dbeta[c] = (float)t; mean_g[c] = (float)(t / count); }
+          else { if (dgamma) dgamma[c] = (float)t; mean_gx[c] = (float)(t / count); }
+        }
+      }
+      __syncthreads();
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      sync[0] = 0u;
+      __threadfence();
+      atomicAdd(&sync[1], 1u);   // release
+    }
+  } else {
+    if (threadIdx.x == 0) {
+      while (vsync[1] == s_gen) __nanosleep(100);
+      __threadfence();
+    }
+    __syncthreads();
+  }
+  // ---- phase 2: dx = gamma*invstd * (g - mean_g - xhat*mean_gx), block range walked backwards
+  {
+    const int G = (C + 7) >> 3;
+    const int per = (pixels + gridDim.x - 1) / gridDim.x;
+    const int p0 = blockIdx.x * per, p1 = min(pixels, p0 + per);
+    for (int g0 = 0; g0 < G; g0 += blockDim.x) {
+      const int GP = min(G - g0, (int)blockDim.x);
+      const int PL = blockDim.x / GP;
+      const int pl = threadIdx.x / GP, g = g0 + (threadIdx.x - pl * GP);
+      if (pl >= PL || p0 + pl >= p1) continue;
+      const int c = g * 8;
+      BwdConsts k;
+      k.mu = ldc8(mean, c, C); k.is = ldc8(invstd, c, C);
+      if (!y && relu) { k.sc = ldc8(scale, c, C); k.sh = ldc8(shift, c, C); }
+      k.mg = ldc8_cg(mean_g, c, C); k.mgx = ldc8_cg(mean_gx, c, C);
+      if (gamma) k.a = ldc8(gamma, c, C);
+      else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) k.a.v[i] = 1.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) k.a.v[i] *= k.is.v[i];
+      auto one = [&](int p) {
+        f8 gq, xh;
+        bn_bwd_gx(dz, lddz, x, ldx, y, ldy, relu, p, c, C, k, gq, xh);
+        f8 o;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o.v[i] = k.a.v[i] * (gq.v[i] - k.mg.v[i] - xh.v[i] * k.mgx.v[i]);
+        __nv_bfloat16* dst = dx + (long long)p * lddx + c;
+        if (accumulate) {
+          const f8 old = ld8(dst);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o.v[i] += old.v[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (c + i >= C) o.v[i] = 0.f;
+        st8(dst, o);
+      };
+      int p = p0 + pl + ((p1 - 1 - p0 - pl) / PL) * PL;   // last pixel of this lane
+      for (; p - 3 * PL >= p0; p -= 4 * PL) {   // four pixels in flight per thread
+        one(p);
+        one(p - PL);
+        one(p - 2 * PL);
+        one(p - 3 * PL);
+      }
+      for (; p >= p0; p -= PL) one(p);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ MaxPool 3x3 s2 p1
 __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                    uint8_t* __restrict__ idx, int N, int H, int W, int C, int ld) {
@@ -542,6 +693,39 @@ extern "C" int b2u_bn_bwd_apply(const void* dz, int32_t lddz, const void* x, int
   bn_bwd_apply_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>(
       (cbf)dz, lddz, (cbf)x, ldx, (cbf)y, ldy, scale, shift, mean, invstd, gamma, mean_g, mean_gx, relu, accumulate,
       (bf)dx, lddx, (int)pixels, C);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" int b2u_bn_bwd_fused(const void* dz, int32_t lddz, const void* x, int32_t ldx, const void* y, int32_t ldy,
+                                const float* scale, const float* shift, const float* mean, const float* invstd,
+                                const float* gamma, int32_t relu, int32_t accumulate, void* dx, int32_t lddx,
+                                int64_t pixels, int32_t C, float* partial, int32_t rows, int32_t part_ld, double count,
+                                float* dgamma, float* dbeta, float* mean_g, float* mean_gx, uint32_t* sync,
+                                void* stream) {
+  B2U_CHECK_ARG(dz && x && dx && mean && invstd && partial && mean_g && mean_gx && sync && rows > 0 && count > 0,
+                "bn_bwd_fused: bad argument");
+  B2U_CHECK_ARG(part_ld >= C && part_ld % 4 == 0, "bn_bwd_fused: part_ld=%d must be >= C and a multiple of 4", part_ld);
+  B2U_CHECK_ARG(y || !relu || (scale && shift), "bn_bwd_fused: relu mask needs scale/shift");
+  B2U_CHECK_ARG(pixels > 0 && pixels < (1ll << 31), "bn_bwd_fused: bad pixel count");
+  const int threads = 256;
+  const size_t smem = (size_t)threads * 16 * sizeof(float);
+  // the in-kernel grid barrier needs every block resident at once
+  static int max_blocks = 0;
+  if (max_blocks == 0) {
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_bwd_fused_kernel, threads, smem);
+    if (e != cudaSuccess || per_sm < 1) { set_error("bn_bwd_fused: occupancy query failed"); return B2U_ERR_CUDA; }
+    if (per_sm > 4) per_sm = 4;
+    max_blocks = per_sm * sm_count();
+  }
+  int grid = rows < max_blocks ? rows : max_blocks;
+  const long long by_work = (pixels * ((C + 7) / 8) + 1023) / 1024;   // >= ~4 (pixel, 8-channel group) items per thread
+  if (grid > by_work) grid = (int)by_work;
+  if (grid < 1) grid = 1;
+  bn_bwd_fused_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(
+      (cbf)dz, lddz, (cbf)x, ldx, (cbf)y, ldy, scale, shift, mean, invstd, gamma, relu, accumulate, (bf)dx, lddx,
+      (int)pixels, C, partial, part_ld, count, dgamma, dbeta, mean_g, mean_gx, sync);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }

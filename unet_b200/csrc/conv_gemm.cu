@@ -48,9 +48,10 @@ struct ConvParams {
   int stats_ld;
   float* out_f32;
   int out_f32_ld;
+  b2u_bn_fin fin;   // counter != nullptr: the last CTA to retire finalizes the BatchNorm statistics
 };
 
-static constexpr int kThreads = 256;
+static constexpr int kThreads = 384;   // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 epilogue
 static constexpr uint32_t kABytes = 128 * 128;       // 128 pixels x 64 bf16
 static constexpr uint32_t kStagingBytes = 128 * 128; // 128 pixels x 64 bf16, one output chunk
 static constexpr uint32_t kTmemCols = 512;
@@ -62,9 +63,6 @@ __device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&o)[8]) {
   o[4] = bf16_lo(u.z); o[5] = bf16_hi(u.z); o[6] = bf16_lo(u.w); o[7] = bf16_hi(u.w);
 }
 
-struct Aux {
-  uint4 r[4], m[4], z[4];  // residual, residual mask, output mask: 32 channels (4 x 16 B) of this thread's pixel
-};
 __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
@@ -91,6 +89,10 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane)
   return v[0];
 }
 
+// kAux: residual / mask operands in the epilogue; kStats: BatchNorm partial sums; kF32: fp32 logits output (head).
+// Compile-time switches: the epilogue is the critical path of the memory-/issue-bound layers, unused features must not
+// cost instructions there.
+template <bool kAux, bool kStats, bool kF32>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
@@ -129,7 +131,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     for (int s = 0; s < n_ring_bars; ++s) mbar_init(bar_base + 8u * (uint32_t)s, 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 128);
+      mbar_init(tempty_bar(a), 256);
       mbar_init(aux_bar(a), 1);
     }
     fence_mbar_init();
@@ -320,18 +322,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------ epilogue: 128 threads, thread e <-> tile row e
+    // ------------------------------------------------------------ epilogue: 8 warps = 2 per TMEM lane quarter.
+    // Warp (q4, hsel) owns tile rows q4*32.. (its TMEM lanes) and the 32-column groups g with g % 2 == hsel, so the two
+    // halves of every 64-channel output chunk are produced concurrently and each scheduler has two warps to overlap the
+    // tcgen05.ld / shared-memory / barrier latencies of one with the arithmetic of the other.
     const int e = threadIdx.x - 128;
-    const int ewarp = e >> 5;
+    const int ew = e >> 5;
+    const int q4 = ew & 3, hsel = ew >> 2;
+    const int row = q4 * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t chunk_ctr = 0;
     const int n_groups = (p.BN + 31) >> 5;
+    const int n_chunks = (n_groups + 1) >> 1;
     const int twth = p.tw * p.th;
-    const bool out_f32 = (p.flags & B2U_EPI_OUT_F32) != 0;
     const bool do_relu = (p.flags & B2U_EPI_RELU) != 0;
-    const bool do_stats = (p.flags & B2U_EPI_STATS) != 0;
-    const bool has_res = p.res.ptr != nullptr, has_rm = p.res_mask.ptr != nullptr, has_zm = p.zmask.ptr != nullptr;
+    const bool has_res = kAux && p.res.ptr != nullptr, has_rm = kAux && p.res_mask.ptr != nullptr,
+               has_zm = kAux && p.zmask.ptr != nullptr;
+    const int slot_rm = has_res ? 1 : 0, slot_zm = (has_res ? 1 : 0) + (has_rm ? 1 : 0);
     auto issue_aux = [&](int t, int chunk, uint32_t buf) {
       const int m2 = t / p.n_tiles, nt2 = t - m2 * p.n_tiles;
       const int bn2 = m2 / tiles_xy, rem2 = m2 - bn2 * tiles_xy;
@@ -341,161 +349,161 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         tma_load_4d(aux_base + (uint32_t)i * 2 * kStagingBytes + buf * kStagingBytes, &p.tm_aux[i], aux_bar(buf),
                     nt2 * p.BN + chunk * 64, bx2 * p.tw, by2 * p.th, bn2 * p.tn);
     };
-    if (p.n_aux > 0 && e == 0 && (int)blockIdx.x < total_tiles) issue_aux(blockIdx.x, 0, 0);
+    if (kAux && e == 0 && (int)blockIdx.x < total_tiles) issue_aux(blockIdx.x, 0, 0);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m = tile / p.n_tiles, nt = tile - m * p.n_tiles;
       const int bn = m / tiles_xy, rem = m - bn * tiles_xy;
       const int by = rem / p.tiles_x, bx = rem - by * p.tiles_x;
       const int x0 = bx * p.tw, y0 = by * p.th, n0 = bn * p.tn;
-      const int rn = e / twth, rr = e - rn * twth;
+      const int rn = row / twth, rr = row - rn * twth;
       const int ry = rr / p.tw, rx = rr - ry * p.tw;
       const int px = x0 + rx, py = y0 + ry, pn = n0 + rn;
       const bool valid = (px < p.Wo) && (py < p.Ho) && (pn < p.N);
 
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t)acc * kAccStride + ((uint32_t)(ewarp * 32) << 16);
+      const uint32_t taddr = tmem_base + (uint32_t)acc * kAccStride + ((uint32_t)(q4 * 32) << 16);
 
-      auto process = [&](int g) {
-        if (p.n_aux > 0 && (g & 1) == 0) {
+#pragma unroll 1
+      for (int j = 0; j < n_chunks; ++j) {
+        const int g = 2 * j + hsel;
+        const bool active = g < n_groups;   // warp-uniform
+        if (kAux) {
           // residual / mask tiles arrive through TMA (coalesced, asynchronous), one 64-channel chunk ahead
           if (e == 0) {
-            int t2 = tile, g2 = g + 2;
-            if (g2 >= n_groups) { t2 = tile + gridDim.x; g2 = 0; }
-            if (t2 < total_tiles) issue_aux(t2, g2 >> 1, (chunk_ctr + 1u) & 1u);
+            int t2 = tile, j2 = j + 1;
+            if (j2 >= n_chunks) { t2 = tile + gridDim.x; j2 = 0; }
+            if (t2 < total_tiles) issue_aux(t2, j2, (chunk_ctr + 1u) & 1u);
           }
           mbar_wait(aux_bar(chunk_ctr & 1u), (chunk_ctr >> 1) & 1u);
         }
-        Aux ax;
-        {
-          const uint32_t abase = aux_base + (chunk_ctr & 1u) * kStagingBytes + (uint32_t)e * 128u;
-          int slot = 0;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint32_t off = (((uint32_t)((g & 1) * 4 + q)) ^ ((uint32_t)e & 7u)) << 4;
-            slot = 0;
-            if (has_res) { ax.r[q] = ld_shared_v4(abase + (uint32_t)slot * 2 * kStagingBytes + off); ++slot; }
-            if (has_rm) { ax.m[q] = ld_shared_v4(abase + (uint32_t)slot * 2 * kStagingBytes + off); ++slot; }
-            if (has_zm) { ax.z[q] = ld_shared_v4(abase + (uint32_t)slot * 2 * kStagingBytes + off); ++slot; }
-          }
-        }
         uint32_t r[32];
-        tmem_ld32(taddr + (uint32_t)(g * 32), r);
-        tmem_ld_wait();
-        if (g == n_groups - 1) {
-          // all TMEM reads of this accumulator are in registers: hand it back to the MMA warp
+        if (active) {
+          tmem_ld32(taddr + (uint32_t)(g * 32), r);
+          tmem_ld_wait();
+        }
+        if (j == n_chunks - 1) {
+          // all TMEM reads of this accumulator by this thread are in registers: hand it back to the MMA warp
           tc_fence_before();
           mbar_arrive(tempty_bar(acc));
         }
         const int c0 = nt * p.BN + g * 32;
         float v[32];
+        if (active) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        // per-channel scale / shift: arrays are padded to a multiple of 32 floats (see b2u.h), uniform 16-byte loads
-        if (p.scale) {
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          // per-channel scale / shift: arrays are padded to a multiple of 32 floats (see b2u.h), uniform 16-byte loads
+          if (p.scale) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + c0) + q);
-            v[4 * q] *= sc.x; v[4 * q + 1] *= sc.y; v[4 * q + 2] *= sc.z; v[4 * q + 3] *= sc.w;
-          }
-        }
-        if (p.shift) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + c0) + q);
-            v[4 * q] += sh.x; v[4 * q + 1] += sh.y; v[4 * q + 2] += sh.z; v[4 * q + 3] += sh.w;
-          }
-        }
-        if (has_res) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float rv[8], mv[8];
-            unpack8(ax.r[q], rv);
-            if (has_rm) {
-              unpack8(ax.m[q], mv);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[q * 8 + i] += (mv[i] > 0.f) ? rv[i] : 0.f;
-            } else {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[q * 8 + i] += rv[i];
+            for (int q = 0; q < 8; ++q) {
+              const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + c0) + q);
+              v[4 * q] *= sc.x; v[4 * q + 1] *= sc.y; v[4 * q + 2] *= sc.z; v[4 * q + 3] *= sc.w;
             }
           }
-        }
-        if (do_relu) {
+          if (p.shift) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-        }
-        if (has_zm) {
+            for (int q = 0; q < 8; ++q) {
+              const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + c0) + q);
+              v[4 * q] += sh.x; v[4 * q + 1] += sh.y; v[4 * q + 2] += sh.z; v[4 * q + 3] += sh.w;
+            }
+          }
+          if (kAux) {
+            const uint32_t abase = aux_base + (chunk_ctr & 1u) * kStagingBytes + (uint32_t)row * 128u;
+            if (has_res) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float zv[8];
-            unpack8(ax.z[q], zv);
+              for (int q = 0; q < 4; ++q) {
+                const uint32_t off = (((uint32_t)(hsel * 4 + q)) ^ ((uint32_t)row & 7u)) << 4;
+                float rv[8];
+                unpack8(ld_shared_v4(abase + off), rv);
+                if (has_rm) {
+                  float mv[8];
+                  unpack8(ld_shared_v4(abase + (uint32_t)slot_rm * 2 * kStagingBytes + off), mv);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[q * 8 + i] = (zv[i] > 0.f) ? v[q * 8 + i] : 0.f;
+                  for (int i = 0; i < 8; ++i) v[q * 8 + i] += (mv[i] > 0.f) ? rv[i] : 0.f;
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) v[q * 8 + i] += rv[i];
+                }
+              }
+            }
+          }
+          if (do_relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          if (kAux) {
+            if (has_zm) {
+              const uint32_t abase = aux_base + (chunk_ctr & 1u) * kStagingBytes + (uint32_t)row * 128u +
+                                     (uint32_t)slot_zm * 2 * kStagingBytes;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint32_t off = (((uint32_t)(hsel * 4 + q)) ^ ((uint32_t)row & 7u)) << 4;
+                float zv[8];
+                unpack8(ld_shared_v4(abase + off), zv);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[q * 8 + i] = (zv[i] > 0.f) ? v[q * 8 + i] : 0.f;
+              }
+            }
+          }
+          if (c0 + 32 > p.Cout) {
+            // lanes past Cout (channel padding up to the pitch) are stored as zeros, never as garbage
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c0 + i >= p.Cout) v[i] = 0.f;
           }
         }
-        if (c0 + 32 > p.Cout) {
-          // lanes past Cout (channel padding up to the pitch) are stored as zeros, never as garbage
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c0 + i >= p.Cout) v[i] = 0.f;
-        }
 
-        if (out_f32) {
-          if (valid) {
+        if (kF32) {
+          if (active && valid) {
             float* op = p.out_f32 + ((long long)(pn * p.Ho + py) * p.Wo + px) * p.out_f32_ld + c0;
 #pragma unroll
             for (int i = 0; i < 32; ++i)
               if (c0 + i < p.Cout) op[i] = v[i];
           }
         } else {
-          // bf16 pack -> swizzled staging (SWIZZLE_128B: 16-byte chunk j of row e lands at chunk j ^ (e & 7))
+          // bf16 pack -> swizzled staging (SWIZZLE_128B: 16-byte chunk j of row r lands at chunk j ^ (r & 7))
           const uint32_t buf = p.stg_bufs == 2 ? (chunk_ctr & 1u) : 0u;
-          if ((g & 1) == 0) {
-            // the store that last used this staging buffer has finished reading it
-            if (e == 0) { if (p.stg_bufs == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
-            named_bar_sync(1, 128);
-          }
-          uint32_t pk[16];
+          // the store that last used this staging buffer has finished reading it
+          if (e == 0) { if (p.stg_bufs == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
+          named_bar_sync(1, 256);
+          const uint32_t row_addr = stg_base + buf * kStagingBytes + (uint32_t)row * 128u;
+          if (active) {
+            uint32_t pk[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
-          const uint32_t row_addr = stg_base + buf * kStagingBytes + (uint32_t)e * 128u;
+            for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint32_t j = (uint32_t)((g & 1) * 4 + q);
-            const uint32_t addr = row_addr + ((j ^ ((uint32_t)e & 7u)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
-                         "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
-                         : "memory");
-          }
-          if ((g & 1) == 0 && g == n_groups - 1) {
-            // odd number of 32-channel groups: the upper half of this 64-channel staging chunk has no accumulator
-            // columns behind it; it is stored as zeros (those lanes are channel padding of the output view)
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t addr = row_addr + ((((uint32_t)(hsel * 4 + q)) ^ ((uint32_t)row & 7u)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
+                           "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
+                           : "memory");
+            }
+            if (kStats) {
+              // statistics of what is actually stored (bf16-rounded), so that BN forward/backward are self-consistent
 #pragma unroll
-            for (int q = 4; q < 8; ++q) {
-              const uint32_t addr = row_addr + (((uint32_t)q ^ ((uint32_t)e & 7u)) << 4);
+              for (int i = 0; i < 16; ++i) {
+                v[2 * i] = bf16_lo(pk[i]);
+                v[2 * i + 1] = bf16_hi(pk[i]);
+              }
+            }
+          } else {
+            // odd number of 32-channel groups: this half of the 64-channel staging chunk has no accumulator columns
+            // behind it; it is stored as zeros (those lanes are channel padding of the output view)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t addr = row_addr + ((((uint32_t)(hsel * 4 + q)) ^ ((uint32_t)row & 7u)) << 4);
               asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0u) : "memory");
             }
           }
-          if (do_stats) {
-            // statistics of what is actually stored (bf16-rounded), so that BN forward/backward are self-consistent
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              v[2 * i] = bf16_lo(pk[i]);
-              v[2 * i + 1] = bf16_hi(pk[i]);
-            }
-          }
-          if ((g & 1) == 1 || g == n_groups - 1) {
-            fence_proxy_async_smem();
-            named_bar_sync(1, 128);
-            if (e == 0) {
-              tma_store_4d(&p.tm_out, stg_base + buf * kStagingBytes, nt * p.BN + (g >> 1) * 64, x0, y0, n0);
-              tma_store_commit();
-            }
-            ++chunk_ctr;
+          fence_proxy_async_smem();
+          named_bar_sync(1, 256);
+          if (e == 0) {
+            tma_store_4d(&p.tm_out, stg_base + buf * kStagingBytes, nt * p.BN + j * 64, x0, y0, n0);
+            tma_store_commit();
           }
         }
-        if (do_stats) {
+        ++chunk_ctr;
+        if (kStats && active) {
           float s1[32], s2[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
@@ -507,29 +515,36 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           const float sq = warp_transpose_reduce(s2, lane);
           const int c = c0 + lane;
           if (p.stats_cols > 0) {
-            if (c < p.stats_cols) {   // this warp's private accumulators: no race, fixed (tile) order
-              s_stats[(ewarp * 2 + 0) * p.stats_cols + c] += sum;
-              s_stats[(ewarp * 2 + 1) * p.stats_cols + c] += sq;
+            if (c < p.stats_cols) {   // this lane quarter's private accumulators (column groups are disjoint): no race
+              s_stats[(q4 * 2 + 0) * p.stats_cols + c] += sum;
+              s_stats[(q4 * 2 + 1) * p.stats_cols + c] += sq;
             }
           } else if (c < p.stats_ld) {
-            float* sp = p.stats + (size_t)(m * 4 + ewarp) * 2 * p.stats_ld;
+            float* sp = p.stats + (size_t)(m * 4 + q4) * 2 * p.stats_ld;
             sp[c] = sum;
             sp[p.stats_ld + c] = sq;
           }
         }
-      };
-
-      for (int g = 0; g < n_groups; ++g) process(g);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
-    if (e == 0 && !out_f32) tma_store_wait_all<0>();
-    if (do_stats && p.stats_cols > 0) {
-      float* sp = p.stats + (size_t)(blockIdx.x * 4 + ewarp) * 2 * p.stats_ld;
-      for (int c = lane; c < p.stats_cols && c < p.stats_ld; c += 32) {
-        sp[c] = s_stats[(ewarp * 2 + 0) * p.stats_cols + c];
-        sp[p.stats_ld + c] = s_stats[(ewarp * 2 + 1) * p.stats_cols + c];
+    if (e == 0 && !kF32) tma_store_wait_all<0>();
+    if (kStats && p.stats_cols > 0) {
+      // one partial row per CTA: the four lane quarters' accumulators are combined in a fixed order
+      named_bar_sync(1, 256);
+      float* sp = p.stats + (size_t)blockIdx.x * 2 * p.stats_ld;
+      for (int c = e; c < p.stats_cols && c < p.stats_ld; c += 256) {
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          s1 += s_stats[(w * 2 + 0) * p.stats_cols + c];
+          s2 += s_stats[(w * 2 + 1) * p.stats_cols + c];
+        }
+        sp[c] = s1;
+        sp[p.stats_ld + c] = s2;
       }
+      __threadfence();   // visible device-wide before this CTA takes its ticket below
     }
   }
 
@@ -538,6 +553,62 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
+  }
+
+  // ---------------------------------------------------------------- fused BatchNorm finalize (last CTA to retire)
+  if (p.fin.counter != nullptr) {
+    volatile int* s_last = reinterpret_cast<volatile int*>(
+        smem + (size_t)ring_bytes + (size_t)(p.stg_bufs + 2 * p.n_aux) * kStagingBytes + 504);
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned int ticket = atomicAdd(p.fin.counter, 1u);
+      *s_last = (ticket == gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (*s_last) {
+      __threadfence();
+      // every pipeline stage has been consumed and every store has left the staging buffers: the ring is scratch now
+      double* sh = reinterpret_cast<double*>(smem);
+      const int ld = p.stats_ld, rows = (int)gridDim.x;
+      const int ncol4 = ld >> 1;                 // float4 columns of one partial row [2][ld]
+      const int RL = kThreads / ncol4 > 0 ? kThreads / ncol4 : 1;
+      const int rl = (int)threadIdx.x / ncol4, c4 = (int)threadIdx.x - rl * ncol4;
+      if (rl < RL) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        const float4* src = reinterpret_cast<const float4*>(p.stats) + c4;
+#pragma unroll 8
+        for (int r = rl; r < rows; r += RL) {
+          const float4 v = __ldcg(src + (size_t)r * ncol4);
+          a0 += (double)v.x; a1 += (double)v.y; a2 += (double)v.z; a3 += (double)v.w;
+        }
+        double* d = sh + ((size_t)rl * ncol4 + c4) * 4;
+        d[0] = a0; d[1] = a1; d[2] = a2; d[3] = a3;
+      }
+      __syncthreads();
+      for (int c = threadIdx.x; c < p.Cout; c += kThreads) {
+        double s0 = 0.0, s1 = 0.0;
+        for (int q = 0; q < RL; ++q) {
+          s0 += sh[(size_t)q * ncol4 * 4 + c];
+          s1 += sh[(size_t)q * ncol4 * 4 + ld + c];
+        }
+        const double m = s0 / p.fin.count;
+        double var = s1 / p.fin.count - m * m;
+        if (var < 0) var = 0;
+        const double istd = 1.0 / sqrt(var + (double)p.fin.eps);
+        const float g = p.fin.gamma ? p.fin.gamma[c] : 1.f, b = p.fin.beta ? p.fin.beta[c] : 0.f;
+        p.fin.mean[c] = (float)m;
+        p.fin.invstd[c] = (float)istd;
+        p.fin.scale[c] = (float)(g * istd);
+        p.fin.shift[c] = (float)(b - m * g * istd);
+        if (p.fin.running_mean) {
+          const double unbiased = p.fin.count > 1 ? var * p.fin.count / (p.fin.count - 1) : var;
+          const double mom = (double)p.fin.momentum;
+          p.fin.running_mean[c] = (float)((1.0 - mom) * p.fin.running_mean[c] + mom * m);
+          p.fin.running_var[c] = (float)((1.0 - mom) * p.fin.running_var[c] + mom * unbiased);
+        }
+      }
+      if (threadIdx.x == 0) *p.fin.counter = 0u;   // ready for the next launch of this plan
+    }
   }
 }
 
@@ -699,7 +770,20 @@ static int conv_plan_fill(const b2u_conv_desc* d, b2u_conv_plan* plan, bool enco
   const int sms = encode ? sm_count() : 148;
   info.grid = total < sms ? total : sms;
   // rows of the statistics partial buffer: one per (CTA, epilogue warp) when accumulated on chip, else per (tile, warp)
-  info.stats_rows = p.stats_cols > 0 ? 4 * (total < 148 ? total : 148) : 4 * p.m_tiles;
+  info.stats_rows = p.stats_cols > 0 ? info.grid : 4 * p.m_tiles;
+  memset(&p.fin, 0, sizeof(p.fin));
+  info.fused_finalize = 0;
+  if (p.stats_cols > 0 && d->stats_ld > 0 && d->stats_ld <= 512 && d->stats_ld % 4 == 0) {
+    info.fused_finalize = 1;
+    if (d->fin.counter != nullptr) {
+      B2U_CHECK_ARG(d->fin.count > 0 && d->fin.mean && d->fin.invstd && d->fin.scale && d->fin.shift,
+                    "conv: fused BatchNorm finalize needs count, mean, invstd, scale and shift");
+      p.fin = d->fin;
+    }
+  } else {
+    B2U_CHECK_ARG(d->fin.counter == nullptr || !encode,
+                  "conv: fused BatchNorm finalize is not available for this shape (query info.fused_finalize first)");
+  }
 
   if (encode) {
     for (int i = 0; i < d->num_a; ++i) {
@@ -767,8 +851,13 @@ extern "C" int b2u_conv_plan_create(const b2u_conv_desc* d, b2u_conv_plan** out)
   if (rc) { delete plan; return rc; }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(conv_gemm_kernel): %s", cudaGetErrorString(e)); delete plan; return B2U_ERR_CUDA; }
+    const void* variants[] = {(const void*)conv_gemm_kernel<false, false, false>, (const void*)conv_gemm_kernel<false, true, false>,
+                              (const void*)conv_gemm_kernel<true, false, false>, (const void*)conv_gemm_kernel<true, true, false>,
+                              (const void*)conv_gemm_kernel<false, false, true>};
+    for (const void* f : variants) {
+      cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+      if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(conv_gemm_kernel): %s", cudaGetErrorString(e)); delete plan; return B2U_ERR_CUDA; }
+    }
     attr_set = true;
   }
   *out = plan;
@@ -783,7 +872,15 @@ extern "C" int b2u_conv_plan_info(const b2u_conv_plan* plan, b2u_conv_info* info
 
 extern "C" int b2u_conv_run(const b2u_conv_plan* plan, void* stream) {
   B2U_CHECK_ARG(plan != nullptr, "conv_run: null plan");
-  conv_gemm_kernel<<<plan->info.grid, kThreads, plan->smem_bytes, (cudaStream_t)stream>>>(plan->p);
+  const ConvParams& p = plan->p;
+  const dim3 grid(plan->info.grid), block(kThreads);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool aux = p.n_aux > 0, stats = (p.flags & B2U_EPI_STATS) != 0, f32 = (p.flags & B2U_EPI_OUT_F32) != 0;
+  if (f32) conv_gemm_kernel<false, false, true><<<grid, block, plan->smem_bytes, st>>>(p);
+  else if (aux && stats) conv_gemm_kernel<true, true, false><<<grid, block, plan->smem_bytes, st>>>(p);
+  else if (aux) conv_gemm_kernel<true, false, false><<<grid, block, plan->smem_bytes, st>>>(p);
+  else if (stats) conv_gemm_kernel<false, true, false><<<grid, block, plan->smem_bytes, st>>>(p);
+  else conv_gemm_kernel<false, false, false><<<grid, block, plan->smem_bytes, st>>>(p);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }

@@ -47,7 +47,10 @@ struct WStageItem {
   int block_start;      // first block of this item in the batched launch
 };
 
-__global__ void stage_weights_kernel(const WStageItem* __restrict__ items, int n_items) {
+// One block = a 32 (output channels) x 32 (input channels) tile of one layer with all kh*kw taps: the fp32 master rows are
+// read as contiguous runs, transposed through shared memory and written as 64-byte runs of BOTH bf16 layouts (the
+// dgrad layout is the channel transpose of the fprop layout, so a direct scatter would write 2 bytes per sector).
+__global__ void __launch_bounds__(256) stage_weights_kernel(const WStageItem* __restrict__ items, int n_items) {
   // binary search for the item owning this block
   int lo = 0, hi = n_items - 1;
   while (lo < hi) {
@@ -55,22 +58,33 @@ __global__ void stage_weights_kernel(const WStageItem* __restrict__ items, int n
     if (items[mid].block_start <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
   }
   const WStageItem it = items[lo];
-  const long long total = (long long)it.Cout * it.kk * it.Cin;
-  const long long i = (long long)(blockIdx.x - it.block_start) * blockDim.x + threadIdx.x;
-  if (i < total) {
-    const int ci = (int)(i % it.Cin);
-    const int t = (int)((i / it.Cin) % it.kk);
-    const int co = (int)(i / ((long long)it.Cin * it.kk));
-    const float v = it.w[((size_t)co * it.Cin + ci) * it.kk + t];
-    const int row = it.row_of_co ? it.row_of_co[co] : co;
-    it.wf[((size_t)row * it.kk + t) * it.wf_cinp + ci] = __float2bfloat16_rn(v * it.scale);
-    if (it.wd) it.wd[((size_t)ci * it.kk + (it.kk - 1 - t)) * it.wd_coutp + row] = __float2bfloat16_rn(v * it.scale);
+  __shared__ __nv_bfloat16 tile[32][32 * 9 + 2];   // +2: odd word stride, conflict-free column reads
+  const int kk = it.kk;
+  const int tiles_ci = (it.Cin + 31) >> 5;
+  const int b = (int)blockIdx.x - it.block_start;
+  const int co0 = (b / tiles_ci) * 32, ci0 = (b % tiles_ci) * 32;
+  const int nco = min(32, it.Cout - co0), nci = min(32, it.Cin - ci0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int run = nci * kk;
+  for (int r = warp; r < nco; r += 8) {
+    const float* src = it.w + ((size_t)(co0 + r) * it.Cin + ci0) * kk;
+    for (int j = lane; j < run; j += 32) tile[r][j] = __float2bfloat16_rn(src[j] * it.scale);
   }
-  if (it.bias && it.bias_rows && i < it.Cout) {
-    const int co = (int)i;
-    const int row = it.row_of_co ? it.row_of_co[co] : co;
-    it.bias_rows[row] = it.bias[co];
+  int row_l = co0 + lane;   // GEMM row of output channel co0 + lane
+  if (it.row_of_co && lane < nco) row_l = it.row_of_co[co0 + lane];
+  __syncthreads();
+  for (int q = warp; q < nco * kk; q += 8) {
+    const int r = q / kk, t = q - r * kk;
+    const int row = __shfl_sync(0xffffffffu, row_l, r);
+    if (lane < nci) it.wf[((size_t)row * kk + t) * it.wf_cinp + ci0 + lane] = tile[r][lane * kk + t];
   }
+  if (it.wd) {
+    for (int q = warp; q < nci * kk; q += 8) {
+      const int ci = q / kk, t = q - ci * kk;
+      if (lane < nco) it.wd[((size_t)(ci0 + ci) * kk + (kk - 1 - t)) * it.wd_coutp + row_l] = tile[lane][ci * kk + t];
+    }
+  }
+  if (ci0 == 0 && it.bias && it.bias_rows && warp == 0 && lane < nco) it.bias_rows[row_l] = it.bias[co0 + lane];
 }
 
 // ------------------------------------------------------------------------------------------------ decoder glue
@@ -91,11 +105,29 @@ __device__ __forceinline__ void for_each_pixel_group_xy(int N, int H, int W, int
     int n = p / (H * W), rem = p - n * H * W;
     int y = rem / W, x = rem - y * W;
     const int dy = PL / W, dx = PL - dy * W;    // step of PL pixels in (y, x)
+    auto adv = [&](int& nn, int& yy, int& xx) {
+      xx += dx; yy += dy;
+      if (xx >= W) { xx -= W; ++yy; }
+      while (yy >= H) { yy -= H; ++nn; }
+    };
+    // four pixels per trip: their loads are independent, so four times the bytes are in flight per thread
+    for (; p + 3 * PL < p1; p += 4 * PL) {
+      int n1 = n, y1 = y, x1 = x;
+      adv(n1, y1, x1);
+      int n2 = n1, y2 = y1, x2 = x1;
+      adv(n2, y2, x2);
+      int n3 = n2, y3 = y2, x3 = x2;
+      adv(n3, y3, x3);
+      body(p, n, y, x, g * 8);
+      body(p + PL, n1, y1, x1, g * 8);
+      body(p + 2 * PL, n2, y2, x2, g * 8);
+      body(p + 3 * PL, n3, y3, x3, g * 8);
+      n = n3; y = y3; x = x3;
+      adv(n, y, x);
+    }
     for (; p < p1; p += PL) {
       body(p, n, y, x, g * 8);
-      x += dx; y += dy;
-      if (x >= W) { x -= W; ++y; }
-      while (y >= H) { y -= H; ++n; }
+      adv(n, y, x);
     }
   }
 }

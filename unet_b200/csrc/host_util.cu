@@ -116,3 +116,16 @@ extern "C" int b2u_device_check(void) {
   if (!b2u::get_encode()) return B2U_ERR_CUDA;
   return B2U_OK;
 }
+
+extern "C" int b2u_abi_sizeof(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(b2u_view);
+    case 1: return (int)sizeof(b2u_conv_desc);
+    case 2: return (int)sizeof(b2u_conv_info);
+    case 3: return (int)sizeof(b2u_wgrad_desc);
+    case 4: return (int)sizeof(b2u_wgrad_info);
+    case 5: return (int)sizeof(b2u_wstage_item);
+    case 6: return (int)sizeof(b2u_bn_fin);
+    default: return -1;
+  }
+}

@@ -294,13 +294,43 @@ __global__ void __launch_bounds__(1024) wgrad_reduce_kernel(const float* __restr
 #pragma unroll
   for (int k = 0; k < KS; ++k) acc[k] = 0.f;
   if (ci < Cin) {
-    for (int t = 0; t < taps; ++t) {
-      const int kidx = tap_kidx[t];
-      const float* src = partial + ((size_t)t * co_pad + co) * ci_pad + ci;
-      float a = 0.f;
-      for (int s = sl; s < splits; s += L) a += src[(size_t)s * sstride];
+    if (taps == KS) {
+      // the common case (one tap per kernel position): KS independent loads in flight per split, two splits per trip
+      int kidx[KS];
 #pragma unroll
-      for (int k = 0; k < KS; ++k) acc[k] += (k == kidx) ? a : 0.f;
+      for (int t = 0; t < KS; ++t) kidx[t] = tap_kidx[t];
+      const float* src = partial + (size_t)co * ci_pad + ci;
+      const size_t tstride = (size_t)co_pad * ci_pad;
+      float a[KS], b[KS];
+#pragma unroll
+      for (int t = 0; t < KS; ++t) { a[t] = 0.f; b[t] = 0.f; }
+      int s = sl;
+      for (; s + L < splits; s += 2 * L) {
+#pragma unroll
+        for (int t = 0; t < KS; ++t) {
+          a[t] += __ldcg(src + (size_t)s * sstride + t * tstride);
+          b[t] += __ldcg(src + (size_t)(s + L) * sstride + t * tstride);
+        }
+      }
+      if (s < splits) {
+#pragma unroll
+        for (int t = 0; t < KS; ++t) a[t] += __ldcg(src + (size_t)s * sstride + t * tstride);
+      }
+#pragma unroll
+      for (int t = 0; t < KS; ++t) {
+        const float v = a[t] + b[t];
+#pragma unroll
+        for (int k = 0; k < KS; ++k) acc[k] += (k == kidx[t]) ? v : 0.f;
+      }
+    } else {
+      for (int t = 0; t < taps; ++t) {
+        const int kidx = tap_kidx[t];
+        const float* src = partial + ((size_t)t * co_pad + co) * ci_pad + ci;
+        float a = 0.f;
+        for (int s = sl; s < splits; s += L) a += __ldcg(src + (size_t)s * sstride);
+#pragma unroll
+        for (int k = 0; k < KS; ++k) acc[k] += (k == kidx) ? a : 0.f;
+      }
     }
   }
 #pragma unroll
@@ -408,10 +438,25 @@ static int wgrad_fill(const b2u_wgrad_desc* d, b2u_wgrad_plan* plan, bool encode
   p.b_box_bytes = (p.b_box_tx + 1023u) & ~1023u;
   const int base_units = p.n_co * p.inner;
   const int sms = encode ? sm_count() : 148;
-  int splits = (2 * sms) / base_units;
-  const int max_splits = p.k_steps / 16 > 0 ? p.k_steps / 16 : 1;
-  if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
+  // Split count from a small cost model (microseconds): a CTA runs its units back to back (one accumulator set, so the
+  // epilogue is not overlapped), every split adds one partial tile set that is written here and read by the reduce.
+  //   wave cost  = steps * t_step + t_epi,   t_step ~ T taps x 4 MMAs of 128 x BN x 16 (measured ~1.8x the MMA floor)
+  //   split cost = 2 x partial bytes / ~4 TB/s
+  int splits = 1;
+  {
+    const double t_step = p.T * 4 * (p.BN > 96 ? p.BN : 96) / 2.0 / 1900.0 * 1.8;
+    const double t_epi = p.T * p.BN * 512.0 / 57000.0;
+    const double t_split = (double)(d->num_taps + (d->want_bias ? 1 : 0)) * (p.n_co * 128) * (p.n_ci * p.BN) * 8.0 / 4.0e6;
+    const int max_splits = p.k_steps / 8 > 0 ? p.k_steps / 8 : 1;
+    double best = -1.0;
+    for (int sp = 1; sp <= max_splits && sp * base_units <= 4 * sms; ++sp) {
+      const int steps = ceil_div(p.k_steps, sp);
+      if (ceil_div(p.k_steps, steps) != sp) continue;   // not a distinct partition
+      const int waves = ceil_div(sp * base_units, sms);
+      const double cost = waves * (steps * t_step + t_epi) + sp * t_split;
+      if (best < 0 || cost < best) { best = cost; splits = sp; }
+    }
+  }
   p.steps_per_split = ceil_div(p.k_steps, splits);
   splits = ceil_div(p.k_steps, p.steps_per_split);
   p.splits = splits;
@@ -500,7 +545,7 @@ extern "C" int b2u_wgrad_reduce(const float* partial, int32_t splits, int32_t ta
   dim3 grid((unsigned)ceil_div(Cin, 32), (unsigned)Cout);
   int lanes = 1;
   const int lane_cap = ksize == 9 ? 8 : 32;               // shared-memory budget: 32*KS*33 floats per 32 lanes
-  while (lanes < lane_cap && lanes * 4 < splits) lanes <<= 1;   // ~4 sequential loads per lane and tap
+  while (lanes < lane_cap && lanes * 2 < splits) lanes <<= 1;   // ~2 sequential loads per lane and tap
   const int tt = taps + (has_bias_cols ? 1 : 0);
   if (ksize == 9)
     wgrad_reduce_kernel<9><<<grid, 32 * lanes, 0, (cudaStream_t)stream>>>(partial, splits, taps, tt, co_pad, ci_pad, Cout,

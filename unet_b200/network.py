@@ -230,7 +230,7 @@ class UNetB200:
         blocks = 0
         for i, it in enumerate(self._wstage):
             it.block_start = blocks
-            blocks += (it.Cout * it.Cin * it.kk + 255) // 256
+            blocks += ((it.Cout + 31) // 32) * ((it.Cin + 31) // 32)   # one block per 32x32 channel tile
             arr[i] = it
         raw = bytes(arr)
         host = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
@@ -264,12 +264,13 @@ class UNetB200:
         self.launches_bwd += n
 
     def _conv_fwd(self, cs: ConvSpec, x: Act, y: Act, *, out_C: Optional[int] = None, scale=None, shift=None,
-                  relu=False, res: Optional[Act] = None, stats=False, out_f32: Optional[torch.Tensor] = None):
+                  relu=False, res: Optional[Act] = None, stats=False, out_f32: Optional[torch.Tensor] = None,
+                  fin: Optional[dict] = None):
         w = self._w[cs.name]
         views, taps = self._views_taps(cs, x)
         plan = ConvPlan(views, view_nhwc(y.t, out_C or cs.nf), w["wf"], cs.ni, taps, scale=scale, shift=shift,
                         res=view_nhwc(res.t, cs.nf) if res is not None else None, relu=relu, stats=stats,
-                        out_f32=out_f32)
+                        out_f32=out_f32, fin=fin)
         self._keep.append(plan)
         self._fwd(plan.run)
         return plan
@@ -308,25 +309,24 @@ class UNetB200:
     # ---- backward helpers ---------------------------------------------------------------------------------------
     def _bn_bwd(self, bn: BNState, dz: torch.Tensor, lddz: int, x: torch.Tensor, ldx: int, y: Optional[torch.Tensor],
                 ldy: int, relu: bool, dx: torch.Tensor, lddx: int, pixels: int, accumulate: bool):
-        """reduce -> finalize -> apply; dgamma/dbeta land in the flat gradient buffer."""
+        """reduce -> finalize -> apply in one launch (grid barrier inside); dgamma/dbeta land in the flat gradient
+        buffer."""
         rows = max(1, min(STATS_ROWS, pixels // 64))
         partial = torch.zeros((rows, 2, padc(bn.C)), dtype=torch.float32, device=self.device)
-        lib, sc = self.lib, self._scratch
+        lib = self.lib
         ld = padc(bn.C)
+        if not hasattr(self, "_bn_sync"):
+            self._bn_sync = torch.zeros(2, dtype=torch.int32, device=self.device)
+        sync = self._bn_sync
 
         def run(s):
-            _lib.check(lib.b2u_bn_bwd_reduce(dz.data_ptr(), lddz, x.data_ptr(), ldx, _p(y), ldy, _p(bn.scale),
-                                             _p(bn.shift), _p(bn.mean), _p(bn.invstd), int(relu), pixels, bn.C,
-                                             partial.data_ptr(), rows, ld, s), "b2u_bn_bwd_reduce")
-            _lib.check(lib.b2u_bn_bwd_finalize(partial.data_ptr(), rows, ld, bn.C, float(pixels), _p(bn.dgamma),
-                                               _p(bn.dbeta), _p(bn.mean_g), _p(bn.mean_gx), sc.data_ptr(), sc.numel(),
-                                               s), "b2u_bn_bwd_finalize")
-            _lib.check(lib.b2u_bn_bwd_apply(dz.data_ptr(), lddz, x.data_ptr(), ldx, _p(y), ldy, _p(bn.scale),
-                                            _p(bn.shift), _p(bn.mean), _p(bn.invstd), _p(bn.gamma), _p(bn.mean_g),
-                                            _p(bn.mean_gx), int(relu), int(accumulate), dx.data_ptr(), lddx, pixels,
-                                            bn.C, s), "b2u_bn_bwd_apply")
+            _lib.check(lib.b2u_bn_bwd_fused(dz.data_ptr(), lddz, x.data_ptr(), ldx, _p(y), ldy, _p(bn.scale),
+                                            _p(bn.shift), _p(bn.mean), _p(bn.invstd), _p(bn.gamma), int(relu),
+                                            int(accumulate), dx.data_ptr(), lddx, pixels, bn.C, partial.data_ptr(),
+                                            rows, ld, float(pixels), _p(bn.dgamma), _p(bn.dbeta), _p(bn.mean_g),
+                                            _p(bn.mean_gx), sync.data_ptr(), s), "b2u_bn_bwd_fused")
         self._keep.append(partial)
-        self._bwd(run, 3 + (1 if rows > 128 else 0))
+        self._bwd(run, 1)
 
     def _wgrad(self, cs: ConvSpec, dy: torch.Tensor, x: Act):
         """dW (and db) of conv `cs` from dy (bf16 NHWC tensor [N,Ho,Wo,padc(nf)]) and its input activation x."""
@@ -395,9 +395,14 @@ class UNetB200:
             bn = self._bn_state(cs.bn_prefix, cs.nf)
             if train:
                 R = self._act(h, w_, cs.nf, cs.name + ".raw")
-                plan = self._conv_fwd(cs, x, R, stats=True)
-                fin, nl = self._bn_finalize_op(bn, plan.stats, N * h * w_)
-                self._fwd(fin, nl)
+                # the conv kernel's last CTA finalizes the batch statistics (mean/invstd/scale/shift, running stats)
+                plan = self._conv_fwd(cs, x, R, stats=True, fin=dict(
+                    count=N * h * w_, gamma=bn.gamma, beta=bn.beta, eps=BN_EPS, momentum=BN_MOMENTUM,
+                    running_mean=bn.running_mean, running_var=bn.running_var, mean=bn.mean, invstd=bn.invstd,
+                    scale=bn.scale, shift=bn.shift))
+                if not plan.fused_finalize:   # Cout > 512 (xresnet50/101): per-tile partial rows, separate finalize
+                    fin, nl = self._bn_finalize_op(bn, plan.stats, N * h * w_)
+                    self._fwd(fin, nl)
                 Z = None
                 if apply:
                     Z = self._act(h, w_, cs.nf, cs.name + ".out")

@@ -133,7 +133,10 @@ class ConvPlan:
                  scale: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None,
                  res: Optional[View] = None, res_mask: Optional[View] = None, zmask: Optional[View] = None,
                  relu: bool = False, stats: bool = False, out_f32: Optional[torch.Tensor] = None,
-                 stats_ld: Optional[int] = None):
+                 stats_ld: Optional[int] = None, fin: Optional[dict] = None):
+        """fin (with stats=True): dict(count, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, scale,
+        shift) of fp32 tensors -> the kernel's last CTA finalizes the BatchNorm statistics itself when the shape allows
+        (self.fused_finalize tells the caller whether a separate b2u_bn_finalize launch is still needed)."""
         assert w.dtype == torch.bfloat16 and w.dim() == 3 and w.is_contiguous()
         lib = _lib.load()
         d = ConvDesc()
@@ -168,15 +171,27 @@ class ConvPlan:
             d.out_f32_ld = out_f32.shape[-1]
         d.flags = flags
         self.stats = None
+        self.fused_finalize = False
         if stats:
             info = ConvInfo()
             d.flags = flags | _lib.EPI_STATS   # the partial-row count depends on the statistics mode: query WITH the flag
-            _lib.check(lib.b2u_conv_query(C.byref(d), C.byref(info)), "b2u_conv_query")
             ld = stats_ld or padc(out_view.C)
-            self.stats = torch.zeros((info.stats_rows, 2, ld), dtype=torch.float32, device=w.device)
-            d.flags = flags | _lib.EPI_STATS
-            d.stats = self.stats.data_ptr()
             d.stats_ld = ld
+            _lib.check(lib.b2u_conv_query(C.byref(d), C.byref(info)), "b2u_conv_query")
+            self.stats = torch.zeros((info.stats_rows, 2, ld), dtype=torch.float32, device=w.device)
+            d.stats = self.stats.data_ptr()
+            if fin is not None and info.fused_finalize:
+                self.fused_finalize = True
+                self._fin_counter = torch.zeros(1, dtype=torch.int32, device=w.device)
+                d.fin.counter = self._fin_counter.data_ptr()
+                d.fin.count = float(fin["count"])
+                d.fin.eps, d.fin.momentum = float(fin["eps"]), float(fin["momentum"])
+                for k in ("gamma", "beta", "running_mean", "running_var", "mean", "invstd", "scale", "shift"):
+                    t = fin.get(k)
+                    if t is not None:
+                        assert t.dtype == torch.float32 and t.is_contiguous()
+                        setattr(d.fin, k, t.data_ptr())
+                        self._keep.append(t)
         self.desc = d
         h = C.c_void_p()
         _lib.check(lib.b2u_conv_plan_create(C.byref(d), C.byref(h)), "b2u_conv_plan_create")
