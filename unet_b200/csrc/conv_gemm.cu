@@ -33,6 +33,8 @@ struct ConvParams {
   // (profiles/r01_swizzle_offset_probe.txt).  A and B have separate rings: SA halo stages, SB weight stages.
   int stats_cols;  // > 0: BN partial sums are accumulated per warp in smem over all tiles of the CTA (4*grid rows)
   int halo, SA, SB, hw;
+  int wres;          // halo mode with ALL weights of the (single) N tile resident in shared memory for the whole launch:
+                     // SB = 3*k_chunks filter-row blocks loaded once; only the activation halo tiles stream per tile
   int rowmode;       // halo mode with one weight stage per FILTER ROW (3 taps, one barrier): amortises the issue-side cost
   int stg_bufs;      // output staging buffers (2, or 1 in row mode to make room for the larger weight stages)
   CUtensorMap tm_b3; // weights viewed as (Cin, Cout, tap): a box of 3 taps lands as [3][BN][64] in smem
@@ -92,13 +94,16 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane)
 // kAux: residual / mask operands in the epilogue; kStats: BatchNorm partial sums; kF32: fp32 logits output (head).
 // Compile-time switches: the epilogue is the critical path of the memory-/issue-bound layers, unused features must not
 // cost instructions there.
-template <bool kAux, bool kStats, bool kF32>
+// kPair: CTA-pair mode (cluster of 2, tcgen05 cta_group::2): CTA rank r of a pair owns pixel tile 2*pm + r and HALF of the
+// weight rows of every stage; the leader's MMA thread issues M = 256 instructions that drive both SMs' tensor cores.
+template <bool kAux, bool kStats, bool kF32, bool kPair>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t smem_base = smem_u32(smem);
-  const uint32_t b_bytes = (uint32_t)p.BN * 128u;
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+  const uint32_t b_bytes = (uint32_t)(kPair ? p.BN / 2 : p.BN) * 128u;   // weight rows held by THIS CTA per tap
   const uint32_t stage_bytes = kABytes + b_bytes;
   const int S = p.stages;
   const uint32_t bs_bytes = p.rowmode ? 3u * b_bytes : b_bytes;   // one weight stage
@@ -131,7 +136,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     for (int s = 0; s < n_ring_bars; ++s) mbar_init(bar_base + 8u * (uint32_t)s, 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 256);
+      mbar_init(tempty_bar(a), kPair ? 257 : 256);   // pair: + one remote arrive from the peer's epilogue
       mbar_init(aux_bar(a), 1);
     }
     fence_mbar_init();
@@ -144,17 +149,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     if (p.halo) tma_prefetch_desc(&p.tm_ah);
     if (p.rowmode) tma_prefetch_desc(&p.tm_b3);
   }
+  if (kPair) cluster_sync_all();   // the peer's barriers are initialised before any TMA / commit can signal them
   if (warp == 2) {
-    tmem_alloc(tmem_slot, kTmemCols);
-    tmem_relinquish();
+    if (kPair) { tmem_alloc2(tmem_slot, kTmemCols); tmem_relinquish2(); }
+    else { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int total_tiles = p.m_tiles * p.n_tiles;
   const int tiles_xy = p.tiles_x * p.tiles_y;
+  // persistent schedule: loop index t -> (pixel tile m, channel tile nt); a pair walks pair-tiles and splits them by rank
+  const int t_begin = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int t_step = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int t_end = kPair ? ((p.m_tiles + 1) >> 1) * p.n_tiles : p.m_tiles * p.n_tiles;
+  auto tile_m = [&](int t) { return kPair ? 2 * (t / p.n_tiles) + (int)rank : t / p.n_tiles; };
+  auto tile_nt = [&](int t) { return t - (t / p.n_tiles) * p.n_tiles; };
+  // TMA loads: in pair mode the bytes are credited to the leader's barrier (which expects both CTAs' bytes)
+  auto load4 = [&](uint32_t dst, const CUtensorMap* mp, uint32_t bar, int c0, int c1, int c2, int c3) {
+    if (kPair) tma_load_4d_pair(dst, mp, bar, c0, c1, c2, c3); else tma_load_4d(dst, mp, bar, c0, c1, c2, c3);
+  };
+  auto load3 = [&](uint32_t dst, const CUtensorMap* mp, uint32_t bar, int c0, int c1, int c2) {
+    if (kPair) tma_load_3d_pair(dst, mp, bar, c0, c1, c2); else tma_load_3d(dst, mp, bar, c0, c1, c2);
+  };
+  const uint32_t tx_mult = kPair ? 2u : 1u;
+  const int b_row0 = kPair ? (int)rank * (p.BN / 2) : 0;   // first weight row of this CTA inside an N tile
 
   if (warp == 0) {
     const bool elected = elect_one();
@@ -163,28 +183,36 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       const uint32_t b_ring = smem_base + (uint32_t)p.SA * p.a_stage_bytes;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m = tile / p.n_tiles, nt = tile - m * p.n_tiles;
+      if (p.wres && t_begin < t_end) {
+        // resident weights: every filter row of every K chunk, once (n_tiles == 1); fullB(0) collects all of it
+        if (rank == 0) mbar_expect_tx(fullB(0), tx_mult * (uint32_t)(3 * p.k_chunks) * bs_bytes);
+        for (int kc = 0; kc < p.k_chunks; ++kc)
+          for (int r = 0; r < 3; ++r)
+            load3(b_ring + (uint32_t)(kc * 3 + r) * bs_bytes, &p.tm_b3, fullB(0), kc * 64, b_row0, 3 * r);
+      }
+      for (int tt = t_begin; tt < t_end; tt += t_step) {
+        const int m = tile_m(tt), nt = tile_nt(tt);
         const int bn = m / tiles_xy, rem = m - bn * tiles_xy;
         const int by = rem / p.tiles_x, bx = rem - by * p.tiles_x;
         const int x0 = bx * p.tw, y0 = by * p.th, n0 = bn * p.tn;
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           mbar_wait(emptyA(sa), pa ^ 1u);
-          mbar_expect_tx(fullA(sa), p.a_tx_bytes);
-          tma_load_4d(smem_base + (uint32_t)sa * p.a_stage_bytes, &p.tm_ah, fullA(sa), kc * 64, x0 - 1, y0 - 1, n0);
+          if (rank == 0) mbar_expect_tx(fullA(sa), tx_mult * p.a_tx_bytes);
+          load4(smem_base + (uint32_t)sa * p.a_stage_bytes, &p.tm_ah, fullA(sa), kc * 64, x0 - 1, y0 - 1, n0);
           if (++sa == p.SA) { sa = 0; pa ^= 1u; }
+          if (p.wres) continue;
           if (p.rowmode) {
             for (int r = 0; r < 3; ++r) {
               mbar_wait(emptyB(sb), pb ^ 1u);
-              mbar_expect_tx(fullB(sb), bs_bytes);
-              tma_load_3d(b_ring + (uint32_t)sb * bs_bytes, &p.tm_b3, fullB(sb), kc * 64, nt * p.BN, 3 * r);
+              if (rank == 0) mbar_expect_tx(fullB(sb), tx_mult * bs_bytes);
+              load3(b_ring + (uint32_t)sb * bs_bytes, &p.tm_b3, fullB(sb), kc * 64, nt * p.BN + b_row0, 3 * r);
               if (++sb == p.SB) { sb = 0; pb ^= 1u; }
             }
           } else {
             for (int t = 0; t < p.num_taps; ++t) {
               mbar_wait(emptyB(sb), pb ^ 1u);
-              mbar_expect_tx(fullB(sb), b_bytes);
-              tma_load_3d(b_ring + (uint32_t)sb * b_bytes, &p.tm_b, fullB(sb), kc * 64, p.tap_w[t], nt * p.BN);
+              if (rank == 0) mbar_expect_tx(fullB(sb), tx_mult * b_bytes);
+              load3(b_ring + (uint32_t)sb * b_bytes, &p.tm_b, fullB(sb), kc * 64, p.tap_w[t], nt * p.BN + b_row0);
               if (++sb == p.SB) { sb = 0; pb ^= 1u; }
             }
           }
@@ -194,8 +222,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       // ------------------------------------------------------------ TMA producer
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m = tile / p.n_tiles, nt = tile - m * p.n_tiles;
+      for (int tt = t_begin; tt < t_end; tt += t_step) {
+        const int m = tile_m(tt), nt = tile_nt(tt);
         const int bn = m / tiles_xy, rem = m - bn * tiles_xy;
         const int by = rem / p.tiles_x, bx = rem - by * p.tiles_x;
         const int x0 = bx * p.tw, y0 = by * p.th, n0 = bn * p.tn;
@@ -205,28 +233,39 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           for (int kc = 0; kc < p.k_chunks; ++kc) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t a_dst = smem_base + (uint32_t)stage * stage_bytes;
-            mbar_expect_tx(full_bar(stage), stage_bytes);
-            tma_load_4d(a_dst, ma, full_bar(stage), kc * 64, xx, yy, n0);
-            tma_load_3d(a_dst + kABytes, &p.tm_b, full_bar(stage), kc * 64, wt, nt * p.BN);
+            if (rank == 0) mbar_expect_tx(full_bar(stage), tx_mult * stage_bytes);
+            load4(a_dst, ma, full_bar(stage), kc * 64, xx, yy, n0);
+            load3(a_dst + kABytes, &p.tm_b, full_bar(stage), kc * 64, wt, nt * p.BN + b_row0);
             if (++stage == S) { stage = 0; phase ^= 1u; }
           }
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
+  } else if (warp == 1 && rank == 0) {
+    // ------------------------------------------------------------ MMA issuer (pair mode: the leader CTA only)
     // The whole warp runs the loop convergently (waits included); only the leader lane's tcgen05 instructions execute.
     const uint32_t leader = elect_one() ? 1u : 0u;
     int acc = 0;
     uint32_t acc_phase = 0;
     const uint32_t lo_const = 1u << 16;  // LBO field (unused for K-major swizzled operands)
     const uint32_t hiB = (uint32_t)(make_smem_desc(0, 0, 1024) >> 32);
+    auto mma = [&](uint32_t d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t accum) {
+      if (kPair) umma2_bf16_lohi_if(leader, d, alo, ahi, blo, bhi, p.idesc, accum);
+      else umma_bf16_lohi_if(leader, d, alo, ahi, blo, bhi, p.idesc, accum);
+    };
+    auto commit = [&](uint32_t bar) {
+      if (kPair) umma2_commit_if(leader, bar); else umma_commit_if(leader, bar);
+    };
     if (p.halo) {
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       const uint32_t b_ring = smem_base + (uint32_t)p.SA * p.a_stage_bytes;
       const uint32_t hiA = (uint32_t)(make_smem_desc(0, 0, (uint32_t)p.hw * 128u) >> 32);  // SBO = one halo row
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      if (p.wres && t_begin < t_end) {
+        mbar_wait_warp(fullB(0), 0);   // the resident weights have landed (both CTAs' halves in pair mode)
+        tc_fence_after();
+      }
+      for (int tt = t_begin; tt < t_end; tt += t_step) {
         mbar_wait_warp(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccStride;
@@ -235,6 +274,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           mbar_wait_warp(fullA(sa), pa);
           const uint32_t a16 = lo_const | ((smem_base + (uint32_t)sa * p.a_stage_bytes) >> 4);
           const int nm = (kc == p.k_chunks - 1) ? p.last_mmas : 4;
+          if (p.wres) {
+            // 9 taps x nm MMAs back to back against the resident weights: one wait and one commit per K chunk
+            tc_fence_after();
+            uint32_t a_rw = a16;
+            uint32_t b_lo = lo_const | ((b_ring + (uint32_t)(kc * 3) * bs_bytes) >> 4);
+#pragma unroll 1
+            for (int r = 0; r < 3; ++r) {
+              uint32_t a_lo = a_rw;
+#pragma unroll 1
+              for (int sx = 0; sx < 3; ++sx) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  if (k < nm) {
+                    mma(d_tmem, a_lo + 2u * k, hiA, b_lo + 2u * k, hiB, accumulate);
+                    accumulate = 1;
+                  }
+                }
+                a_lo += 8u;
+                b_lo += b_bytes >> 4;
+              }
+              a_rw += (uint32_t)p.hw * 8u;
+            }
+            commit(emptyA(sa));
+            if (++sa == p.SA) { sa = 0; pa ^= 1u; }
+            continue;
+          }
           // halo mode is always the 3x3 pattern: tap (r,s) reads the halo tile from pixel row r*(tw+2) + s
           // (8 x 16-byte units per 128-byte pixel row): plain adds, no table lookups on the issue path
           uint32_t a_row = a16;
@@ -251,14 +316,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                   if (k < nm) {
-                    umma_bf16_lohi_if(leader, d_tmem, a_lo + 2u * k, hiA, b_lo + 2u * k, hiB, p.idesc, accumulate);
+                    mma(d_tmem, a_lo + 2u * k, hiA, b_lo + 2u * k, hiB, accumulate);
                     accumulate = 1;
                   }
                 }
                 a_lo += 8u;
                 b_lo += b_bytes >> 4;
               }
-              umma_commit_if(leader, emptyB(sb));
+              commit(emptyB(sb));
               if (++sb == p.SB) { sb = 0; pb ^= 1u; }
               a_row += (uint32_t)p.hw * 8u;
               continue;
@@ -272,27 +337,27 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
               for (int k = 0; k < 4; ++k) {
                 if (k < nm) {
                   // 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-                  umma_bf16_lohi_if(leader, d_tmem, a_lo + 2u * k, hiA, b_lo + 2u * k, hiB, p.idesc, accumulate);
+                  mma(d_tmem, a_lo + 2u * k, hiA, b_lo + 2u * k, hiB, accumulate);
                   accumulate = 1;
                 }
               }
-              umma_commit_if(leader, emptyB(sb));
+              commit(emptyB(sb));
               if (++sb == p.SB) { sb = 0; pb ^= 1u; }
               a_lo += 8u;
             }
             a_row += (uint32_t)p.hw * 8u;
           }
-          umma_commit_if(leader, emptyA(sa));
+          commit(emptyA(sa));
           if (++sa == p.SA) { sa = 0; pa ^= 1u; }
         }
-        umma_commit_if(leader, tfull_bar(acc));
+        commit(tfull_bar(acc));
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
     } else {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tt = t_begin; tt < t_end; tt += t_step) {
         mbar_wait_warp(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccStride;
@@ -307,16 +372,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               if (k < nm) {
-                umma_bf16_if(leader, d_tmem, ((uint64_t)hiB << 32) | (a_lo + 2u * k), ((uint64_t)hiB << 32) | (b_lo + 2u * k),
-                             p.idesc, accumulate);
+                mma(d_tmem, a_lo + 2u * k, hiB, b_lo + 2u * k, hiB, accumulate);
                 accumulate = 1;
               }
             }
-            umma_commit_if(leader, empty_bar(stage));
+            commit(empty_bar(stage));
             if (++stage == S) { stage = 0; phase ^= 1u; }
           }
         }
-        umma_commit_if(leader, tfull_bar(acc));
+        commit(tfull_bar(acc));
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -341,7 +405,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                has_zm = kAux && p.zmask.ptr != nullptr;
     const int slot_rm = has_res ? 1 : 0, slot_zm = (has_res ? 1 : 0) + (has_rm ? 1 : 0);
     auto issue_aux = [&](int t, int chunk, uint32_t buf) {
-      const int m2 = t / p.n_tiles, nt2 = t - m2 * p.n_tiles;
+      const int m2 = tile_m(t), nt2 = tile_nt(t);
       const int bn2 = m2 / tiles_xy, rem2 = m2 - bn2 * tiles_xy;
       const int by2 = rem2 / p.tiles_x, bx2 = rem2 - by2 * p.tiles_x;
       mbar_expect_tx(aux_bar(buf), (uint32_t)p.n_aux * kStagingBytes);
@@ -349,9 +413,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         tma_load_4d(aux_base + (uint32_t)i * 2 * kStagingBytes + buf * kStagingBytes, &p.tm_aux[i], aux_bar(buf),
                     nt2 * p.BN + chunk * 64, bx2 * p.tw, by2 * p.th, bn2 * p.tn);
     };
-    if (kAux && e == 0 && (int)blockIdx.x < total_tiles) issue_aux(blockIdx.x, 0, 0);
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m = tile / p.n_tiles, nt = tile - m * p.n_tiles;
+    if (kAux && e == 0 && t_begin < t_end) issue_aux(t_begin, 0, 0);
+    for (int tt = t_begin; tt < t_end; tt += t_step) {
+      const int m = tile_m(tt), nt = tile_nt(tt);
       const int bn = m / tiles_xy, rem = m - bn * tiles_xy;
       const int by = rem / p.tiles_x, bx = rem - by * p.tiles_x;
       const int x0 = bx * p.tw, y0 = by * p.th, n0 = bn * p.tn;
@@ -371,9 +435,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         if (kAux) {
           // residual / mask tiles arrive through TMA (coalesced, asynchronous), one 64-channel chunk ahead
           if (e == 0) {
-            int t2 = tile, j2 = j + 1;
-            if (j2 >= n_chunks) { t2 = tile + gridDim.x; j2 = 0; }
-            if (t2 < total_tiles) issue_aux(t2, j2, (chunk_ctr + 1u) & 1u);
+            int t2 = tt, j2 = j + 1;
+            if (j2 >= n_chunks) { t2 = tt + t_step; j2 = 0; }
+            if (t2 < t_end) issue_aux(t2, j2, (chunk_ctr + 1u) & 1u);
           }
           mbar_wait(aux_bar(chunk_ctr & 1u), (chunk_ctr >> 1) & 1u);
         }
@@ -384,8 +448,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         }
         if (j == n_chunks - 1) {
           // all TMEM reads of this accumulator by this thread are in registers: hand it back to the MMA warp
+          // (the peer CTA of a pair reports once, remotely, after the barrier below has collected its 256 threads)
           tc_fence_before();
-          mbar_arrive(tempty_bar(acc));
+          if (rank == 0) mbar_arrive(tempty_bar(acc));
         }
         const int c0 = nt * p.BN + g * 32;
         float v[32];
@@ -498,6 +563,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           fence_proxy_async_smem();
           named_bar_sync(1, 256);
           if (e == 0) {
+            if (kPair && rank != 0 && j == n_chunks - 1) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
             tma_store_4d(&p.tm_out, stg_base + buf * kStagingBytes, nt * p.BN + j * 64, x0, y0, n0);
             tma_store_commit();
           }
@@ -519,7 +585,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
               s_stats[(q4 * 2 + 0) * p.stats_cols + c] += sum;
               s_stats[(q4 * 2 + 1) * p.stats_cols + c] += sq;
             }
-          } else if (c < p.stats_ld) {
+          } else if (c < p.stats_ld && m < p.m_tiles) {
             float* sp = p.stats + (size_t)(m * 4 + q4) * 2 * p.stats_ld;
             sp[c] = sum;
             sp[p.stats_ld + c] = sq;
@@ -549,10 +615,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all(); else __syncthreads();   // pair: neither CTA may retire while the other still signals it
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (kPair) tmem_dealloc2(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
   }
 
   // ---------------------------------------------------------------- fused BatchNorm finalize (last CTA to retire)
@@ -621,6 +687,7 @@ struct b2u_conv_plan {
   ConvParams p;
   b2u_conv_info info;
   size_t smem_bytes;
+  bool pair;   // launched as clusters of 2 CTAs (tcgen05 cta_group::2)
 };
 
 static bool view_ok(const b2u_view& v, const char* name) {
@@ -699,9 +766,19 @@ static int conv_plan_fill(const b2u_conv_desc* d, b2u_conv_plan* plan, bool enco
   p.hw = tw + 2;
   p.tw = tw; p.th = th; p.tn = tn; p.tiles_x = tx; p.tiles_y = ty;
   p.m_tiles = tx * ty * tb; p.n_tiles = n_tiles; p.BN = BN;
+  // CTA-pair mode: two pixel tiles share every weight stage (each SM holds half of its rows) and one M = 256 MMA stream
+  static const bool pair_disabled = getenv("B2U_CONV_NO_PAIR") != nullptr;  // A/B switch for profiling
+  // (tiles with little MMA work - 1x1 convolutions over few channels - are epilogue/store-bound: pairing only adds sync)
+  const bool pair = !pair_disabled && !out_f32 && BN % 16 == 0 && p.m_tiles >= 2 &&
+                    (halo || d->num_taps * ceil_div(Cin, 64) >= 8);
+  plan->pair = pair;
+  const int b_rows = pair ? BN / 2 : BN;   // weight rows per CTA and tap
   p.num_taps = d->num_taps;
   p.k_chunks = ceil_div(Cin, 64);
-  p.last_mmas = ceil_div(Cin - 64 * (p.k_chunks - 1), 16);
+  // MMAs (K = 16) of the last chunk: counted from the TRUE channel count - whole-chunk TMA boxes may carry zero pad lanes
+  // (Cin = 100 at pitch 128), but K slices that hold nothing but padding are not multiplied
+  p.last_mmas = ceil_div(d->w_cin - 64 * (p.k_chunks - 1), 16);
+  if (p.last_mmas < 1) p.last_mmas = 1;
   for (int t = 0; t < d->num_taps; ++t) {
     p.tap_a[t] = d->tap_a[t]; p.tap_dy[t] = d->tap_dy[t]; p.tap_dx[t] = d->tap_dx[t]; p.tap_w[t] = d->tap_w[t];
   }
@@ -709,7 +786,7 @@ static int conv_plan_fill(const b2u_conv_desc* d, b2u_conv_plan* plan, bool enco
   B2U_CHECK_ARG(n_aux == 0 || !out_f32, "conv: residual / mask operands need the bf16 output path");
   B2U_CHECK_ARG(!d->res_mask.ptr || d->res.ptr, "conv: res_mask without res");
   p.n_aux = n_aux;
-  const uint32_t stage_bytes = kABytes + (uint32_t)BN * 128u;
+  const uint32_t stage_bytes = kABytes + (uint32_t)b_rows * 128u;
   p.stats_cols = ((d->flags & B2U_EPI_STATS) && n_tiles * BN <= 512) ? n_tiles * BN : 0;
   p.stg_bufs = 2;
   p.rowmode = 0;
@@ -718,15 +795,31 @@ static int conv_plan_fill(const b2u_conv_desc* d, b2u_conv_plan* plan, bool enco
   if (halo) {
     p.a_tx_bytes = (uint32_t)((tw + 2) * (th + 2)) * 128u;
     p.a_stage_bytes = (p.a_tx_bytes + 1023u) & ~1023u;
-    uint32_t bb = (uint32_t)BN * 128u;
+    uint32_t bb = (uint32_t)b_rows * 128u;
     // row mode (one weight stage = one filter row = 3 taps): the single issuing thread pays its wait/commit cost once per
     // 3 taps.  Used for N <= 128 (the wide tiles are MMA-bound already) when >= 3 such stages fit next to 2 halo
     // stages; the output staging drops to a single buffer to make room.
     static const bool row_disabled = getenv("B2U_CONV_NO_ROWMODE") != nullptr;
+    static const bool wres_disabled = getenv("B2U_CONV_NO_WRES") != nullptr;
     bool tapw_ok = true;
     for (int t = 0; t < 9; ++t) tapw_ok = tapw_ok && d->tap_w[t] == t;
+    // resident weights: when all 9 x k_chunks weight blocks of this CTA (half of the rows in pair mode) fit next to
+    // >= 2 halo stages, they are loaded once per launch; the per-tile stream is the activation halo only
+    p.wres = 0;
+    if (!wres_disabled && n_tiles == 1 && tapw_ok && d->w_taps == 9) {
+      const uint32_t wbytes = (uint32_t)p.k_chunks * 9u * bb;
+      const int try_sa[3] = {3, 2, 2}, try_stg[3] = {1, 2, 1};
+      for (int i = 0; i < 3 && !p.wres; ++i) {
+        const uint32_t fx = fixed - (2u - (uint32_t)try_stg[i]) * kStagingBytes;
+        if ((uint32_t)try_sa[i] * p.a_stage_bytes + wbytes + fx <= 232448u) {
+          p.wres = 1; p.rowmode = 1; p.SA = try_sa[i]; p.SB = 3 * p.k_chunks; p.stg_bufs = try_stg[i];
+          fixed = fx;
+          bb *= 3;
+        }
+      }
+    }
     // (measured: a partial last K chunk, e.g. Cin = 100, makes row mode slower than per-tap stages, so it is excluded)
-    if (!row_disabled && BN <= 128 && tapw_ok && d->w_taps == 9 && Cin % 64 == 0) {
+    if (!p.wres && !row_disabled && BN <= 128 && tapw_ok && d->w_taps == 9 && Cin % 64 == 0) {
       const uint32_t fixed1 = fixed - kStagingBytes;
       const int sb3 = (int)((232448u - fixed1 - 2u * p.a_stage_bytes) / (3u * bb));
       if (sb3 >= 3) {
@@ -754,7 +847,7 @@ static int conv_plan_fill(const b2u_conv_desc* d, b2u_conv_plan* plan, bool enco
   p.stages = stages;
   // at least half of the SM's shared memory, so that exactly one CTA (and its 512 TMEM columns) lives on an SM
   if (plan->smem_bytes < 120 * 1024) plan->smem_bytes = 120 * 1024;
-  p.idesc = make_idesc_bf16(128, BN, 0, 0);
+  p.idesc = make_idesc_bf16(pair ? 256 : 128, BN, 0, 0);
   p.N = d->out.N; p.Ho = d->out.H; p.Wo = d->out.W; p.Cout = Cout; p.CoutP8 = round_up(Cout, 8);
   p.scale = d->scale; p.shift = d->shift;
   auto ev = [](const b2u_view& v) { EpiView e; e.ptr = (const __nv_bfloat16*)v.ptr; e.sW = v.sW; e.sH = v.sH; e.sN = v.sN; return e; };
@@ -768,7 +861,12 @@ static int conv_plan_fill(const b2u_conv_desc* d, b2u_conv_plan* plan, bool enco
   info.stages = stages; info.k_chunks = p.k_chunks;
   const int total = p.m_tiles * n_tiles;
   const int sms = encode ? sm_count() : 148;
-  info.grid = total < sms ? total : sms;
+  if (pair) {
+    const int pair_tiles = ((p.m_tiles + 1) / 2) * n_tiles;
+    info.grid = 2 * (pair_tiles < sms / 2 ? pair_tiles : sms / 2);
+  } else {
+    info.grid = total < sms ? total : sms;
+  }
   // rows of the statistics partial buffer: one per (CTA, epilogue warp) when accumulated on chip, else per (tile, warp)
   info.stats_rows = p.stats_cols > 0 ? info.grid : 4 * p.m_tiles;
   memset(&p.fin, 0, sizeof(p.fin));
@@ -800,7 +898,7 @@ static int conv_plan_fill(const b2u_conv_desc* d, b2u_conv_plan* plan, bool enco
       const int cin_ext = round_up(Cin, 16) <= d->w_cinp ? round_up(Cin, 16) : (round_up(Cin, 8) <= d->w_cinp ? round_up(Cin, 8) : Cin);
       uint64_t dims[3] = {(uint64_t)cin_ext, (uint64_t)d->w_taps, (uint64_t)d->w_rows};
       uint64_t str[3] = {2, (uint64_t)d->w_cinp * 2, (uint64_t)d->w_cinp * 2 * (uint64_t)d->w_taps};
-      uint32_t box[3] = {64, 1, (uint32_t)BN};
+      uint32_t box[3] = {64, 1, (uint32_t)b_rows};
       int rc = encode_tmap_bf16(&p.tm_b, d->w, 3, dims, str, box);
       if (rc) return rc;
     }
@@ -809,7 +907,7 @@ static int conv_plan_fill(const b2u_conv_desc* d, b2u_conv_plan* plan, bool enco
       const int cin_ext = round_up(Cin, 16) <= d->w_cinp ? round_up(Cin, 16) : (round_up(Cin, 8) <= d->w_cinp ? round_up(Cin, 8) : Cin);
       uint64_t dims[3] = {(uint64_t)cin_ext, (uint64_t)d->w_rows, (uint64_t)d->w_taps};
       uint64_t str[3] = {2, (uint64_t)d->w_cinp * 2 * (uint64_t)d->w_taps, (uint64_t)d->w_cinp * 2};
-      uint32_t box[3] = {64, (uint32_t)BN, 3};
+      uint32_t box[3] = {64, (uint32_t)b_rows, 3};
       int rc = encode_tmap_bf16(&p.tm_b3, d->w, 3, dims, str, box);
       if (rc) return rc;
     }
@@ -851,9 +949,12 @@ extern "C" int b2u_conv_plan_create(const b2u_conv_desc* d, b2u_conv_plan** out)
   if (rc) { delete plan; return rc; }
   static bool attr_set = false;
   if (!attr_set) {
-    const void* variants[] = {(const void*)conv_gemm_kernel<false, false, false>, (const void*)conv_gemm_kernel<false, true, false>,
-                              (const void*)conv_gemm_kernel<true, false, false>, (const void*)conv_gemm_kernel<true, true, false>,
-                              (const void*)conv_gemm_kernel<false, false, true>};
+    const void* variants[] = {
+        (const void*)conv_gemm_kernel<false, false, false, false>, (const void*)conv_gemm_kernel<false, true, false, false>,
+        (const void*)conv_gemm_kernel<true, false, false, false>,  (const void*)conv_gemm_kernel<true, true, false, false>,
+        (const void*)conv_gemm_kernel<false, false, true, false>,
+        (const void*)conv_gemm_kernel<false, false, false, true>,  (const void*)conv_gemm_kernel<false, true, false, true>,
+        (const void*)conv_gemm_kernel<true, false, false, true>,   (const void*)conv_gemm_kernel<true, true, false, true>};
     for (const void* f : variants) {
       cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
       if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(conv_gemm_kernel): %s", cudaGetErrorString(e)); delete plan; return B2U_ERR_CUDA; }
@@ -873,14 +974,35 @@ extern "C" int b2u_conv_plan_info(const b2u_conv_plan* plan, b2u_conv_info* info
 extern "C" int b2u_conv_run(const b2u_conv_plan* plan, void* stream) {
   B2U_CHECK_ARG(plan != nullptr, "conv_run: null plan");
   const ConvParams& p = plan->p;
-  const dim3 grid(plan->info.grid), block(kThreads);
-  cudaStream_t st = (cudaStream_t)stream;
   const bool aux = p.n_aux > 0, stats = (p.flags & B2U_EPI_STATS) != 0, f32 = (p.flags & B2U_EPI_OUT_F32) != 0;
-  if (f32) conv_gemm_kernel<false, false, true><<<grid, block, plan->smem_bytes, st>>>(p);
-  else if (aux && stats) conv_gemm_kernel<true, true, false><<<grid, block, plan->smem_bytes, st>>>(p);
-  else if (aux) conv_gemm_kernel<true, false, false><<<grid, block, plan->smem_bytes, st>>>(p);
-  else if (stats) conv_gemm_kernel<false, true, false><<<grid, block, plan->smem_bytes, st>>>(p);
-  else conv_gemm_kernel<false, false, false><<<grid, block, plan->smem_bytes, st>>>(p);
+  void (*kern)(const ConvParams) = nullptr;
+  if (f32) kern = conv_gemm_kernel<false, false, true, false>;
+  else if (plan->pair) {
+    if (aux && stats) kern = conv_gemm_kernel<true, true, false, true>;
+    else if (aux) kern = conv_gemm_kernel<true, false, false, true>;
+    else if (stats) kern = conv_gemm_kernel<false, true, false, true>;
+    else kern = conv_gemm_kernel<false, false, false, true>;
+  } else {
+    if (aux && stats) kern = conv_gemm_kernel<true, true, false, false>;
+    else if (aux) kern = conv_gemm_kernel<true, false, false, false>;
+    else if (stats) kern = conv_gemm_kernel<false, true, false, false>;
+    else kern = conv_gemm_kernel<false, false, false, false>;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(plan->info.grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = plan->smem_bytes;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = plan->pair ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, p);
+  if (le != cudaSuccess) { set_error("conv_run: launch failed: %s", cudaGetErrorString(le)); return B2U_ERR_CUDA; }
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }
