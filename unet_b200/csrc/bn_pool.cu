@@ -130,9 +130,18 @@ __device__ __forceinline__ bool final_sums(const float* partial, int rows, int l
 #pragma unroll
   for (int k = 0; k < K; ++k) s[k] = 0.0;
   if (c < C)
-    for (int r = rl; r < rows; r += 4)
+    for (int r = rl; r < rows; r += 32) {   // eight rows per trip, loads first (latency paid once per trip)
+      float v[8][K];
 #pragma unroll
-      for (int k = 0; k < K; ++k) s[k] += (double)partial[((size_t)r * K + k) * ld + c];
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+          v[u][k] = (r + 4 * u < rows) ? __ldg(partial + ((size_t)(r + 4 * u) * K + k) * ld + c) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int k = 0; k < K; ++k) s[k] += (double)v[u][k];
+    }
 #pragma unroll
   for (int k = 0; k < K; ++k) sh[rl][cl][k] = s[k];
   __syncthreads();
@@ -382,16 +391,17 @@ __global__ void __launch_bounds__(256) bn_bwd_fused_kernel(
       }
     });
   }
-  // ---- grid barrier; the last block to arrive finalizes
-  __threadfence();
+  // ---- grid barrier; the last block to arrive finalizes.  One fence per block: bar.sync orders the block's partial-row
+  // stores before thread 0's gpu-scope fence (fences are cumulative), which orders them before the ticket.
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence();
     const unsigned int ticket = atomicAdd(&sync[0], 1u);
     s_last = (ticket == gridDim.x - 1) ? 1 : 0;
+    if (s_last) __threadfence();
   }
   __syncthreads();
   if (s_last) {
-    __threadfence();
     double* sh = reinterpret_cast<double*>(red);   // 256 x 4 doubles = 8 KB of the 16 KB dynamic buffer
     const int rows = (int)gridDim.x;
     const int ncol4 = part_ld >> 1;                // float4 columns of one partial row [2][part_ld]
@@ -402,10 +412,18 @@ __global__ void __launch_bounds__(256) bn_bwd_fused_kernel(
       if (rl < RL) {
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
         const float4* src = reinterpret_cast<const float4*>(partial) + cb + c4;
-#pragma unroll 8
-        for (int r = rl; r < rows; r += RL) {
-          const float4 v = __ldcg(src + (size_t)r * ncol4);
-          a0 += (double)v.x; a1 += (double)v.y; a2 += (double)v.z; a3 += (double)v.w;
+        // eight rows per trip, all loads issued before the first add: the L2 latency is paid once per trip, not per row
+        for (int r = rl; r < rows; r += 8 * RL) {
+          float4 v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int rr = r + u * RL;
+            v[u] = rr < rows ? __ldcg(src + (size_t)rr * ncol4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            a0 += (double)v[u].x; a1 += (double)v[u].y; a2 += (double)v[u].z; a3 += (double)v[u].w;
+          }
         }
         double* d = sh + ((size_t)rl * nc + c4) * 4;
         d[0] = a0; d[1] = a1; d[2] = a2; d[3] = a3;
@@ -423,7 +441,6 @@ __global__ void __launch_bounds__(256) bn_bwd_fused_kernel(
       }
       __syncthreads();
     }
-    __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
       sync[0] = 0u;
@@ -432,8 +449,10 @@ __global__ void __launch_bounds__(256) bn_bwd_fused_kernel(
     }
   } else {
     if (threadIdx.x == 0) {
-      while (vsync[1] == s_gen) __nanosleep(100);
-      __threadfence();
+      unsigned int g;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(g) : "l"(sync + 1) : "memory");
+      } while (g == s_gen);
     }
     __syncthreads();
   }
