@@ -6,39 +6,9 @@
 // fastai's ConvLayer / XResNet / UnetBlock.bn (reference train.py:128,141).
 #include "host_util.h"
 #include "ptx.cuh"
+#include "stream.cuh"
 
 namespace b2u {
-
-struct f8 {
-  float v[8];
-};
-__device__ __forceinline__ f8 ld8(const __nv_bfloat16* p) {
-  uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
-  f8 o;
-  o.v[0] = bf16_lo(u.x); o.v[1] = bf16_hi(u.x); o.v[2] = bf16_lo(u.y); o.v[3] = bf16_hi(u.y);
-  o.v[4] = bf16_lo(u.z); o.v[5] = bf16_hi(u.z); o.v[6] = bf16_lo(u.w); o.v[7] = bf16_hi(u.w);
-  return o;
-}
-__device__ __forceinline__ void st8(__nv_bfloat16* p, const f8& a) {
-  uint4 u;
-  u.x = pack_bf16x2(a.v[0], a.v[1]); u.y = pack_bf16x2(a.v[2], a.v[3]);
-  u.z = pack_bf16x2(a.v[4], a.v[5]); u.w = pack_bf16x2(a.v[6], a.v[7]);
-  *reinterpret_cast<uint4*>(p) = u;
-}
-// per-channel fp32 constants: the arrays are padded to a multiple of 32 floats and 16-byte aligned (b2u.h), so a
-// group of 8 channels is two 16-byte loads; lanes >= C are zeroed
-__device__ __forceinline__ f8 ldc8(const float* p, int c, int C) {
-  const float4 a = __ldg(reinterpret_cast<const float4*>(p + c));
-  const float4 b = __ldg(reinterpret_cast<const float4*>(p + c) + 1);
-  f8 o;
-  o.v[0] = a.x; o.v[1] = a.y; o.v[2] = a.z; o.v[3] = a.w; o.v[4] = b.x; o.v[5] = b.y; o.v[6] = b.z; o.v[7] = b.w;
-  if (c + 8 > C) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if (c + i >= C) o.v[i] = 0.f;
-  }
-  return o;
-}
 
 // ------------------------------------------------------------------------------------------------ column reductions
 // Generic "sum K quantities per channel over many pixels": each block owns a contiguous pixel range and writes one
@@ -184,50 +154,31 @@ __global__ void bn_eval_affine_kernel(int C, const float* gamma, const float* be
   shift[c] = b - rm[c] * g * istd;
 }
 
-// Streaming iteration used by the elementwise kernels: every block owns a contiguous pixel range and every thread a
-// FIXED 8-channel group, so per-channel constants are loaded once per thread and the loop has no integer division.
-template <class Init, class Body>
-__device__ __forceinline__ void for_each_pixel_group(int pixels, int C, Init init, Body body) {
-  const int G = (C + 7) >> 3;
-  const int per = (pixels + gridDim.x - 1) / gridDim.x;
-  const int p0 = blockIdx.x * per, p1 = min(pixels, p0 + per);
-  for (int g0 = 0; g0 < G; g0 += blockDim.x) {
-    const int GP = min(G - g0, (int)blockDim.x);
-    const int PL = blockDim.x / GP;
-    const int pl = threadIdx.x / GP, g = g0 + (threadIdx.x - pl * GP);
-    if (pl < PL) {
-      auto consts = init(g * 8);
-      int p = p0 + pl;
-      // two independent pixels per iteration: twice the bytes in flight per thread (inputs are __restrict__)
-      for (; p + PL < p1; p += 2 * PL) {
-        body(p, g * 8, consts);
-        body(p + PL, g * 8, consts);
-      }
-      if (p < p1) body(p, g * 8, consts);
-    }
-  }
-}
-
 struct ApplyConsts { f8 sc, sh, rs, rh; };
+struct ApplyRegs { uint4 x, r; };
 
 // y = act(x*scale+shift [+ r*rscale+rshift | + r])
-__global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ scale,
-                                const float* __restrict__ shift, const __nv_bfloat16* __restrict__ r, int ldr,
-                                const float* __restrict__ rscale, const float* __restrict__ rshift, int relu,
-                                __nv_bfloat16* __restrict__ y, int ldy, int pixels, int C) {
-  for_each_pixel_group(pixels, C,
+__global__ void __launch_bounds__(256) bn_apply_kernel(
+    const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ scale, const float* __restrict__ shift,
+    const __nv_bfloat16* __restrict__ r, int ldr, const float* __restrict__ rscale, const float* __restrict__ rshift,
+    int relu, __nv_bfloat16* __restrict__ y, int ldy, int pixels, int C) {
+  stream_pixel_groups<4, ApplyRegs>(pixels, (C + 7) >> 3,
       [&](int c) {
         ApplyConsts k;
         k.sc = ldc8(scale, c, C); k.sh = ldc8(shift, c, C);
         if (rscale) { k.rs = ldc8(rscale, c, C); k.rh = ldc8(rshift, c, C); }
         return k;
       },
-      [&](int p, int c, const ApplyConsts& k) {
-        f8 a = ld8(x + (long long)p * ldx + c);
+      [&](int p, int c, const ApplyConsts&, ApplyRegs& q) {
+        q.x = ldq(x + (long long)p * ldx + c);
+        if (r) q.r = ldq(r + (long long)p * ldr + c);
+      },
+      [&](int p, int c, const ApplyConsts& k, const ApplyRegs& q) {
+        f8 a = unpack_f8(q.x);
 #pragma unroll
         for (int i = 0; i < 8; ++i) a.v[i] = a.v[i] * k.sc.v[i] + k.sh.v[i];
         if (r) {
-          f8 b = ld8(r + (long long)p * ldr + c);
+          f8 b = unpack_f8(q.r);
           if (rscale) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) b.v[i] = b.v[i] * k.rs.v[i] + k.rh.v[i];
@@ -247,13 +198,23 @@ __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx, co
 // backward: g = dz * mask; mask = (y > 0) if y else (x*scale+shift > 0) if relu else 1
 struct BwdConsts { f8 sc, sh, mu, is, a, mg, mgx; };
 
-__device__ __forceinline__ void bn_bwd_gx(const __nv_bfloat16* dz, int lddz, const __nv_bfloat16* x, int ldx,
-                                          const __nv_bfloat16* y, int ldy, int relu, int p, int c, int C,
-                                          const BwdConsts& k, f8& g, f8& xh) {
-  g = ld8(dz + (long long)p * lddz + c);
-  const f8 xv = ld8(x + (long long)p * ldx + c);
-  if (y) {
-    const f8 yv = ld8(y + (long long)p * ldy + c);
+struct BwdRegs { uint4 dz, x, y, old; };
+
+__device__ __forceinline__ void bn_bwd_load(const __nv_bfloat16* dz, int lddz, const __nv_bfloat16* x, int ldx,
+                                            const __nv_bfloat16* y, int ldy, const __nv_bfloat16* old, int ldo, int p,
+                                            int c, BwdRegs& q) {
+  q.dz = ldq(dz + (long long)p * lddz + c);
+  q.x = ldq(x + (long long)p * ldx + c);
+  if (y) q.y = ldq(y + (long long)p * ldy + c);
+  if (old) q.old = ldq(old + (long long)p * ldo + c);
+}
+
+__device__ __forceinline__ void bn_bwd_math(const BwdRegs& q, bool has_y, int relu, int c, int C, const BwdConsts& k,
+                                            f8& g, f8& xh) {
+  g = unpack_f8(q.dz);
+  const f8 xv = unpack_f8(q.x);
+  if (has_y) {
+    const f8 yv = unpack_f8(q.y);
 #pragma unroll
     for (int i = 0; i < 8; ++i) g.v[i] = yv.v[i] > 0.f ? g.v[i] : 0.f;
   } else if (relu) {
@@ -265,6 +226,33 @@ __device__ __forceinline__ void bn_bwd_gx(const __nv_bfloat16* dz, int lddz, con
     xh.v[i] = (xv.v[i] - k.mu.v[i]) * k.is.v[i];
     if (c + i >= C) { g.v[i] = 0.f; xh.v[i] = 0.f; }
   }
+}
+
+__device__ __forceinline__ void bn_bwd_gx(const __nv_bfloat16* dz, int lddz, const __nv_bfloat16* x, int ldx,
+                                          const __nv_bfloat16* y, int ldy, int relu, int p, int c, int C,
+                                          const BwdConsts& k, f8& g, f8& xh) {
+  BwdRegs q;
+  bn_bwd_load(dz, lddz, x, ldx, y, ldy, nullptr, 0, p, c, q);
+  bn_bwd_math(q, y != nullptr, relu, c, C, k, g, xh);
+}
+
+// dx = gamma*invstd * (g - mean_g - xhat*mean_gx) [+ old dx]
+__device__ __forceinline__ void bn_bwd_store(const BwdRegs& q, bool has_y, int relu, bool accumulate, int c, int C,
+                                             const BwdConsts& k, __nv_bfloat16* dst) {
+  f8 g, xh;
+  bn_bwd_math(q, has_y, relu, c, C, k, g, xh);
+  f8 o;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o.v[i] = k.a.v[i] * (g.v[i] - k.mg.v[i] - xh.v[i] * k.mgx.v[i]);
+  if (accumulate) {
+    const f8 old = unpack_f8(q.old);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o.v[i] += old.v[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (c + i >= C) o.v[i] = 0.f;
+  st8(dst, o);
 }
 
 __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dz, int lddz, const __nv_bfloat16* __restrict__ x,
@@ -308,7 +296,7 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz, int ld
                                     const float* shift, const float* mean, const float* invstd, const float* gamma,
                                     const float* mean_g, const float* mean_gx, int relu, int accumulate,
                                     __nv_bfloat16* __restrict__ dx, int lddx, int pixels, int C) {
-  for_each_pixel_group(pixels, C,
+  stream_pixel_groups<4, BwdRegs>(pixels, (C + 7) >> 3,
       [&](int c) {
         BwdConsts k;
         k.mu = ldc8(mean, c, C); k.is = ldc8(invstd, c, C);
@@ -323,22 +311,11 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz, int ld
         for (int i = 0; i < 8; ++i) k.a.v[i] *= k.is.v[i];   // gamma * invstd
         return k;
       },
-      [&](int p, int c, const BwdConsts& k) {
-        f8 g, xh;
-        bn_bwd_gx(dz, lddz, x, ldx, y, ldy, relu, p, c, C, k, g, xh);
-        f8 o;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o.v[i] = k.a.v[i] * (g.v[i] - k.mg.v[i] - xh.v[i] * k.mgx.v[i]);
-        __nv_bfloat16* dst = dx + (long long)p * lddx + c;
-        if (accumulate) {
-          const f8 old = ld8(dst);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) o.v[i] += old.v[i];
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (c + i >= C) o.v[i] = 0.f;
-        st8(dst, o);
+      [&](int p, int c, const BwdConsts&, BwdRegs& q) {
+        bn_bwd_load(dz, lddz, x, ldx, y, ldy, accumulate ? dx : nullptr, lddx, p, c, q);
+      },
+      [&](int p, int c, const BwdConsts& k, const BwdRegs& q) {
+        bn_bwd_store(q, y != nullptr, relu, accumulate != 0, c, C, k, dx + (long long)p * lddx + c);
       });
 }
 
@@ -348,6 +325,30 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz, int ld
 // and releases the others; phase 2 is bn_bwd_apply over the SAME per-block pixel ranges walked backwards, so the lines
 // read last in phase 1 are re-read first (they are still in the 126 MB L2 for all but the largest tensors).
 // The grid must be co-resident (the host caps it with the occupancy API); `sync` = {arrive counter, generation}.
+// Sense-reversing grid barrier on {arrive counter, generation}; all blocks must be co-resident.  bar.sync orders the
+// block's earlier global stores before thread 0's gpu-scope fence (fences are cumulative), which orders them before the
+// arrival; the generation is read BEFORE arriving (it cannot advance until this block has arrived).
+__device__ __forceinline__ void grid_barrier(unsigned int* sync, unsigned int nblocks) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int gen, g;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(sync + 1) : "memory");
+    __threadfence();
+    const unsigned int ticket = atomicAdd(&sync[0], 1u);
+    if (ticket == nblocks - 1) {
+      sync[0] = 0u;
+      __threadfence();
+      atomicAdd(&sync[1], 1u);   // release
+    } else {
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(g) : "l"(sync + 1) : "memory");
+      } while (g == gen);
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
 __device__ __forceinline__ f8 ldc8_cg(const float* p, int c, int C) {
   const float4 a = __ldcg(reinterpret_cast<const float4*>(p + c));
   const float4 b = __ldcg(reinterpret_cast<const float4*>(p + c) + 1);
@@ -368,10 +369,6 @@ __global__ void __launch_bounds__(256) bn_bwd_fused_kernel(
     int pixels, int C, float* partial, int part_ld, double count, float* dgamma, float* dbeta, float* mean_g,
     float* mean_gx, unsigned int* sync) {
   extern __shared__ float red[];
-  __shared__ unsigned int s_gen;
-  __shared__ int s_last;
-  volatile unsigned int* vsync = sync;
-  if (threadIdx.x == 0) s_gen = vsync[1];
   // ---- phase 1: partial sums of g and g*xhat over this block's pixel range
   {
     int cached_c = -1;
@@ -391,48 +388,35 @@ __global__ void __launch_bounds__(256) bn_bwd_fused_kernel(
       }
     });
   }
-  // ---- grid barrier; the last block to arrive finalizes.  One fence per block: bar.sync orders the block's partial-row
-  // stores before thread 0's gpu-scope fence (fences are cumulative), which orders them before the ticket.
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const unsigned int ticket = atomicAdd(&sync[0], 1u);
-    s_last = (ticket == gridDim.x - 1) ? 1 : 0;
-    if (s_last) __threadfence();
-  }
-  __syncthreads();
-  if (s_last) {
+  // ---- grid barrier A: every block's partial row is visible
+  grid_barrier(sync, gridDim.x);
+  // ---- finalize, spread over the grid: block b owns the float4 columns b, b + grid, ... of the [2][part_ld] partial
+  // rows; its 256 threads fetch one row each (a single L2 round trip per 256 rows) and combine them with a fixed tree in
+  // double precision - the same result whatever the scheduling
+  {
     double* sh = reinterpret_cast<double*>(red);   // 256 x 4 doubles = 8 KB of the 16 KB dynamic buffer
     const int rows = (int)gridDim.x;
     const int ncol4 = part_ld >> 1;                // float4 columns of one partial row [2][part_ld]
-    for (int cb = 0; cb < ncol4; cb += 256) {
-      const int nc = min(256, ncol4 - cb);
-      const int RL = 256 / nc;
-      const int rl = (int)threadIdx.x / nc, c4 = (int)threadIdx.x - rl * nc;
-      if (rl < RL) {
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        const float4* src = reinterpret_cast<const float4*>(partial) + cb + c4;
-        // eight rows per trip, all loads issued before the first add: the L2 latency is paid once per trip, not per row
-        for (int r = rl; r < rows; r += 8 * RL) {
-          float4 v[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int rr = r + u * RL;
-            v[u] = rr < rows ? __ldcg(src + (size_t)rr * ncol4) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            a0 += (double)v[u].x; a1 += (double)v[u].y; a2 += (double)v[u].z; a3 += (double)v[u].w;
-          }
-        }
-        double* d = sh + ((size_t)rl * nc + c4) * 4;
-        d[0] = a0; d[1] = a1; d[2] = a2; d[3] = a3;
+    for (int c4 = blockIdx.x; c4 < ncol4; c4 += gridDim.x) {
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      const float4* src = reinterpret_cast<const float4*>(partial) + c4;
+      for (int r = threadIdx.x; r < rows; r += 256) {
+        const float4 v = __ldcg(src + (size_t)r * ncol4);
+        a0 += (double)v.x; a1 += (double)v.y; a2 += (double)v.z; a3 += (double)v.w;
       }
+      double* d = sh + (size_t)threadIdx.x * 4;
+      d[0] = a0; d[1] = a1; d[2] = a2; d[3] = a3;
       __syncthreads();
-      for (int j = threadIdx.x; j < nc * 4; j += 256) {
-        double t = 0.0;
-        for (int q = 0; q < RL; ++q) t += sh[(size_t)q * nc * 4 + j];
-        const int col = cb * 4 + j;                // position inside [2][part_ld]
+      for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+          double* e = sh + (size_t)(threadIdx.x + o) * 4;
+          d[0] += e[0]; d[1] += e[1]; d[2] += e[2]; d[3] += e[3];
+        }
+        __syncthreads();
+      }
+      if (threadIdx.x < 4) {
+        const double t = sh[threadIdx.x];
+        const int col = c4 * 4 + (int)threadIdx.x;   // position inside [2][part_ld]
         const int kk = col >= part_ld ? 1 : 0, c = col - kk * part_ld;
         if (c < C) {
           if (kk == 0) { if (dbeta) dbeta[c] = (float)t; mean_g[c] = (float)(t / count); }
@@ -441,21 +425,9 @@ __global__ void __launch_bounds__(256) bn_bwd_fused_kernel(
       }
       __syncthreads();
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      sync[0] = 0u;
-      __threadfence();
-      atomicAdd(&sync[1], 1u);   // release
-    }
-  } else {
-    if (threadIdx.x == 0) {
-      unsigned int g;
-      do {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(g) : "l"(sync + 1) : "memory");
-      } while (g == s_gen);
-    }
-    __syncthreads();
   }
+  // ---- grid barrier B: mean_g / mean_gx are visible
+  grid_barrier(sync, gridDim.x);
   // ---- phase 2: dx = gamma*invstd * (g - mean_g - xhat*mean_gx), block range walked backwards
   {
     const int G = (C + 7) >> 3;
@@ -478,31 +450,21 @@ __global__ void __launch_bounds__(256) bn_bwd_fused_kernel(
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) k.a.v[i] *= k.is.v[i];
-      auto one = [&](int p) {
-        f8 gq, xh;
-        bn_bwd_gx(dz, lddz, x, ldx, y, ldy, relu, p, c, C, k, gq, xh);
-        f8 o;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o.v[i] = k.a.v[i] * (gq.v[i] - k.mg.v[i] - xh.v[i] * k.mgx.v[i]);
-        __nv_bfloat16* dst = dx + (long long)p * lddx + c;
-        if (accumulate) {
-          const f8 old = ld8(dst);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) o.v[i] += old.v[i];
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (c + i >= C) o.v[i] = 0.f;
-        st8(dst, o);
-      };
+      const __nv_bfloat16* oldp = accumulate ? dx : nullptr;
       int p = p0 + pl + ((p1 - 1 - p0 - pl) / PL) * PL;   // last pixel of this lane
-      for (; p - 3 * PL >= p0; p -= 4 * PL) {   // four pixels in flight per thread
-        one(p);
-        one(p - PL);
-        one(p - 2 * PL);
-        one(p - 3 * PL);
+      for (; p - 3 * PL >= p0; p -= 4 * PL) {   // four pixels in flight per thread: all loads, then all stores
+        BwdRegs q[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) bn_bwd_load(dz, lddz, x, ldx, y, ldy, oldp, lddx, p - u * PL, c, q[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          bn_bwd_store(q[u], y != nullptr, relu, accumulate != 0, c, C, k, dx + (long long)(p - u * PL) * lddx + c);
       }
-      for (; p >= p0; p -= PL) one(p);
+      for (; p >= p0; p -= PL) {
+        BwdRegs q;
+        bn_bwd_load(dz, lddz, x, ldx, y, ldy, oldp, lddx, p, c, q);
+        bn_bwd_store(q, y != nullptr, relu, accumulate != 0, c, C, k, dx + (long long)p * lddx + c);
+      }
     }
   }
 }

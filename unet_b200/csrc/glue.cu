@@ -6,25 +6,9 @@
 // (train.py:218), softmax + numpy sum/count/argmax merge (predict.py:193-203, 284-334).
 #include "host_util.h"
 #include "ptx.cuh"
+#include "stream.cuh"
 
 namespace b2u {
-
-struct f8 {
-  float v[8];
-};
-__device__ __forceinline__ f8 ld8(const __nv_bfloat16* p) {
-  uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
-  f8 o;
-  o.v[0] = bf16_lo(u.x); o.v[1] = bf16_hi(u.x); o.v[2] = bf16_lo(u.y); o.v[3] = bf16_hi(u.y);
-  o.v[4] = bf16_lo(u.z); o.v[5] = bf16_hi(u.z); o.v[6] = bf16_lo(u.w); o.v[7] = bf16_hi(u.w);
-  return o;
-}
-__device__ __forceinline__ void st8(__nv_bfloat16* p, const f8& a) {
-  uint4 u;
-  u.x = pack_bf16x2(a.v[0], a.v[1]); u.y = pack_bf16x2(a.v[2], a.v[3]);
-  u.z = pack_bf16x2(a.v[4], a.v[5]); u.w = pack_bf16x2(a.v[6], a.v[7]);
-  *reinterpret_cast<uint4*>(p) = u;
-}
 
 static inline int grid_for(long long work_items, int threads, int per_sm = 8) {
   long long b = (work_items + threads - 1) / threads;
@@ -88,134 +72,118 @@ __global__ void __launch_bounds__(256) stage_weights_kernel(const WStageItem* __
 }
 
 // ------------------------------------------------------------------------------------------------ decoder glue
-// Streaming iteration over (pixel, 8-channel group) with block-contiguous pixel ranges, a fixed channel group per thread
-// and incrementally maintained (n, y, x) coordinates: no integer division inside the loop.
-template <class Body>
-__device__ __forceinline__ void for_each_pixel_group_xy(int N, int H, int W, int G, Body body) {
-  const int pixels = N * H * W;
-  const int per = (pixels + gridDim.x - 1) / gridDim.x;
-  const int p0 = blockIdx.x * per, p1 = min(pixels, p0 + per);
-  for (int g0 = 0; g0 < G; g0 += blockDim.x) {
-    const int GP = min(G - g0, (int)blockDim.x);
-    const int PL = blockDim.x / GP;
-    const int pl = threadIdx.x / GP, g = g0 + (threadIdx.x - pl * GP);
-    if (pl >= PL) continue;
-    int p = p0 + pl;
-    if (p >= p1) continue;
-    int n = p / (H * W), rem = p - n * H * W;
-    int y = rem / W, x = rem - y * W;
-    const int dy = PL / W, dx = PL - dy * W;    // step of PL pixels in (y, x)
-    auto adv = [&](int& nn, int& yy, int& xx) {
-      xx += dx; yy += dy;
-      if (xx >= W) { xx -= W; ++yy; }
-      while (yy >= H) { yy -= H; ++nn; }
-    };
-    // four pixels per trip: their loads are independent, so four times the bytes are in flight per thread
-    for (; p + 3 * PL < p1; p += 4 * PL) {
-      int n1 = n, y1 = y, x1 = x;
-      adv(n1, y1, x1);
-      int n2 = n1, y2 = y1, x2 = x1;
-      adv(n2, y2, x2);
-      int n3 = n2, y3 = y2, x3 = x2;
-      adv(n3, y3, x3);
-      body(p, n, y, x, g * 8);
-      body(p + PL, n1, y1, x1, g * 8);
-      body(p + 2 * PL, n2, y2, x2, g * 8);
-      body(p + 3 * PL, n3, y3, x3, g * 8);
-      n = n3; y = y3; x = x3;
-      adv(n, y, x);
-    }
-    for (; p < p1; p += PL) {
-      body(p, n, y, x, g * 8);
-      adv(n, y, x);
-    }
-  }
-}
-
 // cat[n,Y,X,0:cu]      = blur(PixelShuffle(u))       u: [N,h,w,4cu], channel order (i,j,c)
 // cat[n,Y,X,cu:cu+cs]  = act(skip*sscale+sshift)     (sscale null: plain copy)
 // cat[n,Y,X,cu+cs:ldc] = 0
-__global__ void shuffle_cat_fwd_kernel(const __nv_bfloat16* __restrict__ u, int ldu, int cu, int blur,
-                                       const __nv_bfloat16* __restrict__ skip, int lds, int cs,
-                                       const float* __restrict__ sscale, const float* __restrict__ sshift,
-                                       int skip_relu, __nv_bfloat16* __restrict__ cat, int ldc, int N, int h, int w) {
+// Every thread owns a fixed 8-channel group of the concat, hence a fixed ROLE (shuffle / skip / zero pad): the role
+// switch sits outside the pixel loop, the skip constants are loaded once per thread, and the loads of four pixels (up to
+// 16 x 16 B for the blurred shuffle) are in flight before the first store.
+struct CatRegs { uint4 a, b, d, e; };
+
+__global__ void __launch_bounds__(256) shuffle_cat_fwd_kernel(
+    const __nv_bfloat16* __restrict__ u, int ldu, int cu, int blur, const __nv_bfloat16* __restrict__ skip, int lds,
+    int cs, const float* __restrict__ sscale, const float* __restrict__ sshift, int skip_relu,
+    __nv_bfloat16* __restrict__ cat, int ldc, int N, int h, int w) {
   const int H = 2 * h, W = 2 * w;
-  for_each_pixel_group_xy(N, H, W, ldc >> 3, [&](int p, int n, int Y, int X, int c) {
-    f8 o;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) o.v[k] = 0.f;
-    if (c < cu) {
-      auto ps = [&](int yy, int xx) {
-        return ld8(u + ((long long)(n * h + (yy >> 1)) * w + (xx >> 1)) * ldu + (((yy & 1) * 2 + (xx & 1)) * cu + c));
-      };
-      if (blur) {
-        const int y0 = Y > 0 ? Y - 1 : 0, x0 = X > 0 ? X - 1 : 0;
-        const f8 a = ps(y0, x0), b = ps(y0, X), d = ps(Y, x0), e = ps(Y, X);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) o.v[k] = 0.25f * ((a.v[k] + b.v[k]) + (d.v[k] + e.v[k]));
-      } else {
-        o = ps(Y, X);
-      }
-    } else if (skip && c < cu + cs) {
-      const int sc0 = c - cu;
-      o = ld8(skip + (long long)p * lds + sc0);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        if (sc0 + k < cs) {
-          if (sscale) o.v[k] = o.v[k] * __ldg(sscale + sc0 + k) + __ldg(sshift + sc0 + k);
-          if (skip_relu) o.v[k] = fmaxf(o.v[k], 0.f);
-        } else {
-          o.v[k] = 0.f;
+  auto ps = [&](int n, int yy, int xx, int c) {
+    return ldq(u + ((long long)(n * h + (yy >> 1)) * w + (xx >> 1)) * ldu + (((yy & 1) * 2 + (xx & 1)) * cu + c));
+  };
+  auto store = [&](int p, int c, const f8& o) { st8(cat + (long long)p * ldc + c, o); };
+  struct SkipConsts { f8 sc, sh; };
+  stream_pixel_groups_xy<4, CatRegs>(N, H, W, ldc >> 3,
+      [&](int c) {
+        // skip role: BatchNorm affine of this thread's channel group (arrays padded to a multiple of 32 floats, b2u.h)
+        SkipConsts k;
+        if (sscale && c >= cu && c < cu + cs) { k.sc = ldc8(sscale, c - cu, cs); k.sh = ldc8(sshift, c - cu, cs); }
+        return k;
+      },
+      [&](int p, int n, int Y, int X, int c, const SkipConsts&, CatRegs& q) {
+        if (c < cu) {
+          if (blur) {
+            const int y0 = Y > 0 ? Y - 1 : 0, x0 = X > 0 ? X - 1 : 0;
+            q.a = ps(n, y0, x0, c); q.b = ps(n, y0, X, c); q.d = ps(n, Y, x0, c); q.e = ps(n, Y, X, c);
+          } else {
+            q.a = ps(n, Y, X, c);
+          }
+        } else if (skip && c < cu + cs) {
+          q.a = ldq(skip + (long long)p * lds + (c - cu));
         }
-      }
-    }
-    st8(cat + (long long)p * ldc + c, o);
-  });
+      },
+      [&](int p, int n, int Y, int X, int c, const SkipConsts& k, const CatRegs& q) {
+        f8 o;
+        if (c < cu) {
+          if (blur) {
+            const f8 a = unpack_f8(q.a), b = unpack_f8(q.b), d = unpack_f8(q.d), e = unpack_f8(q.e);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o.v[k] = 0.25f * ((a.v[k] + b.v[k]) + (d.v[k] + e.v[k]));
+          } else {
+            o = unpack_f8(q.a);
+          }
+        } else if (skip && c < cu + cs) {
+          const int sc0 = c - cu;
+          o = unpack_f8(q.a);
+          if (sscale) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o.v[i] = o.v[i] * k.sc.v[i] + k.sh.v[i];
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (skip_relu) o.v[i] = fmaxf(o.v[i], 0.f);
+            if (sc0 + i >= cs) o.v[i] = 0.f;
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o.v[k] = 0.f;
+        }
+        store(p, c, o);
+      });
 }
 
 // du[n,y,x,(i,j,c)] = (u>0) * blur^T(dcat[..., 0:cu])[n, 2y+i, 2x+j, c]
-__global__ void shuffle_bwd_kernel(const __nv_bfloat16* __restrict__ dcat, int ldc, const __nv_bfloat16* __restrict__ u,
-                                   __nv_bfloat16* __restrict__ du, int ldu, int cu, int blur, int N, int h, int w) {
+struct ShufBwdRegs { uint4 a, b, d, e, u; };
+
+__global__ void __launch_bounds__(256) shuffle_bwd_kernel(
+    const __nv_bfloat16* __restrict__ dcat, int ldc, const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__ du,
+    int ldu, int cu, int blur, int N, int h, int w) {
   const int H = 2 * h, W = 2 * w;
   const int gpc = cu >> 3;   // 8-channel groups per (i,j) phase
-  for_each_pixel_group_xy(N, h, w, (4 * cu) >> 3, [&](int p, int n, int y, int x, int ch) {
-    const int ij = (ch >> 3) / gpc, c = ch - ij * cu;
-    const int Y = 2 * y + (ij >> 1), X = 2 * x + (ij & 1);
-    auto dc = [&](int yy, int xx) { return ld8(dcat + ((long long)(n * H + yy) * W + xx) * ldc + c); };
-    f8 o;
-    if (blur) {
-      // PS[Y,X] feeds outputs (Y+a, X+b), a,b in {0,1}; the replicated first row/column counts twice
-      const float wy0 = (Y == 0) ? 2.f : 1.f, wx0 = (X == 0) ? 2.f : 1.f;
-      const bool hy = (Y + 1 < H), hx = (X + 1 < W);
-      const f8 a = dc(Y, X);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) o.v[k] = wy0 * wx0 * a.v[k];
-      if (hx) {
-        const f8 b = dc(Y, X + 1);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) o.v[k] += wy0 * b.v[k];
-      }
-      if (hy) {
-        const f8 d = dc(Y + 1, X);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) o.v[k] += wx0 * d.v[k];
-        if (hx) {
-          const f8 e = dc(Y + 1, X + 1);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) o.v[k] += e.v[k];
+  auto dc = [&](int n, int yy, int xx, int c) { return ldq(dcat + ((long long)(n * H + yy) * W + xx) * ldc + c); };
+  stream_pixel_groups_xy<4, ShufBwdRegs>(N, h, w, (4 * cu) >> 3,
+      [](int) { return 0; },
+      [&](int p, int n, int y, int x, int ch, int, ShufBwdRegs& q) {
+        const int ij = (ch >> 3) / gpc, c = ch - ij * cu;
+        const int Y = 2 * y + (ij >> 1), X = 2 * x + (ij & 1);
+        q.u = ldq(u + (long long)p * ldu + ch);
+        q.a = dc(n, Y, X, c);
+        if (blur) {
+          // out-of-range neighbours are fetched from a clamped (valid) address and weighted by zero below
+          const int Y1 = min(Y + 1, H - 1), X1 = min(X + 1, W - 1);
+          q.b = dc(n, Y, X1, c); q.d = dc(n, Y1, X, c); q.e = dc(n, Y1, X1, c);
         }
-      }
+      },
+      [&](int p, int n, int y, int x, int ch, int, const ShufBwdRegs& q) {
+        const int ij = (ch >> 3) / gpc;
+        const int Y = 2 * y + (ij >> 1), X = 2 * x + (ij & 1);
+        f8 o = unpack_f8(q.a);
+        if (blur) {
+          // PS[Y,X] feeds outputs (Y+a, X+b), a,b in {0,1}; the replicated first row/column counts twice
+          const float wy0 = (Y == 0) ? 2.f : 1.f, wx0 = (X == 0) ? 2.f : 1.f;
+          const float hy = (Y + 1 < H) ? 1.f : 0.f, hx = (X + 1 < W) ? 1.f : 0.f;
+          const f8 b = unpack_f8(q.b), d = unpack_f8(q.d), e = unpack_f8(q.e);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) o.v[k] *= 0.25f;
-    } else {
-      o = dc(Y, X);
-    }
-    const long long up = (long long)p * ldu + ch;
-    const f8 uv = ld8(u + up);
+          for (int k = 0; k < 8; ++k) {
+            float s = wy0 * wx0 * o.v[k];
+            s += (wy0 * hx) * b.v[k];
+            s += (wx0 * hy) * d.v[k];
+            s += (hx * hy) * e.v[k];
+            o.v[k] = 0.25f * s;
+          }
+        }
+        const f8 uv = unpack_f8(q.u);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) o.v[k] = uv.v[k] > 0.f ? o.v[k] : 0.f;
-    st8(du + up, o);
-  });
+        for (int k = 0; k < 8; ++k) o.v[k] = uv.v[k] > 0.f ? o.v[k] : 0.f;
+        st8(du + (long long)p * ldu + ch, o);
+      });
 }
 
 // ------------------------------------------------------------------------------------------------ small-K pointwise

@@ -22,7 +22,10 @@ from . import _lib, ops
 from .layout import ConvSpec, NetSpec, ParamLayout, build_spec, conv_flops, shuffle_row_of_co
 from .ops import ConvPlan, WgradPlan, padc, view_nhwc
 
+import os
+
 BN_EPS = 1e-5
+SIDE_STREAM_WGRAD = os.environ.get("B2U_NO_SIDE_STREAM") is None   # A/B switch for profiling
 BN_MOMENTUM = 0.1
 STATS_ROWS = 592  # block partial rows of the standalone reductions (4 per SM)
 
@@ -103,6 +106,8 @@ class UNetB200:
         self.named_acts: Dict[str, Act] = {}
         self.fwd_ops: List[Callable[[int], None]] = []
         self.bwd_ops: List[Callable[[int], None]] = []
+        self.bwd_side: List[bool] = []   # weight-gradient launches: independent of the dgrad chain -> second stream
+        self._side_stream: Optional[torch.cuda.Stream] = None
         self._bwd_builders: List[Callable[[], None]] = []
         self._wstage: List[_lib.WStageItem] = []
         self._wgrad_specs: List[dict] = []
@@ -258,8 +263,9 @@ class UNetB200:
         self.op_tags.append(("fwd", sys._getframe(1).f_code.co_name, sys._getframe(1).f_lineno))
         self.launches_fwd += n
 
-    def _bwd(self, fn: Callable[[int], None], n: int = 1) -> None:
+    def _bwd(self, fn: Callable[[int], None], n: int = 1, side: bool = False) -> None:
         self.bwd_ops.append(fn)
+        self.bwd_side.append(side)
         self.op_tags.append(("bwd", sys._getframe(1).f_code.co_name, sys._getframe(1).f_lineno))
         self.launches_bwd += n
 
@@ -343,7 +349,7 @@ class UNetB200:
 
         def run(s, slot=slot):
             self._wgrad_plans[slot].run(s)
-        self._bwd(run, 2)
+        self._bwd(run, 2, side=True)
 
     def _dgrad(self, cs: ConvSpec, dy: torch.Tensor, x: Act, *, zmask: bool = False, res: Optional[torch.Tensor] = None,
                res_mask: Optional[torch.Tensor] = None, out_C: Optional[int] = None):
@@ -703,9 +709,36 @@ class UNetB200:
         return self.loss
 
     def backward(self, stream: Optional[int] = None) -> None:
-        s = stream if stream is not None else ops.stream_ptr()
-        for op in self.bwd_ops:
-            op(s)
+        """Runs the backward plan.  The critical path is the chain of activation gradients (BN backward -> dgrad -> ...);
+        the weight gradients (wgrad GEMM + split-K reduce) hang off it as leaves, so they are issued on a second stream:
+        each one waits for the ops recorded before it and the streams join before the optimizer.  The small encoder
+        layers are latency-bound single-wave launches - the two streams fill each other's ramp-up and tail bubbles.
+        (Works the same under CUDA-graph capture: the fork/join become graph edges.)"""
+        main = torch.cuda.current_stream()
+        s = stream if stream is not None else main.cuda_stream
+        two = (SIDE_STREAM_WGRAD and ops.PROFILE is None and s == main.cuda_stream)
+        if not two:
+            for op in self.bwd_ops:
+                op(s)
+            return
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(device=self.device)
+        side = self._side_stream
+        ss = side.cuda_stream
+        pending = False   # main-stream work issued since the last fork: the next side op must wait for it
+        first = True
+        for op, is_side in zip(self.bwd_ops, self.bwd_side):
+            if is_side:
+                if pending or first:
+                    ev = torch.cuda.Event()
+                    ev.record(main)
+                    side.wait_event(ev)
+                    pending, first = False, False
+                op(ss)
+            else:
+                op(s)
+                pending = True
+        main.wait_stream(side)
 
     def sgd_step(self, lr: float, stream: Optional[int] = None) -> None:
         s = stream if stream is not None else ops.stream_ptr()
