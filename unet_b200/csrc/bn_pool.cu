@@ -61,6 +61,7 @@ __device__ __forceinline__ void block_column_sums(long long pixels, int C, float
 
 __global__ void bn_stats_kernel(const __nv_bfloat16* __restrict__ x, int ldx, long long pixels, int C, float* partial,
                                 int part_ld) {
+  pdl_enter();
   block_column_sums<2>(pixels, C, partial, part_ld, [&](long long p, int c, float (&acc)[2][8]) {
     f8 a = ld8(x + p * ldx + c);
 #pragma unroll
@@ -74,6 +75,7 @@ __global__ void bn_stats_kernel(const __nv_bfloat16* __restrict__ x, int ldx, lo
 
 // rows [rows][K][ld] -> [ceil(rows/128)][K][ld], fixed order
 __global__ void reduce_rows_kernel(const float* __restrict__ in, int rows, int width, float* __restrict__ out) {
+  pdl_enter();
   // 256 threads = 64 columns x 4 row lanes; each lane sums every 4th row, lanes are combined in a fixed order
   __shared__ float sh[4][64];
   const int r0 = blockIdx.x * 128, r1 = min(rows, r0 + 128);
@@ -125,6 +127,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int rows, 
                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                    float momentum, float* running_mean, float* running_var, float* mean, float* invstd,
                                    float* scale, float* shift) {
+  pdl_enter();
   double s[2];
   int c;
   if (!final_sums<2>(partial, rows, ld, C, s, c)) return;
@@ -146,6 +149,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int rows, 
 
 __global__ void bn_eval_affine_kernel(int C, const float* gamma, const float* beta, const float* rm, const float* rv,
                                       float eps, float* scale, float* shift) {
+  pdl_enter();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float istd = 1.f / sqrtf(rv[c] + eps);
@@ -162,6 +166,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(
     const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ scale, const float* __restrict__ shift,
     const __nv_bfloat16* __restrict__ r, int ldr, const float* __restrict__ rscale, const float* __restrict__ rshift,
     int relu, __nv_bfloat16* __restrict__ y, int ldy, int pixels, int C) {
+  pdl_enter();
   stream_pixel_groups<4, ApplyRegs>(pixels, (C + 7) >> 3,
       [&](int c) {
         ApplyConsts k;
@@ -259,6 +264,7 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dz, int l
                                      int ldx, const __nv_bfloat16* __restrict__ y, int ldy, const float* scale,
                                      const float* shift, const float* mean, const float* invstd, int relu,
                                      long long pixels, int C, float* partial, int part_ld) {
+  pdl_enter();
   // block_column_sums gives every thread a fixed channel group per outer iteration: cache the constants per group
   int cached_c = -1;
   BwdConsts k;
@@ -281,6 +287,7 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dz, int l
 // sums -> dgamma/dbeta and the per-channel means used by the apply pass
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int rows, int ld, int C, double count,
                                        float* dgamma, float* dbeta, float* mean_g, float* mean_gx) {
+  pdl_enter();
   double s[2];
   int c;
   if (!final_sums<2>(partial, rows, ld, C, s, c)) return;
@@ -296,6 +303,7 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz, int ld
                                     const float* shift, const float* mean, const float* invstd, const float* gamma,
                                     const float* mean_g, const float* mean_gx, int relu, int accumulate,
                                     __nv_bfloat16* __restrict__ dx, int lddx, int pixels, int C) {
+  pdl_enter();
   stream_pixel_groups<4, BwdRegs>(pixels, (C + 7) >> 3,
       [&](int c) {
         BwdConsts k;
@@ -368,6 +376,7 @@ __global__ void __launch_bounds__(256) bn_bwd_fused_kernel(
     const float* invstd, const float* gamma, int relu, int accumulate, __nv_bfloat16* __restrict__ dx, int lddx,
     int pixels, int C, float* partial, int part_ld, double count, float* dgamma, float* dbeta, float* mean_g,
     float* mean_gx, unsigned int* sync) {
+  pdl_enter();
   extern __shared__ float red[];
   // ---- phase 1: partial sums of g and g*xhat over this block's pixel range
   {
@@ -472,6 +481,7 @@ __global__ void __launch_bounds__(256) bn_bwd_fused_kernel(
 // ------------------------------------------------------------------------------------------------ MaxPool 3x3 s2 p1
 __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                    uint8_t* __restrict__ idx, int N, int H, int W, int C, int ld) {
+  pdl_enter();
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2, G = ld >> 3;
   const long long total = (long long)N * Ho * Wo * G;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -514,6 +524,7 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfl
 
 __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx,
                                    __nv_bfloat16* dx, int accumulate, int N, int H, int W, int C, int ld) {
+  pdl_enter();
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2, G = ld >> 3;
   const long long total = (long long)N * H * W * G;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -577,7 +588,7 @@ extern "C" int b2u_bn_stats(const void* x, int32_t ldx, int64_t pixels, int32_t 
   B2U_CHECK_ARG(x && partial && rows > 0 && C > 0 && ldx % 8 == 0 && part_ld >= C, "bn_stats: bad argument");
   const int threads = 256;
   const size_t smem = (size_t)threads * 16 * sizeof(float);
-  bn_stats_kernel<<<rows, threads, smem, (cudaStream_t)stream>>>((cbf)x, ldx, pixels, C, partial, part_ld);
+  launch_k(bn_stats_kernel, dim3(rows), dim3(threads), smem, (cudaStream_t)stream, (cbf)x, ldx, pixels, C, partial, part_ld);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }
@@ -591,7 +602,7 @@ static int collapse_rows(const float** partial, int* rows, int width, float* scr
     const int out_rows = ceil_div(*rows, 128);
     const size_t need = (size_t)out_rows * width;
     B2U_CHECK_ARG(dst && avail >= need, "bn finalize: scratch too small (%zu < %zu floats)", avail, need);
-    reduce_rows_kernel<<<out_rows, 256, 0, st>>>(*partial, *rows, width, dst);
+    launch_k(reduce_rows_kernel, dim3(out_rows), dim3(256), 0, st, *partial, *rows, width, dst);
     *partial = dst;
     *rows = out_rows;
     dst += need;
@@ -608,7 +619,7 @@ extern "C" int b2u_bn_finalize(const float* partial, int32_t rows, int32_t ld, i
   cudaStream_t st = (cudaStream_t)stream;
   int rc = collapse_rows(&partial, &rows, 2 * ld, scratch, scratch_floats, st);
   if (rc) return rc;
-  bn_finalize_kernel<<<ceil_div(C, 64), 256, 0, st>>>(partial, rows, ld, C, count, gamma, beta, eps, momentum,
+  launch_k(bn_finalize_kernel, dim3(ceil_div(C, 64)), dim3(256), 0, st, partial, rows, ld, C, count, gamma, beta, eps, momentum,
                                                       running_mean, running_var, mean, invstd, scale, shift);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
@@ -617,7 +628,7 @@ extern "C" int b2u_bn_finalize(const float* partial, int32_t rows, int32_t ld, i
 extern "C" int b2u_bn_eval_affine(int32_t C, const float* gamma, const float* beta, const float* running_mean,
                                   const float* running_var, float eps, float* scale, float* shift, void* stream) {
   B2U_CHECK_ARG(C > 0 && running_mean && running_var && scale && shift, "bn_eval_affine: bad argument");
-  bn_eval_affine_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(C, gamma, beta, running_mean, running_var,
+  launch_k(bn_eval_affine_kernel, dim3(ceil_div(C, 128)), dim3(128), 0, (cudaStream_t)stream, C, gamma, beta, running_mean, running_var,
                                                                           eps, scale, shift);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
@@ -630,7 +641,7 @@ extern "C" int b2u_bn_apply(const void* x, int32_t ldx, const float* scale, cons
                 "bn_apply: bad argument");
   B2U_CHECK_ARG(pixels < (1ll << 31), "bn_apply: too many pixels");
   const long long items = pixels * ((C + 7) / 8);
-  bn_apply_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>((cbf)x, ldx, scale, shift, (cbf)r, ldr, rscale,
+  launch_k(bn_apply_kernel, dim3(grid_for(items, 256)), dim3(256), 0, (cudaStream_t)stream, (cbf)x, ldx, scale, shift, (cbf)r, ldr, rscale,
                                                                         rshift, relu, (bf)y, ldy, (int)pixels, C);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
@@ -644,7 +655,7 @@ extern "C" int b2u_bn_bwd_reduce(const void* dz, int32_t lddz, const void* x, in
   B2U_CHECK_ARG(y || !relu || (scale && shift), "bn_bwd_reduce: relu mask needs scale/shift");
   const int threads = 256;
   const size_t smem = (size_t)threads * 16 * sizeof(float);
-  bn_bwd_reduce_kernel<<<rows, threads, smem, (cudaStream_t)stream>>>((cbf)dz, lddz, (cbf)x, ldx, (cbf)y, ldy, scale,
+  launch_k(bn_bwd_reduce_kernel, dim3(rows), dim3(threads), smem, (cudaStream_t)stream, (cbf)dz, lddz, (cbf)x, ldx, (cbf)y, ldy, scale,
                                                                      shift, mean, invstd, relu, pixels, C, partial,
                                                                      part_ld);
   B2U_LAUNCH_CHECK();
@@ -658,7 +669,7 @@ extern "C" int b2u_bn_bwd_finalize(const float* partial, int32_t rows, int32_t p
   cudaStream_t st = (cudaStream_t)stream;
   int rc = collapse_rows(&partial, &rows, 2 * part_ld, scratch, scratch_floats, st);
   if (rc) return rc;
-  bn_bwd_finalize_kernel<<<ceil_div(C, 64), 256, 0, st>>>(partial, rows, part_ld, C, count, dgamma, dbeta, mean_g,
+  launch_k(bn_bwd_finalize_kernel, dim3(ceil_div(C, 64)), dim3(256), 0, st, partial, rows, part_ld, C, count, dgamma, dbeta, mean_g,
                                                           mean_gx);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
@@ -671,7 +682,7 @@ extern "C" int b2u_bn_bwd_apply(const void* dz, int32_t lddz, const void* x, int
   B2U_CHECK_ARG(dz && x && dx && mean && invstd && mean_g && mean_gx, "bn_bwd_apply: bad argument");
   B2U_CHECK_ARG(pixels < (1ll << 31), "bn_bwd_apply: too many pixels");
   const long long items = pixels * ((C + 7) / 8);
-  bn_bwd_apply_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>(
+  launch_k(bn_bwd_apply_kernel, dim3(grid_for(items, 256)), dim3(256), 0, (cudaStream_t)stream, 
       (cbf)dz, lddz, (cbf)x, ldx, (cbf)y, ldy, scale, shift, mean, invstd, gamma, mean_g, mean_gx, relu, accumulate,
       (bf)dx, lddx, (int)pixels, C);
   B2U_LAUNCH_CHECK();
@@ -704,7 +715,7 @@ extern "C" int b2u_bn_bwd_fused(const void* dz, int32_t lddz, const void* x, int
   const long long by_work = (pixels * ((C + 7) / 8) + 1023) / 1024;   // >= ~4 (pixel, 8-channel group) items per thread
   if (grid > by_work) grid = (int)by_work;
   if (grid < 1) grid = 1;
-  bn_bwd_fused_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(
+  launch_k(bn_bwd_fused_kernel, dim3(grid), dim3(threads), smem, (cudaStream_t)stream, 
       (cbf)dz, lddz, (cbf)x, ldx, (cbf)y, ldy, scale, shift, mean, invstd, gamma, relu, accumulate, (bf)dx, lddx,
       (int)pixels, C, partial, part_ld, count, dgamma, dbeta, mean_g, mean_gx, sync);
   B2U_LAUNCH_CHECK();
@@ -715,7 +726,7 @@ extern "C" int b2u_maxpool_fwd(const void* x, void* y, uint8_t* idx, int32_t N, 
                                int32_t ld, void* stream) {
   B2U_CHECK_ARG(x && y && ld % 8 == 0 && C <= ld, "maxpool_fwd: bad argument");
   const long long items = (long long)N * ((H + 1) / 2) * ((W + 1) / 2) * (ld / 8);
-  maxpool_fwd_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>((cbf)x, (bf)y, idx, N, H, W, C, ld);
+  launch_k(maxpool_fwd_kernel, dim3(grid_for(items, 256)), dim3(256), 0, (cudaStream_t)stream, (cbf)x, (bf)y, idx, N, H, W, C, ld);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }
@@ -724,7 +735,7 @@ extern "C" int b2u_maxpool_bwd(const void* dy, const uint8_t* idx, void* dx, int
                                int32_t W, int32_t C, int32_t ld, void* stream) {
   B2U_CHECK_ARG(dy && idx && dx && ld % 8 == 0, "maxpool_bwd: bad argument");
   const long long items = (long long)N * H * W * (ld / 8);
-  maxpool_bwd_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>((cbf)dy, idx, (bf)dx, accumulate, N, H, W,
+  launch_k(maxpool_bwd_kernel, dim3(grid_for(items, 256)), dim3(256), 0, (cudaStream_t)stream, (cbf)dy, idx, (bf)dx, accumulate, N, H, W,
                                                                            C, ld);
   B2U_LAUNCH_CHECK();
   return B2U_OK;

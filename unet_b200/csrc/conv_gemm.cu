@@ -158,6 +158,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // everything above is on-chip set-up and overlaps the tail of the preceding kernel (programmatic dependent launch)
+  pdl_enter();
 
   const int tiles_xy = p.tiles_x * p.tiles_y;
   // persistent schedule: loop index t -> (pixel tile m, channel tile nt); a pair walks pair-tiles and splits them by rank
@@ -1002,13 +1004,15 @@ extern "C" int b2u_conv_run(const b2u_conv_plan* plan, void* stream) {
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = plan->smem_bytes;
   cfg.stream = (cudaStream_t)stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = plan->pair ? 2 : 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   cudaError_t le = cudaLaunchKernelEx(&cfg, kern, p);
   if (le != cudaSuccess) { set_error("conv_run: launch failed: %s", cudaGetErrorString(le)); return B2U_ERR_CUDA; }
   B2U_LAUNCH_CHECK();

@@ -35,6 +35,7 @@ struct WStageItem {
 // read as contiguous runs, transposed through shared memory and written as 64-byte runs of BOTH bf16 layouts (the
 // dgrad layout is the channel transpose of the fprop layout, so a direct scatter would write 2 bytes per sector).
 __global__ void __launch_bounds__(256) stage_weights_kernel(const WStageItem* __restrict__ items, int n_items) {
+  pdl_enter();
   // binary search for the item owning this block
   int lo = 0, hi = n_items - 1;
   while (lo < hi) {
@@ -84,6 +85,7 @@ __global__ void __launch_bounds__(256) shuffle_cat_fwd_kernel(
     const __nv_bfloat16* __restrict__ u, int ldu, int cu, int blur, const __nv_bfloat16* __restrict__ skip, int lds,
     int cs, const float* __restrict__ sscale, const float* __restrict__ sshift, int skip_relu,
     __nv_bfloat16* __restrict__ cat, int ldc, int N, int h, int w) {
+  pdl_enter();
   const int H = 2 * h, W = 2 * w;
   auto ps = [&](int n, int yy, int xx, int c) {
     return ldq(u + ((long long)(n * h + (yy >> 1)) * w + (xx >> 1)) * ldu + (((yy & 1) * 2 + (xx & 1)) * cu + c));
@@ -145,6 +147,7 @@ struct ShufBwdRegs { uint4 a, b, d, e, u; };
 __global__ void __launch_bounds__(256) shuffle_bwd_kernel(
     const __nv_bfloat16* __restrict__ dcat, int ldc, const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__ du,
     int ldu, int cu, int blur, int N, int h, int w) {
+  pdl_enter();
   const int H = 2 * h, W = 2 * w;
   const int gpc = cu >> 3;   // 8-channel groups per (i,j) phase
   auto dc = [&](int n, int yy, int xx, int c) { return ldq(dcat + ((long long)(n * H + yy) * W + xx) * ldc + c); };
@@ -194,6 +197,7 @@ __global__ void pointwise_smallk_kernel(const __nv_bfloat16* __restrict__ a, int
                                         const __nv_bfloat16* __restrict__ w, int ldw,
                                         const __nv_bfloat16* __restrict__ z, int ldz, __nv_bfloat16* __restrict__ out,
                                         int ldo, int pixels, int C) {
+  pdl_enter();
   const int G = ldo >> 3;   // every lane of the output pitch is written (zeros beyond C)
   const int per = (pixels + gridDim.x - 1) / gridDim.x;
   const int p0 = blockIdx.x * per, p1 = min(pixels, p0 + per);
@@ -242,6 +246,7 @@ __global__ void pointwise_smallk_kernel(const __nv_bfloat16* __restrict__ a, int
 // 8-channel group(s) touched are zeroed when zero_pad is set.
 __global__ void nchw_to_nhwc_kernel(const void* __restrict__ x, int is_u8, __nv_bfloat16* __restrict__ y, int N, int C,
                                     int H, int W, int ld, int ch_off, int Cw) {
+  pdl_enter();
   const long long HW = (long long)H * W;
   const long long total = (long long)N * HW;
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
@@ -275,6 +280,7 @@ __global__ void nchw_to_nhwc_kernel(const void* __restrict__ x, int is_u8, __nv_
 __global__ void crop_tiles_kernel(const uint8_t* __restrict__ raster, int C, long long Y, long long X,
                                   const int* __restrict__ ty0, const int* __restrict__ tx0, int T, int P,
                                   __nv_bfloat16* __restrict__ out, int ld) {
+  pdl_enter();
   const long long PP = (long long)P * P, total = (long long)T * PP;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int t = (int)(i / PP);
@@ -293,6 +299,7 @@ __global__ void crop_tiles_kernel(const uint8_t* __restrict__ raster, int C, lon
 
 __global__ void nhwc_to_nchw_f32_kernel(const void* __restrict__ x, int is_f32, int ld, float* __restrict__ y, int N,
                                         int C, int H, int W) {
+  pdl_enter();
   const long long HW = (long long)H * W;
   const long long total = (long long)N * C * HW;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -320,6 +327,7 @@ __device__ __forceinline__ float block_sum(float v, float* sh) {
 
 __global__ void ce_weight_sum_kernel(const uint8_t* __restrict__ labels, long long P, const float* __restrict__ weight,
                                      int C, float* __restrict__ partial) {
+  pdl_enter();
   __shared__ float sh[32];
   float s = 0.f;
   const long long per = (P + gridDim.x - 1) / gridDim.x;
@@ -339,6 +347,7 @@ __global__ void ce_fwd_bwd_kernel(const float* __restrict__ logits, int ld, cons
                                   const float* __restrict__ wsum_partial, int wsum_rows,
                                   __nv_bfloat16* __restrict__ dlogits, int ldg, float* __restrict__ loss_partial,
                                   float grad_scale) {
+  pdl_enter();
   __shared__ float sh[32];
   __shared__ float s_wsum;
   if (threadIdx.x == 0) {
@@ -401,6 +410,7 @@ __global__ void ce_fwd_bwd_kernel(const float* __restrict__ logits, int ld, cons
 
 __global__ void ce_finalize_kernel(const float* loss_partial, int rows, const float* wsum_partial, int wsum_rows,
                                    float* loss) {
+  pdl_enter();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     double l = 0, w = 0;
     for (int i = 0; i < rows; ++i) l += loss_partial[i];
@@ -411,6 +421,7 @@ __global__ void ce_finalize_kernel(const float* loss_partial, int rows, const fl
 
 // ------------------------------------------------------------------------------------------------ optimizers
 __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, long long n, float lr, float gs) {
+  pdl_enter();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     p[i] -= lr * gs * g[i];
 }
@@ -419,6 +430,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
                             float* __restrict__ v, long long n, const long long* __restrict__ seg_end,
                             const float* __restrict__ seg_lr, const float* __restrict__ seg_wd, int nseg,
                             const float* __restrict__ hyper) {
+  pdl_enter();
   // hyper (device): {mom, sqr_mom, eps, debias1 = 1-mom^step, debias2 = 1-sqr_mom^step, grad_scale}
   const float mom = hyper[0], sqr_mom = hyper[1], eps = hyper[2], debias1 = hyper[3], debias2 = hyper[4], gs = hyper[5];
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -448,6 +460,7 @@ __global__ void stitch_accumulate_kernel(const float* __restrict__ logits, int l
                                          const int* __restrict__ sel, int n_sel, float* __restrict__ acc,
                                          uint8_t* __restrict__ cnt, long long Y, long long X, long long y_off,
                                          long long x_off) {
+  pdl_enter();
   const long long per_tile = (long long)th * tw;
   const int nt = sel ? n_sel : T;
   const long long total = (long long)nt * per_tile;
@@ -483,6 +496,7 @@ __global__ void stitch_accumulate_kernel(const float* __restrict__ logits, int l
 
 __global__ void stitch_finalize_kernel(const float* __restrict__ acc, const uint8_t* __restrict__ cnt, int C,
                                        long long YX, uint8_t* __restrict__ mask) {
+  pdl_enter();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < YX; i += (long long)gridDim.x * blockDim.x) {
     const int n = cnt[i];
     int best = 0;
@@ -501,6 +515,7 @@ __global__ void stitch_finalize_kernel(const float* __restrict__ acc, const uint
 template <int MAXC>
 __global__ void softmax_nchw_kernel(const float* __restrict__ logits, int ld, int C, long long tiles, int H, int W,
                                     float* __restrict__ probs, uint8_t* __restrict__ amax) {
+  pdl_enter();
   const long long HW = (long long)H * W, total = tiles * HW;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const float* z = logits + i * ld;
@@ -543,7 +558,7 @@ extern "C" int b2u_stage_weights(const b2u_wstage_item* items_dev, int32_t n_ite
                                  void* stream) {
   B2U_CHECK_ARG(items_dev && n_items > 0 && total_blocks > 0, "stage_weights: bad argument");
   static_assert(sizeof(b2u_wstage_item) == sizeof(WStageItem), "b2u_wstage_item layout drifted");
-  stage_weights_kernel<<<total_blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const WStageItem*>(items_dev),
+  launch_k(stage_weights_kernel, dim3(total_blocks), dim3(256), 0, (cudaStream_t)stream, reinterpret_cast<const WStageItem*>(items_dev),
                                                                       n_items);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
@@ -557,7 +572,7 @@ extern "C" int b2u_shuffle_cat_fwd(const void* u, int32_t ldu, int32_t cu, int32
   B2U_CHECK_ARG(!skip || (lds % 8 == 0 && cs > 0 && cu + cs <= ldc), "shuffle_cat_fwd: bad skip");
   B2U_CHECK_ARG(!sscale || sshift, "shuffle_cat_fwd: sscale without sshift");
   const long long items = (long long)N * 4 * h * w * (ldc / 8);
-  shuffle_cat_fwd_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>(
+  launch_k(shuffle_cat_fwd_kernel, dim3(grid_for(items, 256)), dim3(256), 0, (cudaStream_t)stream, 
       (cbf)u, ldu, cu, blur, (cbf)skip, lds, cs, sscale, sshift, skip_relu, (bf)cat, ldc, N, h, w);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
@@ -567,7 +582,7 @@ extern "C" int b2u_shuffle_bwd(const void* dcat, int32_t ldc, const void* u, voi
                                int32_t blur, int32_t N, int32_t h, int32_t w, void* stream) {
   B2U_CHECK_ARG(dcat && u && du && cu % 8 == 0 && ldu % 8 == 0 && ldc % 8 == 0, "shuffle_bwd: bad argument");
   const long long items = (long long)N * h * w * (4 * cu / 8);
-  shuffle_bwd_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>((cbf)dcat, ldc, (cbf)u, (bf)du, ldu, cu,
+  launch_k(shuffle_bwd_kernel, dim3(grid_for(items, 256)), dim3(256), 0, (cudaStream_t)stream, (cbf)dcat, ldc, (cbf)u, (bf)du, ldu, cu,
                                                                            blur, N, h, w);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
@@ -582,11 +597,11 @@ extern "C" int b2u_pointwise_smallk(const void* a, int32_t lda, int32_t K, const
   const int grid = grid_for(items, 256);
   cudaStream_t st = (cudaStream_t)stream;
   if (K <= 2)
-    pointwise_smallk_kernel<2><<<grid, 256, 0, st>>>((cbf)a, lda, K, (cbf)w, ldw, (cbf)z, ldz, (bf)out, ldo, (int)pixels, C);
+    launch_k(pointwise_smallk_kernel<2>, dim3(grid), dim3(256), 0, st, (cbf)a, lda, K, (cbf)w, ldw, (cbf)z, ldz, (bf)out, ldo, (int)pixels, C);
   else if (K <= 4)
-    pointwise_smallk_kernel<4><<<grid, 256, 0, st>>>((cbf)a, lda, K, (cbf)w, ldw, (cbf)z, ldz, (bf)out, ldo, (int)pixels, C);
+    launch_k(pointwise_smallk_kernel<4>, dim3(grid), dim3(256), 0, st, (cbf)a, lda, K, (cbf)w, ldw, (cbf)z, ldz, (bf)out, ldo, (int)pixels, C);
   else
-    pointwise_smallk_kernel<8><<<grid, 256, 0, st>>>((cbf)a, lda, K, (cbf)w, ldw, (cbf)z, ldz, (bf)out, ldo, (int)pixels, C);
+    launch_k(pointwise_smallk_kernel<8>, dim3(grid), dim3(256), 0, st, (cbf)a, lda, K, (cbf)w, ldw, (cbf)z, ldz, (bf)out, ldo, (int)pixels, C);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }
@@ -595,7 +610,7 @@ extern "C" int b2u_nchw_to_nhwc(const void* x, int32_t x_is_u8, void* y, int32_t
                                 int32_t ld, int32_t ch_off, int32_t write_c, void* stream) {
   B2U_CHECK_ARG(x && y && C > 0 && write_c >= C && ch_off + write_c <= ld, "nchw_to_nhwc: bad argument");
   const long long items = (long long)N * H * W;
-  nchw_to_nhwc_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>(x, x_is_u8, (bf)y, N, C, H, W, ld, ch_off,
+  launch_k(nchw_to_nhwc_kernel, dim3(grid_for(items, 256)), dim3(256), 0, (cudaStream_t)stream, x, x_is_u8, (bf)y, N, C, H, W, ld, ch_off,
                                                                             write_c);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
@@ -605,7 +620,7 @@ extern "C" int b2u_crop_tiles(const uint8_t* raster, int32_t C, int64_t Y, int64
                               const int32_t* x0, int32_t T, int32_t P, void* out, int32_t ld, void* stream) {
   B2U_CHECK_ARG(raster && y0 && x0 && out && C > 0 && C <= ld && T > 0 && P > 0, "crop_tiles: bad argument");
   const long long items = (long long)T * P * P;
-  crop_tiles_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>(raster, C, Y, X, y0, x0, T, P, (bf)out, ld);
+  launch_k(crop_tiles_kernel, dim3(grid_for(items, 256)), dim3(256), 0, (cudaStream_t)stream, raster, C, Y, X, y0, x0, T, P, (bf)out, ld);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }
@@ -614,7 +629,7 @@ extern "C" int b2u_nhwc_to_nchw_f32(const void* x, int32_t x_is_f32, int32_t ld,
                                     int32_t H, int32_t W, void* stream) {
   B2U_CHECK_ARG(x && y && C > 0 && C <= ld, "nhwc_to_nchw_f32: bad argument");
   const long long items = (long long)N * C * H * W;
-  nhwc_to_nchw_f32_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>(x, x_is_f32, ld, y, N, C, H, W);
+  launch_k(nhwc_to_nchw_f32_kernel, dim3(grid_for(items, 256)), dim3(256), 0, (cudaStream_t)stream, x, x_is_f32, ld, y, N, C, H, W);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }
@@ -622,7 +637,7 @@ extern "C" int b2u_nhwc_to_nchw_f32(const void* x, int32_t x_is_f32, int32_t ld,
 extern "C" int b2u_ce_weight_sum(const uint8_t* labels, int64_t P, const float* weight, int32_t C, float* wsum_partial,
                                  int32_t rows, void* stream) {
   B2U_CHECK_ARG(labels && wsum_partial && rows > 0 && C > 0, "ce_weight_sum: bad argument");
-  ce_weight_sum_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(labels, P, weight, C, wsum_partial);
+  launch_k(ce_weight_sum_kernel, dim3(rows), dim3(256), 0, (cudaStream_t)stream, labels, P, weight, C, wsum_partial);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }
@@ -635,10 +650,10 @@ extern "C" int b2u_ce_fwd_bwd(const float* logits, int32_t ld, const uint8_t* la
                 "ce_fwd_bwd: C=%d ld=%d ldg=%d unsupported (ldg must be a multiple of 8)", C, ld, ldg);
   cudaStream_t st = (cudaStream_t)stream;
   if (C <= 8)
-    ce_fwd_bwd_kernel<8><<<rows, 256, 0, st>>>(logits, ld, labels, P, C, weight, wsum_partial, wsum_rows, (bf)dlogits,
+    launch_k(ce_fwd_bwd_kernel<8>, dim3(rows), dim3(256), 0, st, logits, ld, labels, P, C, weight, wsum_partial, wsum_rows, (bf)dlogits,
                                                ldg, loss_partial, grad_scale);
   else
-    ce_fwd_bwd_kernel<32><<<rows, 256, 0, st>>>(logits, ld, labels, P, C, weight, wsum_partial, wsum_rows, (bf)dlogits,
+    launch_k(ce_fwd_bwd_kernel<32>, dim3(rows), dim3(256), 0, st, logits, ld, labels, P, C, weight, wsum_partial, wsum_rows, (bf)dlogits,
                                                 ldg, loss_partial, grad_scale);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
@@ -647,14 +662,14 @@ extern "C" int b2u_ce_fwd_bwd(const float* logits, int32_t ld, const uint8_t* la
 extern "C" int b2u_ce_finalize(const float* loss_partial, int32_t rows, const float* wsum_partial, int32_t wsum_rows,
                                float* loss, void* stream) {
   B2U_CHECK_ARG(loss_partial && wsum_partial && loss, "ce_finalize: bad argument");
-  ce_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(loss_partial, rows, wsum_partial, wsum_rows, loss);
+  launch_k(ce_finalize_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, loss_partial, rows, wsum_partial, wsum_rows, loss);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }
 
 extern "C" int b2u_sgd_step(float* p, const float* g, int64_t n, float lr, float grad_scale, void* stream) {
   B2U_CHECK_ARG(p && g && n > 0, "sgd_step: bad argument");
-  sgd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, n, lr, grad_scale);
+  launch_k(sgd_kernel, dim3(grid_for(n, 256)), dim3(256), 0, (cudaStream_t)stream, p, g, n, lr, grad_scale);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }
@@ -664,7 +679,7 @@ extern "C" int b2u_adam_step(float* p, const float* g, float* m, float* v, int64
                              void* stream) {
   B2U_CHECK_ARG(p && g && m && v && n > 0 && seg_end && seg_lr && seg_wd && nseg > 0 && hyper,
                 "adam_step: bad argument");
-  adam_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, (const long long*)seg_end, seg_lr,
+  launch_k(adam_kernel, dim3(grid_for(n, 256)), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, n, (const long long*)seg_end, seg_lr,
                                                                   seg_wd, nseg, hyper);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
@@ -680,10 +695,10 @@ extern "C" int b2u_stitch_accumulate(const float* logits, int32_t ld, int32_t C,
   const long long items = (long long)nt * th * tw;
   cudaStream_t st = (cudaStream_t)stream;
   if (C <= 8)
-    stitch_accumulate_kernel<8><<<grid_for(items, 256), 256, 0, st>>>(logits, ld, C, T, th, tw, y0, x0, sel, n_sel,
+    launch_k(stitch_accumulate_kernel<8>, dim3(grid_for(items, 256)), dim3(256), 0, st, logits, ld, C, T, th, tw, y0, x0, sel, n_sel,
                                                                       acc, cnt, Y, X, y_off, x_off);
   else
-    stitch_accumulate_kernel<32><<<grid_for(items, 256), 256, 0, st>>>(logits, ld, C, T, th, tw, y0, x0, sel, n_sel,
+    launch_k(stitch_accumulate_kernel<32>, dim3(grid_for(items, 256)), dim3(256), 0, st, logits, ld, C, T, th, tw, y0, x0, sel, n_sel,
                                                                        acc, cnt, Y, X, y_off, x_off);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
@@ -692,7 +707,7 @@ extern "C" int b2u_stitch_accumulate(const float* logits, int32_t ld, int32_t C,
 extern "C" int b2u_stitch_finalize(const float* acc, const uint8_t* cnt, int32_t C, int64_t Y, int64_t X, uint8_t* mask,
                                    void* stream) {
   B2U_CHECK_ARG(acc && cnt && mask && C >= 1, "stitch_finalize: bad argument");
-  stitch_finalize_kernel<<<grid_for(Y * X, 256), 256, 0, (cudaStream_t)stream>>>(acc, cnt, C, Y * X, mask);
+  launch_k(stitch_finalize_kernel, dim3(grid_for(Y * X, 256)), dim3(256), 0, (cudaStream_t)stream, acc, cnt, C, Y * X, mask);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }
@@ -703,9 +718,9 @@ extern "C" int b2u_softmax_nchw(const float* logits, int32_t ld, int32_t C, int6
   const long long items = tiles * H * W;
   cudaStream_t st = (cudaStream_t)stream;
   if (C <= 8)
-    softmax_nchw_kernel<8><<<grid_for(items, 256), 256, 0, st>>>(logits, ld, C, tiles, H, W, probs, argmax);
+    launch_k(softmax_nchw_kernel<8>, dim3(grid_for(items, 256)), dim3(256), 0, st, logits, ld, C, tiles, H, W, probs, argmax);
   else
-    softmax_nchw_kernel<32><<<grid_for(items, 256), 256, 0, st>>>(logits, ld, C, tiles, H, W, probs, argmax);
+    launch_k(softmax_nchw_kernel<32>, dim3(grid_for(items, 256)), dim3(256), 0, st, logits, ld, C, tiles, H, W, probs, argmax);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }

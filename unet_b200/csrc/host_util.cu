@@ -1,11 +1,17 @@
 #include "host_util.h"
 
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace b2u {
 
 static thread_local char g_err[512] = "";
+
+bool pdl_enabled() {
+  static const bool on = getenv("B2U_NO_PDL") == nullptr;
+  return on;
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;

@@ -45,6 +45,7 @@ struct WgradParams {
 };
 
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_constant__ WgradParams p) {
+  pdl_enter();
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
   const uint32_t smem_base = smem_u32(smem);
@@ -91,6 +92,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_enter();   // the set-up above overlaps the tail of the preceding kernel (programmatic dependent launch)
   const int tiles_xy = p.tiles_x * p.tiles_y;
 
   // unit -> (split, co tile, ci tile, tap group).  The bias gradient (row sums of dY = an MMA against an all-ones
@@ -285,6 +287,7 @@ __global__ void __launch_bounds__(1024) wgrad_reduce_kernel(const float* __restr
                                                             const int* __restrict__ tap_kidx,
                                                             const int* __restrict__ row_perm, float alpha,
                                                             float* __restrict__ dw, float* __restrict__ db) {
+  pdl_enter();
   __shared__ float sh[KS == 9 ? 8 : 32][KS][33];
   const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5, L = blockDim.x >> 5;  // L split lanes (power of two)
   const int co = blockIdx.y;
@@ -528,7 +531,7 @@ extern "C" int b2u_wgrad_plan_create(const b2u_wgrad_desc* d, b2u_wgrad_plan** o
 
 extern "C" int b2u_wgrad_run(const b2u_wgrad_plan* plan, void* stream) {
   B2U_CHECK_ARG(plan != nullptr, "wgrad_run: null plan");
-  wgrad_gemm_kernel<<<plan->info.grid, kWgThreads, plan->smem_bytes, (cudaStream_t)stream>>>(plan->p);
+  launch_k(wgrad_gemm_kernel, dim3(plan->info.grid), dim3(kWgThreads), plan->smem_bytes, (cudaStream_t)stream, plan->p);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }
@@ -548,10 +551,10 @@ extern "C" int b2u_wgrad_reduce(const float* partial, int32_t splits, int32_t ta
   while (lanes < lane_cap && lanes * 2 < splits) lanes <<= 1;   // ~2 sequential loads per lane and tap
   const int tt = taps + (has_bias_cols ? 1 : 0);
   if (ksize == 9)
-    wgrad_reduce_kernel<9><<<grid, 32 * lanes, 0, (cudaStream_t)stream>>>(partial, splits, taps, tt, co_pad, ci_pad, Cout,
+    launch_k(wgrad_reduce_kernel<9>, grid, dim3(32 * lanes), 0, (cudaStream_t)stream, partial, splits, taps, tt, co_pad, ci_pad, Cout,
                                                                          Cin, tap_kidx, row_perm, alpha, dw, db);
   else
-    wgrad_reduce_kernel<1><<<grid, 32 * lanes, 0, (cudaStream_t)stream>>>(partial, splits, taps, tt, co_pad, ci_pad, Cout,
+    launch_k(wgrad_reduce_kernel<1>, grid, dim3(32 * lanes), 0, (cudaStream_t)stream, partial, splits, taps, tt, co_pad, ci_pad, Cout,
                                                                          Cin, tap_kidx, row_perm, alpha, dw, db);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
