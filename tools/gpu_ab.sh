@@ -1,14 +1,14 @@
 mkdir -p gpurun_out
 ( time timeout 900 python -m pytest tests -m gpu -x -q ) > gpurun_out/pytest_gpu.log 2>&1
 tail -3 gpurun_out/pytest_gpu.log
-B2U_NO_PDL=1 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_a.json 2> gpurun_out/bench_a.err
 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_b.json 2> gpurun_out/bench_b.err
 python - <<'PY'
 import json
-for f in ("a","b"):
+for f in ("b",):
     try:
         d=json.load(open(f"gpurun_out/bench_{f}.json"))
         print(f, "ms/step", round(d["ms_per_step"],3), "tiles/s", round(d["value"],1), "e2e", round(d["e2e"]["value"],1), "conv ms", round(d["kernels"]["conv"]["ms"],2), "wgrad ms", round(d["kernels"]["wgrad"]["ms"],2), "loss", d["final_loss"])
     except Exception as e: print(f, "failed", e, open(f"gpurun_out/bench_{f}.err").read()[-800:])
 PY
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 1200 -c 800 --csv --log-file gpurun_out/launches_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-profile > gpurun_out/ncu_bench.log 2>&1
+B2U_NO_SIDE_STREAM=1 timeout 300 python tools/op_profile.py 64 > gpurun_out/op_profile.log 2>&1
+head -45 gpurun_out/op_profile.log

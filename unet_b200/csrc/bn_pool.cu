@@ -162,12 +162,12 @@ struct ApplyConsts { f8 sc, sh, rs, rh; };
 struct ApplyRegs { uint4 x, r; };
 
 // y = act(x*scale+shift [+ r*rscale+rshift | + r])
-__global__ void __launch_bounds__(256) bn_apply_kernel(
+__global__ void __launch_bounds__(256, 2) bn_apply_kernel(
     const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ scale, const float* __restrict__ shift,
     const __nv_bfloat16* __restrict__ r, int ldr, const float* __restrict__ rscale, const float* __restrict__ rshift,
     int relu, __nv_bfloat16* __restrict__ y, int ldy, int pixels, int C) {
   pdl_enter();
-  stream_pixel_groups<4, ApplyRegs>(pixels, (C + 7) >> 3,
+  stream_pixel_groups<6, ApplyRegs>(pixels, (C + 7) >> 3,
       [&](int c) {
         ApplyConsts k;
         k.sc = ldc8(scale, c, C); k.sh = ldc8(shift, c, C);
@@ -200,8 +200,21 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(
       });
 }
 
+__device__ __forceinline__ f8 ldc8_cg(const float* p, int c, int C) {
+  const float4 a = __ldcg(reinterpret_cast<const float4*>(p + c));
+  const float4 b = __ldcg(reinterpret_cast<const float4*>(p + c) + 1);
+  f8 o;
+  o.v[0] = a.x; o.v[1] = a.y; o.v[2] = a.z; o.v[3] = a.w; o.v[4] = b.x; o.v[5] = b.y; o.v[6] = b.z; o.v[7] = b.w;
+  if (c + 8 > C) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (c + i >= C) o.v[i] = 0.f;
+  }
+  return o;
+}
+
 // backward: g = dz * mask; mask = (y > 0) if y else (x*scale+shift > 0) if relu else 1
-struct BwdConsts { f8 sc, sh, mu, is, a, mg, mgx; };
+struct BwdConsts { f8 sc, sh, mu, is; };
 
 struct BwdRegs { uint4 dz, x, y, old; };
 
@@ -241,14 +254,49 @@ __device__ __forceinline__ void bn_bwd_gx(const __nv_bfloat16* dz, int lddz, con
   bn_bwd_math(q, y != nullptr, relu, c, C, k, g, xh);
 }
 
-// dx = gamma*invstd * (g - mean_g - xhat*mean_gx) [+ old dx]
+// dx = gamma*invstd * (g - mean_g - xhat*mean_gx) [+ old dx], evaluated as A*g + (B*x + D) with per-channel
+//   A = gamma*invstd,  B = -A*mean_gx*invstd,  D = A*(mean_gx*invstd*mean - mean_g)
+// (three constant vectors instead of five: the register budget goes to loads in flight)
+struct BwdApplyConsts { f8 A, B, D, sc, sh; };
+
+__device__ __forceinline__ BwdApplyConsts bn_bwd_apply_consts(const float* mean, const float* invstd, const float* gamma,
+                                                              const float* mean_g, const float* mean_gx,
+                                                              const float* scale, const float* shift, bool mask_from_x,
+                                                              int c, int C) {
+  BwdApplyConsts k;
+  const f8 mu = ldc8(mean, c, C), is = ldc8(invstd, c, C);
+  const f8 mg = ldc8_cg(mean_g, c, C), mgx = ldc8_cg(mean_gx, c, C);
+  if (gamma) k.A = ldc8(gamma, c, C);
+  else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) k.A.v[i] = (c + i < C) ? 1.f : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    k.A.v[i] *= is.v[i];
+    const float t = mgx.v[i] * is.v[i];
+    k.B.v[i] = -k.A.v[i] * t;
+    k.D.v[i] = k.A.v[i] * (t * mu.v[i] - mg.v[i]);
+  }
+  if (mask_from_x) { k.sc = ldc8(scale, c, C); k.sh = ldc8(shift, c, C); }
+  return k;
+}
+
 __device__ __forceinline__ void bn_bwd_store(const BwdRegs& q, bool has_y, int relu, bool accumulate, int c, int C,
-                                             const BwdConsts& k, __nv_bfloat16* dst) {
-  f8 g, xh;
-  bn_bwd_math(q, has_y, relu, c, C, k, g, xh);
+                                             const BwdApplyConsts& k, __nv_bfloat16* dst) {
+  f8 g = unpack_f8(q.dz);
+  const f8 xv = unpack_f8(q.x);
+  if (has_y) {
+    const f8 yv = unpack_f8(q.y);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g.v[i] = yv.v[i] > 0.f ? g.v[i] : 0.f;
+  } else if (relu) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g.v[i] = (xv.v[i] * k.sc.v[i] + k.sh.v[i]) > 0.f ? g.v[i] : 0.f;
+  }
   f8 o;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) o.v[i] = k.a.v[i] * (g.v[i] - k.mg.v[i] - xh.v[i] * k.mgx.v[i]);
+  for (int i = 0; i < 8; ++i) o.v[i] = k.A.v[i] * g.v[i] + (k.B.v[i] * xv.v[i] + k.D.v[i]);
   if (accumulate) {
     const f8 old = unpack_f8(q.old);
 #pragma unroll
@@ -305,24 +353,11 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz, int ld
                                     __nv_bfloat16* __restrict__ dx, int lddx, int pixels, int C) {
   pdl_enter();
   stream_pixel_groups<4, BwdRegs>(pixels, (C + 7) >> 3,
-      [&](int c) {
-        BwdConsts k;
-        k.mu = ldc8(mean, c, C); k.is = ldc8(invstd, c, C);
-        if (!y && relu) { k.sc = ldc8(scale, c, C); k.sh = ldc8(shift, c, C); }
-        k.mg = ldc8(mean_g, c, C); k.mgx = ldc8(mean_gx, c, C);
-        if (gamma) k.a = ldc8(gamma, c, C);
-        else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) k.a.v[i] = 1.f;
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) k.a.v[i] *= k.is.v[i];   // gamma * invstd
-        return k;
-      },
-      [&](int p, int c, const BwdConsts&, BwdRegs& q) {
+      [&](int c) { return bn_bwd_apply_consts(mean, invstd, gamma, mean_g, mean_gx, scale, shift, !y && relu, c, C); },
+      [&](int p, int c, const BwdApplyConsts&, BwdRegs& q) {
         bn_bwd_load(dz, lddz, x, ldx, y, ldy, accumulate ? dx : nullptr, lddx, p, c, q);
       },
-      [&](int p, int c, const BwdConsts& k, const BwdRegs& q) {
+      [&](int p, int c, const BwdApplyConsts& k, const BwdRegs& q) {
         bn_bwd_store(q, y != nullptr, relu, accumulate != 0, c, C, k, dx + (long long)p * lddx + c);
       });
 }
@@ -357,20 +392,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int* sync, unsigned int nb
   __syncthreads();
 }
 
-__device__ __forceinline__ f8 ldc8_cg(const float* p, int c, int C) {
-  const float4 a = __ldcg(reinterpret_cast<const float4*>(p + c));
-  const float4 b = __ldcg(reinterpret_cast<const float4*>(p + c) + 1);
-  f8 o;
-  o.v[0] = a.x; o.v[1] = a.y; o.v[2] = a.z; o.v[3] = a.w; o.v[4] = b.x; o.v[5] = b.y; o.v[6] = b.z; o.v[7] = b.w;
-  if (c + 8 > C) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if (c + i >= C) o.v[i] = 0.f;
-  }
-  return o;
-}
-
-__global__ void __launch_bounds__(256) bn_bwd_fused_kernel(
+__global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(
     const __nv_bfloat16* __restrict__ dz, int lddz, const __nv_bfloat16* __restrict__ x, int ldx,
     const __nv_bfloat16* __restrict__ y, int ldy, const float* scale, const float* shift, const float* mean,
     const float* invstd, const float* gamma, int relu, int accumulate, __nv_bfloat16* __restrict__ dx, int lddx,
@@ -448,17 +470,7 @@ __global__ void __launch_bounds__(256) bn_bwd_fused_kernel(
       const int pl = threadIdx.x / GP, g = g0 + (threadIdx.x - pl * GP);
       if (pl >= PL || p0 + pl >= p1) continue;
       const int c = g * 8;
-      BwdConsts k;
-      k.mu = ldc8(mean, c, C); k.is = ldc8(invstd, c, C);
-      if (!y && relu) { k.sc = ldc8(scale, c, C); k.sh = ldc8(shift, c, C); }
-      k.mg = ldc8_cg(mean_g, c, C); k.mgx = ldc8_cg(mean_gx, c, C);
-      if (gamma) k.a = ldc8(gamma, c, C);
-      else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) k.a.v[i] = 1.f;
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) k.a.v[i] *= k.is.v[i];
+      const BwdApplyConsts k = bn_bwd_apply_consts(mean, invstd, gamma, mean_g, mean_gx, scale, shift, !y && relu, c, C);
       const __nv_bfloat16* oldp = accumulate ? dx : nullptr;
       int p = p0 + pl + ((p1 - 1 - p0 - pl) / PL) * PL;   // last pixel of this lane
       for (; p - 3 * PL >= p0; p -= 4 * PL) {   // four pixels in flight per thread: all loads, then all stores
@@ -641,7 +653,7 @@ extern "C" int b2u_bn_apply(const void* x, int32_t ldx, const float* scale, cons
                 "bn_apply: bad argument");
   B2U_CHECK_ARG(pixels < (1ll << 31), "bn_apply: too many pixels");
   const long long items = pixels * ((C + 7) / 8);
-  launch_k(bn_apply_kernel, dim3(grid_for(items, 256)), dim3(256), 0, (cudaStream_t)stream, (cbf)x, ldx, scale, shift, (cbf)r, ldr, rscale,
+  launch_k(bn_apply_kernel, dim3(grid_for(items, 256, 2)), dim3(256), 0, (cudaStream_t)stream, (cbf)x, ldx, scale, shift, (cbf)r, ldr, rscale,
                                                                         rshift, relu, (bf)y, ldy, (int)pixels, C);
   B2U_LAUNCH_CHECK();
   return B2U_OK;

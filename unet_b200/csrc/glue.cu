@@ -79,10 +79,12 @@ __global__ void __launch_bounds__(256) stage_weights_kernel(const WStageItem* __
 // Every thread owns a fixed 8-channel group of the concat, hence a fixed ROLE (shuffle / skip / zero pad): the role
 // switch sits outside the pixel loop, the skip constants are loaded once per thread, and the loads of four pixels (up to
 // 16 x 16 B for the blurred shuffle) are in flight before the first store.
-struct CatRegs { uint4 a, b, d, e; };
+template <bool kBlur> struct CatRegs { uint4 a, b, d, e; };
+template <> struct CatRegs<false> { uint4 a; };
 
-__global__ void __launch_bounds__(256) shuffle_cat_fwd_kernel(
-    const __nv_bfloat16* __restrict__ u, int ldu, int cu, int blur, const __nv_bfloat16* __restrict__ skip, int lds,
+template <bool kBlur>
+__global__ void __launch_bounds__(256, 2) shuffle_cat_fwd_kernel(
+    const __nv_bfloat16* __restrict__ u, int ldu, int cu, const __nv_bfloat16* __restrict__ skip, int lds,
     int cs, const float* __restrict__ sscale, const float* __restrict__ sshift, int skip_relu,
     __nv_bfloat16* __restrict__ cat, int ldc, int N, int h, int w) {
   pdl_enter();
@@ -92,16 +94,17 @@ __global__ void __launch_bounds__(256) shuffle_cat_fwd_kernel(
   };
   auto store = [&](int p, int c, const f8& o) { st8(cat + (long long)p * ldc + c, o); };
   struct SkipConsts { f8 sc, sh; };
-  stream_pixel_groups_xy<4, CatRegs>(N, H, W, ldc >> 3,
+  // bytes in flight per thread: 4 pixels x 4 loads (blur) or 8 pixels x 1 load
+  stream_pixel_groups_xy<kBlur ? 4 : 8, CatRegs<kBlur>>(N, H, W, ldc >> 3,
       [&](int c) {
         // skip role: BatchNorm affine of this thread's channel group (arrays padded to a multiple of 32 floats, b2u.h)
         SkipConsts k;
         if (sscale && c >= cu && c < cu + cs) { k.sc = ldc8(sscale, c - cu, cs); k.sh = ldc8(sshift, c - cu, cs); }
         return k;
       },
-      [&](int p, int n, int Y, int X, int c, const SkipConsts&, CatRegs& q) {
+      [&](int p, int n, int Y, int X, int c, const SkipConsts&, CatRegs<kBlur>& q) {
         if (c < cu) {
-          if (blur) {
+          if constexpr (kBlur) {
             const int y0 = Y > 0 ? Y - 1 : 0, x0 = X > 0 ? X - 1 : 0;
             q.a = ps(n, y0, x0, c); q.b = ps(n, y0, X, c); q.d = ps(n, Y, x0, c); q.e = ps(n, Y, X, c);
           } else {
@@ -111,10 +114,10 @@ __global__ void __launch_bounds__(256) shuffle_cat_fwd_kernel(
           q.a = ldq(skip + (long long)p * lds + (c - cu));
         }
       },
-      [&](int p, int n, int Y, int X, int c, const SkipConsts& k, const CatRegs& q) {
+      [&](int p, int n, int Y, int X, int c, const SkipConsts& k, const CatRegs<kBlur>& q) {
         f8 o;
         if (c < cu) {
-          if (blur) {
+          if constexpr (kBlur) {
             const f8 a = unpack_f8(q.a), b = unpack_f8(q.b), d = unpack_f8(q.d), e = unpack_f8(q.e);
 #pragma unroll
             for (int k = 0; k < 8; ++k) o.v[k] = 0.25f * ((a.v[k] + b.v[k]) + (d.v[k] + e.v[k]));
@@ -142,33 +145,35 @@ __global__ void __launch_bounds__(256) shuffle_cat_fwd_kernel(
 }
 
 // du[n,y,x,(i,j,c)] = (u>0) * blur^T(dcat[..., 0:cu])[n, 2y+i, 2x+j, c]
-struct ShufBwdRegs { uint4 a, b, d, e, u; };
+template <bool kBlur> struct ShufBwdRegs { uint4 a, b, d, e, u; };
+template <> struct ShufBwdRegs<false> { uint4 a, u; };
 
-__global__ void __launch_bounds__(256) shuffle_bwd_kernel(
+template <bool kBlur>
+__global__ void __launch_bounds__(256, 2) shuffle_bwd_kernel(
     const __nv_bfloat16* __restrict__ dcat, int ldc, const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__ du,
-    int ldu, int cu, int blur, int N, int h, int w) {
+    int ldu, int cu, int N, int h, int w) {
   pdl_enter();
   const int H = 2 * h, W = 2 * w;
   const int gpc = cu >> 3;   // 8-channel groups per (i,j) phase
   auto dc = [&](int n, int yy, int xx, int c) { return ldq(dcat + ((long long)(n * H + yy) * W + xx) * ldc + c); };
-  stream_pixel_groups_xy<4, ShufBwdRegs>(N, h, w, (4 * cu) >> 3,
+  stream_pixel_groups_xy<kBlur ? 3 : 8, ShufBwdRegs<kBlur>>(N, h, w, (4 * cu) >> 3,
       [](int) { return 0; },
-      [&](int p, int n, int y, int x, int ch, int, ShufBwdRegs& q) {
+      [&](int p, int n, int y, int x, int ch, int, ShufBwdRegs<kBlur>& q) {
         const int ij = (ch >> 3) / gpc, c = ch - ij * cu;
         const int Y = 2 * y + (ij >> 1), X = 2 * x + (ij & 1);
         q.u = ldq(u + (long long)p * ldu + ch);
         q.a = dc(n, Y, X, c);
-        if (blur) {
+        if constexpr (kBlur) {
           // out-of-range neighbours are fetched from a clamped (valid) address and weighted by zero below
           const int Y1 = min(Y + 1, H - 1), X1 = min(X + 1, W - 1);
           q.b = dc(n, Y, X1, c); q.d = dc(n, Y1, X, c); q.e = dc(n, Y1, X1, c);
         }
       },
-      [&](int p, int n, int y, int x, int ch, int, const ShufBwdRegs& q) {
+      [&](int p, int n, int y, int x, int ch, int, const ShufBwdRegs<kBlur>& q) {
         const int ij = (ch >> 3) / gpc;
         const int Y = 2 * y + (ij >> 1), X = 2 * x + (ij & 1);
         f8 o = unpack_f8(q.a);
-        if (blur) {
+        if constexpr (kBlur) {
           // PS[Y,X] feeds outputs (Y+a, X+b), a,b in {0,1}; the replicated first row/column counts twice
           const float wy0 = (Y == 0) ? 2.f : 1.f, wx0 = (X == 0) ? 2.f : 1.f;
           const float hy = (Y + 1 < H) ? 1.f : 0.f, hx = (X + 1 < W) ? 1.f : 0.f;
@@ -572,8 +577,14 @@ extern "C" int b2u_shuffle_cat_fwd(const void* u, int32_t ldu, int32_t cu, int32
   B2U_CHECK_ARG(!skip || (lds % 8 == 0 && cs > 0 && cu + cs <= ldc), "shuffle_cat_fwd: bad skip");
   B2U_CHECK_ARG(!sscale || sshift, "shuffle_cat_fwd: sscale without sshift");
   const long long items = (long long)N * 4 * h * w * (ldc / 8);
-  launch_k(shuffle_cat_fwd_kernel, dim3(grid_for(items, 256)), dim3(256), 0, (cudaStream_t)stream, 
-      (cbf)u, ldu, cu, blur, (cbf)skip, lds, cs, sscale, sshift, skip_relu, (bf)cat, ldc, N, h, w);
+  // 2 resident blocks per SM (register budget of the 4- or 8-pixel load batches): one block per slot, one range each
+  const dim3 grid(grid_for(items, 256, 2));
+  if (blur)
+    launch_k(shuffle_cat_fwd_kernel<true>, grid, dim3(256), 0, (cudaStream_t)stream, (cbf)u, ldu, cu, (cbf)skip, lds, cs,
+             sscale, sshift, skip_relu, (bf)cat, ldc, N, h, w);
+  else
+    launch_k(shuffle_cat_fwd_kernel<false>, grid, dim3(256), 0, (cudaStream_t)stream, (cbf)u, ldu, cu, (cbf)skip, lds, cs,
+             sscale, sshift, skip_relu, (bf)cat, ldc, N, h, w);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }
@@ -582,8 +593,13 @@ extern "C" int b2u_shuffle_bwd(const void* dcat, int32_t ldc, const void* u, voi
                                int32_t blur, int32_t N, int32_t h, int32_t w, void* stream) {
   B2U_CHECK_ARG(dcat && u && du && cu % 8 == 0 && ldu % 8 == 0 && ldc % 8 == 0, "shuffle_bwd: bad argument");
   const long long items = (long long)N * h * w * (4 * cu / 8);
-  launch_k(shuffle_bwd_kernel, dim3(grid_for(items, 256)), dim3(256), 0, (cudaStream_t)stream, (cbf)dcat, ldc, (cbf)u, (bf)du, ldu, cu,
-                                                                           blur, N, h, w);
+  const dim3 grid(grid_for(items, 256, 2));
+  if (blur)
+    launch_k(shuffle_bwd_kernel<true>, grid, dim3(256), 0, (cudaStream_t)stream, (cbf)dcat, ldc, (cbf)u, (bf)du, ldu, cu, N,
+             h, w);
+  else
+    launch_k(shuffle_bwd_kernel<false>, grid, dim3(256), 0, (cudaStream_t)stream, (cbf)dcat, ldc, (cbf)u, (bf)du, ldu, cu, N,
+             h, w);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }
