@@ -118,7 +118,7 @@ def cpu_oracle_step_time(batch: int, steps: int, warmup: int):
     return sum(times) / len(times), cores, float(loss)
 
 
-def run_reference(args, rank: int):
+def run_reference(args, rank: int, out):
     """--impl reference: the reference's own CPU implementation of the path (oracle port) on the host cores."""
     if rank != 0:
         return
@@ -140,10 +140,81 @@ def run_reference(args, rank: int):
                          "sample": f"{sample} tiles per step of the batch-64 workload, {args.steps} timed steps"},
         "e2e": {"value": tiles_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=out, flush=True)
+
+
+def _guard_stdout():
+    """The driver parses ONE JSON line from stdout; libraries (NCCL prints its version banner there) must not share
+    it.  fd 1 is pointed at stderr for the whole run and the saved descriptor is used for the result line only."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, "w")
+
+
+def load_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/r01_traffic.json)."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f)
+    return None
+
+
+def predict_section(dev, rank, world, side, batch, max_over_ranks, barrier):
+    """The other half of BASELINE's metric: tiled prediction (256x256 tiles, 32-px overlap, overlap-average + argmax) of
+    a synthetic 4-band raster, tiles sharded over the ranks by output column strips.  `value`: raster resident in HBM;
+    `e2e`: the raster strip comes from pinned host memory and the uint8 mask strip is read back, inside the timed region."""
+    from unet_b200.network import UNetB200
+    from unet_b200.predict_engine import TiledPredictor
+    from unet_b200.tiling import compute_windows, shard_windows_by_columns
+    net = UNetB200(ARCH, N_IN, N_OUT, (SIZE, SIZE), batch, training=False, device=dev)
+    net.init_parameters(seed=0)
+    pred = TiledPredictor(net)
+    g = torch.Generator(device=dev).manual_seed(1234)
+    raster = torch.randint(0, 256, (N_IN, side, side), dtype=torch.uint8, device=dev, generator=g)
+    pred.predict_raster(raster[:, :1024, :1024].contiguous(), 0.125)   # warm-up
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    mask, xb, xe = pred.predict_raster(raster, 0.125, rank, world)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    n_tiles = len(compute_windows(side, side, SIZE, 0.125))
+    # e2e: this rank's input strip (the tile columns it runs) from pinned host memory, mask strip back to the host
+    windows = compute_windows(side, side, SIZE, 0.125)
+    idx, xb, xe = shard_windows_by_columns(windows, side, rank, world)
+    xs0 = min(windows[i][0] for i in idx)
+    xs1 = max(windows[i][0] + windows[i][2] for i in idx)
+    host = raster[:, :, xs0:xs1].contiguous().cpu().pin_memory()
+    host_mask = torch.empty((side, xe - xb), dtype=torch.uint8).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    strip = host.to(dev, non_blocking=True)
+    if world == 1:
+        m2, _, _ = pred.predict_raster(strip, 0.125, 0, 1)
+    else:
+        # the strip holds exactly this rank's tile columns: a 1-rank prediction of the strip, cropped to the owned columns
+        m2, _, _ = pred.predict_raster(strip, 0.125, 0, 1)
+        m2 = m2[:, xb - xs0:xe - xs0]
+    host_mask.copy_(m2, non_blocking=True)
+    torch.cuda.synchronize()
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    same = bool(torch.equal(m2, mask))
+    flops = n_tiles * net.flops_fwd_per_tile
+    return {"metric": "predict tiles/sec (256x256x4-band xresnet34-DynamicUnet, bf16, tiled predict + stitch + argmax)",
+            "workload": f"{side}x{side} 4-band raster, 256-px tiles, 32-px overlap: {n_tiles} tiles (BASELINE configs[2] is 20000x20000 = 8100 tiles: tools/predict_bench.py, profiles/r01_predict_20000.jsonl)",
+            "value": n_tiles / (ms * 1e-3), "unit": UNIT, "seconds": ms * 1e-3, "tiles": n_tiles,
+            "tiles_run_rank0": len(idx), "fwd_gflop_per_tile": net.flops_fwd_per_tile / 1e9,
+            "algorithmic_tflops_per_gpu": flops / (ms * 1e-3) / 1e12 / world,
+            "e2e": {"value": n_tiles / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes": host.numel() * world,
+                    "d2h_bytes": host_mask.numel() * world, "strip_mask_equals_sharded_mask": same}}
 
 
 def main():
+    out = _guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -152,12 +223,14 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="tiles per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--no-predict", action="store_true")
+    ap.add_argument("--predict-side", type=int, default=10240, help="side of the synthetic raster of the predict section")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b2u" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, out)
         return
 
     import torch.distributed as dist
@@ -256,15 +329,23 @@ def main():
             kernels[kind] = {"launches": len(rows), "ms": ms, "tflops": fl / (ms * 1e-3) / 1e12 if ms > 0 else None,
                              "share_of_step": ms / (dev_ms / args.steps)}
         c = kernels["conv"]
+        tr_ncu = load_traffic()
         roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel (fprop+dgrad launches)",
                     "achieved": c["tflops"], "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                    "frac": c["tflops"] / peaks["tf_sustained"], "traffic": None,
+                    "frac": c["tflops"] / peaks["tf_sustained"],
+                    "traffic": tr_ncu["conv_gemm_kernel"]["dram_bytes_per_launch"] if tr_ncu else None,
+                    "traffic_source": tr_ncu["source"] if tr_ncu else None,
+                    "algorithmic_flops_per_launch": sum(p.flops for k, p, a, b in prof if k == "conv") / max(1, c["launches"]),
                     "avg_launch_ms": c["ms"] / max(1, c["launches"]), "launches_per_step": c["launches"],
                     "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)"}
 
     # ---- whole-step tensor-core fraction from algorithmic FLOPs (fwd + dgrad + wgrad = 3x fwd conv FLOPs)
     train_flops_per_tile = 3 * net.flops_fwd_per_tile
     step_tflops = value * train_flops_per_tile / 1e12 / world
+
+    predict = None
+    if not args.no_predict:
+        predict = predict_section(dev, rank, world, args.predict_side, B, max_over_ranks, barrier)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -291,9 +372,9 @@ def main():
                                       "of_burst_peak": step_tflops / peaks["tf_burst"],
                                       "of_sustained_peak": step_tflops / peaks["tf_sustained"],
                                       "train_gflop_per_tile": train_flops_per_tile / 1e9},
-            "final_loss": loss_val,
+            "final_loss": loss_val, "predict": predict,
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -284,6 +284,14 @@ int b2u_stitch_accumulate(const float* logits, int32_t ld, int32_t C, int32_t T,
 /* mask[y][x] = argmax_c acc[c][y][x]/cnt (first max wins like np.argmax, unplaced pixels -> 0), uint8 */
 int b2u_stitch_finalize(const float* acc, const uint8_t* cnt, int32_t C, int64_t Y, int64_t X, uint8_t* mask,
                         void* stream);
+/* `large_file` mode of the merge (predict.py:217-219, 318-323): every tile's probabilities are quantised to
+ * np.around(p * 31) (int8 in the reference; the sums <= 4*31 are exact in the fp32 accumulator), the sums are
+ * floor-divided by the count and arg-maxed.  Same arguments as the two entry points above. */
+int b2u_stitch_accumulate_q31(const float* logits, int32_t ld, int32_t C, int32_t T, int32_t th, int32_t tw,
+                              const int32_t* y0, const int32_t* x0, const int32_t* sel, int32_t n_sel, float* acc,
+                              uint8_t* cnt, int64_t Y, int64_t X, int64_t y_off, int64_t x_off, void* stream);
+int b2u_stitch_finalize_q31(const float* acc, const uint8_t* cnt, int32_t C, int64_t Y, int64_t X, uint8_t* mask,
+                            void* stream);
 /* per-tile softmax probabilities (fp32 NCHW, what learn.predict returns, predict.py:193-203) and argmax */
 int b2u_softmax_nchw(const float* logits, int32_t ld, int32_t C, int64_t tiles, int32_t H, int32_t W, float* probs,
                      uint8_t* argmax, void* stream);

@@ -137,6 +137,8 @@ def _declare(lib):
         "b2u_adam_step": [vp, vp, vp, vp, i64, vp, vp, vp, i32, vp, vp],
         "b2u_stitch_accumulate": [vp, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp, u8p, i64, i64, i64, i64, vp],
         "b2u_stitch_finalize": [vp, u8p, i32, i64, i64, u8p, vp],
+        "b2u_stitch_accumulate_q31": [vp, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp, u8p, i64, i64, i64, i64, vp],
+        "b2u_stitch_finalize_q31": [vp, u8p, i32, i64, i64, u8p, vp],
         "b2u_softmax_nchw": [vp, i32, i32, i64, i32, i32, vp, u8p, vp],
     }
     for name, args in sigs.items():

@@ -464,7 +464,7 @@ __global__ void stitch_accumulate_kernel(const float* __restrict__ logits, int l
                                          const int* __restrict__ ty0, const int* __restrict__ tx0,
                                          const int* __restrict__ sel, int n_sel, float* __restrict__ acc,
                                          uint8_t* __restrict__ cnt, long long Y, long long X, long long y_off,
-                                         long long x_off) {
+                                         long long x_off, float quant) {
   pdl_enter();
   const long long per_tile = (long long)th * tw;
   const int nt = sel ? n_sel : T;
@@ -494,21 +494,27 @@ __global__ void stitch_accumulate_kernel(const float* __restrict__ logits, int l
     const long long o = gy * X + gx;
 #pragma unroll
     for (int c = 0; c < MAXC; ++c)
-      if (c < C) acc[(long long)c * Y * X + o] += e[c] * inv;
+      if (c < C) {
+        // quant > 0: the reference's `large_file` mode (predict.py:217-219): prob * 31 -> np.around (half to even) -> int8
+        const float pr = e[c] * inv;
+        acc[(long long)c * Y * X + o] += quant > 0.f ? rintf(pr * quant) : pr;
+      }
     cnt[o] += 1;
   }
 }
 
 __global__ void stitch_finalize_kernel(const float* __restrict__ acc, const uint8_t* __restrict__ cnt, int C,
-                                       long long YX, uint8_t* __restrict__ mask) {
+                                       long long YX, uint8_t* __restrict__ mask, int int_div) {
   pdl_enter();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < YX; i += (long long)gridDim.x * blockDim.x) {
     const int n = cnt[i];
     int best = 0;
     if (n > 0) {
-      float bv = acc[i] / (float)n;
+      // int_div: the int8 sums of `large_file` mode are floor-divided by the count (predict.py:318-323 `//=`)
+      float bv = int_div ? floorf(acc[i] / (float)n) : acc[i] / (float)n;
       for (int c = 1; c < C; ++c) {
-        const float v = acc[(long long)c * YX + i] / (float)n;
+        float v = acc[(long long)c * YX + i] / (float)n;
+        if (int_div) v = floorf(v);
         if (v > bv) { bv = v; best = c; }
       }
     }
@@ -701,29 +707,51 @@ extern "C" int b2u_adam_step(float* p, const float* g, float* m, float* v, int64
   return B2U_OK;
 }
 
-extern "C" int b2u_stitch_accumulate(const float* logits, int32_t ld, int32_t C, int32_t T, int32_t th, int32_t tw,
-                                     const int32_t* y0, const int32_t* x0, const int32_t* sel, int32_t n_sel,
-                                     float* acc, uint8_t* cnt, int64_t Y, int64_t X, int64_t y_off, int64_t x_off,
-                                     void* stream) {
+static int stitch_accumulate_impl(const float* logits, int32_t ld, int32_t C, int32_t T, int32_t th, int32_t tw,
+                                  const int32_t* y0, const int32_t* x0, const int32_t* sel, int32_t n_sel, float* acc,
+                                  uint8_t* cnt, int64_t Y, int64_t X, int64_t y_off, int64_t x_off, float quant,
+                                  void* stream) {
   B2U_CHECK_ARG(logits && y0 && x0 && acc && cnt && C >= 1 && C <= 32 && C <= ld, "stitch_accumulate: bad argument");
   const int nt = sel ? n_sel : T;
   if (nt <= 0) return B2U_OK;
   const long long items = (long long)nt * th * tw;
   cudaStream_t st = (cudaStream_t)stream;
   if (C <= 8)
-    launch_k(stitch_accumulate_kernel<8>, dim3(grid_for(items, 256)), dim3(256), 0, st, logits, ld, C, T, th, tw, y0, x0, sel, n_sel,
-                                                                      acc, cnt, Y, X, y_off, x_off);
+    launch_k(stitch_accumulate_kernel<8>, dim3(grid_for(items, 256)), dim3(256), 0, st, logits, ld, C, T, th, tw, y0, x0,
+             sel, n_sel, acc, cnt, Y, X, y_off, x_off, quant);
   else
-    launch_k(stitch_accumulate_kernel<32>, dim3(grid_for(items, 256)), dim3(256), 0, st, logits, ld, C, T, th, tw, y0, x0, sel, n_sel,
-                                                                       acc, cnt, Y, X, y_off, x_off);
+    launch_k(stitch_accumulate_kernel<32>, dim3(grid_for(items, 256)), dim3(256), 0, st, logits, ld, C, T, th, tw, y0, x0,
+             sel, n_sel, acc, cnt, Y, X, y_off, x_off, quant);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
+}
+
+extern "C" int b2u_stitch_accumulate(const float* logits, int32_t ld, int32_t C, int32_t T, int32_t th, int32_t tw,
+                                     const int32_t* y0, const int32_t* x0, const int32_t* sel, int32_t n_sel,
+                                     float* acc, uint8_t* cnt, int64_t Y, int64_t X, int64_t y_off, int64_t x_off,
+                                     void* stream) {
+  return stitch_accumulate_impl(logits, ld, C, T, th, tw, y0, x0, sel, n_sel, acc, cnt, Y, X, y_off, x_off, 0.f, stream);
+}
+
+extern "C" int b2u_stitch_accumulate_q31(const float* logits, int32_t ld, int32_t C, int32_t T, int32_t th, int32_t tw,
+                                         const int32_t* y0, const int32_t* x0, const int32_t* sel, int32_t n_sel,
+                                         float* acc, uint8_t* cnt, int64_t Y, int64_t X, int64_t y_off, int64_t x_off,
+                                         void* stream) {
+  return stitch_accumulate_impl(logits, ld, C, T, th, tw, y0, x0, sel, n_sel, acc, cnt, Y, X, y_off, x_off, 31.f, stream);
 }
 
 extern "C" int b2u_stitch_finalize(const float* acc, const uint8_t* cnt, int32_t C, int64_t Y, int64_t X, uint8_t* mask,
                                    void* stream) {
   B2U_CHECK_ARG(acc && cnt && mask && C >= 1, "stitch_finalize: bad argument");
-  launch_k(stitch_finalize_kernel, dim3(grid_for(Y * X, 256)), dim3(256), 0, (cudaStream_t)stream, acc, cnt, C, Y * X, mask);
+  launch_k(stitch_finalize_kernel, dim3(grid_for(Y * X, 256)), dim3(256), 0, (cudaStream_t)stream, acc, cnt, C, Y * X, mask, 0);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" int b2u_stitch_finalize_q31(const float* acc, const uint8_t* cnt, int32_t C, int64_t Y, int64_t X,
+                                       uint8_t* mask, void* stream) {
+  B2U_CHECK_ARG(acc && cnt && mask && C >= 1, "stitch_finalize_q31: bad argument");
+  launch_k(stitch_finalize_kernel, dim3(grid_for(Y * X, 256)), dim3(256), 0, (cudaStream_t)stream, acc, cnt, C, Y * X, mask, 1);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }

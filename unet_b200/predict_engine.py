@@ -24,9 +24,10 @@ class TiledPredictor:
         assert net.H == net.W
 
     def predict_raster(self, raster: torch.Tensor, patch_overlap: float, rank: int = 0, world: int = 1,
-                       return_probs: bool = False):
+                       return_probs: bool = False, large_file: bool = False):
         """raster: uint8 [C, Y, X] on the device. Returns (mask uint8 [Y, x_end-x_begin], x_begin, x_end) for the
-        column strip this rank owns (the whole raster when world == 1)."""
+        column strip this rank owns (the whole raster when world == 1).  `large_file`: the reference's int8 merge
+        (predict.py:217-219, 318-323).  `return_probs` also returns the accumulators (sum of probabilities, counts)."""
         net, lib, dev, P, B = self.net, self.lib, self.dev, self.P, self.B
         assert raster.is_cuda and raster.dtype == torch.uint8 and raster.dim() == 3 and raster.is_contiguous()
         Cc, Y, X = raster.shape
@@ -51,14 +52,15 @@ class TiledPredictor:
             _lib.check(lib.b2u_crop_tiles(raster.data_ptr(), Cc, Y, X, y0.data_ptr(), x0.data_ptr(), B, P,
                                           net.x_in.t.data_ptr(), net.x_in.ld, s), "b2u_crop_tiles")
             net.forward(s)
+            accumulate = lib.b2u_stitch_accumulate_q31 if large_file else lib.b2u_stitch_accumulate
             for cls in colour_classes(wins):
                 sel = torch.tensor(cls, dtype=torch.int32).to(dev, non_blocking=True)
-                _lib.check(lib.b2u_stitch_accumulate(net.logits.data_ptr(), ld, net.n_out, B, P, P, y0.data_ptr(),
-                                                     x0.data_ptr(), sel.data_ptr(), len(cls), acc.data_ptr(),
-                                                     cnt.data_ptr(), Y, SX, 0, xb, s), "b2u_stitch_accumulate")
+                _lib.check(accumulate(net.logits.data_ptr(), ld, net.n_out, B, P, P, y0.data_ptr(), x0.data_ptr(),
+                                      sel.data_ptr(), len(cls), acc.data_ptr(), cnt.data_ptr(), Y, SX, 0, xb, s),
+                           "b2u_stitch_accumulate")
                 self._keep = (y0, x0, sel)
-        _lib.check(lib.b2u_stitch_finalize(acc.data_ptr(), cnt.data_ptr(), net.n_out, Y, SX, mask.data_ptr(), s),
-                   "b2u_stitch_finalize")
+        finalize = lib.b2u_stitch_finalize_q31 if large_file else lib.b2u_stitch_finalize
+        _lib.check(finalize(acc.data_ptr(), cnt.data_ptr(), net.n_out, Y, SX, mask.data_ptr(), s), "b2u_stitch_finalize")
         if return_probs:
             return mask, xb, xe, acc, cnt
         return mask, xb, xe

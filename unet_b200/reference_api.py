@@ -9,12 +9,15 @@ running on the B200 plan instead of fastai.
     learn.predict(tile) -> (dec, argmax, probs)             Learner.predict(tile_u8)
                                            predict.py:193
     learn.export(path) / load_learner(path) train.py:373    Learner.export(path) / load_learner(path)   (state_dict with fastai keys)
-    predict.save_predictions(...)          predict.py:146   save_predictions(...) over in-memory tiles / .npy tiles
+    predict.save_predictions(...)          predict.py:146   save_predictions(...) over GeoTIFF (or .npy) tiles
+    train.train_func(...)                  train.py:287     train_func(...) over data_path/{trai,vali}/{img,mask}_tiles/*.tif
     create_tiles_unet.compute_windows      :30              unet_b200.tiling.compute_windows
 
 Data enters as uint8 tiles `[B, n_in, H, W]` (the reference reads GeoTIFF bands as int32 -> float32 and fastai divides by
 255, data.py:24 + IntToFloatTensor; both happen inside the cast kernel) and class-id masks `[B, H, W]`.
-GeoTIFF file I/O itself is out of the measured path; tiles on disk are read from `.npy`.
+Tiles on disk are GeoTIFFs (`unet_b200/geotiff.py`, a numpy restatement of the rasterio/GDAL calls of the path) or `.npy`
+arrays; `train_func` / `save_predictions` keep the reference's positional signatures, `predict_geotiff` is the tile-free
+whole-raster variant.
 """
 from __future__ import annotations
 
@@ -33,7 +36,8 @@ from . import _lib, ops
 from .engine import Trainer, one_cycle
 from .network import UNetB200
 from .predict_engine import TiledPredictor
-from .tiling import compute_windows, placement_from_geotransform
+from .geotiff import GeoInfo, geotiff_info, open_mask, open_tile, read_geotiff, write_geotiff
+from .tiling import colour_classes, compute_windows, placement_from_geotransform
 
 ARCHITECTURES = ("xresnet18", "xresnet34", "xresnet50", "xresnet101")   # params_and_main.py:12,99
 
@@ -193,92 +197,266 @@ def load_learner(path, batch_size: Optional[int] = None) -> Learner:
     return learn
 
 
+def _load_tile(path: Path):
+    """(uint8 [n_in,H,W] tile, GeoInfo or None).  `.tif` tiles carry their own georeferencing (predict.py:206-215)."""
+    if path.suffix.lower() in (".tif", ".tiff"):
+        arr, geo = read_geotiff(path)
+        if arr.dtype != np.uint8:
+            raise ValueError(f"{path}: {arr.dtype} tiles are not supported by the uint8 fast path")
+        return arr, geo
+    return np.load(path), None
+
+
+def _store(path: Path, arr: np.ndarray, geo: Optional[GeoInfo], nodata, class_zero: bool) -> Path:
+    """`store_tif` (predict.py:19-52) for `.tif` tiles; `.npy` otherwise (same class_zero un-shift)."""
+    if geo is not None:
+        write_geotiff(path, arr, geo, nodata=nodata, class_zero=class_zero)
+        return path
+    if class_zero and arr.dtype.kind in "ui":
+        arr = np.where(arr == 0, 0 if nodata is None else nodata, arr - 1).astype(arr.dtype)
+    path = path.with_suffix(".npy")
+    np.save(path, arr)
+    return path
+
+
 def save_predictions(predict_model, predict_path, regression: bool = False, merge: bool = False,
                      all_classes: bool = False, specific_class: Optional[int] = None, large_file: bool = False,
                      AOI=None, year=None, validation_vision: bool = False, class_zero: bool = False,
                      geotransforms: Optional[Dict[str, Sequence[float]]] = None):
-    """predict.py:146-355 over `.npy` tiles ([n_in,H,W] uint8) in `predict_path`.  Without `merge` one `<tile>.npy`
-    prediction per tile is written to `../predicted_tiles_<model>/` (argmax uint8, `specific_class` probabilities or all
-    probabilities); with `merge` the tiles are placed by their geotransform (`geotransforms[name] = (ulx, xres, xskew,
-    uly, yskew, yres)`, GDAL order) exactly as predict.py:294-297 does, averaged over overlaps and arg-maxed, and ONE
-    `<AOI>_<year>_<model>_prediction.npy` is written next to the tile folder.  Returns the output path(s)."""
+    """predict.py:146-355 over the tiles in `predict_path`: GeoTIFF tiles (`*.tif`, `[n_in,H,W]` uint8 - georeferencing
+    is read from every tile as the reference does) or `.npy` tiles (then `geotransforms[name] = (ulx, xres, xskew, uly,
+    yskew, yres)` must be given for `merge`).  Without `merge` one prediction per tile goes to
+    `../predicted_tiles_<model>/` (argmax Byte, `specific_class` or `all_classes` probabilities Float32 - or int8 x31
+    with `large_file`, predict.py:226-254); with `merge` the tiles are placed by their geotransform with the same
+    python `round()` arithmetic as predict.py:294-297, overlap-averaged and arg-maxed on the device, and ONE
+    `<AOI>_<year>_<model>_prediction.tif` is written next to the tile folder (`all_classes` / `specific_class` write the
+    averaged probabilities instead; `large_file` uses the int8 x31 / floor-division merge).  Returns the output path(s)."""
     if regression:
         raise NotImplementedError("regression prediction is outside the built hot path")
-    if large_file:
-        raise NotImplementedError("int8 'large_file' accumulation is not built yet (SURVEY.md 8(f) rank 4)")
+    if validation_vision:
+        warnings.warn("validation_vision (confusion-matrix plots, predict.py:56-143) is outside the built path; skipped")
     learn = predict_model if isinstance(predict_model, Learner) else load_learner(predict_model)
     path = Path(predict_path)
     model_name = "model" if isinstance(predict_model, Learner) else os.path.basename(str(predict_model)).split(".")[0]
-    tiles = sorted(path.glob("*.npy"))
+    tiles = sorted(path.glob("*.tif")) or sorted(path.glob("*.npy"))
     if not tiles:
-        raise FileNotFoundError(f"no .npy tiles in {path}")
+        raise FileNotFoundError(f"no .tif / .npy tiles in {path}")
     out_dir = path.parent if merge else path.parent / ("predicted_tiles_" + model_name)
     out_dir.mkdir(parents=True, exist_ok=True)
     net = learn._eval_net()
     pred = TiledPredictor(net)
-    B = net.N
+    B, P = net.N, net.H
+    dev, lib = net.device, net.lib
+
+    def batches():
+        for b0 in range(0, len(tiles), B):
+            chunk = tiles[b0:b0 + B]
+            loaded = [_load_tile(t) for t in chunk]
+            x = torch.from_numpy(np.stack([a for a, _ in loaded]))
+            if tuple(x.shape[1:]) != (net.n_in, P, P):
+                raise ValueError(f"tiles must be [{net.n_in},{P},{P}], got {tuple(x.shape[1:])}")
+            yield b0, chunk, [g for _, g in loaded], x
+
     if merge:
-        # predict.py:257-337 on the device: placement from the geotransforms (same python round() arithmetic as
-        # predict.py:294-297), softmax + overlap accumulate + normalise + argmax in the stitch kernels
-        if geotransforms is None:
-            raise ValueError("merge=True needs the tiles' geotransforms")
-        if all_classes or specific_class is not None:
-            raise NotImplementedError("merged probability outputs are not built yet (SURVEY.md 8(f) rank 4); argmax only")
-        names = [t.name for t in tiles]
-        P = net.H
-        gts = np.array([[geotransforms[n][0], P, geotransforms[n][1], geotransforms[n][3], P, geotransforms[n][5]]
-                        for n in names], dtype=np.float64)
+        # ---- pass 1 over the headers: extent of the mosaic (predict.py:257-276)
+        geos: List[Optional[GeoInfo]] = []
+        gts = []
+        for t in tiles:
+            if t.suffix.lower() in (".tif", ".tiff"):
+                nb, h, w, _, g = geotiff_info(t)
+                geos.append(g)
+                gt = g.geotransform
+            else:
+                if geotransforms is None:
+                    raise ValueError("merge=True over .npy tiles needs the tiles' geotransforms")
+                geos.append(None)
+                gt, h, w = geotransforms[t.name], P, P
+            gts.append([gt[0], w, gt[1], gt[3], h, gt[5]])
+        gts = np.array(gts, dtype=np.float64)
+        if geos[0] is not None and any(not geos[0].same_projection(g) for g in geos[1:]):
+            warnings.warn("Geoprojection is not the same for all prediction tiles.")          # predict.py:211-212
+        if len(set(gts[:, 1])) != 1 or len(set(gts[:, 4])) != 1:
+            warnings.warn("Not all tiles have the same resolution.")                           # predict.py:272-273
         ulx_full, uly_full = gts[:, 0].min(), gts[:, 3].max()
         xmax_r, ymin_r = int(np.argmax(gts[:, 0])), int(np.argmin(gts[:, 3]))
         x_len = round((gts[:, 0].max() + gts[xmax_r, 1] * gts[xmax_r, 2] - ulx_full) / gts[0, 2])
         y_len = round((gts[:, 3].min() + gts[ymin_r, 4] * gts[ymin_r, 5] - uly_full) / gts[0, 5])
         place = [placement_from_geotransform(g[0], P, g[2], g[3], P, g[5], ulx_full, uly_full) for g in gts]
-        dev, lib = net.device, net.lib
         acc = torch.zeros((net.n_out, y_len, x_len), dtype=torch.float32, device=dev)
         cnt = torch.zeros((y_len, x_len), dtype=torch.uint8, device=dev)
         mask = torch.empty((y_len, x_len), dtype=torch.uint8, device=dev)
-        from .tiling import colour_classes
+        accumulate = lib.b2u_stitch_accumulate_q31 if large_file else lib.b2u_stitch_accumulate
         s_ = ops.stream_ptr()
-        for b0 in range(0, len(tiles), B):
-            chunk = tiles[b0:b0 + B]
+        for b0, chunk, _, x in batches():
             n = len(chunk)
-            x = torch.from_numpy(np.stack([np.load(t) for t in chunk]))
             if n < B:
                 x = torch.cat([x, x[:1].expand(B - n, -1, -1, -1)], 0)
             net.set_input(x.to(dev).contiguous())
             net.forward()
             wins = [(place[b0 + i][0], place[b0 + i][1], P, P) for i in range(n)]
-            y0 = torch.tensor([w[1] for w in wins] + [0] * (B - n), dtype=torch.int32, device=dev)
-            x0 = torch.tensor([w[0] for w in wins] + [0] * (B - n), dtype=torch.int32, device=dev)
+            y0 = torch.tensor([w_[1] for w_ in wins] + [0] * (B - n), dtype=torch.int32, device=dev)
+            x0 = torch.tensor([w_[0] for w_ in wins] + [0] * (B - n), dtype=torch.int32, device=dev)
             for cls in colour_classes(wins):
                 sel = torch.tensor(cls, dtype=torch.int32, device=dev)
-                _lib.check(lib.b2u_stitch_accumulate(net.logits.data_ptr(), net.logits.shape[-1], net.n_out, B, P, P,
-                                                     y0.data_ptr(), x0.data_ptr(), sel.data_ptr(), len(cls),
-                                                     acc.data_ptr(), cnt.data_ptr(), y_len, x_len, 0, 0, s_),
-                           "b2u_stitch_accumulate")
+                _lib.check(accumulate(net.logits.data_ptr(), net.logits.shape[-1], net.n_out, B, P, P, y0.data_ptr(),
+                                      x0.data_ptr(), sel.data_ptr(), len(cls), acc.data_ptr(), cnt.data_ptr(), y_len,
+                                      x_len, 0, 0, s_), "b2u_stitch_accumulate")
             torch.cuda.synchronize()
-        _lib.check(lib.b2u_stitch_finalize(acc.data_ptr(), cnt.data_ptr(), net.n_out, y_len, x_len, mask.data_ptr(), s_),
-                   "b2u_stitch_finalize")
-        name = "_".join([p_ for p_ in (AOI, year, model_name, "prediction") if p_]) + ".npy"
-        out = mask.cpu().numpy()
-        if class_zero:
-            out = out + 1
-        np.save(out_dir / name, out)
-        return out_dir / name
-    results, names = [], []
-    for b0 in range(0, len(tiles), B):
-        chunk = tiles[b0:b0 + B]
-        n = len(chunk)
-        x = torch.from_numpy(np.stack([np.load(t) for t in chunk])).to(net.device).contiguous()
-        probs, amax = pred.predict_tiles(x)
-        for i, t in enumerate(chunk):
-            names.append(t.name)
-            results.append((probs[i].cpu().numpy(), amax[i].cpu().numpy()))
+        if all_classes or specific_class is not None:
+            # averaged probabilities: the reference's own host arithmetic on the device sums (predict.py:318-337)
+            m = acc.cpu().numpy()
+            c8 = cnt.cpu().numpy().astype(np.int8)
+            if large_file:
+                m = m.astype(np.int8)
+                mk = np.broadcast_to(c8 > 0, m.shape)
+                m[mk] //= np.broadcast_to(c8, m.shape)[mk]
+            else:
+                mk = np.broadcast_to(c8 > 0, m.shape)
+                m[mk] /= np.broadcast_to(c8, m.shape)[mk]
+            out = m if all_classes else m[specific_class]
+        else:
+            finalize = lib.b2u_stitch_finalize_q31 if large_file else lib.b2u_stitch_finalize
+            _lib.check(finalize(acc.data_ptr(), cnt.data_ptr(), net.n_out, y_len, x_len, mask.data_ptr(), s_),
+                       "b2u_stitch_finalize")
+            out = mask.cpu().numpy()
+        name = "_".join([p_ for p_ in (AOI, year, model_name, "prediction") if p_])
+        geo = None
+        if geos[0] is not None:
+            g0 = geos[0]
+            geo = GeoInfo((float(ulx_full), float(gts[0, 2]), 0.0, float(uly_full), 0.0, float(gts[0, 5])), g0.geokeys,
+                          g0.geodoubles, g0.geoascii, None, True)                                # predict.py:350-352
+        return _store(out_dir / (name + ".tif"), out, geo, None, class_zero)
+
     outs = []
-    for name, (pr, am) in zip(names, results):
-        arr = pr if all_classes else (am if specific_class is None else pr[specific_class])
-        if class_zero and arr.dtype == np.uint8:
-            arr = arr + 1          # store_tif un-shifts the class_zero label shift (predict.py:19-52)
-        np.save(out_dir / name, arr)
-        outs.append(out_dir / name)
+    for b0, chunk, geos, x in batches():
+        probs, amax = pred.predict_tiles(x.to(dev).contiguous())
+        probs, amax = probs.cpu().numpy(), amax.cpu().numpy()
+        for i, t in enumerate(chunk):
+            if all_classes:
+                arr = probs[i]
+            elif specific_class is None:
+                arr = amax[i]                                           # decoded argmax (predict.py:232)
+            else:
+                arr = probs[i][specific_class]
+            if large_file and (all_classes or specific_class):          # predict.py:245-249 (sic: class 0 is falsy there)
+                arr = np.around(arr * ((128 / 4) - 1)).astype(np.int8)
+            outs.append(_store(out_dir / t.name, arr, geos[i], None, class_zero))
     return outs
+
+
+def predict_geotiff(predict_model, raster_path, out_path=None, patch_overlap: float = 0.125, large_file: bool = False,
+                    class_zero: bool = False, rank: int = 0, world: int = 1):
+    """Tile-free variant of the predict path: what `split_raster` (create_tiles_unet.py:252-431) + `save_predictions(merge=
+    True)` produce together - the stitched argmax mask of a whole 4-band GeoTIFF - without writing tiles to disk: the
+    raster is read once, uploaded, windowed on the device with `compute_windows` offsets, predicted and stitched in HBM.
+    With `world > 1` every rank writes the column strip it owns (`<out>.part<rank>.tif`, georeferenced to its origin)."""
+    learn = predict_model if isinstance(predict_model, Learner) else load_learner(predict_model)
+    raster, geo = read_geotiff(raster_path)
+    if raster.dtype != np.uint8:
+        raise ValueError(f"{raster_path}: {raster.dtype} rasters are not supported by the uint8 fast path")
+    net = learn._eval_net()
+    if raster.shape[0] != net.n_in:
+        raise ValueError(f"raster has {raster.shape[0]} bands, the model expects {net.n_in}")
+    dev_r = torch.from_numpy(raster).pin_memory().to(net.device, non_blocking=True)
+    mask, xb, xe = TiledPredictor(net).predict_raster(dev_r, patch_overlap, rank, world, large_file=large_file)
+    out_path = Path(out_path) if out_path is not None else Path(raster_path).with_name(Path(raster_path).stem + "_prediction.tif")
+    if world > 1:
+        out_path = out_path.with_suffix(f".part{rank}.tif")
+    write_geotiff(out_path, mask.cpu().numpy(), geo.window(xb, 0), nodata=None, class_zero=class_zero)
+    return out_path
+
+
+# ---------------------------------------------------------------------------------------------------- training entry
+def _tile_batches(files: Sequence[Path], batch_size: int, n_classes: int, class_zero: bool, shuffle_seed: Optional[int],
+                  drop_last: bool):
+    """Batches of (uint8 [B,n_in,H,W], uint8 [B,H,W]) from `img_tiles/*.tif` + `mask_tiles/*.tif` (data.py:100-105,
+    utils.py:40-55).  The last partial batch is padded by repetition only when `drop_last` is False."""
+    def gen():
+        order = list(range(len(files)))
+        if shuffle_seed is not None:
+            np.random.default_rng(shuffle_seed + gen.epoch).shuffle(order)
+            gen.epoch += 1
+        for b0 in range(0, len(order), batch_size):
+            idx = order[b0:b0 + batch_size]
+            if len(idx) < batch_size:
+                if drop_last:
+                    break
+                idx = idx + [idx[0]] * (batch_size - len(idx))
+            xs, ys = [], []
+            for i in idx:
+                x = open_tile(files[i])
+                if x.dtype != np.uint8:
+                    raise ValueError(f"{files[i]}: only uint8 tiles are supported by the training fast path")
+                y = open_mask(files[i]).astype(np.int64)
+                if y.max() >= n_classes:
+                    raise ValueError(f"{files[i]}: mask label {int(y.max())} >= number of classes {n_classes}")
+                xs.append(x)
+                ys.append(y.astype(np.uint8))
+            yield torch.from_numpy(np.stack(xs)), torch.from_numpy(np.stack(ys))
+    gen.epoch = 0
+    return gen
+
+
+def train_func(data_path, existing_model, model_Path, description, BATCH_SIZE, visualize_data_example=False,
+               enable_regression=False, CLASS_WEIGHTS="even", ARCHITECTURE="xresnet34", EPOCHS=1, LEARNING_RATE=1e-3,
+               ENCODER_FACTOR=10, LR_FINDER=None, loss_func=None, monitor="dice_multi", self_attention=False,
+               VALID_SCENES=("vali",), CODES=("background", "class1"), transforms=False, split_idx=None,
+               export_model_summary=False, aug_pipe=None, n_transform_imgs=0, info=False, class_zero=False):
+    """`train_func` (train.py:287-375) with the reference's positional signature, on the B200 plan.  Expects
+    `data_path/{trai,vali}/{img_tiles,mask_tiles}/*.tif` (utils.py:25-36, data.py:102-105); trains with fastai's recipe
+    (Adam, wd 0.01, discriminative lrs `slice(lr/ENCODER_FACTOR, lr)`, one-cycle) and writes
+    `<model_Path>/<description>/<description>.pkl`, `.json` and `_history.csv` (train.py:314-320, 234, 255).
+    Augmentation (`transforms`, `aug_pipe`), the LR finder, plots and the model summary are outside the built path and
+    are refused or skipped with a warning.  Returns the trained Learner."""
+    import json
+    if enable_regression:
+        raise NotImplementedError("the regression variant is outside the built hot path")
+    if LR_FINDER:
+        warnings.warn("LR_FINDER is outside the built path; training proceeds with LEARNING_RATE")
+    if transforms or aug_pipe:
+        warnings.warn("albumentations pipelines are outside the built path; training proceeds without augmentation")
+    data_path = Path(data_path)
+    valid_scenes = [VALID_SCENES] if isinstance(VALID_SCENES, str) else list(VALID_SCENES)
+    train_files, valid_files = [], []
+    if not data_path.exists():
+        raise FileNotFoundError(data_path)                                         # train.py:54
+    for scene in sorted(p for p in data_path.iterdir() if p.is_dir()):
+        files = sorted((scene / "img_tiles").glob("*.tif"))
+        (valid_files if scene.name in valid_scenes else train_files).extend(files)
+    if not train_files:
+        raise FileNotFoundError(f"no training tiles under {data_path}/*/img_tiles")
+    nb, h, w, _, _ = geotiff_info(train_files[0])                                  # train.py:124-125 probes the first item
+    codes = list(CODES)
+    n_classes = len(codes)
+    if isinstance(CLASS_WEIGHTS, str):
+        if CLASS_WEIGHTS == "even":
+            cw = [1.0 / n_classes] * n_classes                                     # train.py:338-339
+        elif CLASS_WEIGHTS == "weighted":
+            counts = np.zeros(n_classes, dtype=np.float64)                         # inverse class frequency (utils.py:106-117)
+            for f in train_files:
+                counts += np.bincount(open_mask(f).ravel(), minlength=n_classes)[:n_classes]
+            inv = 1.0 / np.maximum(counts, 1.0)
+            cw = list(inv / inv.sum())
+        else:
+            raise ValueError(f"CLASS_WEIGHTS {CLASS_WEIGHTS!r} not understood")
+    else:
+        cw = list(CLASS_WEIGHTS)
+    learn = unet_learner_MS(nb, n_classes, ARCHITECTURE, (h, w), BATCH_SIZE, class_weights=cw, lr=LEARNING_RATE,
+                            encoder_factor=ENCODER_FACTOR, self_attention=self_attention)
+    if existing_model:
+        if not os.path.exists(existing_model):
+            raise FileNotFoundError(existing_model)
+        learn.load_state_dict(torch.load(existing_model, map_location="cpu", weights_only=False)["state_dict"])
+    out_dir = Path(model_Path) / description
+    out_dir.mkdir(parents=True, exist_ok=True)
+    tb = _tile_batches(train_files, BATCH_SIZE, n_classes, class_zero, shuffle_seed=0, drop_last=len(train_files) >= BATCH_SIZE)
+    vb = _tile_batches(valid_files, BATCH_SIZE, n_classes, class_zero, None, False) if valid_files else None
+    learn.fit_one_cycle(EPOCHS, LEARNING_RATE, tb, vb, history_csv=str(out_dir / f"{description}_history.csv"),
+                        monitor=monitor if monitor in ("dice_multi", "valid_loss", "train_loss") else "dice_multi")
+    learn.export(out_dir / f"{description}.pkl")
+    with open(out_dir / f"{description}.json", "w") as f:
+        json.dump({"description": description, "architecture": learn.arch, "bands": nb, "tile": [h, w], "codes": codes,
+                   "class_weights": cw, "batch_size": BATCH_SIZE, "epochs": EPOCHS, "learning_rate": LEARNING_RATE,
+                   "encoder_factor": ENCODER_FACTOR, "train_tiles": len(train_files), "valid_tiles": len(valid_files),
+                   "class_zero": bool(class_zero), "history": learn.history}, f, indent=1)
+    return learn
