@@ -263,3 +263,38 @@ def test_data_parallel_gradient_average_gloo(tmp_path):
     torch.nn.functional.cross_entropy(model(x), y).backward()
     ref = torch.cat([p.grad.flatten() for p in model.parameters()])
     assert torch.allclose(got, ref, atol=1e-6)       # equal shards: mean of shard means == full-batch mean
+
+
+def _gather_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from unet_b200.predict_engine import gather_mask_strips
+    from unet_b200.tiling import compute_windows, shard_windows_by_columns
+    Y, X = 37, 101                                   # odd width: strips of 51 and 50 columns
+    full = (torch.arange(Y * X, dtype=torch.int64).reshape(Y, X) % 251).to(torch.uint8)
+    wins = compute_windows(Y, X, 32, 0.25)
+    idx, xb, xe = shard_windows_by_columns(wins, X, rank, world)
+    got = gather_mask_strips(full[:, xb:xe].contiguous(), X, rank, world)
+    if rank == 0:
+        torch.save(got, out)
+    else:
+        assert got is None
+    dist.destroy_process_group()
+
+
+def test_prediction_strip_gather_gloo(tmp_path):
+    """world_size 2: the column strips the ranks own reassemble to the full mask on rank 0; every tile is
+    run by at least one rank and boundary tile columns by both."""
+    import torch.multiprocessing as mp
+    from unet_b200.tiling import compute_windows, shard_windows_by_columns
+    out = str(tmp_path / "m.pt")
+    port = 29500 + ((os.getpid() + 7) % 500)
+    mp.spawn(_gather_worker, args=(2, port, out), nprocs=2, join=True)
+    Y, X = 37, 101
+    full = (torch.arange(Y * X, dtype=torch.int64).reshape(Y, X) % 251).to(torch.uint8)
+    assert torch.equal(torch.load(out), full)
+    wins = compute_windows(Y, X, 32, 0.25)
+    i0, b0, e0 = shard_windows_by_columns(wins, X, 0, 2)
+    i1, b1, e1 = shard_windows_by_columns(wins, X, 1, 2)
+    assert (b0, e0, b1, e1) == (0, 51, 51, 101) and set(i0) | set(i1) == set(range(len(wins))) and set(i0) & set(i1)

@@ -82,3 +82,35 @@ def test_tile_helpers_and_class_zero(tmp_path):
     assert np.array_equal(b[0], np.where(msk == 0, 255, msk - 1)) and g.nodata == 255
     with pytest.raises(FileNotFoundError):
         read_geotiff(tmp_path / "missing.tif")
+
+
+def test_split_raster_tiles_filter_and_split(tmp_path):
+    """create_tiles_unet.py:252-431: window order / offsets (slidingwindow semantics), empty-tile filter, per-tile
+    georeferencing, class_zero shift and the trai/vali/test distribution."""
+    from unet_b200.create_tiles import compute_windows, split_raster
+    rng = np.random.default_rng(3)
+    H, W, P, ov = 300, 420, 128, 0.25
+    img = rng.integers(1, 256, size=(4, H, W), dtype=np.uint8)
+    img[:, :, :140] = 0                                 # an empty band on the left: tiles there are dropped
+    msk = rng.integers(0, 2, size=(H, W), dtype=np.uint8)
+    write_geotiff(tmp_path / "scene.tif", img, GEO)
+    write_geotiff(tmp_path / "scene_mask.tif", msk, GEO)
+    wins = compute_windows(np.zeros((H, W, 4)), P, ov)
+    assert wins[0] == (0, 0, P, P) and wins[1][0] == 0 and wins[1][1] == 96     # x-outer, y-inner; step = 128 - 32
+    out = split_raster(str(tmp_path / "scene.tif"), str(tmp_path / "scene_mask.tif"), str(tmp_path / "ds"), P, ov,
+                       [0.5, 0.5, 0.0], 0.5, True)
+    kept = [i for i, (x, y, w, h) in enumerate(wins)
+            if np.sum(img[:, y:y + h, x:x + w] != 0) >= 4 * w * h * 0.5]
+    assert sorted(int(p.stem.split("_")[-1]) for p in out) == kept and 0 < len(kept) < len(wins)
+    assert {p.parent.parent.name for p in out} == {"trai", "vali"} and not (tmp_path / "ds" / "img_tiles").exists()
+    p0 = out[0]
+    i0 = int(p0.stem.split("_")[-1])
+    x, y, w, h = wins[i0]
+    tile, g = read_geotiff(p0)
+    assert np.array_equal(tile, img[:, y:y + h, x:x + w])
+    assert g.geotransform[0] == pytest.approx(GEO.geotransform[0] + x * 0.2) and g.geotransform[3] == pytest.approx(GEO.geotransform[3] - y * 0.2)
+    m, _ = read_geotiff(str(p0).replace("img_tiles", "mask_tiles"))
+    keep_px = ~(img[:, y:y + h, x:x + w] == 0).all(axis=0) | True
+    assert np.array_equal(m[0], msk[y:y + h, x:x + w] + 1)              # class_zero: labels shifted by one
+    with pytest.raises(ValueError):
+        split_raster(str(tmp_path / "scene.tif"), None, str(tmp_path / "ds2"), 512, ov)

@@ -644,16 +644,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       if (rl < RL) {
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
         const float4* src = reinterpret_cast<const float4*>(p.stats) + c4;
-        // eight rows per trip, all loads issued before the first add: the L2 latency is paid once per trip, not per row
-        for (int r = rl; r < rows; r += 8 * RL) {
-          float4 v[8];
+        // sixteen rows per trip, all loads issued before the first add: the L2 latency is paid once per trip, not per row
+        for (int r = rl; r < rows; r += 16 * RL) {
+          float4 v[16];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
+          for (int u = 0; u < 16; ++u) {
             const int rr = r + u * RL;
             v[u] = rr < rows ? __ldcg(src + (size_t)rr * ncol4) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
+          for (int u = 0; u < 16; ++u) {
             a0 += (double)v[u].x; a1 += (double)v[u].y; a2 += (double)v[u].z; a3 += (double)v[u].w;
           }
         }

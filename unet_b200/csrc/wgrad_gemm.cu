@@ -124,8 +124,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_
         const uint32_t bytes = p.halo ? (2 * kBoxBytes + (uint32_t)p.NB * p.b_box_tx)
                                       : kBoxBytes * (uint32_t)(2 + nt * p.NB);
         for (int ks = k_begin; ks < k_end; ++ks) {
+          // pixel tiles are walked DOWN the image (y fastest): the X rows that filter row +1 reads at this step are the
+          // rows that filter rows 0 / -1 read one / two steps later, so the re-reads hit L2 (walked along x, the reuse
+          // distance was a whole tile row and the X operand came from DRAM ~2.7 times: profiles/r01_gemm_kernel_metrics.txt)
           const int bn = ks / tiles_xy, rem = ks - bn * tiles_xy;
-          const int by = rem / p.tiles_x, bx = rem - by * p.tiles_x;
+          const int bx = rem / p.tiles_y, by = rem - bx * p.tiles_y;
           const int x0 = bx * p.tw, y0 = by * p.th, n0 = bn * p.tn;
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t base = smem_base + (uint32_t)stage * stage_bytes;

@@ -16,6 +16,30 @@ from .network import UNetB200
 from .tiling import Window, colour_classes, compute_windows, shard_windows_by_columns
 
 
+def gather_mask_strips(strip: torch.Tensor, width: int, rank: int, world: int, dst: int = 0) -> Optional[torch.Tensor]:
+    """The only collective of the prediction path: the uint8 column strips every rank owns are gathered
+    on rank `dst` into the full `[Y, width]` mask (NCCL over NVLink on GPUs, gloo on CPU).  Strips are the balanced
+    column partition of `shard_windows_by_columns`; they are padded to the widest strip for the all_gather."""
+    import torch.distributed as dist
+    if world == 1:
+        return strip
+    Y = strip.shape[0]
+    base, rem = divmod(width, world)
+    widest = base + (1 if rem else 0)
+    # all_gather of column-major strips: [widest, Y] rows are contiguous columns of the mask
+    buf = torch.zeros((widest, Y), dtype=strip.dtype, device=strip.device)
+    buf[:strip.shape[1]] = strip.t()
+    parts = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(parts, buf)
+    if rank != dst:
+        return None
+    cols = []
+    for r in range(world):
+        w_r = base + (1 if r < rem else 0)
+        cols.append(parts[r][:w_r])
+    return torch.cat(cols, 0).t().contiguous()
+
+
 class TiledPredictor:
     def __init__(self, net: UNetB200):
         assert not net.training, "prediction uses the eval plan (running BN statistics folded into the convolutions)"
