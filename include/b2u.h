@@ -100,6 +100,12 @@ typedef struct b2u_conv_desc {
   float* out_f32;     /* B2U_EPI_OUT_F32 */
   int32_t out_f32_ld;
   b2u_bn_fin fin;     /* counter NULL = no fused finalize */
+  /* num_out > 1: the output channels are split into num_out equal N tiles (Cout / num_out, a multiple of 16) and N
+   * tile i is stored to out_nt[i] (channels 0..) instead of `out` - e.g. the four (i,j) phases of a PixelShuffle land
+   * directly in the four stride-2 parity planes of the upsampled tensor (fastai PixelShuffle_ICNR without blur).
+   * `out` still gives the GEMM geometry (N,H,W) and the total channel count. */
+  int32_t num_out;
+  b2u_view out_nt[4];
 } b2u_conv_desc;
 
 typedef struct b2u_conv_info {
@@ -232,6 +238,14 @@ int b2u_shuffle_cat_fwd(const void* u, int32_t ldu, int32_t cu, int32_t blur, co
 /* backward of the shuffle(+blur) part: du[n,h,w,(i,j,c)] = (u>0) * blur^T(dcat[..., 0:cu]) */
 int b2u_shuffle_bwd(const void* dcat, int32_t ldc, const void* u, void* du, int32_t ldu, int32_t cu, int32_t blur,
                     int32_t N, int32_t h, int32_t w, void* stream);
+/* the same without blur, with the ReLU mask taken from the upsampled tensor itself (cat[n,2y+i,2x+j,c] = relu(u[...])),
+ * so that the pre-shuffle activation need not exist (the conv stores its phases straight into the parity planes) */
+int b2u_shuffle_bwd_from_cat(const void* dcat, const void* cat, int32_t ldc, void* du, int32_t ldu, int32_t cu,
+                             int32_t N, int32_t h, int32_t w, void* stream);
+/* dst[p][dst_off .. dst_off+lanes) = src[p][src_off .. src_off+lanes) for `pixels` pixels (lanes, offsets and pitches
+ * multiples of 8): fastai MergeLayer(dense=True) `torch.cat([x, input], dim=1)` of the final stage (unet.py layers.10) */
+int b2u_copy_lanes(const void* src, int32_t lds, int32_t src_off, void* dst, int32_t ldd, int32_t dst_off,
+                   int32_t lanes, int64_t pixels, void* stream);
 
 /* out[p,c] = (z[p,c] > 0 ? 1 : 0) * sum_{k<K} a[p,k] * w[c][k], K <= 8, all bf16 (z nullable): the input gradient of the 1x1
  * head conv (GEMM K = number of classes), i.e. cudnnConvolutionBackwardData for layers.12 of the DynamicUnet.  w is the

@@ -309,3 +309,54 @@ def test_conv_fused_bn_finalize(N, Cin, Cout, H, W):
     F.batch_norm(got, rm_ref, rv_ref, gamma, beta, True, 0.1, 1e-5)
     assert rel_err(rm, rm_ref) <= 1e-4 and rel_err(rv, rv_ref) <= 1e-4
     assert plan._fin_counter.item() == 0
+
+
+@pytest.mark.parametrize("N,Cin,cu,H,W", [(2, 96, 96, 32, 32), (1, 64, 64, 16, 24), (2, 96, 96, 7, 9)])
+def test_conv_pixel_shuffle_store(N, Cin, cu, H, W):
+    """num_out = 4: the 1x1 PixelShuffle_ICNR convolution (+bias, ReLU) stores its four (i,j) phases straight into the
+    stride-2 parity planes of the upsampled tensor == F.pixel_shuffle(relu(conv(x))) (fastai layers.py
+    PixelShuffle_ICNR, blur=False); lanes past cu are zero-filled by the store; b2u_copy_lanes then appends the image
+    bands (MergeLayer dense) and b2u_shuffle_bwd_from_cat reproduces the plain shuffle backward bit for bit."""
+    from unet_b200 import _lib, ops
+    from unet_b200.layout import shuffle_row_of_co
+    L = _lib.load()
+    Cout = 4 * cu
+    x = rnd(N, Cin, H, W, seed=1)
+    w = rnd(Cout, Cin, 1, 1, seed=2, scale=Cin ** -0.5)
+    b = rnd(Cout, seed=3)
+    ref = F.pixel_shuffle(F.relu(F.conv2d(x, w, b)), 2)                       # [N, cu, 2H, 2W]
+    roc = shuffle_row_of_co(Cout)                                             # torch channel co -> GEMM row (i,j,c)
+    wg = torch.zeros((Cout, 1, ops.padc(Cin)), dtype=torch.bfloat16, device="cuda")
+    bg = torch.zeros(ops.pad32(Cout), dtype=torch.float32, device="cuda")
+    for co, r in enumerate(roc):
+        wg[r, 0, :Cin] = w[co, :, 0, 0].to(torch.bfloat16)
+        bg[r] = b[co]
+    xa = to_nhwc(x)
+    ldc = ops.padc(cu + 4)
+    cat = torch.full((N, 2 * H, 2 * W, ldc), 7.0, dtype=torch.bfloat16, device="cuda")     # poisoned: every lane is written
+    outs = [ops.view_nhwc(cat, cu, parity=(i, j)) for i in range(2) for j in range(2)]
+    geom = ops.view_nhwc(cat, cu, parity=(0, 0))
+    geom.C = Cout
+    plan = ops.ConvPlan([ops.view_nhwc(xa, Cin)], geom, wg, Cin, ops.taps_conv(1), shift=bg, relu=True, outs=outs)
+    plan.run()
+    img = rnd(N, 4, 2 * H, 2 * W, seed=4)
+    xi = to_nhwc(img)
+    lanes = min(xi.shape[-1], ldc - cu)
+    _lib.check(L.b2u_copy_lanes(xi.data_ptr(), xi.shape[-1], 0, cat.data_ptr(), ldc, cu, lanes, N * 4 * H * W,
+                                ops.stream_ptr()), "b2u_copy_lanes")
+    torch.cuda.synchronize()
+    got = cat[..., :cu].permute(0, 3, 1, 2).float()
+    assert rel_err(got, ref) <= 1e-2
+    assert torch.equal(cat[..., cu:cu + 4], xi[..., :4]) and not cat[..., cu + 4:cu + lanes].any()
+    # backward of the shuffle with the mask taken from cat == the plain kernel fed with the pre-shuffle activation
+    P = torch.zeros((N, H, W, ops.padc(Cout)), dtype=torch.bfloat16, device="cuda")
+    for ij in range(4):
+        P[..., ij * cu:(ij + 1) * cu] = cat[:, ij // 2::2, ij % 2::2, :cu]
+    dcat = to_nhwc(rnd(N, cu + 4, 2 * H, 2 * W, seed=5), ldc)
+    d1, d2 = torch.zeros_like(P), torch.zeros_like(P)
+    _lib.check(L.b2u_shuffle_bwd(dcat.data_ptr(), ldc, P.data_ptr(), d1.data_ptr(), P.shape[-1], cu, 0, N, H, W,
+                                 ops.stream_ptr()), "b2u_shuffle_bwd")
+    _lib.check(L.b2u_shuffle_bwd_from_cat(dcat.data_ptr(), cat.data_ptr(), ldc, d2.data_ptr(), P.shape[-1], cu, N, H, W,
+                                          ops.stream_ptr()), "b2u_shuffle_bwd_from_cat")
+    torch.cuda.synchronize()
+    assert torch.equal(d1, d2)

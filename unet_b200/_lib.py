@@ -45,6 +45,7 @@ class ConvDesc(C.Structure):
         ("flags", C.c_uint32), ("stats", C.c_void_p), ("stats_ld", C.c_int32),
         ("out_f32", C.c_void_p), ("out_f32_ld", C.c_int32),
         ("fin", BNFin),
+        ("num_out", C.c_int32), ("out_nt", View * 4),
     ]
 
 
@@ -126,6 +127,8 @@ def _declare(lib):
         "b2u_maxpool_bwd": [vp, u8p, vp, i32, i32, i32, i32, i32, i32, vp],
         "b2u_shuffle_cat_fwd": [vp, i32, i32, i32, vp, i32, i32, vp, vp, i32, vp, i32, i32, i32, i32, vp],
         "b2u_shuffle_bwd": [vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, vp],
+        "b2u_shuffle_bwd_from_cat": [vp, vp, i32, vp, i32, i32, i32, i32, i32, vp],
+        "b2u_copy_lanes": [vp, i32, i32, vp, i32, i32, i32, i64, vp],
         "b2u_nchw_to_nhwc": [vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp],
         "b2u_pointwise_smallk": [vp, i32, i32, vp, i32, vp, i32, vp, i32, i64, i32, vp],
         "b2u_crop_tiles": [u8p, i32, i64, i64, vp, vp, i32, i32, vp, i32, vp],

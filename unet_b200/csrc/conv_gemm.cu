@@ -51,6 +51,8 @@ struct ConvParams {
   float* out_f32;
   int out_f32_ld;
   b2u_bn_fin fin;   // counter != nullptr: the last CTA to retire finalizes the BatchNorm statistics
+  int multi_out;    // N tile nt is stored through tm_out_nt[nt] at channel 0 (PixelShuffle phases -> parity planes)
+  CUtensorMap tm_out_nt[4];
 };
 
 static constexpr int kThreads = 384;   // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 epilogue
@@ -145,6 +147,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     for (int i = 0; i < B2U_MAX_VIEWS; ++i) tma_prefetch_desc(&p.tm_a[i]);
     tma_prefetch_desc(&p.tm_b);
     tma_prefetch_desc(&p.tm_out);
+    for (int i = 0; i < p.multi_out; ++i) tma_prefetch_desc(&p.tm_out_nt[i]);
     for (int i = 0; i < p.n_aux; ++i) tma_prefetch_desc(&p.tm_aux[i]);
     if (p.halo) tma_prefetch_desc(&p.tm_ah);
     if (p.rowmode) tma_prefetch_desc(&p.tm_b3);
@@ -566,7 +569,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           named_bar_sync(1, 256);
           if (e == 0) {
             if (kPair && rank != 0 && j == n_chunks - 1) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
-            tma_store_4d(&p.tm_out, stg_base + buf * kStagingBytes, nt * p.BN + j * 64, x0, y0, n0);
+            if (p.multi_out) tma_store_4d(&p.tm_out_nt[nt], stg_base + buf * kStagingBytes, j * 64, x0, y0, n0);
+            else tma_store_4d(&p.tm_out, stg_base + buf * kStagingBytes, nt * p.BN + j * 64, x0, y0, n0);
             tma_store_commit();
           }
         }
@@ -734,8 +738,8 @@ static int conv_plan_fill(const b2u_conv_desc* d, b2u_conv_plan* plan, bool enco
   const bool out_f32 = (d->flags & B2U_EPI_OUT_F32) != 0;
   B2U_CHECK_ARG(d->out.C > 0 && d->out.W > 0 && d->out.H > 0 && d->out.N > 0, "conv: bad output geometry");
   B2U_CHECK_ARG(d->out.C == d->w_rows, "conv: out.C=%d != w_rows=%d", d->out.C, d->w_rows);
-  if (!out_f32) { if (!view_ok(d->out, "conv.out")) return B2U_ERR_ARG; }
-  else B2U_CHECK_ARG(d->out_f32 != nullptr && d->out_f32_ld >= d->out.C, "conv: out_f32 / out_f32_ld invalid");
+  if (out_f32) B2U_CHECK_ARG(d->out_f32 != nullptr && d->out_f32_ld >= d->out.C, "conv: out_f32 / out_f32_ld invalid");
+  else if (d->num_out <= 1) { if (!view_ok(d->out, "conv.out")) return B2U_ERR_ARG; }
   for (int i = 0; i < d->num_a; ++i) {
     if (!view_ok(d->a[i], "conv.a")) return B2U_ERR_ARG;
     B2U_CHECK_ARG(d->a[i].C == d->w_cin, "conv: a[%d].C=%d != w_cin=%d", i, d->a[i].C, d->w_cin);
@@ -762,6 +766,20 @@ static int conv_plan_fill(const b2u_conv_desc* d, b2u_conv_plan* plan, bool enco
   int n_tiles, BN;
   if (Cout <= 256) { n_tiles = 1; BN = round_up(Cout, 16); }
   else { n_tiles = ceil_div(Cout, 256); BN = round_up(ceil_div(Cout, n_tiles), 64); n_tiles = ceil_div(Cout, BN); }
+  const bool multi_out = d->num_out > 1;
+  if (multi_out) {
+    B2U_CHECK_ARG(d->num_out <= 4 && Cout % d->num_out == 0 && (Cout / d->num_out) % 16 == 0 && Cout / d->num_out <= 256,
+                  "conv: num_out=%d needs Cout/num_out to be a multiple of 16 and <= 256", d->num_out);
+    B2U_CHECK_ARG(!out_f32 && !(d->flags & B2U_EPI_STATS) && !d->res.ptr && !d->res_mask.ptr && !d->zmask.ptr,
+                  "conv: num_out > 1 supports the plain bf16 epilogue only");
+    n_tiles = d->num_out;
+    BN = Cout / d->num_out;
+    for (int i = 0; i < d->num_out; ++i) {
+      if (!view_ok(d->out_nt[i], "conv.out_nt")) return B2U_ERR_ARG;
+      B2U_CHECK_ARG(d->out_nt[i].C == BN && d->out_nt[i].W == d->out.W && d->out_nt[i].H == d->out.H &&
+                    d->out_nt[i].N == d->out.N, "conv: out_nt[%d] geometry differs from the GEMM space", i);
+    }
+  }
   int tw, th, tn, tx, ty, tb;
   pick_m_tile(d->out.N, d->out.H, d->out.W, &tw, &th, &tn, &tx, &ty, &tb);
   // halo mode: 3x3 stride-1 tap table over a single view (fprop and dgrad of the 3x3 convolutions), images >= 16 x 8
@@ -779,7 +797,7 @@ static int conv_plan_fill(const b2u_conv_desc* d, b2u_conv_plan* plan, bool enco
   // CTA-pair mode: two pixel tiles share every weight stage (each SM holds half of its rows) and one M = 256 MMA stream
   static const bool pair_disabled = getenv("B2U_CONV_NO_PAIR") != nullptr;  // A/B switch for profiling
   // (tiles with little MMA work - 1x1 convolutions over few channels - are epilogue/store-bound: pairing only adds sync)
-  const bool pair = !pair_disabled && !out_f32 && BN % 16 == 0 && p.m_tiles >= 2 &&
+  const bool pair = !pair_disabled && !out_f32 && !multi_out && BN % 16 == 0 && p.m_tiles >= 2 &&
                     (halo || d->num_taps * ceil_div(Cin, 64) >= 8);
   plan->pair = pair;
   const int b_rows = pair ? BN / 2 : BN;   // weight rows per CTA and tap
@@ -863,6 +881,7 @@ static int conv_plan_fill(const b2u_conv_desc* d, b2u_conv_plan* plan, bool enco
   auto ev = [](const b2u_view& v) { EpiView e; e.ptr = (const __nv_bfloat16*)v.ptr; e.sW = v.sW; e.sH = v.sH; e.sN = v.sN; return e; };
   p.res = ev(d->res); p.res_mask = ev(d->res_mask); p.zmask = ev(d->zmask);
   p.flags = d->flags; p.stats = d->stats; p.stats_ld = d->stats_ld;
+  p.multi_out = multi_out ? d->num_out : 0;
   p.out_f32 = d->out_f32; p.out_f32_ld = d->out_f32_ld;
   if ((d->flags & B2U_EPI_STATS) && encode) B2U_CHECK_ARG(d->stats_ld >= Cout, "conv: stats_ld=%d < Cout=%d", d->stats_ld, Cout);
 
@@ -921,7 +940,14 @@ static int conv_plan_fill(const b2u_conv_desc* d, b2u_conv_plan* plan, bool enco
       int rc = encode_tmap_bf16(&p.tm_b3, d->w, 3, dims, str, box);
       if (rc) return rc;
     }
-    if (!out_f32) {
+    if (multi_out) {
+      for (int i = 0; i < d->num_out; ++i) {
+        int rc = view_tmap(&p.tm_out_nt[i], d->out_nt[i], 64, (uint32_t)tw, (uint32_t)th, (uint32_t)tn);
+        if (rc) return rc;
+      }
+      for (int i = d->num_out; i < 4; ++i) p.tm_out_nt[i] = p.tm_out_nt[0];
+      p.tm_out = p.tm_out_nt[0];
+    } else if (!out_f32) {
       int rc = view_tmap(&p.tm_out, d->out, 64, (uint32_t)tw, (uint32_t)th, (uint32_t)tn);
       if (rc) return rc;
     } else {

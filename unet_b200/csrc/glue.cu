@@ -148,10 +148,12 @@ __global__ void __launch_bounds__(256, 2) shuffle_cat_fwd_kernel(
 template <bool kBlur> struct ShufBwdRegs { uint4 a, b, d, e, u; };
 template <> struct ShufBwdRegs<false> { uint4 a, u; };
 
+// `u` null: the ReLU mask is read from `ucat` (the upsampled tensor itself, same addressing as dcat) - without blur
+// cat[n,2y+i,2x+j,c] IS relu(u[n,y,x,(i,j,c)]), so the pre-shuffle activation need not be kept.
 template <bool kBlur>
 __global__ void __launch_bounds__(256, 2) shuffle_bwd_kernel(
-    const __nv_bfloat16* __restrict__ dcat, int ldc, const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__ du,
-    int ldu, int cu, int N, int h, int w) {
+    const __nv_bfloat16* __restrict__ dcat, int ldc, const __nv_bfloat16* __restrict__ u,
+    const __nv_bfloat16* __restrict__ ucat, __nv_bfloat16* __restrict__ du, int ldu, int cu, int N, int h, int w) {
   pdl_enter();
   const int H = 2 * h, W = 2 * w;
   const int gpc = cu >> 3;   // 8-channel groups per (i,j) phase
@@ -161,7 +163,7 @@ __global__ void __launch_bounds__(256, 2) shuffle_bwd_kernel(
       [&](int p, int n, int y, int x, int ch, int, ShufBwdRegs<kBlur>& q) {
         const int ij = (ch >> 3) / gpc, c = ch - ij * cu;
         const int Y = 2 * y + (ij >> 1), X = 2 * x + (ij & 1);
-        q.u = ldq(u + (long long)p * ldu + ch);
+        q.u = u ? ldq(u + (long long)p * ldu + ch) : ldq(ucat + ((long long)(n * H + Y) * W + X) * ldc + c);
         q.a = dc(n, Y, X, c);
         if constexpr (kBlur) {
           // out-of-range neighbours are fetched from a clamped (valid) address and weighted by zero below
@@ -192,6 +194,34 @@ __global__ void __launch_bounds__(256, 2) shuffle_bwd_kernel(
         for (int k = 0; k < 8; ++k) o.v[k] = uv.v[k] > 0.f ? o.v[k] : 0.f;
         st8(du + (long long)p * ldu + ch, o);
       });
+}
+
+// dst[p, dst_off : dst_off + 8*groups] = src[p, src_off : ...] for every pixel (16-byte groups): MergeLayer(dense=True) of
+// the final stage - the image bands are concatenated behind the shuffled channels (fastai unet.py layers.10).
+__global__ void copy_lanes_kernel(const __nv_bfloat16* __restrict__ src, int lds, int src_off,
+                                  __nv_bfloat16* __restrict__ dst, int ldd, int dst_off, int groups, long long pixels) {
+  pdl_enter();
+  const long long total = pixels * groups;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < total; i += 4 * stride) {
+    uint4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long j = i + k * stride, p = j / groups;
+      v[k] = ldq(src + p * lds + src_off + (int)(j - p * groups) * 8);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long j = i + k * stride, p = j / groups;
+      *reinterpret_cast<uint4*>(dst + p * ldd + dst_off + (int)(j - p * groups) * 8) = v[k];
+    }
+  }
+  for (; i < total; i += stride) {
+    const long long p = i / groups;
+    const int g = (int)(i - p * groups);
+    *reinterpret_cast<uint4*>(dst + p * ldd + dst_off + g * 8) = ldq(src + p * lds + src_off + g * 8);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ small-K pointwise
@@ -595,17 +625,41 @@ extern "C" int b2u_shuffle_cat_fwd(const void* u, int32_t ldu, int32_t cu, int32
   return B2U_OK;
 }
 
-extern "C" int b2u_shuffle_bwd(const void* dcat, int32_t ldc, const void* u, void* du, int32_t ldu, int32_t cu,
-                               int32_t blur, int32_t N, int32_t h, int32_t w, void* stream) {
-  B2U_CHECK_ARG(dcat && u && du && cu % 8 == 0 && ldu % 8 == 0 && ldc % 8 == 0, "shuffle_bwd: bad argument");
+static int shuffle_bwd_impl(const void* dcat, int32_t ldc, const void* u, const void* ucat, void* du, int32_t ldu,
+                            int32_t cu, int32_t blur, int32_t N, int32_t h, int32_t w, void* stream) {
+  B2U_CHECK_ARG(dcat && (u || ucat) && du && cu % 8 == 0 && ldu % 8 == 0 && ldc % 8 == 0, "shuffle_bwd: bad argument");
+  B2U_CHECK_ARG(u || !blur, "shuffle_bwd: the mask can only come from the upsampled tensor when there is no blur");
   const long long items = (long long)N * h * w * (4 * cu / 8);
   const dim3 grid(grid_for(items, 256, 2));
   if (blur)
-    launch_k(shuffle_bwd_kernel<true>, grid, dim3(256), 0, (cudaStream_t)stream, (cbf)dcat, ldc, (cbf)u, (bf)du, ldu, cu, N,
-             h, w);
+    launch_k(shuffle_bwd_kernel<true>, grid, dim3(256), 0, (cudaStream_t)stream, (cbf)dcat, ldc, (cbf)u, (cbf)ucat, (bf)du,
+             ldu, cu, N, h, w);
   else
-    launch_k(shuffle_bwd_kernel<false>, grid, dim3(256), 0, (cudaStream_t)stream, (cbf)dcat, ldc, (cbf)u, (bf)du, ldu, cu, N,
-             h, w);
+    launch_k(shuffle_bwd_kernel<false>, grid, dim3(256), 0, (cudaStream_t)stream, (cbf)dcat, ldc, (cbf)u, (cbf)ucat, (bf)du,
+             ldu, cu, N, h, w);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" int b2u_shuffle_bwd(const void* dcat, int32_t ldc, const void* u, void* du, int32_t ldu, int32_t cu,
+                               int32_t blur, int32_t N, int32_t h, int32_t w, void* stream) {
+  B2U_CHECK_ARG(u != nullptr, "shuffle_bwd: null u");
+  return shuffle_bwd_impl(dcat, ldc, u, nullptr, du, ldu, cu, blur, N, h, w, stream);
+}
+
+extern "C" int b2u_shuffle_bwd_from_cat(const void* dcat, const void* cat, int32_t ldc, void* du, int32_t ldu, int32_t cu,
+                                        int32_t N, int32_t h, int32_t w, void* stream) {
+  B2U_CHECK_ARG(cat != nullptr, "shuffle_bwd_from_cat: null cat");
+  return shuffle_bwd_impl(dcat, ldc, nullptr, cat, du, ldu, cu, 0, N, h, w, stream);
+}
+
+extern "C" int b2u_copy_lanes(const void* src, int32_t lds, int32_t src_off, void* dst, int32_t ldd, int32_t dst_off,
+                              int32_t lanes, int64_t pixels, void* stream) {
+  B2U_CHECK_ARG(src && dst && lanes > 0 && lanes % 8 == 0 && lds % 8 == 0 && ldd % 8 == 0 && src_off % 8 == 0 &&
+                dst_off % 8 == 0 && src_off + lanes <= lds && dst_off + lanes <= ldd, "copy_lanes: bad argument");
+  const long long items = pixels * (lanes / 8);
+  launch_k(copy_lanes_kernel, dim3(grid_for(items, 256)), dim3(256), 0, (cudaStream_t)stream, (cbf)src, lds, src_off,
+           (bf)dst, ldd, dst_off, lanes / 8, (long long)pixels);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }

@@ -25,7 +25,8 @@ from .ops import ConvPlan, WgradPlan, padc, view_nhwc
 import os
 
 BN_EPS = 1e-5
-SIDE_STREAM_WGRAD = os.environ.get("B2U_NO_SIDE_STREAM") is None   # A/B switch for profiling
+SIDE_STREAM_WGRAD = os.environ.get("B2U_NO_SIDE_STREAM") is None   # A/B switches for profiling
+FUSED_FINAL_SHUFFLE = os.environ.get("B2U_NO_FUSED_SHUFFLE") is None
 BN_MOMENTUM = 0.1
 STATS_ROWS = 592  # block partial rows of the standalone reductions (4 per SM)
 
@@ -606,15 +607,38 @@ class UNetB200:
         # ---- final PixelShuffle_ICNR (no blur) + MergeLayer(dense) + ResBlock(no norm) + head
         U = x
         fs = spec.final_shuf
-        P8 = conv_bias(fs, U, h, w_)
         cu = fs.nf // 4
+        xin = self.x_in
+        # no blur in this stage, so PixelShuffle is a pure permutation: the 1x1 convolution stores its four (i,j) phases
+        # straight into the four stride-2 parity planes of the concat tensor (one launch, four N tiles, four output
+        # maps) - no pre-shuffle tensor, no shuffle pass.  Needs cu (= one N tile) to be a multiple of 16 and <= 256.
+        # (the TMA store covers whole 64-lane chunks: they must stay inside the pixel's pitch, or a parity plane would
+        # write into its neighbour's lanes)
+        fused_shuffle = (FUSED_FINAL_SHUFFLE and cu % 16 == 0 and cu <= 256 and
+                         (cu + 63) // 64 * 64 <= padc(cu + spec.n_in))
+        P8 = None if fused_shuffle else conv_bias(fs, U, h, w_)
+        hs, ws = h, w_
         h, w_ = 2 * h, 2 * w_
         assert (h, w_) == (H, W)
         cat = self._act(h, w_, cu + spec.n_in, "layers.10.cat", zero=True)
-        xin = self.x_in
-        self._fwd(lambda s: _lib.check(
-            lib.b2u_shuffle_cat_fwd(P8.t.data_ptr(), P8.ld, cu, 0, xin.t.data_ptr(), xin.ld, xin.C, None, None, 0,
-                                    cat.t.data_ptr(), cat.ld, N, P8.H, P8.W, s), "b2u_shuffle_cat_fwd"))
+        if fused_shuffle:
+            wfs = self._w[fs.name]
+            outs = [view_nhwc(cat.t, cu, parity=(i, j)) for i in range(2) for j in range(2)]
+            geom = view_nhwc(cat.t, cu, parity=(0, 0))
+            geom.C = fs.nf                      # GEMM space: (N, hs, ws) pixels x 4*cu output channels
+            plan = ConvPlan([view_nhwc(U.t, U.C)], geom, wfs["wf"], fs.ni, ops.taps_conv(1), shift=wfs["bias_rows"],
+                            relu=True, outs=outs)
+            self._keep.append(plan)
+            self._fwd(plan.run)
+            # MergeLayer(dense=True): the image bands go behind the shuffled channels (the conv zeroed lanes >= cu)
+            lanes = min(xin.ld, cat.ld - cu)
+            self._fwd(lambda s: _lib.check(
+                lib.b2u_copy_lanes(xin.t.data_ptr(), xin.ld, 0, cat.t.data_ptr(), cat.ld, cu, lanes, cat.pixels, s),
+                "b2u_copy_lanes"))
+        else:
+            self._fwd(lambda s: _lib.check(
+                lib.b2u_shuffle_cat_fwd(P8.t.data_ptr(), P8.ld, cu, 0, xin.t.data_ptr(), xin.ld, xin.C, None, None, 0,
+                                        cat.t.data_ptr(), cat.ld, N, P8.H, P8.W, s), "b2u_shuffle_cat_fwd"))
         ra, rb = spec.final_res
         A1 = conv_bias(ra, cat, h, w_)
         A2 = conv_bias(rb, A1, h, w_, res=cat, relu=True)  # relu(convpath(x) + x)
@@ -651,12 +675,22 @@ class UNetB200:
                 self._wgrad(ra, A1.grad, cat)
                 # only the shuffled channels need a gradient (the image does not): restrict dgrad to [0, cu)
                 self._dgrad(ra, A1.grad, cat, res=A2.grad, out_C=cu)
-                dP8 = P8.ensure_grad()
-                self._bwd(lambda s: _lib.check(lib.b2u_shuffle_bwd(cat.grad.data_ptr(), cat.ld, P8.t.data_ptr(),
-                                                                   dP8.data_ptr(), P8.ld, cu, 0, N, P8.H, P8.W, s),
-                                               "b2u_shuffle_bwd"))
-                P8.grad_written = True
-                conv_bias_bwd(fs, U, P8)()
+                if fused_shuffle:
+                    dP8 = torch.zeros((N, hs, ws, padc(fs.nf)), dtype=torch.bfloat16, device=dev)
+                    self._keep.append(dP8)
+                    # the ReLU mask of the shuffle conv is read from cat itself (cat[..., :cu] = relu(conv) shuffled)
+                    self._bwd(lambda s: _lib.check(lib.b2u_shuffle_bwd_from_cat(
+                        cat.grad.data_ptr(), cat.t.data_ptr(), cat.ld, dP8.data_ptr(), dP8.shape[-1], cu, N, hs, ws, s),
+                        "b2u_shuffle_bwd_from_cat"))
+                    self._wgrad(fs, dP8, U)
+                    self._dgrad(fs, dP8, U, zmask=U.pre_relu_grad)
+                else:
+                    dP8 = P8.ensure_grad()
+                    self._bwd(lambda s: _lib.check(lib.b2u_shuffle_bwd(cat.grad.data_ptr(), cat.ld, P8.t.data_ptr(),
+                                                                       dP8.data_ptr(), P8.ld, cu, 0, N, P8.H, P8.W, s),
+                                                   "b2u_shuffle_bwd"))
+                    P8.grad_written = True
+                    conv_bias_bwd(fs, U, P8)()
             bwd_layers.append(tail_bwd)
 
             # build backward in true reverse order (gradient accumulation flags depend on it)

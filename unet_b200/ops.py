@@ -133,7 +133,7 @@ class ConvPlan:
                  scale: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None,
                  res: Optional[View] = None, res_mask: Optional[View] = None, zmask: Optional[View] = None,
                  relu: bool = False, stats: bool = False, out_f32: Optional[torch.Tensor] = None,
-                 stats_ld: Optional[int] = None, fin: Optional[dict] = None):
+                 stats_ld: Optional[int] = None, fin: Optional[dict] = None, outs: Optional[Sequence[View]] = None):
         """fin (with stats=True): dict(count, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, scale,
         shift) of fp32 tensors -> the kernel's last CTA finalizes the BatchNorm statistics itself when the shape allows
         (self.fused_finalize tells the caller whether a separate b2u_bn_finalize launch is still needed)."""
@@ -144,6 +144,12 @@ class ConvPlan:
             d.a[i] = v
         d.num_a = len(a_views)
         d.out = out_view
+        if outs:
+            # N tile i (Cout / len(outs) channels) is stored to outs[i]; out_view gives the geometry and the total Cout
+            assert 2 <= len(outs) <= 4
+            d.num_out = len(outs)
+            for i, v in enumerate(outs):
+                d.out_nt[i] = v
         d.w = w.data_ptr()
         d.w_rows, d.w_taps, d.w_cinp = w.shape
         d.w_cin = w_cin
