@@ -296,12 +296,15 @@ def main():
     loss_val = float(net.loss.item())
 
     # ---- e2e: public API with HOST buffers, H2D of the tiles and D2H of the loss every step inside the timed region
+    # (every step copies its own batch from pinned host memory; the copy of batch i+1 is enqueued on a copy stream
+    # behind the kernels of step i - `prefetch=` of the public Trainer.step - and the loss of every step is read back)
+    nxt = lambda i: (host_x[(i + 1) % n_pool], host_y[(i + 1) % n_pool])
     for i in range(2):
-        float(trainer.step(host_x[i % n_pool], host_y[i % n_pool]).item())
+        float(trainer.step(host_x[i % n_pool], host_y[i % n_pool], prefetch=nxt(i)).item())
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        loss = trainer.step(host_x[i % n_pool], host_y[i % n_pool])
+        loss = trainer.step(host_x[(i + 2) % n_pool], host_y[(i + 2) % n_pool], prefetch=nxt(i + 2))
         _ = float(loss.item())
     barrier()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)

@@ -756,6 +756,7 @@ class UNetB200:
                 op(s)
             return
         if self._side_stream is None:
+            # (both streams at the default priority: raising either one measured slower - 21.6 / 24.0 vs 20.4 ms/step)
             self._side_stream = torch.cuda.Stream(device=self.device)
         side = self._side_stream
         ss = side.cuda_stream

@@ -81,16 +81,21 @@ class Learner:
         for ep in range(epochs):
             t0 = time.time()
             run, n = 0.0, 0
-            for x, y in train_batches():
+            it = iter(train_batches())
+            cur = next(it, None)
+            while cur is not None:
+                nxt = next(it, None)
+                x, y = cur
                 lr, mom = one_cycle(step / total, lr_max, moms=self.moms)
                 if self.trainer.optimizer == "adam":
                     self.trainer.set_adam_hyper(lr, mom)
                 else:
                     self.trainer.lr = lr
-                loss = self.trainer.step(x, y)
+                loss = self.trainer.step(x, y, prefetch=nxt)       # the next batch's H2D copy runs behind this step
                 run += float(loss.item())
                 n += 1
                 step += 1
+                cur = nxt
             row = {"epoch": ep, "train_loss": run / max(1, n)}
             if valid_batches is not None:
                 row["valid_loss"], row["dice_multi"] = self.validate(valid_batches())
