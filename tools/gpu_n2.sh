@@ -1,5 +1,14 @@
 mkdir -p gpurun_out
-timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/ddp_smoke.py > gpurun_out/ddp_smoke.log 2>&1; echo "ddp_smoke rc=$?"; tail -8 gpurun_out/ddp_smoke.log
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; echo "bench n2 rc=$?"; tail -c 1500 gpurun_out/bench_n2.json
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 tools/predict_bench.py 20000 64 > gpurun_out/predict_n2.json 2> gpurun_out/predict_n2.err; echo "predict n2 rc=$?"; tail -3 gpurun_out/predict_n2.json
-timeout 300 python tools/predict_bench.py 20000 64 > gpurun_out/predict_n1.json 2> gpurun_out/predict_n1.err; echo "predict n1 rc=$?"; tail -3 gpurun_out/predict_n1.json
+timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/ddp_smoke.py > gpurun_out/ddp_smoke.log 2>&1; echo "ddp_smoke rc=$?"; grep -E "identical|graph steps|done" gpurun_out/ddp_smoke.log | head -6
+for v in a b; do
+  if [ $v = a ]; then export B2U_NO_AR_OVERLAP=1; else unset B2U_NO_AR_OVERLAP; fi
+  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 2952$( [ $v = a ] && echo 1 || echo 2 ) bench.py --gpus 2 --steps 20 --warmup 5 --no-profile --no-predict > gpurun_out/bench_n2_$v.json 2> gpurun_out/bench_n2_$v.err; echo "bench n2 $v rc=$?"
+done
+python - <<'PY'
+import json
+for f in ("a","b"):
+    try:
+        d=json.load(open(f"gpurun_out/bench_n2_{f}.json"))
+        print(f, "ms/step", round(d["ms_per_step"],3), "tiles/s", round(d["value"],1), "e2e", round(d["e2e"]["value"],1), "loss", d["final_loss"])
+    except Exception as e: print(f, "failed", e, open(f"gpurun_out/bench_n2_{f}.err").read()[-1500:])
+PY

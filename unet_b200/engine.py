@@ -46,6 +46,7 @@ class Trainer:
         self._stage_free: Optional[torch.cuda.Event] = None
         self.step_count = 0
         self.bucket_elems = int(bucket_mb * (1 << 20) / 4)
+        self.overlap_allreduce = os.environ.get("B2U_NO_AR_OVERLAP") is None   # A/B switch
         if self.optimizer == "adam":
             L = net.layout
             self.m = torch.zeros_like(net.params)
@@ -75,27 +76,39 @@ class Trainer:
                                       dtype=torch.float32), non_blocking=True)
 
     # ------------------------------------------------------------------------------------------------ device step
-    def _allreduce(self) -> None:
+    def _allreduce(self, lo: int = 0, hi: Optional[int] = None, async_op: bool = False):
         if self.world == 1:
-            return
+            return []
         g = self.net.grads
-        n = g.numel()
+        hi = g.numel() if hi is None else hi
         # bucketed so that NCCL pipelines over NVLink; summed here, divided by world inside the optimizer kernel
-        for start in range(0, n, self.bucket_elems):
-            dist.all_reduce(g[start:min(n, start + self.bucket_elems)], op=dist.ReduceOp.SUM)
+        works = []
+        for start in range(lo, hi, self.bucket_elems):
+            w = dist.all_reduce(g[start:min(hi, start + self.bucket_elems)], op=dist.ReduceOp.SUM, async_op=async_op)
+            if async_op:
+                works.append(w)
+        return works
 
     def _device_step(self) -> None:
         self._fwd_bwd()
         self._allreduce()
         self._update()
 
-    def _fwd_bwd(self) -> None:
+    def _fwd_bwd(self, part: int = 0) -> None:
+        """part 0: everything; 1: input cast + forward + loss + the DECODER's backward (ops before bwd_split);
+        2: the encoder's backward."""
         net = self.net
         s = ops.stream_ptr()
-        net.set_input(self.x_static, s)
-        net.forward(s)
-        net.loss_and_grad(s)
-        net.backward(s)
+        if part in (0, 1):
+            net.set_input(self.x_static, s)
+            net.forward(s)
+            net.loss_and_grad(s)
+        if part == 0:
+            net.backward(s)
+        elif part == 1:
+            net.backward(s, 0, net.bwd_split)
+        else:
+            net.backward(s, net.bwd_split, None)
 
     def _update(self) -> None:
         net = self.net
@@ -139,6 +152,18 @@ class Trainer:
         if self.world == 1:
             with torch.cuda.graph(self.graph, stream=cap):
                 self._device_step()
+        elif self.overlap_allreduce:
+            # three graphs: [fwd + loss + decoder backward] -> async all-reduce of the decoder gradients, running behind
+            # [encoder backward] -> all-reduce of the encoder gradients -> [optimizer + weight staging]
+            with torch.cuda.graph(self.graph, stream=cap):
+                self._fwd_bwd(1)
+            self.graph_enc = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_enc, pool=self.graph.pool(), stream=cap):
+                self._fwd_bwd(2)
+            self.graph_update = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_update, pool=self.graph.pool(), stream=cap):
+                self._update()
+            return
         else:
             with torch.cuda.graph(self.graph, stream=cap):
                 self._fwd_bwd()
@@ -191,7 +216,15 @@ class Trainer:
         self._load_batch(x, y)
         if self.use_graph:
             self.graph.replay()
-            if self.world > 1:
+            if self.world > 1 and self.overlap_allreduce:
+                split = self.net.param_split
+                works = self._allreduce(split, None, async_op=True)    # decoder + head gradients are complete
+                self.graph_enc.replay()                                 # ... while the encoder's backward runs
+                for w in works:
+                    w.wait()                                            # stream-level wait, the host does not block
+                self._allreduce(0, split)
+                self.graph_update.replay()
+            elif self.world > 1:
                 self._allreduce()
                 self.graph_update.replay()
         else:

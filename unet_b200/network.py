@@ -543,6 +543,7 @@ class UNetB200:
                 dE = E.ensure_grad()
                 self._bn_bwd(bnE, ZE.grad, ZE.ld, E.t, E.ld, None, 0, True, dE, E.ld, E.pixels, E.grad_written)
                 E.grad_written = True
+            post_bwd.is_encoder_boundary = True
             bwd_layers.append(post_bwd)
 
         # ---- decoder conv (+bias, ReLU fused): gradient buffers hold PRE-activation gradients
@@ -694,8 +695,12 @@ class UNetB200:
             bwd_layers.append(tail_bwd)
 
             # build backward in true reverse order (gradient accumulation flags depend on it)
+            self.bwd_split = None     # index of the first encoder op: everything before it yields the decoder gradients
             for b in reversed(bwd_layers):
                 b()
+                if getattr(b, "is_encoder_boundary", False):
+                    self.bwd_split = len(self.bwd_ops)
+            self.param_split = self.layout.by_name[self.spec.post_bn + ".weight"].offset   # [0, split) = encoder (layers.0)
             ws_bytes = max(sp["bytes"] for sp in self._wgrad_specs)
             self._wgrad_ws = torch.zeros((ws_bytes + 3) // 4, dtype=torch.float32, device=dev)
             self._wgrad_plans = []
@@ -742,8 +747,9 @@ class UNetB200:
                                        self._ce_rows, self.loss.data_ptr(), s), "b2u_ce_finalize")
         return self.loss
 
-    def backward(self, stream: Optional[int] = None) -> None:
-        """Runs the backward plan.  The critical path is the chain of activation gradients (BN backward -> dgrad -> ...);
+    def backward(self, stream: Optional[int] = None, begin: int = 0, end: Optional[int] = None) -> None:
+        """Runs the backward plan (ops [begin, end): the engine splits it at `bwd_split` to overlap the gradient
+        all-reduce of the decoder with the encoder's backward).  The critical path is the chain of activation gradients (BN backward -> dgrad -> ...);
         the weight gradients (wgrad GEMM + split-K reduce) hang off it as leaves, so they are issued on a second stream:
         each one waits for the ops recorded before it and the streams join before the optimizer.  The small encoder
         layers are latency-bound single-wave launches - the two streams fill each other's ramp-up and tail bubbles.
@@ -751,8 +757,9 @@ class UNetB200:
         main = torch.cuda.current_stream()
         s = stream if stream is not None else main.cuda_stream
         two = (SIDE_STREAM_WGRAD and ops.PROFILE is None and s == main.cuda_stream)
+        end = len(self.bwd_ops) if end is None else end
         if not two:
-            for op in self.bwd_ops:
+            for op in self.bwd_ops[begin:end]:
                 op(s)
             return
         if self._side_stream is None:
@@ -762,7 +769,7 @@ class UNetB200:
         ss = side.cuda_stream
         pending = False   # main-stream work issued since the last fork: the next side op must wait for it
         first = True
-        for op, is_side in zip(self.bwd_ops, self.bwd_side):
+        for op, is_side in zip(self.bwd_ops[begin:end], self.bwd_side[begin:end]):
             if is_side:
                 if pending or first:
                     ev = torch.cuda.Event()
