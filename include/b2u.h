@@ -242,6 +242,19 @@ int b2u_shuffle_bwd(const void* dcat, int32_t ldc, const void* u, void* du, int3
  * so that the pre-shuffle activation need not exist (the conv stores its phases straight into the parity planes) */
 int b2u_shuffle_bwd_from_cat(const void* dcat, const void* cat, int32_t ldc, void* du, int32_t ldu, int32_t cu,
                              int32_t N, int32_t h, int32_t w, void* stream);
+/* odd skip sizes (e.g. the reference's default 400-px tiles: 25 -> 13 -> 26 vs 25): the concat / its gradient is
+ * [N,Ho,Wo,ldc] with Ho in {2h, 2h-1}, Wo in {2w, 2w-1} - the last row / column of the upsampled tensor is cropped,
+ * which is what fastai's F.interpolate(up_out, skip.shape[-2:], mode='nearest') computes for 2h -> 2h-1 */
+int b2u_shuffle_cat_fwd_crop(const void* u, int32_t ldu, int32_t cu, int32_t blur, const void* skip, int32_t lds,
+                             int32_t cs, const float* sscale, const float* sshift, int32_t skip_relu, void* cat,
+                             int32_t ldc, int32_t N, int32_t h, int32_t w, int32_t Ho, int32_t Wo, void* stream);
+int b2u_shuffle_bwd_crop(const void* dcat, int32_t ldc, const void* u, void* du, int32_t ldu, int32_t cu, int32_t blur,
+                         int32_t N, int32_t h, int32_t w, int32_t Ho, int32_t Wo, void* stream);
+/* replicate the last row / column of an NHWC bf16 tensor (pitch ld) to even extents, and the adjoint: with it the
+ * 2x2 mean folded into the idpath 1x1 convolution equals nn.AvgPool2d(2, ceil_mode=True) on odd sizes (fastai ResBlock) */
+int b2u_pad_even_fwd(const void* x, void* xp, int32_t ld, int32_t N, int32_t H, int32_t W, void* stream);
+int b2u_pad_even_bwd(const void* dxp, void* dx, int32_t accumulate, int32_t ld, int32_t N, int32_t H, int32_t W,
+                     void* stream);
 /* dst[p][dst_off .. dst_off+lanes) = src[p][src_off .. src_off+lanes) for `pixels` pixels (lanes, offsets and pitches
  * multiples of 8): fastai MergeLayer(dense=True) `torch.cat([x, input], dim=1)` of the final stage (unet.py layers.10) */
 int b2u_copy_lanes(const void* src, int32_t lds, int32_t src_off, void* dst, int32_t ldd, int32_t dst_off,

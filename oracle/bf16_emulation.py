@@ -113,10 +113,15 @@ def emulated_forward(model: DynamicUnetOracle, x: torch.Tensor, training: bool =
         s = feats[idx]
         p = _conv_bias(h, ub.shuf[0])
         up = ub.shuf[3](ub.shuf[2](ub.shuf[1](p)))
+        if s.shape[-2:] != up.shape[-2:]:
+            up = F.interpolate(up, s.shape[-2:], mode="nearest")
         cat = q(F.relu(torch.cat([up, _bn(s, ub.bn, training)], dim=1)))
         h = _conv_bias(_conv_bias(cat, ub.conv1), ub.conv2)
     p8 = _conv_bias(h, L[8][0])
-    cat = torch.cat([L[8][1](p8), x0], dim=1)
+    up8 = L[8][1](p8)
+    if up8.shape[-2:] != x0.shape[-2:]:
+        up8 = F.interpolate(up8, x0.shape[-2:], mode="nearest")
+    cat = torch.cat([up8, x0], dim=1)
     rb = L[11]
     a1 = _conv_bias(cat, rb.convpath[0])
     a2 = _conv_bias(a1, rb.convpath[1], relu=True, res=cat)

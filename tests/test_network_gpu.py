@@ -44,7 +44,11 @@ def _setup(arch, n_in, n_out, size, batch, data):
 
 CASES = [("xresnet34", 4, 2, 256, 2, "uniform"), ("xresnet34", 4, 2, 128, 4, "aerial"),
          ("xresnet18", 3, 2, 128, 8, "aerial"), ("xresnet34", 4, 5, 64, 4, "aerial"),
-         ("xresnet50", 4, 8, 64, 2, "aerial")]   # bottleneck blocks, 2048-wide encoder, 8 classes (BASELINE configs[3])
+         ("xresnet50", 4, 8, 64, 2, "aerial"),   # bottleneck blocks, 2048-wide encoder, 8 classes (BASELINE configs[3])
+         # odd extents: 72 -> 36,18,9,5,3: two AvgPool(ceil_mode) idpaths on odd inputs and two decoder crops (6 vs 5,
+         # 10 vs 9 == F.interpolate nearest); 75 adds an odd tile itself (stem on odd planes, final ResizeToOrig crop)
+         ("xresnet18", 4, 2, 72, 4, "aerial"), ("xresnet34", 4, 3, 75, 2, "aerial"),
+         ("xresnet34", 4, 2, 400, 1, "aerial")]  # the reference's default patch_size (params_and_main.py:36): 25 -> 13 -> 26 vs 25
 
 
 @pytest.mark.parametrize("arch,n_in,n_out,size,batch,data", CASES)

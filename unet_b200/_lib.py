@@ -129,6 +129,10 @@ def _declare(lib):
         "b2u_shuffle_bwd": [vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, vp],
         "b2u_shuffle_bwd_from_cat": [vp, vp, i32, vp, i32, i32, i32, i32, i32, vp],
         "b2u_copy_lanes": [vp, i32, i32, vp, i32, i32, i32, i64, vp],
+        "b2u_shuffle_cat_fwd_crop": [vp, i32, i32, i32, vp, i32, i32, vp, vp, i32, vp, i32, i32, i32, i32, i32, i32, vp],
+        "b2u_shuffle_bwd_crop": [vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp],
+        "b2u_pad_even_fwd": [vp, vp, i32, i32, i32, i32, vp],
+        "b2u_pad_even_bwd": [vp, vp, i32, i32, i32, i32, i32, vp],
         "b2u_nchw_to_nhwc": [vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp],
         "b2u_pointwise_smallk": [vp, i32, i32, vp, i32, vp, i32, vp, i32, i64, i32, vp],
         "b2u_crop_tiles": [u8p, i32, i64, i64, vp, vp, i32, i32, vp, i32, vp],

@@ -86,9 +86,10 @@ template <bool kBlur>
 __global__ void __launch_bounds__(256, 2) shuffle_cat_fwd_kernel(
     const __nv_bfloat16* __restrict__ u, int ldu, int cu, const __nv_bfloat16* __restrict__ skip, int lds,
     int cs, const float* __restrict__ sscale, const float* __restrict__ sshift, int skip_relu,
-    __nv_bfloat16* __restrict__ cat, int ldc, int N, int h, int w) {
+    __nv_bfloat16* __restrict__ cat, int ldc, int N, int h, int w, int H, int W) {
   pdl_enter();
-  const int H = 2 * h, W = 2 * w;
+  // cat is [N, H, W, ldc] with H in {2h, 2h-1}, W in {2w, 2w-1}: an odd skip size crops the last row / column of the
+  // upsampled tensor - what fastai's F.interpolate(up_out, skip.shape[-2:], mode='nearest') does for 2h -> 2h-1
   auto ps = [&](int n, int yy, int xx, int c) {
     return ldq(u + ((long long)(n * h + (yy >> 1)) * w + (xx >> 1)) * ldu + (((yy & 1) * 2 + (xx & 1)) * cu + c));
   };
@@ -153,20 +154,21 @@ template <> struct ShufBwdRegs<false> { uint4 a, u; };
 template <bool kBlur>
 __global__ void __launch_bounds__(256, 2) shuffle_bwd_kernel(
     const __nv_bfloat16* __restrict__ dcat, int ldc, const __nv_bfloat16* __restrict__ u,
-    const __nv_bfloat16* __restrict__ ucat, __nv_bfloat16* __restrict__ du, int ldu, int cu, int N, int h, int w) {
+    const __nv_bfloat16* __restrict__ ucat, __nv_bfloat16* __restrict__ du, int ldu, int cu, int N, int h, int w,
+    int H, int W) {
   pdl_enter();
-  const int H = 2 * h, W = 2 * w;
+  // dcat is [N, H, W, ldc] (H in {2h, 2h-1}, W likewise): shuffled pixels beyond it were cropped and get no gradient
   const int gpc = cu >> 3;   // 8-channel groups per (i,j) phase
   auto dc = [&](int n, int yy, int xx, int c) { return ldq(dcat + ((long long)(n * H + yy) * W + xx) * ldc + c); };
   stream_pixel_groups_xy<kBlur ? 3 : 8, ShufBwdRegs<kBlur>>(N, h, w, (4 * cu) >> 3,
       [](int) { return 0; },
       [&](int p, int n, int y, int x, int ch, int, ShufBwdRegs<kBlur>& q) {
         const int ij = (ch >> 3) / gpc, c = ch - ij * cu;
-        const int Y = 2 * y + (ij >> 1), X = 2 * x + (ij & 1);
+        // out-of-range positions are fetched from a clamped (valid) address and weighted by zero below
+        const int Y = min(2 * y + (ij >> 1), H - 1), X = min(2 * x + (ij & 1), W - 1);
         q.u = u ? ldq(u + (long long)p * ldu + ch) : ldq(ucat + ((long long)(n * H + Y) * W + X) * ldc + c);
         q.a = dc(n, Y, X, c);
         if constexpr (kBlur) {
-          // out-of-range neighbours are fetched from a clamped (valid) address and weighted by zero below
           const int Y1 = min(Y + 1, H - 1), X1 = min(X + 1, W - 1);
           q.b = dc(n, Y, X1, c); q.d = dc(n, Y1, X, c); q.e = dc(n, Y1, X1, c);
         }
@@ -174,11 +176,12 @@ __global__ void __launch_bounds__(256, 2) shuffle_bwd_kernel(
       [&](int p, int n, int y, int x, int ch, int, const ShufBwdRegs<kBlur>& q) {
         const int ij = (ch >> 3) / gpc;
         const int Y = 2 * y + (ij >> 1), X = 2 * x + (ij & 1);
+        const float inb = (Y < H && X < W) ? 1.f : 0.f;      // cropped shuffled pixel: no gradient
         f8 o = unpack_f8(q.a);
         if constexpr (kBlur) {
           // PS[Y,X] feeds outputs (Y+a, X+b), a,b in {0,1}; the replicated first row/column counts twice
-          const float wy0 = (Y == 0) ? 2.f : 1.f, wx0 = (X == 0) ? 2.f : 1.f;
-          const float hy = (Y + 1 < H) ? 1.f : 0.f, hx = (X + 1 < W) ? 1.f : 0.f;
+          const float wy0 = ((Y == 0) ? 2.f : 1.f) * inb, wx0 = (X == 0) ? 2.f : 1.f;
+          const float hy = (Y + 1 < H) ? inb : 0.f, hx = (X + 1 < W) ? 1.f : 0.f;
           const f8 b = unpack_f8(q.b), d = unpack_f8(q.d), e = unpack_f8(q.e);
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
@@ -188,12 +191,64 @@ __global__ void __launch_bounds__(256, 2) shuffle_bwd_kernel(
             s += (hx * hy) * e.v[k];
             o.v[k] = 0.25f * s;
           }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o.v[k] *= inb;
         }
         const f8 uv = unpack_f8(q.u);
 #pragma unroll
         for (int k = 0; k < 8; ++k) o.v[k] = uv.v[k] > 0.f ? o.v[k] : 0.f;
         st8(du + (long long)p * ldu + ch, o);
       });
+}
+
+// AvgPool2d(2, ceil_mode=True) on an odd extent averages its last window over the samples that exist; replicating the
+// last row / column to an even extent first makes the plain 2x2 mean (four taps x 1/4 folded into the idpath's 1x1
+// convolution) produce exactly that: xp[n,y,x] = x[n, min(y,H-1), min(x,W-1)].
+__global__ void pad_even_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ xp, int G, int N,
+                                    int H, int W, int Hp, int Wp) {
+  pdl_enter();
+  const long long total = (long long)N * Hp * Wp * G;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    long long t = i / G;
+    const int xx = (int)(t % Wp); t /= Wp;
+    const int yy = (int)(t % Hp);
+    const int n = (int)(t / Hp);
+    const long long src = (((long long)n * H + min(yy, H - 1)) * W + min(xx, W - 1)) * G + g;
+    reinterpret_cast<uint4*>(xp)[i] = __ldg(reinterpret_cast<const uint4*>(x) + src);
+  }
+}
+
+// its adjoint: every original pixel collects the gradients of its replicas
+__global__ void pad_even_bwd_kernel(const __nv_bfloat16* __restrict__ dxp, __nv_bfloat16* __restrict__ dx, int accumulate,
+                                    int G, int N, int H, int W, int Hp, int Wp) {
+  pdl_enter();
+  const long long total = (long long)N * H * W * G;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    long long t = i / G;
+    const int xx = (int)(t % W); t /= W;
+    const int yy = (int)(t % H);
+    const int n = (int)(t / H);
+    auto at = [&](int y2, int x2) { return ld8(dxp + ((((long long)n * Hp + y2) * Wp + x2) * G + g) * 8); };
+    f8 o = at(yy, xx);
+    const bool ex = (xx == W - 1) && Wp > W, ey = (yy == H - 1) && Hp > H;
+    if (ex) { const f8 a = at(yy, W);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o.v[k] += a.v[k]; }
+    if (ey) { const f8 a = at(H, xx);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o.v[k] += a.v[k]; }
+    if (ex && ey) { const f8 a = at(H, W);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o.v[k] += a.v[k]; }
+    __nv_bfloat16* dst = dx + i * 8;
+    if (accumulate) { const f8 old = ld8(dst);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o.v[k] += old.v[k]; }
+    st8(dst, o);
+  }
 }
 
 // dst[p, dst_off : dst_off + 8*groups] = src[p, src_off : ...] for every pixel (16-byte groups): MergeLayer(dense=True) of
@@ -605,38 +660,51 @@ extern "C" int b2u_stage_weights(const b2u_wstage_item* items_dev, int32_t n_ite
   return B2U_OK;
 }
 
-extern "C" int b2u_shuffle_cat_fwd(const void* u, int32_t ldu, int32_t cu, int32_t blur, const void* skip, int32_t lds,
-                                   int32_t cs, const float* sscale, const float* sshift, int32_t skip_relu, void* cat,
-                                   int32_t ldc, int32_t N, int32_t h, int32_t w, void* stream) {
-  B2U_CHECK_ARG(u && cat && cu > 0 && cu % 8 == 0 && ldu % 8 == 0 && ldc % 8 == 0 && ldu >= 4 * cu,
-                "shuffle_cat_fwd: bad argument (cu must be a multiple of 8)");
+extern "C" int b2u_shuffle_cat_fwd_crop(const void* u, int32_t ldu, int32_t cu, int32_t blur, const void* skip,
+                                        int32_t lds, int32_t cs, const float* sscale, const float* sshift,
+                                        int32_t skip_relu, void* cat, int32_t ldc, int32_t N, int32_t h, int32_t w,
+                                        int32_t Ho, int32_t Wo, void* stream) {
+  B2U_CHECK_ARG(u && cat && cu > 0 && cu % 8 == 0 && ldu % 8 == 0 && ldc % 8 == 0 && 4 * cu <= ldu && cu <= ldc,
+                "shuffle_cat_fwd: bad argument");
   B2U_CHECK_ARG(!skip || (lds % 8 == 0 && cs > 0 && cu + cs <= ldc), "shuffle_cat_fwd: bad skip");
   B2U_CHECK_ARG(!sscale || sshift, "shuffle_cat_fwd: sscale without sshift");
-  const long long items = (long long)N * 4 * h * w * (ldc / 8);
+  B2U_CHECK_ARG((Ho == 2 * h || Ho == 2 * h - 1) && (Wo == 2 * w || Wo == 2 * w - 1) && Ho > 0 && Wo > 0,
+                "shuffle_cat_fwd: output %dx%d is neither the upsampled size %dx%d nor one less", Ho, Wo, 2 * h, 2 * w);
+  const long long items = (long long)N * Ho * Wo * (ldc / 8);
   // 2 resident blocks per SM (register budget of the 4- or 8-pixel load batches): one block per slot, one range each
   const dim3 grid(grid_for(items, 256, 2));
   if (blur)
     launch_k(shuffle_cat_fwd_kernel<true>, grid, dim3(256), 0, (cudaStream_t)stream, (cbf)u, ldu, cu, (cbf)skip, lds, cs,
-             sscale, sshift, skip_relu, (bf)cat, ldc, N, h, w);
+             sscale, sshift, skip_relu, (bf)cat, ldc, N, h, w, Ho, Wo);
   else
     launch_k(shuffle_cat_fwd_kernel<false>, grid, dim3(256), 0, (cudaStream_t)stream, (cbf)u, ldu, cu, (cbf)skip, lds, cs,
-             sscale, sshift, skip_relu, (bf)cat, ldc, N, h, w);
+             sscale, sshift, skip_relu, (bf)cat, ldc, N, h, w, Ho, Wo);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }
 
+extern "C" int b2u_shuffle_cat_fwd(const void* u, int32_t ldu, int32_t cu, int32_t blur, const void* skip, int32_t lds,
+                                   int32_t cs, const float* sscale, const float* sshift, int32_t skip_relu, void* cat,
+                                   int32_t ldc, int32_t N, int32_t h, int32_t w, void* stream) {
+  return b2u_shuffle_cat_fwd_crop(u, ldu, cu, blur, skip, lds, cs, sscale, sshift, skip_relu, cat, ldc, N, h, w, 2 * h,
+                                  2 * w, stream);
+}
+
 static int shuffle_bwd_impl(const void* dcat, int32_t ldc, const void* u, const void* ucat, void* du, int32_t ldu,
-                            int32_t cu, int32_t blur, int32_t N, int32_t h, int32_t w, void* stream) {
+                            int32_t cu, int32_t blur, int32_t N, int32_t h, int32_t w, int32_t Ho, int32_t Wo,
+                            void* stream) {
+  B2U_CHECK_ARG((Ho == 2 * h || Ho == 2 * h - 1) && (Wo == 2 * w || Wo == 2 * w - 1) && Ho > 0 && Wo > 0,
+                "shuffle_bwd: gradient size %dx%d is neither the upsampled size %dx%d nor one less", Ho, Wo, 2 * h, 2 * w);
   B2U_CHECK_ARG(dcat && (u || ucat) && du && cu % 8 == 0 && ldu % 8 == 0 && ldc % 8 == 0, "shuffle_bwd: bad argument");
   B2U_CHECK_ARG(u || !blur, "shuffle_bwd: the mask can only come from the upsampled tensor when there is no blur");
   const long long items = (long long)N * h * w * (4 * cu / 8);
   const dim3 grid(grid_for(items, 256, 2));
   if (blur)
     launch_k(shuffle_bwd_kernel<true>, grid, dim3(256), 0, (cudaStream_t)stream, (cbf)dcat, ldc, (cbf)u, (cbf)ucat, (bf)du,
-             ldu, cu, N, h, w);
+             ldu, cu, N, h, w, Ho, Wo);
   else
     launch_k(shuffle_bwd_kernel<false>, grid, dim3(256), 0, (cudaStream_t)stream, (cbf)dcat, ldc, (cbf)u, (cbf)ucat, (bf)du,
-             ldu, cu, N, h, w);
+             ldu, cu, N, h, w, Ho, Wo);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }
@@ -644,13 +712,41 @@ static int shuffle_bwd_impl(const void* dcat, int32_t ldc, const void* u, const 
 extern "C" int b2u_shuffle_bwd(const void* dcat, int32_t ldc, const void* u, void* du, int32_t ldu, int32_t cu,
                                int32_t blur, int32_t N, int32_t h, int32_t w, void* stream) {
   B2U_CHECK_ARG(u != nullptr, "shuffle_bwd: null u");
-  return shuffle_bwd_impl(dcat, ldc, u, nullptr, du, ldu, cu, blur, N, h, w, stream);
+  return shuffle_bwd_impl(dcat, ldc, u, nullptr, du, ldu, cu, blur, N, h, w, 2 * h, 2 * w, stream);
+}
+
+extern "C" int b2u_shuffle_bwd_crop(const void* dcat, int32_t ldc, const void* u, void* du, int32_t ldu, int32_t cu,
+                                    int32_t blur, int32_t N, int32_t h, int32_t w, int32_t Ho, int32_t Wo,
+                                    void* stream) {
+  B2U_CHECK_ARG(u != nullptr, "shuffle_bwd: null u");
+  return shuffle_bwd_impl(dcat, ldc, u, nullptr, du, ldu, cu, blur, N, h, w, Ho, Wo, stream);
 }
 
 extern "C" int b2u_shuffle_bwd_from_cat(const void* dcat, const void* cat, int32_t ldc, void* du, int32_t ldu, int32_t cu,
                                         int32_t N, int32_t h, int32_t w, void* stream) {
   B2U_CHECK_ARG(cat != nullptr, "shuffle_bwd_from_cat: null cat");
-  return shuffle_bwd_impl(dcat, ldc, nullptr, cat, du, ldu, cu, 0, N, h, w, stream);
+  return shuffle_bwd_impl(dcat, ldc, nullptr, cat, du, ldu, cu, 0, N, h, w, 2 * h, 2 * w, stream);
+}
+
+extern "C" int b2u_pad_even_fwd(const void* x, void* xp, int32_t ld, int32_t N, int32_t H, int32_t W, void* stream) {
+  B2U_CHECK_ARG(x && xp && ld % 8 == 0 && N > 0 && H > 0 && W > 0, "pad_even_fwd: bad argument");
+  const int Hp = H + (H & 1), Wp = W + (W & 1);
+  const long long items = (long long)N * Hp * Wp * (ld / 8);
+  launch_k(pad_even_fwd_kernel, dim3(grid_for(items, 256)), dim3(256), 0, (cudaStream_t)stream, (cbf)x, (bf)xp, ld / 8, N, H,
+           W, Hp, Wp);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" int b2u_pad_even_bwd(const void* dxp, void* dx, int32_t accumulate, int32_t ld, int32_t N, int32_t H,
+                                int32_t W, void* stream) {
+  B2U_CHECK_ARG(dxp && dx && ld % 8 == 0 && N > 0 && H > 0 && W > 0, "pad_even_bwd: bad argument");
+  const int Hp = H + (H & 1), Wp = W + (W & 1);
+  const long long items = (long long)N * H * W * (ld / 8);
+  launch_k(pad_even_bwd_kernel, dim3(grid_for(items, 256)), dim3(256), 0, (cudaStream_t)stream, (cbf)dxp, (bf)dx,
+           accumulate, ld / 8, N, H, W, Hp, Wp);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
 }
 
 extern "C" int b2u_copy_lanes(const void* src, int32_t lds, int32_t src_off, void* dst, int32_t ldd, int32_t dst_off,

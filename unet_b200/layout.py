@@ -235,31 +235,34 @@ def shuffle_row_of_co(nf4: int) -> List[int]:
 
 
 def conv_flops(spec: NetSpec, size: int) -> int:
-    """forward conv FLOPs per tile (2 FLOP/MAC, unpadded channels) — the numerator of SURVEY.md 8(d)."""
+    """forward conv FLOPs per tile (2 FLOP/MAC, unpadded channels) — the numerator of SURVEY.md 8(d).  Odd extents halve
+    upwards (3x3/s2/p1 convs, MaxPool(3,2,1), AvgPool(ceil_mode)); the decoder follows the skip sizes (crop)."""
+    up = lambda v, st: (v + st - 1) // st
     total = 0
-    s = size // 2
+    s = up(size, 2)
     for i, cs in enumerate(spec.stem):
         total += 2 * s * s * cs.ni * cs.nf * 9
-    s //= 2
-    for st in spec.stages:
+    skips = {2: s}
+    s = up(s, 2)
+    for si, st in enumerate(spec.stages):
         for b in st:
-            so = s // b.stride
-            # explicit walk
+            so = up(s, b.stride)
             cur = s
             for cs in b.convpath:
-                cur = cur // cs.stride
+                cur = up(cur, cs.stride)
                 total += 2 * cur * cur * cs.ni * cs.nf * cs.ks * cs.ks
             if b.idconv is not None:
                 total += 2 * so * so * b.idconv.ni * b.idconv.nf
             s = so
+        skips[4 + si] = s
     for cs in spec.middle:
         total += 2 * s * s * cs.ni * cs.nf * 9
     for u in spec.unet:
         total += 2 * s * s * u.shuf.ni * u.shuf.nf
-        s *= 2
+        s = skips[u.skip_child]
         total += 2 * s * s * (u.conv1.ni * u.conv1.nf + u.conv2.ni * u.conv2.nf) * 9
     total += 2 * s * s * spec.final_shuf.ni * spec.final_shuf.nf
-    s *= 2
+    s = size
     for cs in spec.final_res:
         total += 2 * s * s * cs.ni * cs.nf * 9
     total += 2 * s * s * spec.head.ni * spec.head.nf

@@ -86,8 +86,11 @@ class UNetB200:
         self.spec: NetSpec = build_spec(arch, n_in, n_out)
         self.layout = ParamLayout(self.spec)
         self.N, (self.H, self.W) = batch, size
-        if self.H % 32 or self.W % 32:
-            raise ValueError("tile height/width must be multiples of 32 (five stride-2 stages, no interpolate branch)")
+        if self.H < 32 or self.W < 32:
+            raise ValueError("tile height/width must be at least 32 (five stride-2 stages)")
+        # any size works: odd extents halve upwards in the encoder, and where the upsampled size exceeds an odd skip by one
+        # the decoder crops (== fastai's F.interpolate(up_out, skip.shape[-2:], mode='nearest'), unet.py UnetBlock.forward;
+        # the reference's default 400-px tiles reach 25 -> 13 -> 26 vs 25)
         self.training = training
         self.n_in, self.n_out = n_in, n_out
         dev = self.device
@@ -431,7 +434,8 @@ class UNetB200:
             return build
 
         x = self.x_in
-        h, w_ = H // 2, W // 2
+        up2 = lambda v, st=2: (v + st - 1) // st
+        h, w_ = up2(H), up2(W)
         feats: Dict[int, Act] = {}
         for i, cs in enumerate(spec.stem):
             R, Z, bn = conv_bn(cs, x, h, w_, apply=True)
@@ -441,7 +445,7 @@ class UNetB200:
         feats[2] = x
         # ---- maxpool
         mp_in = x
-        h, w_ = h // 2, w_ // 2
+        h, w_ = up2(h), up2(w_)
         mp = self._act(h, w_, mp_in.C, "maxpool")
         idx = torch.zeros((N, h, w_, mp.ld), dtype=torch.uint8, device=dev) if train else None
         self._fwd(lambda s, a=mp_in, b=mp, idx=idx: _lib.check(
@@ -461,18 +465,26 @@ class UNetB200:
         for si, blocks in enumerate(spec.stages):
             for blk in blocks:
                 xin = x
-                ho, wo = h // blk.stride, w_ // blk.stride
+                ho, wo = up2(h, blk.stride), up2(w_, blk.stride)
                 cur, ch, cw = xin, h, w_
                 recs = []
                 for j, cs in enumerate(blk.convpath):
-                    ch, cw = ch // cs.stride, cw // cs.stride
+                    ch, cw = up2(ch, cs.stride), up2(cw, cs.stride)
                     last = j == len(blk.convpath) - 1
                     R, Z, bn = conv_bn(cs, cur, ch, cw, apply=not last)
                     recs.append((cs, cur, R, Z, bn))
                     cur = Z if not last else R
                 idrec = None
+                xid, xpad = xin, None
                 if blk.idconv is not None:
-                    Rid, _, bnid = conv_bn(blk.idconv, xin, ho, wo, apply=False)
+                    if blk.idconv.pool and (h % 2 or w_ % 2):
+                        # AvgPool2d(2, ceil_mode=True) on an odd extent: replicate the last row / column first, then the
+                        # plain 2x2 mean (folded into the 1x1 conv taps) equals torch's clipped-window average
+                        xpad = self._act(h + h % 2, w_ + w_ % 2, xin.C, blk.name + ".idpad")
+                        self._fwd(lambda s, a=xin, b=xpad: _lib.check(
+                            lib.b2u_pad_even_fwd(a.t.data_ptr(), b.t.data_ptr(), a.ld, N, a.H, a.W, s), "b2u_pad_even_fwd"))
+                        xid = xpad
+                    Rid, _, bnid = conv_bn(blk.idconv, xid, ho, wo, apply=False)
                     idrec = (blk.idconv, Rid, bnid)
                 out = self._act(ho, wo, blk.nf, blk.name + ".out")
                 csl, xl, Rl, _, bnl = recs[-1]
@@ -485,13 +497,13 @@ class UNetB200:
                 else:
                     # eval: BN folded into the conv epilogues; the block tail is one fused launch
                     if idrec is not None:
-                        self._conv_fwd(idrec[0], xin, idrec[1], scale=idrec[2].scale, shift=idrec[2].shift)
+                        self._conv_fwd(idrec[0], xid, idrec[1], scale=idrec[2].scale, shift=idrec[2].shift)
                         self._conv_fwd(csl, xl, out, scale=bnl.scale, shift=bnl.shift, relu=True, res=idrec[1])
                     else:
                         self._conv_fwd(csl, xl, out, scale=bnl.scale, shift=bnl.shift, relu=True, res=xin)
 
                 if train:
-                    def blk_bwd(blk=blk, xin=xin, out=out, recs=recs, idrec=idrec):
+                    def blk_bwd(blk=blk, xin=xin, out=out, recs=recs, idrec=idrec, xid=xid, xpad=xpad):
                         dOut = out.grad
                         assert dOut is not None and out.grad_written, blk.name
                         # tail: BN of the last convpath conv, masked by the block output
@@ -505,8 +517,14 @@ class UNetB200:
                             self._keep.append(dRid)
                             self._bn_bwd(bnid, dOut, out.ld, Rid.t, Rid.ld, out.t, out.ld, False, dRid, Rid.ld,
                                          Rid.pixels, False)
-                            self._wgrad(csi, dRid, xin)
-                            self._dgrad(csi, dRid, xin)
+                            self._wgrad(csi, dRid, xid)
+                            self._dgrad(csi, dRid, xid)
+                            if xpad is not None:
+                                g = xin.ensure_grad()
+                                acc = int(xin.grad_written)
+                                self._bwd(lambda s: _lib.check(lib.b2u_pad_even_bwd(
+                                    xpad.grad.data_ptr(), g.data_ptr(), acc, xin.ld, N, xin.H, xin.W, s), "b2u_pad_even_bwd"))
+                                xin.grad_written = True
                         dcur = dRl
                         for j in range(len(recs) - 1, -1, -1):
                             cs, xj, Rj, Zj, bnj = recs[j]
@@ -577,13 +595,13 @@ class UNetB200:
                 self._fwd(st)
                 fin, nl = self._bn_finalize_op(bnS, partial, S.pixels)
                 self._fwd(fin, nl)
-            h, w_ = 2 * h, 2 * w_
-            assert (S.H, S.W) == (h, w_), "skip / upsample size mismatch (odd tile sizes are not supported yet)"
+            assert S.H in (2 * h, 2 * h - 1) and S.W in (2 * w_, 2 * w_ - 1), "skip / upsample size mismatch"
+            h, w_ = S.H, S.W       # an odd skip crops the last row / column of the upsampled tensor (nearest interpolate)
             cat = self._act(h, w_, ub.cu + S.C, ub.name + ".cat")
             cat.pre_relu_grad = True
             self._fwd(lambda s, P=P, S=S, cat=cat, bnS=bnS, cu=ub.cu: _lib.check(
-                lib.b2u_shuffle_cat_fwd(P.t.data_ptr(), P.ld, cu, 1, S.t.data_ptr(), S.ld, S.C, _p(bnS.scale),
-                                        _p(bnS.shift), 1, cat.t.data_ptr(), cat.ld, N, P.H, P.W, s),
+                lib.b2u_shuffle_cat_fwd_crop(P.t.data_ptr(), P.ld, cu, 1, S.t.data_ptr(), S.ld, S.C, _p(bnS.scale),
+                                             _p(bnS.shift), 1, cat.t.data_ptr(), cat.ld, N, P.H, P.W, cat.H, cat.W, s),
                 "b2u_shuffle_cat_fwd"))
             c1 = conv_bias(ub.conv1, cat, h, w_)
             c2 = conv_bias(ub.conv2, c1, h, w_)
@@ -593,9 +611,9 @@ class UNetB200:
                     conv_bias_bwd(ub.conv1, cat, c1)()
                     dP = P.ensure_grad()
                     dcat = cat.grad
-                    self._bwd(lambda s: _lib.check(lib.b2u_shuffle_bwd(dcat.data_ptr(), cat.ld, P.t.data_ptr(),
-                                                                       dP.data_ptr(), P.ld, ub.cu, 1, N, P.H, P.W, s),
-                                                   "b2u_shuffle_bwd"))
+                    self._bwd(lambda s: _lib.check(lib.b2u_shuffle_bwd_crop(dcat.data_ptr(), cat.ld, P.t.data_ptr(),
+                                                                            dP.data_ptr(), P.ld, ub.cu, 1, N, P.H, P.W,
+                                                                            cat.H, cat.W, s), "b2u_shuffle_bwd"))
                     P.grad_written = True
                     dS = S.ensure_grad()
                     self._bn_bwd(bnS, dcat[..., ub.cu:], cat.ld, S.t, S.ld, None, 0, False, dS, S.ld, S.pixels,
@@ -615,12 +633,12 @@ class UNetB200:
         # maps) - no pre-shuffle tensor, no shuffle pass.  Needs cu (= one N tile) to be a multiple of 16 and <= 256.
         # (the TMA store covers whole 64-lane chunks: they must stay inside the pixel's pitch, or a parity plane would
         # write into its neighbour's lanes)
-        fused_shuffle = (FUSED_FINAL_SHUFFLE and cu % 16 == 0 and cu <= 256 and
+        fused_shuffle = (FUSED_FINAL_SHUFFLE and cu % 16 == 0 and cu <= 256 and (2 * h, 2 * w_) == (H, W) and
                          (cu + 63) // 64 * 64 <= padc(cu + spec.n_in))
         P8 = None if fused_shuffle else conv_bias(fs, U, h, w_)
         hs, ws = h, w_
-        h, w_ = 2 * h, 2 * w_
-        assert (h, w_) == (H, W)
+        assert H in (2 * h, 2 * h - 1) and W in (2 * w_, 2 * w_ - 1)
+        h, w_ = H, W               # ResizeToOrig: an odd tile crops the last row / column (nearest interpolate)
         cat = self._act(h, w_, cu + spec.n_in, "layers.10.cat", zero=True)
         if fused_shuffle:
             wfs = self._w[fs.name]
@@ -638,8 +656,9 @@ class UNetB200:
                 "b2u_copy_lanes"))
         else:
             self._fwd(lambda s: _lib.check(
-                lib.b2u_shuffle_cat_fwd(P8.t.data_ptr(), P8.ld, cu, 0, xin.t.data_ptr(), xin.ld, xin.C, None, None, 0,
-                                        cat.t.data_ptr(), cat.ld, N, P8.H, P8.W, s), "b2u_shuffle_cat_fwd"))
+                lib.b2u_shuffle_cat_fwd_crop(P8.t.data_ptr(), P8.ld, cu, 0, xin.t.data_ptr(), xin.ld, xin.C, None, None, 0,
+                                             cat.t.data_ptr(), cat.ld, N, P8.H, P8.W, cat.H, cat.W, s),
+                "b2u_shuffle_cat_fwd"))
         ra, rb = spec.final_res
         A1 = conv_bias(ra, cat, h, w_)
         A2 = conv_bias(rb, A1, h, w_, res=cat, relu=True)  # relu(convpath(x) + x)
@@ -687,9 +706,9 @@ class UNetB200:
                     self._dgrad(fs, dP8, U, zmask=U.pre_relu_grad)
                 else:
                     dP8 = P8.ensure_grad()
-                    self._bwd(lambda s: _lib.check(lib.b2u_shuffle_bwd(cat.grad.data_ptr(), cat.ld, P8.t.data_ptr(),
-                                                                       dP8.data_ptr(), P8.ld, cu, 0, N, P8.H, P8.W, s),
-                                                   "b2u_shuffle_bwd"))
+                    self._bwd(lambda s: _lib.check(lib.b2u_shuffle_bwd_crop(cat.grad.data_ptr(), cat.ld, P8.t.data_ptr(),
+                                                                            dP8.data_ptr(), P8.ld, cu, 0, N, P8.H, P8.W,
+                                                                            cat.H, cat.W, s), "b2u_shuffle_bwd"))
                     P8.grad_written = True
                     conv_bias_bwd(fs, U, P8)()
             bwd_layers.append(tail_bwd)
