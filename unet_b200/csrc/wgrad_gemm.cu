@@ -42,6 +42,7 @@ struct WgradParams {
   int co_pad, ci_pad, taps_total;  // partial layout [splits][taps_total][co_pad][ci_pad]
   float* partial;
   int units;
+  int even_bias; // all units issue the bias MMA (equal cost per unit)
 };
 
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_constant__ WgradParams p) {
@@ -177,6 +178,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_
         mbar_wait(tempty_bar, tphase ^ 1u);
         tc_fence_after();
         uint32_t accumulate = 0;
+        const bool even_units = bias || p.even_bias;
         // The single issuing thread must sustain one MMA per ~N/2 cycles, so the loop is kept to a few integer ops per
         // MMA: descriptor high words are constants, the low word is (start >> 4) | (LBO >> 4) << 16.
         const uint32_t b_lbo = p.halo ? p.b_box_bytes : kBoxBytes;
@@ -192,7 +194,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_
             // MN-major, SW128: 64-channel groups are LBO apart, 8-pixel groups are SBO = 1024 B apart;
             // 16 pixels further along K = 16 rows x 128 B = 2048 B (128 x 16 B).
             const uint64_t a_desc = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo_const | (base16 + (uint32_t)k * 128u));
-            if (bias) {
+            // Every unit issues the bias MMA (only unit (ci 0, tap group 0) stores its result): units of equal cost stay
+            // in lock step, so the filter-row units of one pixel range keep hitting each other's dY / X lines in L2.  With
+            // the extra MMAs on one unit only, that unit fell ~7 % behind per step and re-read both operands from DRAM
+            // (ncu: 4.0 GB instead of 2.15 GB on the 100-channel layers; a fixed start-up skew between the units changed
+            // nothing, equal cost did: 0.965 -> 0.866 ms).
+            if (p.want_bias && even_units) {
               const uint64_t b_desc = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo_const | ((ones_base >> 4) + (uint32_t)k * 128u));
               umma_bf16(tmem_base + (uint32_t)(p.T * p.BN), a_desc, b_desc, p.idesc_bias, accumulate);
             }
@@ -481,6 +488,10 @@ static int wgrad_fill(const b2u_wgrad_desc* d, b2u_wgrad_plan* plan, bool encode
   p.ci_pad = p.n_ci * p.BN;
   p.taps_total = d->num_taps + p.want_bias;
   p.partial = d->partial;
+  {
+    static const bool uneven = getenv("B2U_WGRAD_UNEVEN") != nullptr;   // A/B switch
+    p.even_bias = uneven ? 0 : 1;
+  }
 
   b2u_wgrad_info& info = plan->info;
   info.splits = splits; info.co_pad = p.co_pad; info.ci_pad = p.ci_pad; info.taps_per_unit = p.T;
