@@ -46,7 +46,10 @@ class Trainer:
         self._stage_free: Optional[torch.cuda.Event] = None
         self.step_count = 0
         self.bucket_elems = int(bucket_mb * (1 << 20) / 4)
-        self.overlap_allreduce = os.environ.get("B2U_NO_AR_OVERLAP") is None   # A/B switch
+        self.overlap_allreduce = os.environ.get("B2U_NO_AR_OVERLAP") is None   # A/B switches
+        self.min_seg_mb = float(os.environ.get("B2U_AR_MIN_SEG_MB", "24"))
+        if os.environ.get("B2U_BUCKET_MB"):
+            self.bucket_elems = int(float(os.environ["B2U_BUCKET_MB"]) * (1 << 20) / 4)
         if self.optimizer == "adam":
             L = net.layout
             self.m = torch.zeros_like(net.params)
@@ -94,21 +97,34 @@ class Trainer:
         self._allreduce()
         self._update()
 
-    def _fwd_bwd(self, part: int = 0) -> None:
-        """part 0: everything; 1: input cast + forward + loss + the DECODER's backward (ops before bwd_split);
-        2: the encoder's backward."""
+    def _fwd_bwd(self, part: Optional[int] = None) -> None:
+        """part None: everything; part i: segment i of self.segments (segment 0 also holds input cast + forward + loss)."""
         net = self.net
         s = ops.stream_ptr()
-        if part in (0, 1):
+        if part in (None, 0):
             net.set_input(self.x_static, s)
             net.forward(s)
             net.loss_and_grad(s)
-        if part == 0:
+        if part is None:
             net.backward(s)
-        elif part == 1:
-            net.backward(s, 0, net.bwd_split)
         else:
-            net.backward(s, net.bwd_split, None)
+            b, e, _, _ = self.segments[part]
+            net.backward(s, b, e)
+
+    def _plan_segments(self) -> None:
+        """Backward segments [(op begin, op end, grad lo, grad hi)]: after segment i the gradients [lo, hi) are final and
+        their all-reduce can run behind segment i+1.  Marks that would leave less than `min_seg_mb` of gradients in a
+        segment are merged (launch latency, not bandwidth, is what a small bucket costs over NVSwitch)."""
+        net, total = self.net, self.net.layout.total
+        marks = [(k, off) for k, off in net.bwd_marks if off > 0]
+        segs, prev_k, prev_off = [], 0, total
+        for k, off in marks:
+            if (prev_off - off) * 4 < self.min_seg_mb * (1 << 20):
+                continue
+            segs.append((prev_k, k, off, prev_off))
+            prev_k, prev_off = k, off
+        segs.append((prev_k, len(net.bwd_ops), 0, prev_off))
+        self.segments = segs
 
     def _update(self) -> None:
         net = self.net
@@ -153,13 +169,17 @@ class Trainer:
             with torch.cuda.graph(self.graph, stream=cap):
                 self._device_step()
         elif self.overlap_allreduce:
-            # three graphs: [fwd + loss + decoder backward] -> async all-reduce of the decoder gradients, running behind
-            # [encoder backward] -> all-reduce of the encoder gradients -> [optimizer + weight staging]
-            with torch.cuda.graph(self.graph, stream=cap):
-                self._fwd_bwd(1)
-            self.graph_enc = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph_enc, pool=self.graph.pool(), stream=cap):
-                self._fwd_bwd(2)
+            # one graph per backward segment: [fwd + loss + decoder backward] -> async all-reduce of the decoder gradients
+            # behind [encoder stage 7 backward] -> async all-reduce of stage 7 behind [stages 6..stem] -> all-reduce of
+            # the rest -> [optimizer + weight staging]
+            self._plan_segments()
+            self.graphs = []
+            for i in range(len(self.segments)):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=self.graphs[0].pool() if self.graphs else None, stream=cap):
+                    self._fwd_bwd(i)
+                self.graphs.append(g)
+            self.graph = self.graphs[0]
             self.graph_update = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_update, pool=self.graph.pool(), stream=cap):
                 self._update()
@@ -215,18 +235,21 @@ class Trainer:
             self._prefetched = None
         self._load_batch(x, y)
         if self.use_graph:
-            self.graph.replay()
             if self.world > 1 and self.overlap_allreduce:
-                split = self.net.param_split
-                works = self._allreduce(split, None, async_op=True)    # decoder + head gradients are complete
-                self.graph_enc.replay()                                 # ... while the encoder's backward runs
+                works = []
+                for i, (b, e, lo, hi) in enumerate(self.segments):
+                    self.graphs[i].replay()
+                    last = i == len(self.segments) - 1
+                    # gradients [lo, hi) are final: reduce them while the next segment's backward runs
+                    works += self._allreduce(lo, hi, async_op=not last)
                 for w in works:
                     w.wait()                                            # stream-level wait, the host does not block
-                self._allreduce(0, split)
                 self.graph_update.replay()
-            elif self.world > 1:
-                self._allreduce()
-                self.graph_update.replay()
+            else:
+                self.graph.replay()
+                if self.world > 1:
+                    self._allreduce()
+                    self.graph_update.replay()
         else:
             self._device_step()
         if prefetch is not None:

@@ -542,6 +542,10 @@ class UNetB200:
                                 self._keep.append(dRp)
                                 self._bn_bwd(bnp, Zp.grad, Zp.ld, Rp.t, Rp.ld, None, 0, True, dRp, Rp.ld, Rp.pixels, False)
                                 dcur = dRp
+                    if blk is blocks[0]:
+                        # backward reaches this block LAST within its stage: once it has run, every gradient of the
+                        # stage's parameters is final (all-reduce mark, see engine.Trainer)
+                        blk_bwd.ar_mark = blk.convpath[0].wname
                     bwd_layers.append(blk_bwd)
                 x, h, w_ = out, ho, wo
             feats[4 + si] = x
@@ -714,12 +718,16 @@ class UNetB200:
             bwd_layers.append(tail_bwd)
 
             # build backward in true reverse order (gradient accumulation flags depend on it)
-            self.bwd_split = None     # index of the first encoder op: everything before it yields the decoder gradients
+            # all-reduce marks (op index, parameter offset): after op index k every gradient at offsets >= off is final.
+            # The flat layout is in forward order and backward runs in reverse, so the marks fall out of the build order:
+            # after the decoder + post-encoder BN (off = layers.1), after encoder stage 7, 6, 5, 4 (off = first conv).
+            self.bwd_marks: List[Tuple[int, int]] = []
             for b in reversed(bwd_layers):
                 b()
                 if getattr(b, "is_encoder_boundary", False):
-                    self.bwd_split = len(self.bwd_ops)
-            self.param_split = self.layout.by_name[self.spec.post_bn + ".weight"].offset   # [0, split) = encoder (layers.0)
+                    self.bwd_marks.append((len(self.bwd_ops), self.layout.by_name[self.spec.post_bn + ".weight"].offset))
+                if getattr(b, "ar_mark", None):
+                    self.bwd_marks.append((len(self.bwd_ops), self.layout.by_name[b.ar_mark].offset))
             ws_bytes = max(sp["bytes"] for sp in self._wgrad_specs)
             self._wgrad_ws = torch.zeros((ws_bytes + 3) // 4, dtype=torch.float32, device=dev)
             self._wgrad_plans = []
