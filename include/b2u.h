@@ -172,6 +172,7 @@ typedef struct b2u_wstage_item {
   int32_t Cout, Cin, kk, wf_cinp, wd_coutp;
   float scale;
   int32_t block_start;
+  const float* dscale;   /* nullable: device scalar multiplied on top of `scale` (1/sigma of a spectral-normed weight) */
 } b2u_wstage_item;
 int b2u_stage_weights(const b2u_wstage_item* items_dev, int32_t n_items, int32_t total_blocks, void* stream);
 
@@ -322,6 +323,27 @@ int b2u_stitch_finalize_q31(const float* acc, const uint8_t* cnt, int32_t C, int
 /* per-tile softmax probabilities (fp32 NCHW, what learn.predict returns, predict.py:193-203) and argmax */
 int b2u_softmax_nchw(const float* logits, int32_t ld, int32_t C, int64_t tiles, int32_t H, int32_t W, float* probs,
                      uint8_t* argmax, void* stream);
+
+/* ---- SelfAttention (fastai layers.SelfAttention on UnetBlock.conv2 when self_attention=True, train.py:142) --------
+ * The 1x1 query / key / value convolutions run through b2u_conv_*, the two batched attention products are plain
+ * library GEMMs issued by the host layer; these entry points are the rest of the block. */
+/* torch.nn.utils.spectral_norm of W fp32 [Co][Ci]: training != 0 runs ONE power iteration in place
+ * (v = normalize(W^T u), u = normalize(W v), eps 1e-12); sigma_out[0] = u.(W v), sigma_out[1] = 1/sigma */
+int b2u_spectral_norm(const float* W, int32_t Co, int32_t Ci, float* u, float* v, int32_t training, float* sigma_out,
+                      void* stream);
+/* gradient through W_sn = W / sigma(W) with u, v constant: dW <- (dW - sum(dW * W_sn) u v^T) / sigma, in place */
+int b2u_spectral_norm_bwd(float* dW, const float* W, int32_t Co, int32_t Ci, const float* u, const float* v,
+                          const float* sigma, void* stream);
+/* beta[b][i][j] = softmax over i of S[b][i][j] (F.softmax(..., dim=1)), bf16 [B][n][n] */
+int b2u_softmax_dim1(const void* S, void* beta, int32_t B, int32_t n, void* stream);
+/* dS = beta * (dbeta - sum_i beta * dbeta), column-wise; dS may alias dbeta */
+int b2u_softmax_dim1_bwd(const void* beta, const void* dbeta, void* dS, int32_t B, int32_t n, void* stream);
+/* out = gamma[0] * o + x over `elems` bf16 elements (multiple of 8) */
+int b2u_attn_out(const void* o, const void* x, const float* gamma, void* out, int64_t elems, void* stream);
+/* d_o = gamma[0] * dout (bf16) and dgamma[0] = sum(dout * o) (fp32, fixed-order two-stage reduction;
+ * scratch >= 1024 floats + 1 counter word, zero-initialised once by the caller) */
+int b2u_attn_out_bwd(const void* dout, const void* o, const float* gamma, void* d_o, float* dgamma, float* scratch,
+                     int64_t elems, void* stream);
 
 /* sizeof() of the ABI structs as this library was compiled, for bindings to verify their mirrors:
  * which = 0 b2u_view, 1 b2u_conv_desc, 2 b2u_conv_info, 3 b2u_wgrad_desc, 4 b2u_wgrad_info, 5 b2u_wstage_item, 6 b2u_bn_fin */

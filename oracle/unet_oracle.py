@@ -100,8 +100,29 @@ def pixel_shuffle_icnr(ni: int, nf: int, blur: bool) -> nn.Sequential:
     return nn.Sequential(*layers)
 
 
+class SelfAttention(nn.Module):
+    """fastai layers.SelfAttention(n_channels) [fastai-mem, 2.5.1]: query / key / value are
+    ConvLayer(ndim=1, ks=1, norm_type=NormType.Spectral, act_cls=None, bias=False) = Sequential(spectral_norm(Conv1d));
+    beta = softmax(bmm(f^T, g), dim=1); o = gamma * bmm(h, beta) + x; gamma is initialised to 0.
+    Own parameter (gamma) precedes the children in named_parameters(), as in fastai."""
+
+    def __init__(self, n_channels: int):
+        super().__init__()
+        self.gamma = nn.Parameter(torch.tensor([0.0]))
+        mk = lambda co: nn.Sequential(nn.utils.spectral_norm(nn.Conv1d(n_channels, co, 1, bias=False)))
+        self.query, self.key, self.value = mk(n_channels // 8), mk(n_channels // 8), mk(n_channels)
+
+    def forward(self, x):
+        size = x.size()
+        x = x.view(*size[:2], -1)
+        f, g, h = self.query(x), self.key(x), self.value(x)
+        beta = F.softmax(torch.bmm(f.transpose(1, 2), g), dim=1)
+        o = self.gamma * torch.bmm(h, beta) + x
+        return o.view(*size).contiguous()
+
+
 class UnetBlock(nn.Module):
-    def __init__(self, up_in_c: int, x_in_c: int, final_div: bool, blur: bool):
+    def __init__(self, up_in_c: int, x_in_c: int, final_div: bool, blur: bool, self_attention: bool = False):
         super().__init__()
         self.shuf = pixel_shuffle_icnr(up_in_c, up_in_c // 2, blur)
         self.bn = nn.BatchNorm2d(x_in_c)
@@ -110,6 +131,8 @@ class UnetBlock(nn.Module):
         nf = ni if final_div else ni // 2
         self.conv1 = conv_layer(ni, nf, 3, bn=False)
         self.conv2 = conv_layer(nf, nf, 3, bn=False)
+        if self_attention:      # ConvLayer(nf, nf, xtra=SelfAttention(nf)): appended after the activation -> conv2.2
+            self.conv2.add_module("2", SelfAttention(nf))
         self.relu = nn.ReLU()
         self.nf = nf
 
@@ -131,7 +154,7 @@ class DynamicUnetOracle(nn.Module):
 
     SKIP_IDXS = (6, 5, 4, 2)  # encoder children whose successor halves the resolution, deepest first
 
-    def __init__(self, arch: str = "xresnet34", n_in: int = 4, n_out: int = 2):
+    def __init__(self, arch: str = "xresnet34", n_in: int = 4, n_out: int = 2, self_attention: bool = False):
         super().__init__()
         expansion, _ = ARCHS[arch]
         enc = xresnet_body(arch, n_in)
@@ -144,7 +167,9 @@ class DynamicUnetOracle(nn.Module):
         c = ni
         for i, idx in enumerate(self.SKIP_IDXS):
             not_final = i != len(self.SKIP_IDXS) - 1
-            blk = UnetBlock(c, widths[idx], final_div=not_final, blur=True)
+            # fastai unet.py: sa = self_attention and (i == len(sz_chg_idxs) - 3)  -> the second UnetBlock (layers.5)
+            sa = self_attention and i == len(self.SKIP_IDXS) - 3
+            blk = UnetBlock(c, widths[idx], final_div=not_final, blur=True, self_attention=sa)
             layers.append(blk)
             c = blk.nf
         layers.append(pixel_shuffle_icnr(c, c, blur=False))          # layers.8
@@ -203,10 +228,20 @@ def randomize_bn(model: nn.Module, seed: int = 1) -> None:
             m.bias.data.copy_(torch.randn(m.bias.shape, generator=g) * 0.05)
 
 
-def make_oracle(arch: str = "xresnet34", n_in: int = 4, n_out: int = 2, seed: int = 0) -> DynamicUnetOracle:
-    m = DynamicUnetOracle(arch, n_in, n_out)
+def make_oracle(arch: str = "xresnet34", n_in: int = 4, n_out: int = 2, seed: int = 0,
+                self_attention: bool = False) -> DynamicUnetOracle:
+    torch.manual_seed(seed)          # spectral_norm draws its u / v vectors from the global generator at construction
+    m = DynamicUnetOracle(arch, n_in, n_out, self_attention)
     init_like_fastai(m, seed)
     randomize_bn(m, seed + 1)
+    if self_attention:
+        g = torch.Generator().manual_seed(seed + 2)
+        for mod in m.modules():
+            if isinstance(mod, SelfAttention):
+                mod.gamma.data.fill_(0.5)     # fastai starts at 0 (identity): move it so that parity tests see the block
+                for c in (mod.query[0], mod.key[0], mod.value[0]):
+                    fan_in = c.in_channels
+                    c.weight_orig.data.copy_(torch.randn(c.weight_orig.shape, generator=g) * math.sqrt(2.0 / fan_in))
     return m
 
 

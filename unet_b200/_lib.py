@@ -67,7 +67,7 @@ class WStageItem(C.Structure):
     _fields_ = [("w", C.c_void_p), ("bias", C.c_void_p), ("row_of_co", C.c_void_p), ("wf", C.c_void_p),
                 ("wd", C.c_void_p), ("bias_rows", C.c_void_p), ("Cout", C.c_int32), ("Cin", C.c_int32),
                 ("kk", C.c_int32), ("wf_cinp", C.c_int32), ("wd_coutp", C.c_int32), ("scale", C.c_float),
-                ("block_start", C.c_int32)]
+                ("block_start", C.c_int32), ("dscale", C.c_void_p)]
 
 
 class WgradInfo(C.Structure):
@@ -132,6 +132,12 @@ def _declare(lib):
         "b2u_shuffle_cat_fwd_crop": [vp, i32, i32, i32, vp, i32, i32, vp, vp, i32, vp, i32, i32, i32, i32, i32, i32, vp],
         "b2u_shuffle_bwd_crop": [vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp],
         "b2u_pad_even_fwd": [vp, vp, i32, i32, i32, i32, vp],
+        "b2u_spectral_norm": [vp, i32, i32, vp, vp, i32, vp, vp],
+        "b2u_spectral_norm_bwd": [vp, vp, i32, i32, vp, vp, vp, vp],
+        "b2u_softmax_dim1": [vp, vp, i32, i32, vp],
+        "b2u_softmax_dim1_bwd": [vp, vp, vp, i32, i32, vp],
+        "b2u_attn_out": [vp, vp, vp, vp, i64, vp],
+        "b2u_attn_out_bwd": [vp, vp, vp, vp, vp, vp, i64, vp],
         "b2u_pad_even_bwd": [vp, vp, i32, i32, i32, i32, i32, vp],
         "b2u_nchw_to_nhwc": [vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp],
         "b2u_pointwise_smallk": [vp, i32, i32, vp, i32, vp, i32, vp, i32, i64, i32, vp],

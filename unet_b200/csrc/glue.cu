@@ -29,6 +29,7 @@ struct WStageItem {
   int Cout, Cin, kk, wf_cinp, wd_coutp;
   float scale;
   int block_start;      // first block of this item in the batched launch
+  const float* dscale;  // nullable device scalar on top of `scale` (1/sigma of a spectral-normed weight)
 };
 
 // One block = a 32 (output channels) x 32 (input channels) tile of one layer with all kh*kw taps: the fp32 master rows are
@@ -43,6 +44,7 @@ __global__ void __launch_bounds__(256) stage_weights_kernel(const WStageItem* __
     if (items[mid].block_start <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
   }
   const WStageItem it = items[lo];
+  const float wscale = it.scale * (it.dscale ? __ldg(it.dscale) : 1.f);
   __shared__ __nv_bfloat16 tile[32][32 * 9 + 2];   // +2: odd word stride, conflict-free column reads
   const int kk = it.kk;
   const int tiles_ci = (it.Cin + 31) >> 5;
@@ -53,7 +55,7 @@ __global__ void __launch_bounds__(256) stage_weights_kernel(const WStageItem* __
   const int run = nci * kk;
   for (int r = warp; r < nco; r += 8) {
     const float* src = it.w + ((size_t)(co0 + r) * it.Cin + ci0) * kk;
-    for (int j = lane; j < run; j += 32) tile[r][j] = __float2bfloat16_rn(src[j] * it.scale);
+    for (int j = lane; j < run; j += 32) tile[r][j] = __float2bfloat16_rn(src[j] * wscale);
   }
   int row_l = co0 + lane;   // GEMM row of output channel co0 + lane
   if (it.row_of_co && lane < nco) row_l = it.row_of_co[co0 + lane];

@@ -30,14 +30,15 @@ class ConvSpec:
     act: bool = True
     pool: bool = False   # AvgPool2d(2, ceil_mode=True) in front (ResBlock idpath with stride 2)
     shuffle: bool = False  # 1x1 conv of a PixelShuffle_ICNR: GEMM rows are permuted to (i, j, c) order
+    sn: bool = False     # spectral-normed Conv1d(ks=1, bias=False) of SelfAttention: weight_orig [nf, ni, 1] + u / v buffers
 
     @property
     def wname(self) -> str:
-        return self.name + ".0.weight"
+        return self.name + (".0.weight_orig" if self.sn else ".0.weight")
 
     @property
     def bname(self) -> Optional[str]:
-        return None if self.bn else self.name + ".0.bias"
+        return None if (self.bn or self.sn) else self.name + ".0.bias"
 
     @property
     def bn_prefix(self) -> Optional[str]:
@@ -55,6 +56,23 @@ class BlockSpec:
 
 
 @dataclass
+class SASpec:
+    """fastai SelfAttention(n_channels) appended to UnetBlock.conv2 (`conv2.2`): gamma + query / key / value."""
+    name: str            # "layers.5.conv2.2"
+    c: int
+    query: ConvSpec
+    key: ConvSpec
+    value: ConvSpec
+
+    @property
+    def gamma(self) -> str:
+        return self.name + ".gamma"
+
+    def convs(self) -> List[ConvSpec]:
+        return [self.query, self.key, self.value]
+
+
+@dataclass
 class UnetBlockSpec:
     name: str            # "layers.4" ...
     shuf: ConvSpec
@@ -65,6 +83,7 @@ class UnetBlockSpec:
     x_in_c: int
     cu: int              # channels after the shuffle (up_in_c // 2)
     skip_child: int      # encoder child whose output is concatenated
+    sa: Optional[SASpec] = None
 
 
 @dataclass
@@ -93,11 +112,13 @@ class NetSpec:
         out += self.middle
         for u in self.unet:
             out += [u.shuf, u.conv1, u.conv2]
+            if u.sa is not None:
+                out += u.sa.convs()
         out += [self.final_shuf] + self.final_res + [self.head]
         return out
 
 
-def build_spec(arch: str = "xresnet34", n_in: int = 4, n_out: int = 2) -> NetSpec:
+def build_spec(arch: str = "xresnet34", n_in: int = 4, n_out: int = 2, self_attention: bool = False) -> NetSpec:
     if arch not in ARCHS:
         raise ValueError(f"unsupported architecture {arch!r}; choose from {sorted(ARCHS)}")
     expansion, layers = ARCHS[arch]
@@ -140,6 +161,11 @@ def build_spec(arch: str = "xresnet34", n_in: int = 4, n_out: int = 2) -> NetSpe
         unet.append(UnetBlockSpec(pre, ConvSpec(f"{pre}.shuf.0", up_in_c, 4 * cu, 1, shuffle=True), f"{pre}.bn",
                                   ConvSpec(f"{pre}.conv1", ni, nf, 3), ConvSpec(f"{pre}.conv2", nf, nf, 3),
                                   up_in_c, x_in_c, cu, idx))
+        if self_attention and j == 1:      # fastai unet.py: sa = self_attention and (i == len(sz_chg_idxs) - 3)
+            sp = f"{pre}.conv2.2"
+            unet[-1].sa = SASpec(sp, nf, ConvSpec(f"{sp}.query", nf, nf // 8, 1, act=False, sn=True),
+                                 ConvSpec(f"{sp}.key", nf, nf // 8, 1, act=False, sn=True),
+                                 ConvSpec(f"{sp}.value", nf, nf, 1, act=False, sn=True))
         c = nf
     final_shuf = ConvSpec("layers.8.0", c, 4 * c, 1, shuffle=True)
     cc = c + n_in
@@ -167,6 +193,7 @@ class ParamLayout:
         self.entries: List[ParamEntry] = []
         self.by_name: Dict[str, ParamEntry] = {}
         self.buffers: List[Tuple[str, int]] = []   # BN running stats: (prefix, C)
+        self.sn_buffers: List[Tuple[str, int, int]] = []   # spectral norm u / v vectors: (conv prefix, Cout, Cin)
         self._off = 0
 
         def group_of(name: str) -> int:
@@ -187,6 +214,10 @@ class ParamLayout:
             self._off = off + n
 
         def add_conv(cs: ConvSpec):
+            if cs.sn:
+                add(cs.wname, (cs.nf, cs.ni, 1), True)
+                self.sn_buffers.append((cs.name + ".0", cs.nf, cs.ni))
+                return
             add(cs.wname, (cs.nf, cs.ni, cs.ks, cs.ks), True)
             if cs.bn:
                 add_bn(cs.bn_prefix, cs.nf)
@@ -214,6 +245,10 @@ class ParamLayout:
             add_bn(u.bn_prefix, u.x_in_c)
             add_conv(u.conv1)
             add_conv(u.conv2)
+            if u.sa is not None:
+                add(u.sa.gamma, (1,), True)     # a plain Parameter: fastai's wd_bn_bias=False does not exempt it
+                for cs in u.sa.convs():
+                    add_conv(cs)
         add_conv(spec.final_shuf)
         for cs in spec.final_res:
             add_conv(cs)
@@ -261,6 +296,8 @@ def conv_flops(spec: NetSpec, size: int) -> int:
         total += 2 * s * s * u.shuf.ni * u.shuf.nf
         s = skips[u.skip_child]
         total += 2 * s * s * (u.conv1.ni * u.conv1.nf + u.conv2.ni * u.conv2.nf) * 9
+        if u.sa is not None:      # the three 1x1 convolutions only (the two batched attention products are not convs)
+            total += 2 * s * s * sum(c.ni * c.nf for c in u.sa.convs())
     total += 2 * s * s * spec.final_shuf.ni * spec.final_shuf.nf
     s = size
     for cs in spec.final_res:
