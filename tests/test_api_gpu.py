@@ -148,3 +148,23 @@ def test_train_func_on_geotiff_tiles(tmp_path):
     assert len(learn.history) == 3 and learn.history[-1]["train_loss"] < learn.history[0]["train_loss"]
     again = load_learner(d / "run.pkl")
     assert torch.equal(again.predict(x[0])[1], learn.predict(x[0])[1])
+
+
+def test_learner_with_self_attention(tmp_path):
+    """params_and_main.py:83 default self_attention=True through the reference-facing API: the CUDA-graph training step
+    (attention products captured with the rest of the plan) learns, gamma leaves its zero init, export / load round-trips."""
+    from unet_b200.reference_api import load_learner, unet_learner_MS
+    from unet_b200.synth import aerial_like_tiles
+    learn = unet_learner_MS(4, 2, arch="xresnet18", size=(64, 64), batch_size=8, lr=2e-3, self_attention=True)
+    assert float(learn.net.param("layers.5.conv2.2.gamma")) == 0.0          # fastai init: the block starts as identity
+    x, y = aerial_like_tiles(32, 4, 64, 64, 2, seed=3)
+    batches = lambda: [(x[i:i + 8], y[i:i + 8]) for i in range(0, 32, 8)]
+    hist = learn.fit_one_cycle(4, 2e-3, batches, batches)
+    assert hist[-1]["train_loss"] < hist[0]["train_loss"] and all(np.isfinite(h["train_loss"]) for h in hist)
+    assert float(learn.net.param("layers.5.conv2.2.gamma")) != 0.0
+    learn.export(tmp_path / "sa.pkl")
+    again = load_learner(tmp_path / "sa.pkl")
+    assert again.self_attention and "layers.5.conv2.2.query.0.weight_u" in again.state_dict()
+    _, a1, p1 = learn.predict(x[0])
+    _, a2, p2 = again.predict(x[0])
+    assert torch.equal(a1, a2) and torch.equal(p1, p2)

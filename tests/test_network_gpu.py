@@ -124,6 +124,81 @@ def test_train_step_parity(arch, n_in, n_out, size, batch, data):
     assert torch.equal(g1, net.grads)
 
 
+def test_self_attention_parity():
+    """self_attention=True (the reference's default, params_and_main.py:83): fastai SelfAttention on UnetBlock #1 with
+    spectral-normed query / key / value convolutions - logits, loss, every gradient (incl. gamma and the weight_orig
+    tensors behind the spectral norm), the power-iteration vectors, and the eval-mode forward against the oracle."""
+    from oracle.unet_oracle import make_oracle, weighted_ce
+    from unet_b200.network import UNetB200
+    from unet_b200.synth import aerial_like_tiles
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    arch, n_in, n_out, size, batch = "xresnet18", 4, 2, 128, 4
+    oracle = make_oracle(arch, n_in, n_out, seed=0, self_attention=True).cuda().train()
+    net = UNetB200(arch, n_in, n_out, (size, size), batch, training=True, self_attention=True)
+    sd0 = copy.deepcopy(oracle.state_dict())
+    net.load_state_dict(sd0)
+    x_u8, y = aerial_like_tiles(batch, n_in, size, size, n_out)
+    x_u8, y = x_u8.cuda(), y.cuda()
+    x, yl = x_u8.float() / 255.0, y.long()
+    w = torch.full((n_out,), 1.0 / n_out, device="cuda")
+    o_auto = copy.deepcopy(oracle)
+    logits_ref = oracle(x)
+    loss_ref = weighted_ce(logits_ref, yl, w)
+    loss_ref.backward()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        l_auto = o_auto(x)
+    weighted_ce(l_auto.float(), yl, w).backward()
+    net.set_input(x_u8)
+    net.set_labels(y)
+    net.forward()
+    loss = net.loss_and_grad()
+    net.backward()
+    torch.cuda.synchronize()
+    logits = net.logits_nchw()
+    e_logits, e_auto = rel(logits, logits_ref), rel(l_auto.float(), logits_ref)
+    assert e_logits <= max(3e-2, 1.25 * e_auto), (e_logits, e_auto)
+    assert abs(loss.item() - loss_ref.item()) / abs(loss_ref.item()) <= 5e-3
+    sd = oracle.state_dict()
+    for k, b in net.buffers.items():
+        if k.endswith(("weight_u", "weight_v")):          # one power iteration in fp32 on both sides
+            assert rel(b, sd[k]) <= 1e-4, k
+    grads, pa = net.named_grads(), dict(o_auto.named_parameters())
+    bad = []
+    for name, p in oracle.named_parameters():
+        eo, ea = rel(grads[name], p.grad), rel(pa[name].grad, p.grad)
+        bound = 1.6 * ea + 2e-2 if ea <= 0.5 else 2.0 * ea + 0.25
+        if eo > bound:
+            bad.append((name, eo, ea))
+    assert not bad, bad[:10]
+    sa_names = [n for n in grads if ".conv2.2." in n]
+    assert len(sa_names) == 4 and all(grads[n].abs().max() > 0 for n in sa_names)
+    # eval mode: sigma from the stored u / v, no power iteration
+    oracle.eval()
+    ev = UNetB200(arch, n_in, n_out, (size, size), batch, training=False, self_attention=True)
+    ev.load_state_dict(oracle.state_dict())
+    ev.set_input(x_u8)
+    ev.forward()
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref_eval = oracle(x)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            auto_eval = oracle(x).float()
+    e_ev, e_ev_auto = rel(ev.logits_nchw(), ref_eval), rel(auto_eval, ref_eval)
+    # the same network without the attention block, same weights otherwise: the block must not add error of its own
+    o_plain = make_oracle(arch, n_in, n_out, seed=0).cuda().eval()
+    o_plain.load_state_dict({k: v for k, v in oracle.state_dict().items() if ".conv2.2." not in k})
+    ev_plain = UNetB200(arch, n_in, n_out, (size, size), batch, training=False)
+    ev_plain.load_state_dict(o_plain.state_dict())
+    ev_plain.set_input(x_u8)
+    ev_plain.forward()
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        e_plain = rel(ev_plain.logits_nchw(), o_plain(x))
+    assert e_ev <= max(3e-2, 1.25 * e_ev_auto, 1.5 * e_plain), (e_ev, e_ev_auto, e_plain)
+    assert torch.equal(ev.buffers["layers.5.conv2.2.query.0.weight_u"], oracle.state_dict()["layers.5.conv2.2.query.0.weight_u"])
+
+
 def test_eval_forward_and_tile_prediction():
     from oracle.unet_oracle import make_oracle
     from unet_b200.network import UNetB200

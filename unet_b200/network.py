@@ -77,13 +77,14 @@ class UNetB200:
 
     def __init__(self, arch: str = "xresnet34", n_in: int = 4, n_out: int = 2, size: Tuple[int, int] = (256, 256),
                  batch: int = 8, training: bool = True, device: Optional[torch.device] = None,
-                 class_weights: Optional[Sequence[float]] = None):
+                 class_weights: Optional[Sequence[float]] = None, self_attention: bool = False):
         if not torch.cuda.is_available():
             raise _lib.B2UError("UNetB200 needs a CUDA device (sm_100a); there is no CPU path")
         self.lib = _lib.load()
         _lib.check(self.lib.b2u_device_check(), "b2u_device_check")
         self.device = device or torch.device("cuda", torch.cuda.current_device())
-        self.spec: NetSpec = build_spec(arch, n_in, n_out)
+        self.self_attention = bool(self_attention)
+        self.spec: NetSpec = build_spec(arch, n_in, n_out, self.self_attention)
         self.layout = ParamLayout(self.spec)
         self.N, (self.H, self.W) = batch, size
         if self.H < 32 or self.W < 32:
@@ -100,6 +101,11 @@ class UNetB200:
         for prefix, c in self.layout.buffers:
             self.buffers[prefix + ".running_mean"] = torch.zeros(c, dtype=torch.float32, device=dev)
             self.buffers[prefix + ".running_var"] = torch.ones(c, dtype=torch.float32, device=dev)
+        for prefix, co, ci in self.layout.sn_buffers:      # spectral norm power-iteration vectors (unit norm)
+            g = torch.Generator(device=dev).manual_seed(len(self.buffers))
+            for key, nvec in ((".weight_u", co), (".weight_v", ci)):
+                t = torch.randn(nvec, generator=g, device=dev)
+                self.buffers[prefix + key] = t / t.norm().clamp_min(1e-12)
         cw = [1.0 / n_out] * n_out if class_weights is None else list(class_weights)  # "even" weights, train.py:338-339
         self.class_weights = torch.tensor(cw, dtype=torch.float32, device=dev)
         self.flops_fwd_per_tile = conv_flops(self.spec, self.H) if self.H == self.W else None
@@ -114,6 +120,8 @@ class UNetB200:
         self._side_stream: Optional[torch.cuda.Stream] = None
         self._bwd_builders: List[Callable[[], None]] = []
         self._wstage: List[_lib.WStageItem] = []
+        self._wstage_sa: List[_lib.WStageItem] = []   # spectral-normed weights: re-staged inside every forward (1/sigma)
+        self._sn_sigma: Dict[str, torch.Tensor] = {}
         self._wgrad_specs: List[dict] = []
         self.launches_fwd = 0
         self.launches_bwd = 0
@@ -154,6 +162,10 @@ class UNetB200:
                 if len(e.shape) == 4:
                     fan_in = e.shape[1] * e.shape[2] * e.shape[3]
                     p.copy_(torch.randn(e.shape, generator=g, device=self.device) * (2.0 / fan_in) ** 0.5)
+                elif len(e.shape) == 3:              # spectral-normed Conv1d weight_orig of SelfAttention
+                    p.copy_(torch.randn(e.shape, generator=g, device=self.device) * (2.0 / e.shape[1]) ** 0.5)
+                elif e.name.endswith(".gamma"):      # fastai: 0 (the block starts as the identity)
+                    p.fill_(0.5 if randomize_bn else 0.0)
                 elif e.name.endswith(".0.bias"):
                     p.zero_()
                 elif e.name.endswith(".weight"):   # BN gamma
@@ -167,6 +179,8 @@ class UNetB200:
                     else:
                         p.fill_(1e-3)
             for k, b in self.buffers.items():
+                if k.endswith(("weight_u", "weight_v")):
+                    continue
                 if k.endswith("running_mean"):
                     b.copy_(torch.randn(b.shape, generator=g, device=self.device) * 0.1 if randomize_bn else torch.zeros_like(b))
                 else:
@@ -229,22 +243,32 @@ class UNetB200:
         it.wf, it.wd, it.bias_rows = wf.data_ptr(), _p(wd), _p(w["bias_rows"])
         it.Cout, it.Cin, it.kk, it.wf_cinp, it.wd_coutp = cs.nf, cs.ni, kk, padc(cs.ni), padc(cs.nf)
         it.scale = 0.25 if cs.pool else 1.0
-        self._wstage.append(it)
+        if cs.sn:
+            sig = torch.ones(2, dtype=torch.float32, device=dev)      # {sigma, 1/sigma}, written by b2u_spectral_norm
+            self._sn_sigma[cs.name] = sig
+            it.dscale = sig[1:].data_ptr()
+            self._wstage_sa.append(it)
+        else:
+            self._wstage.append(it)
         self._w[cs.name] = w
         return w
 
-    def _finish_wstage(self) -> None:
-        n = len(self._wstage)
+    def _pack_wstage(self, items):
+        n = len(items)
         arr = (_lib.WStageItem * n)()
         blocks = 0
-        for i, it in enumerate(self._wstage):
+        for i, it in enumerate(items):
             it.block_start = blocks
             blocks += ((it.Cout + 31) // 32) * ((it.Cin + 31) // 32)   # one block per 32x32 channel tile
             arr[i] = it
         raw = bytes(arr)
         host = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
-        self._wstage_dev = host.to(self.device)
-        self._wstage_n, self._wstage_blocks = n, blocks
+        return host.to(self.device), n, blocks
+
+    def _finish_wstage(self) -> None:
+        self._wstage_dev, self._wstage_n, self._wstage_blocks = self._pack_wstage(self._wstage)
+        if self._wstage_sa:
+            self._wstage_sa_dev, self._wstage_sa_n, self._wstage_sa_blocks = self._pack_wstage(self._wstage_sa)
 
     def _stage_weights(self, s: int) -> None:
         _lib.check(self.lib.b2u_stage_weights(self._wstage_dev.data_ptr(), self._wstage_n, self._wstage_blocks, s),
@@ -315,6 +339,75 @@ class UNetB200:
             _lib.check(lib.b2u_bn_stats(x.data_ptr(), ldx, pixels, Cc, partial.data_ptr(), rows, padc(Cc), s),
                        "b2u_bn_stats")
         return run, partial
+
+    def _self_attention(self, sa, c2: Act, h: int, w_: int):
+        """fastai layers.SelfAttention on the output of UnetBlock.conv2 (after its ReLU): spectral-normed 1x1 query / key /
+        value convolutions, beta = softmax(q_i . k_j over i), o_j = sum_i beta_ij v_i, out = gamma * o + x.  The
+        convolutions run on the implicit-GEMM kernel, the two batched attention products are library GEMMs (torch.bmm ->
+        cuBLAS, ~0.1 % of the step's FLOPs), the rest is csrc/attention.cu.  Returns (output Act, backward builder)."""
+        lib, dev, N, train = self.lib, self.device, self.N, self.training
+        n, Cc = h * w_, sa.c
+        convs = sa.convs()
+        gamma = self.param(sa.gamma)
+        for cs in convs:
+            W, sig = self.param(cs.wname), self._sn_sigma[cs.name]
+            u, v = self.buffers[cs.name + ".0.weight_u"], self.buffers[cs.name + ".0.weight_v"]
+            self._fwd(lambda s, W=W, u=u, v=v, sig=sig, cs=cs: _lib.check(
+                lib.b2u_spectral_norm(W.data_ptr(), cs.nf, cs.ni, u.data_ptr(), v.data_ptr(), int(train), sig.data_ptr(), s),
+                "b2u_spectral_norm"))
+        self._fwd(lambda s: _lib.check(lib.b2u_stage_weights(self._wstage_sa_dev.data_ptr(), self._wstage_sa_n,
+                                                             self._wstage_sa_blocks, s), "b2u_stage_weights"))
+        Q = self._act(h, w_, sa.query.nf, sa.name + ".q")
+        K = self._act(h, w_, sa.key.nf, sa.name + ".k")
+        V = self._act(h, w_, sa.value.nf, sa.name + ".v")
+        for cs, y in zip(convs, (Q, K, V)):
+            self._conv_fwd(cs, c2, y)
+        Q3, K3, V3 = (a.t.view(N, n, a.ld) for a in (Q, K, V))
+        S = torch.zeros((N, n, n), dtype=torch.bfloat16, device=dev)       # logits q_i . k_j; reused for d(beta) / dS
+        beta = torch.zeros_like(S)
+        O = self._act(h, w_, Cc, sa.name + ".o")
+        O3 = O.t.view(N, n, O.ld)
+        out = self._act(h, w_, Cc, sa.name + ".out")
+        self._keep += [S, beta]
+        self._fwd(lambda s: torch.bmm(Q3, K3.transpose(1, 2), out=S))
+        self._fwd(lambda s: _lib.check(lib.b2u_softmax_dim1(S.data_ptr(), beta.data_ptr(), N, n, s), "b2u_softmax_dim1"))
+        self._fwd(lambda s: torch.bmm(beta.transpose(1, 2), V3, out=O3))
+        self._fwd(lambda s: _lib.check(lib.b2u_attn_out(O.t.data_ptr(), c2.t.data_ptr(), gamma.data_ptr(), out.t.data_ptr(),
+                                                        out.t.numel(), s), "b2u_attn_out"))
+        if not train:
+            return out, None
+
+        def build_bwd():
+            assert out.grad is not None and out.grad_written, sa.name
+            dOut = out.grad
+            dO = torch.zeros_like(O.t)
+            dQ, dK, dV = torch.zeros_like(Q.t), torch.zeros_like(K.t), torch.zeros_like(V.t)
+            scratch = torch.zeros(1025, dtype=torch.float32, device=dev)
+            self._keep += [dO, dQ, dK, dV, scratch]
+            dO3, dQ3, dK3, dV3 = dO.view(N, n, O.ld), dQ.view(N, n, Q.ld), dK.view(N, n, K.ld), dV.view(N, n, V.ld)
+            dgamma = self.grad(sa.gamma)
+            self._bwd(lambda s: _lib.check(lib.b2u_attn_out_bwd(dOut.data_ptr(), O.t.data_ptr(), gamma.data_ptr(),
+                                                                dO.data_ptr(), dgamma.data_ptr(), scratch.data_ptr(),
+                                                                dO.numel(), s), "b2u_attn_out_bwd"))
+            self._bwd(lambda s: torch.bmm(beta, dO3, out=dV3))                      # dV_i = sum_j beta_ij dO_j
+            self._bwd(lambda s: torch.bmm(V3, dO3.transpose(1, 2), out=S))          # d(beta)_ij = V_i . dO_j
+            self._bwd(lambda s: _lib.check(lib.b2u_softmax_dim1_bwd(beta.data_ptr(), S.data_ptr(), S.data_ptr(), N, n, s),
+                                           "b2u_softmax_dim1_bwd"))                  # dS, in place
+            self._bwd(lambda s: torch.bmm(S, K3, out=dQ3))                          # dQ_i = sum_j dS_ij K_j
+            self._bwd(lambda s: torch.bmm(S.transpose(1, 2), Q3, out=dK3))          # dK_j = sum_i dS_ij Q_i
+            for cs, d in zip(convs, (dQ, dK, dV)):
+                self._wgrad(cs, d, c2)
+                # gradient through W / sigma(W), after the split-K reduce of this weight (same stream as the wgrad)
+                W, dW, sig = self.param(cs.wname), self.grad(cs.wname), self._sn_sigma[cs.name]
+                u, v = self.buffers[cs.name + ".0.weight_u"], self.buffers[cs.name + ".0.weight_v"]
+                self._bwd(lambda s, W=W, dW=dW, u=u, v=v, sig=sig, cs=cs: _lib.check(
+                    lib.b2u_spectral_norm_bwd(dW.data_ptr(), W.data_ptr(), cs.nf, cs.ni, u.data_ptr(), v.data_ptr(),
+                                              sig.data_ptr(), s), "b2u_spectral_norm_bwd"), side=True)
+            # c2.grad = (dOut + Wq^T dQ + Wk^T dK + Wv^T dV) * (c2 > 0): a pre-ReLU gradient, as conv2's backward expects
+            self._dgrad(convs[0], dQ, c2, res=dOut)
+            self._dgrad(convs[1], dK, c2)
+            self._dgrad(convs[2], dV, c2, zmask=True)
+        return out, build_bwd
 
     # ---- backward helpers ---------------------------------------------------------------------------------------
     def _bn_bwd(self, bn: BNState, dz: torch.Tensor, lddz: int, x: torch.Tensor, ldx: int, y: Optional[torch.Tensor],
@@ -609,8 +702,14 @@ class UNetB200:
                 "b2u_shuffle_cat_fwd"))
             c1 = conv_bias(ub.conv1, cat, h, w_)
             c2 = conv_bias(ub.conv2, c1, h, w_)
+            sa_bwd = None
+            x_out = c2
+            if ub.sa is not None:
+                x_out, sa_bwd = self._self_attention(ub.sa, c2, h, w_)
             if train:
-                def ub_bwd(ub=ub, U=U, S=S, P=P, cat=cat, c1=c1, c2=c2, bnS=bnS):
+                def ub_bwd(ub=ub, U=U, S=S, P=P, cat=cat, c1=c1, c2=c2, bnS=bnS, sa_bwd=sa_bwd):
+                    if sa_bwd is not None:
+                        sa_bwd()
                     conv_bias_bwd(ub.conv2, c1, c2)()
                     conv_bias_bwd(ub.conv1, cat, c1)()
                     dP = P.ensure_grad()
@@ -625,7 +724,7 @@ class UNetB200:
                     S.grad_written = True
                     conv_bias_bwd(ub.shuf, U, P)()
                 bwd_layers.append(ub_bwd)
-            x = c2
+            x = x_out
 
         # ---- final PixelShuffle_ICNR (no blur) + MergeLayer(dense) + ResBlock(no norm) + head
         U = x

@@ -55,11 +55,13 @@ class Learner:
 
     def __init__(self, arch: str, n_in: int, n_classes: int, size: Tuple[int, int], batch_size: int,
                  class_weights: Optional[Sequence[float]] = None, opt_func: str = "adam", lr: float = 1e-3,
-                 wd: float = 0.01, encoder_factor: float = 10.0, moms: Sequence[float] = (0.95, 0.85, 0.95)):
+                 wd: float = 0.01, encoder_factor: float = 10.0, moms: Sequence[float] = (0.95, 0.85, 0.95),
+                 self_attention: bool = False):
         self.arch, self.n_in, self.n_classes, self.size, self.bs = arch, n_in, n_classes, tuple(size), batch_size
         self.class_weights = list(class_weights) if class_weights is not None else None
+        self.self_attention = bool(self_attention)
         self.net = UNetB200(arch, n_in, n_classes, self.size, batch_size, training=True,
-                            class_weights=self.class_weights)
+                            class_weights=self.class_weights, self_attention=self.self_attention)
         self.net.init_parameters(seed=0, randomize_bn=False)     # fastai defaults: gamma 1 / 0 (BatchZero), beta 1e-3
         self.trainer = Trainer(self.net, optimizer=opt_func, lr=lr, wd=wd, encoder_factor=encoder_factor)
         self.lr, self.moms = lr, tuple(moms)
@@ -117,7 +119,7 @@ class Learner:
     def _eval_net(self) -> UNetB200:
         if self._eval is None:
             self._eval = UNetB200(self.arch, self.n_in, self.n_classes, self.size, self.bs, training=False,
-                                  class_weights=self.class_weights)
+                                  class_weights=self.class_weights, self_attention=self.self_attention)
         self._eval.load_state_dict(self.net.state_dict())
         return self._eval
 
@@ -168,7 +170,7 @@ class Learner:
         (a pickled fastai Learner cannot be produced without fastai)."""
         Path(path).parent.mkdir(parents=True, exist_ok=True)
         torch.save({"arch": self.arch, "n_in": self.n_in, "n_classes": self.n_classes, "size": self.size,
-                    "batch_size": self.bs, "class_weights": self.class_weights,
+                    "batch_size": self.bs, "class_weights": self.class_weights, "self_attention": self.self_attention,
                     "state_dict": {k: v.cpu() for k, v in self.state_dict().items()}}, path)
 
 
@@ -180,12 +182,10 @@ def unet_learner_MS(n_in: int, n_classes: int, arch="xresnet34", size: Tuple[int
     `n_classes` replaces `len(dls.vocab)` (:140); `pretrained` may be a state_dict with fastai keys."""
     if regression:
         raise NotImplementedError("the regression variant (MSELossFlat, n_out=1) is outside the built hot path")
-    if self_attention:
-        raise NotImplementedError("SelfAttention on UnetBlock #1 is not built yet (SURVEY.md 8(f) rank 2)")
     if loss_func is not None and not isinstance(loss_func, str):
         warnings.warn("loss_func objects are ignored: the plan implements CrossEntropyLossFlat(axis=1) with class weights")
     learn = Learner(_arch_name(arch), n_in, n_classes, size, batch_size, class_weights, opt_func, lr, wd,
-                    encoder_factor, moms)
+                    encoder_factor, moms, self_attention=self_attention)
     if isinstance(pretrained, dict):
         learn.load_state_dict(pretrained)
     return learn
@@ -197,7 +197,7 @@ def load_learner(path, batch_size: Optional[int] = None) -> Learner:
         raise FileNotFoundError(path)
     ck = torch.load(path, map_location="cpu", weights_only=False)
     learn = Learner(ck["arch"], ck["n_in"], ck["n_classes"], tuple(ck["size"]), batch_size or ck["batch_size"],
-                    ck.get("class_weights"))
+                    ck.get("class_weights"), self_attention=ck.get("self_attention", False))
     learn.load_state_dict(ck["state_dict"])
     return learn
 
