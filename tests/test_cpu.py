@@ -265,6 +265,21 @@ def test_data_parallel_gradient_average_gloo(tmp_path):
     assert torch.allclose(got, ref, atol=1e-6)       # equal shards: mean of shard means == full-batch mean
 
 
+def test_allreduce_segments_tile_ops_and_gradients():
+    """engine.plan_segments: the per-segment all-reduce ranges of the data-parallel step cover the flat gradient buffer
+    exactly once, in backward order, and small stages are merged."""
+    from unet_b200.engine import plan_segments
+    total, n_ops = 41_000_000, 300
+    # (op index, offset) in backward order: decoder+post-BN done, then encoder stages 7, 6, 5, 4
+    marks = [(120, 21_300_000), (160, 8_200_000), (220, 1_400_000), (260, 260_000), (285, 30_000)]
+    segs = plan_segments(marks, total, n_ops, 24 * (1 << 20) // 4)
+    assert segs == [(0, 120, 21_300_000, total), (120, 160, 8_200_000, 21_300_000), (160, 220, 1_400_000, 8_200_000),
+                    (220, 300, 0, 1_400_000)]
+    assert segs[0][0] == 0 and segs[-1][1] == n_ops and all(a[1] == b[0] and a[2] == b[3] for a, b in zip(segs, segs[1:]))
+    assert plan_segments(marks, total, n_ops, 10 ** 9) == [(0, n_ops, 0, total)]          # everything merged: one graph
+    assert plan_segments([], total, n_ops, 1) == [(0, n_ops, 0, total)]
+
+
 def _gather_worker(rank, world, port, out):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)

@@ -110,7 +110,6 @@ def test_split_raster_tiles_filter_and_split(tmp_path):
     assert np.array_equal(tile, img[:, y:y + h, x:x + w])
     assert g.geotransform[0] == pytest.approx(GEO.geotransform[0] + x * 0.2) and g.geotransform[3] == pytest.approx(GEO.geotransform[3] - y * 0.2)
     m, _ = read_geotiff(str(p0).replace("img_tiles", "mask_tiles"))
-    keep_px = ~(img[:, y:y + h, x:x + w] == 0).all(axis=0) | True
     assert np.array_equal(m[0], msk[y:y + h, x:x + w] + 1)              # class_zero: labels shifted by one
     with pytest.raises(ValueError):
         split_raster(str(tmp_path / "scene.tif"), None, str(tmp_path / "ds2"), 512, ov)

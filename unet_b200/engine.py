@@ -112,19 +112,9 @@ class Trainer:
             net.backward(s, b, e)
 
     def _plan_segments(self) -> None:
-        """Backward segments [(op begin, op end, grad lo, grad hi)]: after segment i the gradients [lo, hi) are final and
-        their all-reduce can run behind segment i+1.  Marks that would leave less than `min_seg_mb` of gradients in a
-        segment are merged (launch latency, not bandwidth, is what a small bucket costs over NVSwitch)."""
-        net, total = self.net, self.net.layout.total
-        marks = [(k, off) for k, off in net.bwd_marks if off > 0]
-        segs, prev_k, prev_off = [], 0, total
-        for k, off in marks:
-            if (prev_off - off) * 4 < self.min_seg_mb * (1 << 20):
-                continue
-            segs.append((prev_k, k, off, prev_off))
-            prev_k, prev_off = k, off
-        segs.append((prev_k, len(net.bwd_ops), 0, prev_off))
-        self.segments = segs
+        net = self.net
+        self.segments = plan_segments(net.bwd_marks, net.layout.total, len(net.bwd_ops),
+                                      int(self.min_seg_mb * (1 << 20) / 4))
 
     def _update(self) -> None:
         net = self.net
@@ -256,6 +246,23 @@ class Trainer:
             self._prefetch(*prefetch)
         self.step_count += 1
         return self.net.loss
+
+
+def plan_segments(marks: Sequence[Tuple[int, int]], total: int, n_ops: int,
+                  min_seg_elems: int) -> List[Tuple[int, int, int, int]]:
+    """Backward segments [(op begin, op end, grad lo, grad hi)] from the network's all-reduce marks (op index k, offset
+    off: after op k every gradient at offsets >= off is final).  After segment i the gradients [lo, hi) are final and
+    their all-reduce can run behind segment i+1.  Marks that would leave fewer than `min_seg_elems` gradients in a
+    segment are merged into the next one (launch latency, not bandwidth, is what a small bucket costs over NVSwitch).
+    The segments tile the op list [0, n_ops) and the gradient buffer [0, total) exactly."""
+    segs, prev_k, prev_off = [], 0, total
+    for k, off in marks:
+        if off <= 0 or prev_off - off < min_seg_elems:
+            continue
+        segs.append((prev_k, k, off, prev_off))
+        prev_k, prev_off = k, off
+    segs.append((prev_k, n_ops, 0, prev_off))
+    return segs
 
 
 def init_distributed() -> Tuple[int, int, int]:
