@@ -4,6 +4,8 @@
 // Replaces: PixelShuffle_ICNR (+ReplicationPad2d+AvgPool2d blur), torch.cat + ReLU of fastai UnetBlock/MergeLayer
 // (reference train.py:141 DynamicUnet), CrossEntropyLossFlat(axis=1) fwd+bwd (train.py:195,211), fastai Adam / SGD
 // (train.py:218), softmax + numpy sum/count/argmax merge (predict.py:193-203, 284-334).
+#include <stdlib.h>
+
 #include "host_util.h"
 #include "ptx.cuh"
 #include "stream.cuh"
@@ -144,6 +146,79 @@ __global__ void __launch_bounds__(256, 2) shuffle_cat_fwd_kernel(
           for (int k = 0; k < 8; ++k) o.v[k] = 0.f;
         }
         store(p, c, o);
+      });
+}
+
+// The blurred variant, blocked 2x2: one thread produces the four concat pixels (2y+a, 2x+b) of one cell (y, x) of the
+// pre-shuffle grid for its 8-channel group.  Their 2x2 blur windows overlap - the union is the 3x3 patch of shuffled pixels
+// PS[2y-1..2y+1, 2x-1..2x+1] - so a cell costs 9 loads instead of 16 (the per-pixel kernel was bound by load issue, not by
+// DRAM).  Same summation order as the per-pixel kernel: bit-identical results.
+struct CatBlurRegs { uint4 v[9]; };   // shuffle role: the 3x3 patch, row-major; skip role: v[0..3] = the four skip pixels
+
+__global__ void __launch_bounds__(256, 2) shuffle_cat_blur2x2_kernel(
+    const __nv_bfloat16* __restrict__ u, int ldu, int cu, const __nv_bfloat16* __restrict__ skip, int lds,
+    int cs, const float* __restrict__ sscale, const float* __restrict__ sshift, int skip_relu,
+    __nv_bfloat16* __restrict__ cat, int ldc, int N, int h, int w, int H, int W) {
+  pdl_enter();
+  auto ps = [&](int n, int yy, int xx, int c) {   // replication pad: row / column -1 is row / column 0
+    yy = max(yy, 0); xx = max(xx, 0);
+    return ldq(u + ((long long)(n * h + (yy >> 1)) * w + (xx >> 1)) * ldu + (((yy & 1) * 2 + (xx & 1)) * cu + c));
+  };
+  struct SkipConsts { f8 sc, sh; };
+  stream_pixel_groups_xy<1, CatBlurRegs>(N, h, w, ldc >> 3,
+      [&](int c) {
+        SkipConsts k;
+        if (sscale && c >= cu && c < cu + cs) { k.sc = ldc8(sscale, c - cu, cs); k.sh = ldc8(sshift, c - cu, cs); }
+        return k;
+      },
+      [&](int p, int n, int y, int x, int c, const SkipConsts&, CatBlurRegs& q) {
+        const int Y = 2 * y, X = 2 * x;
+        if (c < cu) {
+#pragma unroll
+          for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int t = 0; t < 3; ++t) q.v[r * 3 + t] = ps(n, Y - 1 + r, X - 1 + t, c);
+        } else if (skip && c < cu + cs) {
+#pragma unroll
+          for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+              const int yy = min(Y + a, H - 1), xx = min(X + b, W - 1);     // cropped pixels: clamped load, never stored
+              q.v[a * 2 + b] = ldq(skip + ((long long)(n * H + yy) * W + xx) * lds + (c - cu));
+            }
+        }
+      },
+      [&](int p, int n, int y, int x, int c, const SkipConsts& k, const CatBlurRegs& q) {
+        const int Y = 2 * y, X = 2 * x;
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            if (Y + a >= H || X + b >= W) continue;     // odd skip size: last row / column of the upsampled tensor cropped
+            f8 o;
+            if (c < cu) {
+              const f8 pa = unpack_f8(q.v[a * 3 + b]), pb = unpack_f8(q.v[a * 3 + b + 1]);
+              const f8 pd = unpack_f8(q.v[(a + 1) * 3 + b]), pe = unpack_f8(q.v[(a + 1) * 3 + b + 1]);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) o.v[i] = 0.25f * ((pa.v[i] + pb.v[i]) + (pd.v[i] + pe.v[i]));
+            } else if (skip && c < cu + cs) {
+              const int sc0 = c - cu;
+              o = unpack_f8(q.v[a * 2 + b]);
+              if (sscale) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o.v[i] = o.v[i] * k.sc.v[i] + k.sh.v[i];
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                if (skip_relu) o.v[i] = fmaxf(o.v[i], 0.f);
+                if (sc0 + i >= cs) o.v[i] = 0.f;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) o.v[i] = 0.f;
+            }
+            st8(cat + ((long long)(n * H + Y + a) * W + X + b) * ldc + c, o);
+          }
       });
 }
 
@@ -675,7 +750,12 @@ extern "C" int b2u_shuffle_cat_fwd_crop(const void* u, int32_t ldu, int32_t cu, 
   const long long items = (long long)N * Ho * Wo * (ldc / 8);
   // 2 resident blocks per SM (register budget of the 4- or 8-pixel load batches): one block per slot, one range each
   const dim3 grid(grid_for(items, 256, 2));
-  if (blur)
+  static const bool per_pixel = getenv("B2U_SHUFFLE_PER_PIXEL") != nullptr;   // A/B switch
+  if (blur && !per_pixel)
+    launch_k(shuffle_cat_blur2x2_kernel, dim3(grid_for((long long)N * h * w * (ldc / 8), 256, 2)), dim3(256), 0,
+             (cudaStream_t)stream, (cbf)u, ldu, cu, (cbf)skip, lds, cs, sscale, sshift, skip_relu, (bf)cat, ldc, N, h, w, Ho,
+             Wo);
+  else if (blur)
     launch_k(shuffle_cat_fwd_kernel<true>, grid, dim3(256), 0, (cudaStream_t)stream, (cbf)u, ldu, cu, (cbf)skip, lds, cs,
              sscale, sshift, skip_relu, (bf)cat, ldc, N, h, w, Ho, Wo);
   else
