@@ -124,6 +124,9 @@ def test_geotiff_tiles_merge_modes_and_whole_raster(tmp_path):
     mpath = predict_geotiff(learn, rpath, patch_overlap=ov)
     mm, gm = read_geotiff(mpath)
     assert np.array_equal(mm[0], merged[0]) and gm.geotransform == geo.geotransform
+    # streamed as vertical strips (window reads of the file): bit-identical to the one-shot prediction
+    spath = predict_geotiff(learn, rpath, tmp_path / "aoi" / "streamed.tif", patch_overlap=ov, max_strip_columns=70)
+    assert np.array_equal(read_geotiff(spath)[0], mm)
 
 
 def test_train_func_on_geotiff_tiles(tmp_path):

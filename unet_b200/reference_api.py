@@ -37,7 +37,7 @@ from .engine import Trainer, one_cycle
 from .network import UNetB200
 from .predict_engine import TiledPredictor
 from .geotiff import GeoInfo, geotiff_info, open_mask, open_tile, read_geotiff, write_geotiff
-from .tiling import colour_classes, compute_windows, placement_from_geotransform
+from .tiling import colour_classes, compute_windows, placement_from_geotransform, shard_windows_by_columns
 
 ARCHITECTURES = ("xresnet18", "xresnet34", "xresnet50", "xresnet101")   # params_and_main.py:12,99
 
@@ -350,24 +350,45 @@ def save_predictions(predict_model, predict_path, regression: bool = False, merg
 
 
 def predict_geotiff(predict_model, raster_path, out_path=None, patch_overlap: float = 0.125, large_file: bool = False,
-                    class_zero: bool = False, rank: int = 0, world: int = 1):
+                    class_zero: bool = False, rank: int = 0, world: int = 1, max_strip_columns: Optional[int] = None):
     """Tile-free variant of the predict path: what `split_raster` (create_tiles_unet.py:252-431) + `save_predictions(merge=
     True)` produce together - the stitched argmax mask of a whole 4-band GeoTIFF - without writing tiles to disk: the
-    raster is read once, uploaded, windowed on the device with `compute_windows` offsets, predicted and stitched in HBM.
-    With `world > 1` every rank writes the column strip it owns (`<out>.part<rank>.tif`, georeferenced to its origin)."""
+    raster is windowed on the device with `compute_windows` offsets, predicted and stitched in HBM.
+    `max_strip_columns`: rasters that should not sit in host / device memory at once are streamed as vertical strips of
+    at most that many output columns - each strip reads only the file window of the tile columns it needs
+    (`read_geotiff(window=)`), is predicted as an owner-computes strip and lands in its columns of the mask, so the
+    result is bit-identical to the one-shot prediction.  With `world > 1` every rank writes the column strip it owns
+    (`<out>.part<rank>.tif`, georeferenced to its origin)."""
     learn = predict_model if isinstance(predict_model, Learner) else load_learner(predict_model)
-    raster, geo = read_geotiff(raster_path)
-    if raster.dtype != np.uint8:
-        raise ValueError(f"{raster_path}: {raster.dtype} rasters are not supported by the uint8 fast path")
     net = learn._eval_net()
-    if raster.shape[0] != net.n_in:
-        raise ValueError(f"raster has {raster.shape[0]} bands, the model expects {net.n_in}")
-    dev_r = torch.from_numpy(raster).pin_memory().to(net.device, non_blocking=True)
-    mask, xb, xe = TiledPredictor(net).predict_raster(dev_r, patch_overlap, rank, world, large_file=large_file)
+    bands, Y, X, dt, geo = geotiff_info(raster_path)
+    if dt != np.uint8:
+        raise ValueError(f"{raster_path}: {dt} rasters are not supported by the uint8 fast path")
+    if bands != net.n_in:
+        raise ValueError(f"raster has {bands} bands, the model expects {net.n_in}")
+    P = net.H
+    pred = TiledPredictor(net)
+    windows = compute_windows(Y, X, P, patch_overlap)
+    _, xb, xe = shard_windows_by_columns(windows, X, rank, world)
+    n_strips = 1 if not max_strip_columns else max(1, -(-(xe - xb) // int(max_strip_columns)))
+    mask = np.empty((Y, xe - xb), dtype=np.uint8)
+    for k in range(n_strips):
+        # strip k of this rank's columns: the balanced partition of [xb, xe), then the tile columns intersecting it
+        base, rem = divmod(xe - xb, n_strips)
+        sb = xb + k * base + min(k, rem)
+        se = sb + base + (1 if k < rem else 0)
+        idx = [i for i, (x, y, w, h) in enumerate(windows) if x < se and x + w > sb]
+        xs0 = min(windows[i][0] for i in idx)
+        xs1 = max(windows[i][0] + windows[i][2] for i in idx)
+        strip, _ = read_geotiff(raster_path, window=(xs0, 0, xs1 - xs0, Y))
+        dev_s = torch.from_numpy(np.ascontiguousarray(strip)).pin_memory().to(net.device, non_blocking=True)
+        # the strip holds exactly the tile columns of [sb, se): a one-rank prediction of it reproduces those tiles
+        m, _, _ = pred.predict_raster(dev_s, patch_overlap, 0, 1, large_file=large_file)
+        mask[:, sb - xb:se - xb] = m[:, sb - xs0:se - xs0].cpu().numpy()
     out_path = Path(out_path) if out_path is not None else Path(raster_path).with_name(Path(raster_path).stem + "_prediction.tif")
     if world > 1:
         out_path = out_path.with_suffix(f".part{rank}.tif")
-    write_geotiff(out_path, mask.cpu().numpy(), geo.window(xb, 0), nodata=None, class_zero=class_zero)
+    write_geotiff(out_path, mask, geo.window(xb, 0), nodata=None, class_zero=class_zero)
     return out_path
 
 
