@@ -43,6 +43,30 @@ def test_compressed_and_bigtiff_layouts(tmp_path):
     assert np.array_equal(np.asarray(PIL.open(tmp_path / "rgb.tif")), np.moveaxis(a, 0, 2))
 
 
+@pytest.mark.parametrize("tile,planar,compress", [(64, False, False), (32, True, True), (None, True, False), (48, False, True)])
+def test_tiled_and_planar_layouts(tmp_path, tile, planar, compress):
+    """The layouts large source rasters come in (GDAL TILED=YES / INTERLEAVE=BAND): written here, read back whole and by
+    window, and decoded by Pillow's independent reader (single band and RGB)."""
+    rng = np.random.default_rng(4)
+    a = rng.integers(0, 256, size=(3, 150, 203), dtype=np.uint8)
+    p = tmp_path / "l.tif"
+    write_geotiff(p, a, GEO, tile=tile, planar=planar, compress=compress)
+    b, g = read_geotiff(p)
+    assert np.array_equal(a, b) and g.geotransform == GEO.geotransform
+    w, gw = read_geotiff(p, window=(60, 70, 100, 61))
+    assert np.array_equal(w, a[:, 70:131, 60:160])
+    try:
+        pil = np.asarray(PIL.open(p))
+    except ValueError:
+        pil = None                      # Pillow's own decoder has no raw mode for some planar RGB layouts
+    assert pil is None and planar or np.array_equal(pil, np.moveaxis(a, 0, 2))
+    a16 = rng.integers(0, 60000, size=(1, 97, 130), dtype=np.uint16)
+    write_geotiff(p, a16, None, tile=tile, planar=planar, compress=compress)
+    assert np.array_equal(read_geotiff(p)[0], a16) and np.array_equal(np.asarray(PIL.open(p)), a16[0])
+    with pytest.raises(ValueError):
+        write_geotiff(p, a, GEO, tile=50)
+
+
 @pytest.mark.parametrize("compression", [None, "tiff_lzw", "tiff_adobe_deflate", "packbits"])
 def test_reads_pillow_files(tmp_path, compression):
     rng = np.random.default_rng(1)

@@ -282,11 +282,14 @@ def geotiff_info(path: Union[str, Path]) -> Tuple[int, int, int, np.dtype, GeoIn
 
 # ------------------------------------------------------------------------------------------------------------ writing
 def write_geotiff(path: Union[str, Path], array: np.ndarray, geo: Optional[GeoInfo] = None,
-                  nodata: Optional[float] = None, class_zero: bool = False, compress: bool = False) -> None:
+                  nodata: Optional[float] = None, class_zero: bool = False, compress: bool = False,
+                  tile: Optional[int] = None, planar: bool = False) -> None:
     """`store_tif` (predict.py:19-52): writes `[bands, H, W]` or `[H, W]` as a striped, pixel-interleaved GeoTIFF (GDAL's
     GTiff default) with the geotransform / GeoKeys of `geo`.  `class_zero`: label 0 becomes `nodata` and every other
     label is decremented, exactly as predict.py:34-36 (`np.where(a == 0, nodata, a - 1)`; with nodata None numpy yields
-    an object array there - here 0 stays 0 in that case).  BigTIFF is chosen automatically beyond 4 GB."""
+    an object array there - here 0 stays 0 in that case).  BigTIFF is chosen automatically beyond 4 GB.
+    `tile` (a multiple of 16) writes square tiles instead of strips (GDAL `TILED=YES`), `planar` band-sequential samples
+    (GDAL `INTERLEAVE=BAND`): the layouts large source rasters usually come in."""
     a = np.asarray(array)
     if a.ndim == 2:
         a = a[None]
@@ -307,10 +310,23 @@ def write_geotiff(path: Union[str, Path], array: np.ndarray, geo: Optional[GeoIn
     data = np.ascontiguousarray(np.moveaxis(a, 0, 2)).astype(a.dtype.newbyteorder("<"), copy=False)
     row_bytes = W * bands * a.dtype.itemsize
     rps = max(1, min(H, (1 << 20) // max(1, row_bytes)))
+    if tile is not None and (tile <= 0 or tile % 16):
+        raise ValueError("tile size must be a positive multiple of 16")
+    planes = [data[:, :, b:b + 1] for b in range(bands)] if planar else [data]
     strips = []
-    for r in range(0, H, rps):
-        raw = data[r:r + rps].tobytes()
-        strips.append(zlib.compress(raw, 6) if compress else raw)
+    for pl in planes:
+        if tile is None:
+            for r in range(0, H, rps):
+                raw = np.ascontiguousarray(pl[r:r + rps]).tobytes()
+                strips.append(zlib.compress(raw, 6) if compress else raw)
+        else:
+            for ty in range(0, H, tile):
+                for tx in range(0, W, tile):
+                    blk = np.zeros((tile, tile, pl.shape[2]), dtype=pl.dtype)      # edge tiles are padded to full size
+                    sub = pl[ty:ty + tile, tx:tx + tile]
+                    blk[:sub.shape[0], :sub.shape[1]] = sub
+                    raw = blk.tobytes()
+                    strips.append(zlib.compress(raw, 6) if compress else raw)
     total = sum(len(s) for s in strips)
     big = total + 4096 + 16 * len(strips) > 0xFFFF0000
     geo = geo or GeoInfo()
@@ -331,11 +347,15 @@ def write_geotiff(path: Union[str, Path], array: np.ndarray, geo: Optional[GeoIn
     add(_COMP, 3, [8 if compress else 1])
     rgb = bands >= 3 and a.dtype == np.uint8        # GDAL's GTiff default: RGB photometric for >= 3 byte bands
     add(_PHOTO, 3, [2 if rgb else 1])
-    add(_STRIP_OFF, off_t, [0] * len(strips))            # patched below
+    off_tag, cnt_tag = (_STRIP_OFF, _STRIP_CNT) if tile is None else (_TILE_OFF, _TILE_CNT)
+    add(off_tag, off_t, [0] * len(strips))               # patched below
     add(_SPP, 3, [bands])
-    add(_RPS, 4, [rps])
-    add(_STRIP_CNT, off_t, [len(s) for s in strips])
-    add(_PLANAR, 3, [1])
+    if tile is None:
+        add(_RPS, 4, [rps])
+    else:
+        add(_TILE_W, 4, [tile]); add(_TILE_H, 4, [tile])
+    add(cnt_tag, off_t, [len(s) for s in strips])
+    add(_PLANAR, 3, [2 if planar else 1])
     n_extra = bands - 3 if rgb else bands - 1
     if n_extra > 0:
         add(_EXTRA, 3, [0] * n_extra)
@@ -389,7 +409,7 @@ def write_geotiff(path: Union[str, Path], array: np.ndarray, geo: Optional[GeoIn
             f.write(struct.pack("<H", len(entries)))
         ext = bytearray(ext)
         for tag, typ, cnt, inline, where in placed:
-            if tag == _STRIP_OFF:
+            if tag == off_tag:
                 if where is None:
                     inline = off_bytes.ljust(inl, b"\x00")
                 else:
