@@ -134,3 +134,28 @@ def test_split_raster_tiles_filter_and_split(tmp_path):
     assert np.array_equal(m[0], msk[y:y + h, x:x + w] + 1)              # class_zero: labels shifted by one
     with pytest.raises(ValueError):
         split_raster(str(tmp_path / "scene.tif"), None, str(tmp_path / "ds2"), 512, ov)
+
+
+def test_params_and_main_dispatch(tmp_path):
+    """params_and_main.py:121-181: defaults, the forced resets without enable_extra_parameters, unknown names, and the
+    Create_tiles stage end to end (the Train / Predict stages call the GPU entry points tested in test_api_gpu.py)."""
+    from unet_b200.params_and_main import main, resolve
+    p = resolve({"patch_size": 64, "self_attention": True, "large_file": True})
+    assert p["self_attention"] is False and p["large_file"] is False and p["ARCHITECTURE"] == "xresnet34"   # :134-147
+    with pytest.warns(UserWarning):
+        q = resolve({"enable_extra_parameters": True, "self_attention": True, "ENCODER_FACTOR": 5})
+    assert q["self_attention"] is True and q["ENCODER_FACTOR"] == 5 and q["data_path"] == q["base_dir"]
+    with pytest.raises(KeyError):
+        resolve({"patchsize": 64})
+    rng = np.random.default_rng(5)
+    img = rng.integers(1, 256, size=(4, 160, 160), dtype=np.uint8)
+    msk = rng.integers(0, 3, size=(160, 160), dtype=np.uint8)
+    write_geotiff(tmp_path / "scene.tif", img, GEO)
+    write_geotiff(tmp_path / "scene_mask.tif", msk, GEO)
+    js = tmp_path / "params.json"
+    js.write_text(__import__("json").dumps({"image_path": str(tmp_path / "scene.tif"), "mask_path": str(tmp_path / "scene_mask.tif"),
+                                            "base_dir": str(tmp_path / "ds"), "patch_size": 64, "patch_overlap": 0.25,
+                                            "split": [0.75, 0.25]}))
+    out = main(str(js))
+    assert len(out["tiles"]) == 9 and {t.parent.parent.name for t in out["tiles"]} == {"trai", "vali"}
+    assert "learner" not in out and "predictions" not in out
