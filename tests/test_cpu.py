@@ -313,3 +313,52 @@ def test_prediction_strip_gather_gloo(tmp_path):
     i0, b0, e0 = shard_windows_by_columns(wins, X, 0, 2)
     i1, b1, e1 = shard_windows_by_columns(wins, X, 1, 2)
     assert (b0, e0, b1, e1) == (0, 51, 51, 101) and set(i0) | set(i1) == set(range(len(wins))) and set(i0) & set(i1)
+
+
+def test_ctypes_signatures_match_the_header():
+    """every prototype of include/b2u.h has a ctypes binding with the same number of parameters (a miscounted argtypes
+    list would shift every argument after it), and 64-bit parameters of the header are bound as 64-bit."""
+    import ctypes
+    from unet_b200 import _lib
+    lib = _lib.load()
+    header = re.sub(r"/\*.*?\*/", " ", open(os.path.join(ROOT, "include", "b2u.h")).read(), flags=re.S)
+    protos = re.findall(r"\n(?:int|void|const char\*|size_t)\s+(b2u_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header)
+    assert len(protos) >= 45
+    checked = 0
+    for name, args in protos:
+        params = [a.strip() for a in args.split(",") if a.strip() and a.strip() != "void"]
+        fn = getattr(lib, name)
+        if fn.argtypes is None:
+            continue
+        assert len(fn.argtypes) == len(params), (name, len(fn.argtypes), params)
+        for ct, decl in zip(fn.argtypes, params):
+            if re.match(r"(u?int64_t|size_t)\s", decl):
+                assert ctypes.sizeof(ct) == 8, (name, decl)
+            elif "*" in decl:
+                assert ctypes.sizeof(ct) == ctypes.sizeof(ctypes.c_void_p), (name, decl)
+            elif re.match(r"(double)\s", decl):
+                assert ct is ctypes.c_double, (name, decl)
+        checked += 1
+    assert checked >= 40
+
+
+def test_every_kernel_waits_for_its_predecessor():
+    """Programmatic dependent launch: every kernel is launched with programmatic stream serialization (launch_k), so every
+    __global__ function must execute griddepcontrol.wait (pdl_enter) before it touches global memory - a kernel that
+    does not would race with the tail of its predecessor."""
+    csrc = os.path.join(ROOT, "unet_b200", "csrc")
+    kernels = 0
+    for fn in sorted(os.listdir(csrc)):
+        if not fn.endswith(".cu"):
+            continue
+        src = open(os.path.join(csrc, fn)).read()
+        assert "<<<" not in re.sub(r"//.*", "", src), f"{fn}: raw <<< >>> launch bypasses launch_k / the PDL attribute"
+        for m in re.finditer(r"__global__\s+void[^{;]*?\b(\w+)\s*\([^{;]*?\)\s*\{", src, flags=re.S):
+            # body up to the matching closing brace
+            depth, i = 1, m.end()
+            while depth and i < len(src):
+                depth += {"{": 1, "}": -1}.get(src[i], 0)
+                i += 1
+            assert "pdl_enter()" in src[m.end():i], f"{fn}: kernel {m.group(1)} never calls pdl_enter()"
+            kernels += 1
+    assert kernels >= 35
