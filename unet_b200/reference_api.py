@@ -107,6 +107,9 @@ class Learner:
             if best_path and score is not None and (best is None or (score < best if "loss" in monitor else score > best)):
                 best = score
                 torch.save(self.state_dict(), best_path)
+        if best_path and best is not None and os.path.exists(best_path):
+            # fastai SaveModelCallback(monitor, fname='best-model') reloads the best epoch after fit (train.py:209)
+            self.load_state_dict(torch.load(best_path, map_location="cpu"))
         if history_csv:
             with open(history_csv, "w", newline="") as f:
                 wr = csv.writer(f)
@@ -477,8 +480,13 @@ def train_func(data_path, existing_model, model_Path, description, BATCH_SIZE, v
     out_dir.mkdir(parents=True, exist_ok=True)
     tb = _tile_batches(train_files, BATCH_SIZE, n_classes, class_zero, shuffle_seed=0, drop_last=len(train_files) >= BATCH_SIZE)
     vb = _tile_batches(valid_files, BATCH_SIZE, n_classes, class_zero, None, False) if valid_files else None
+    if monitor not in (None, "train_loss", "valid_loss", "r2_score", "dice_multi"):
+        raise ValueError("Monitor must be one of ['train_loss', 'valid_loss', 'r2_score', 'dice_multi']")    # train.py:207-208
+    mon = monitor if monitor in ("dice_multi", "valid_loss", "train_loss") else "dice_multi"                   # train.py:198-201
+    if vb is None and mon != "train_loss":
+        mon = "train_loss"
     learn.fit_one_cycle(EPOCHS, LEARNING_RATE, tb, vb, history_csv=str(out_dir / f"{description}_history.csv"),
-                        monitor=monitor if monitor in ("dice_multi", "valid_loss", "train_loss") else "dice_multi")
+                        monitor=mon, best_path=str(out_dir / "best-model.pth"))
     learn.export(out_dir / f"{description}.pkl")
     with open(out_dir / f"{description}.json", "w") as f:
         json.dump({"description": description, "architecture": learn.arch, "bands": nb, "tile": [h, w], "codes": codes,
