@@ -461,11 +461,13 @@ def train_func(data_path, existing_model, model_Path, description, BATCH_SIZE, v
         if CLASS_WEIGHTS == "even":
             cw = [1.0 / n_classes] * n_classes                                     # train.py:338-339
         elif CLASS_WEIGHTS == "weighted":
-            counts = np.zeros(n_classes, dtype=np.float64)                         # inverse class frequency (utils.py:106-117)
-            for f in train_files:
+            # utils.py:105-117 get_class_weights: total / count per class over (up to 1200) training masks.  The
+            # reference takes the counts from `unique()`, which silently drops absent classes; here an absent class
+            # keeps its slot (count clamped to 1).  The weighted-mean CE is invariant to the common scale.
+            counts = np.zeros(n_classes, dtype=np.float64)
+            for f in train_files[:1200]:
                 counts += np.bincount(open_mask(f).ravel(), minlength=n_classes)[:n_classes]
-            inv = 1.0 / np.maximum(counts, 1.0)
-            cw = list(inv / inv.sum())
+            cw = list(counts.sum() / np.maximum(counts, 1.0))
         else:
             raise ValueError(f"CLASS_WEIGHTS {CLASS_WEIGHTS!r} not understood")
     else:
