@@ -6,6 +6,7 @@ Every wrapper raises `B2UError` with the library's message on a non-zero status.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
@@ -79,7 +80,9 @@ _lib = None
 
 
 def lib_path() -> Path:
-    return _HERE / "libb2u.so"
+    # B2U_LIB: a diagnostic build of the same sources (tools/conv_timeline.py builds one with -DB2U_TIMELINE)
+    override = os.environ.get("B2U_LIB")
+    return Path(override) if override else _HERE / "libb2u.so"
 
 
 def load():

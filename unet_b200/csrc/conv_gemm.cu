@@ -53,7 +53,25 @@ struct ConvParams {
   b2u_bn_fin fin;   // counter != nullptr: the last CTA to retire finalizes the BatchNorm statistics
   int multi_out;    // N tile nt is stored through tm_out_nt[nt] at channel 0 (PixelShuffle phases -> parity planes)
   CUtensorMap tm_out_nt[4];
+#ifdef B2U_TIMELINE
+  unsigned long long* timeline;   // [4 roles][B2U_TL_EVENTS] clock64 stamps of CTA 0 (diagnostic builds only)
+#endif
 };
+
+// Diagnostic build (-DB2U_TIMELINE, tools/conv_timeline.py): CTA 0 stamps clock64 at the hand-over points of its four
+// roles - producer after an A stage became free, MMA issuer after an A stage arrived / after the accumulator was
+// committed, epilogue after the accumulator arrived / after a chunk was stored - so that the stall between the
+// shared-memory floor and the measured tile time can be read off a timeline.  Compiled out of the product library.
+#ifdef B2U_TIMELINE
+#define B2U_TL_EVENTS 4096
+#define TL_STAMP(role, ctr)                                                                  \
+  do {                                                                                       \
+    if (p.timeline && blockIdx.x == 0 && (ctr) < B2U_TL_EVENTS)                              \
+      p.timeline[(role) * B2U_TL_EVENTS + (ctr)++] = (unsigned long long)clock64();          \
+  } while (0)
+#else
+#define TL_STAMP(role, ctr) do { } while (0)
+#endif
 
 static constexpr int kThreads = 384;   // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 epilogue
 static constexpr uint32_t kABytes = 128 * 128;       // 128 pixels x 64 bf16
@@ -187,6 +205,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       // ------------------------------------------------------------ TMA producer, halo mode
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
+      [[maybe_unused]] int tl_n = 0;
       const uint32_t b_ring = smem_base + (uint32_t)p.SA * p.a_stage_bytes;
       if (p.wres && t_begin < t_end) {
         // resident weights: every filter row of every K chunk, once (n_tiles == 1); fullB(0) collects all of it
@@ -202,6 +221,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         const int x0 = bx * p.tw, y0 = by * p.th, n0 = bn * p.tn;
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           mbar_wait(emptyA(sa), pa ^ 1u);
+          TL_STAMP(0, tl_n);
           if (rank == 0) mbar_expect_tx(fullA(sa), tx_mult * p.a_tx_bytes);
           load4(smem_base + (uint32_t)sa * p.a_stage_bytes, &p.tm_ah, fullA(sa), kc * 64, x0 - 1, y0 - 1, n0);
           if (++sa == p.SA) { sa = 0; pa ^= 1u; }
@@ -261,6 +281,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     auto commit = [&](uint32_t bar) {
       if (kPair) umma2_commit_if(leader, bar); else umma_commit_if(leader, bar);
     };
+    [[maybe_unused]] int tl_n = 0, tl_c = 0;
     if (p.halo) {
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
@@ -277,6 +298,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         uint32_t accumulate = 0;
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           mbar_wait_warp(fullA(sa), pa);
+          if (leader) TL_STAMP(1, tl_n);
           const uint32_t a16 = lo_const | ((smem_base + (uint32_t)sa * p.a_stage_bytes) >> 4);
           const int nm = (kc == p.k_chunks - 1) ? p.last_mmas : 4;
           if (p.wres) {
@@ -356,6 +378,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           if (++sa == p.SA) { sa = 0; pa ^= 1u; }
         }
         commit(tfull_bar(acc));
+        if (leader) TL_STAMP(2, tl_c);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -402,6 +425,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t chunk_ctr = 0;
+    [[maybe_unused]] int tl_e = 0;
     const int n_groups = (p.BN + 31) >> 5;
     const int n_chunks = (n_groups + 1) >> 1;
     const int twth = p.tw * p.th;
@@ -430,6 +454,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       const bool valid = (px < p.Wo) && (py < p.Ho) && (pn < p.N);
 
       mbar_wait(tfull_bar(acc), acc_phase);
+      if (e == 0) TL_STAMP(3, tl_e);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)acc * kAccStride + ((uint32_t)(q4 * 32) << 16);
 
@@ -572,6 +597,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             if (p.multi_out) tma_store_4d(&p.tm_out_nt[nt], stg_base + buf * kStagingBytes, j * 64, x0, y0, n0);
             else tma_store_4d(&p.tm_out, stg_base + buf * kStagingBytes, nt * p.BN + j * 64, x0, y0, n0);
             tma_store_commit();
+            TL_STAMP(3, tl_e);
           }
         }
         ++chunk_ctr;
@@ -882,6 +908,9 @@ static int conv_plan_fill(const b2u_conv_desc* d, b2u_conv_plan* plan, bool enco
   p.res = ev(d->res); p.res_mask = ev(d->res_mask); p.zmask = ev(d->zmask);
   p.flags = d->flags; p.stats = d->stats; p.stats_ld = d->stats_ld;
   p.multi_out = multi_out ? d->num_out : 0;
+#ifdef B2U_TIMELINE
+  p.timeline = nullptr;
+#endif
   p.out_f32 = d->out_f32; p.out_f32_ld = d->out_f32_ld;
   if ((d->flags & B2U_EPI_STATS) && encode) B2U_CHECK_ARG(d->stats_ld >= Cout, "conv: stats_ld=%d < Cout=%d", d->stats_ld, Cout);
 
@@ -1046,3 +1075,12 @@ extern "C" int b2u_conv_run(const b2u_conv_plan* plan, void* stream) {
 }
 
 extern "C" void b2u_conv_plan_destroy(b2u_conv_plan* plan) { delete plan; }
+
+#ifdef B2U_TIMELINE
+// diagnostic builds only: device buffer of 4 * 4096 uint64 that CTA 0 of the next launches of this plan stamps
+extern "C" int b2u_conv_plan_set_timeline(b2u_conv_plan* plan, unsigned long long* buf) {
+  B2U_CHECK_ARG(plan != nullptr, "conv_plan_set_timeline: null plan");
+  plan->p.timeline = buf;
+  return B2U_OK;
+}
+#endif
