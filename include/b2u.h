@@ -268,14 +268,23 @@ int b2u_pointwise_smallk(const void* a, int32_t lda, int32_t K, const void* w, i
                          void* out, int32_t ldo, int64_t pixels, int32_t C, void* stream);
 
 /* ---- layout casts at the API edge --------------------------------------------------------------------------- */
-/* x fp32 NCHW (already /255) or uint8 NCHW (divided by 255 here: data.py:24 + IntToFloatTensor) -> bf16 NHWC pitch ld,
- * channels [ch_off, ch_off+write_c) written (lanes >= C zeroed) */
-int b2u_nchw_to_nhwc(const void* x, int32_t x_is_u8, void* y, int32_t N, int32_t C, int32_t H, int32_t W, int32_t ld,
-                     int32_t ch_off, int32_t write_c, void* stream);
-/* tile t = raster[:, y0[t]:y0[t]+P, x0[t]:x0[t]+P] / 255 -> bf16 NHWC [T,P,P,ld]: the crop of create_tiles_unet.py:410 fused with
- * the input contract of data.py:24 (+ fastai IntToFloatTensor) and the layout cast; raster is uint8 [C][Y][X] on the device */
-int b2u_crop_tiles(const uint8_t* raster, int32_t C, int64_t Y, int64_t X, const int32_t* y0, const int32_t* x0, int32_t T,
-                   int32_t P, void* out, int32_t ld, void* stream);
+/* Input contract (A0): the reference reads every GeoTIFF dtype as int32 -> float32 (data.py:18-28), 16-bit datasets
+ * (utils.py:72-89 get_datatype 'int16') are divided by 255 inside its batch transform (utils.py:248-249, 288-289) and
+ * everything is divided by 255 by fastai's IntToFloatTensor (MaskBlock, data.py:100); the regression variant
+ * (RegressionBlock, data.py:98) skips IntToFloatTensor.  x_dtype: element type of the source; value = (raw / div) / div2
+ * in fp32 (uint8 tiles: div 255, div2 1; 16-bit datasets: 255, 255; fp32 already scaled: 1, 1). */
+#define B2U_DT_F32 0
+#define B2U_DT_U8 1
+#define B2U_DT_U16 2
+#define B2U_DT_I16 3
+/* x NCHW of x_dtype -> bf16 NHWC pitch ld, channels [ch_off, ch_off+write_c) written (lanes >= C zeroed) */
+int b2u_nchw_to_nhwc(const void* x, int32_t x_dtype, float div, float div2, void* y, int32_t N, int32_t C, int32_t H,
+                     int32_t W, int32_t ld, int32_t ch_off, int32_t write_c, void* stream);
+/* tile t = raster[:, y0[t]:y0[t]+P, x0[t]:x0[t]+P] / div / div2 -> bf16 NHWC [T,P,P,ld]: the crop of
+ * create_tiles_unet.py:410 fused with the input contract above and the layout cast; raster is [C][Y][X] of r_dtype on
+ * the device */
+int b2u_crop_tiles(const void* raster, int32_t r_dtype, float div, float div2, int32_t C, int64_t Y, int64_t X,
+                   const int32_t* y0, const int32_t* x0, int32_t T, int32_t P, void* out, int32_t ld, void* stream);
 /* bf16/f32 NHWC -> fp32 NCHW */
 int b2u_nhwc_to_nchw_f32(const void* x, int32_t x_is_f32, int32_t ld, float* y, int32_t N, int32_t C, int32_t H,
                          int32_t W, void* stream);
@@ -290,6 +299,21 @@ int b2u_ce_fwd_bwd(const float* logits, int32_t ld, const uint8_t* labels, int64
                    const float* wsum_partial, int32_t wsum_rows, void* dlogits, int32_t ldg, float* loss_partial,
                    int32_t rows, float grad_scale, void* stream);
 int b2u_ce_finalize(const float* loss_partial, int32_t rows, const float* wsum_partial, int32_t wsum_rows, float* loss,
+                    void* stream);
+
+/* ---- regression variant: MSELossFlat(axis=1) (train.py:189-192) + the sums behind fastai's rmse / R2Score metrics -- */
+/* pred = lane 0 of the fp32 head output [P][ld]; target fp32 [P]; loss = mean (pred - target)^2; dpred bf16 [P][ldg]
+ * (NULL: loss only) lane 0 = grad_scale * 2 (pred - target) / P, other lanes 0.  `rows` block partials, then finalize. */
+int b2u_mse_fwd_bwd(const float* pred, int32_t ld, const float* target, int64_t P, void* dpred, int32_t ldg,
+                    float* loss_partial, int32_t rows, float grad_scale, void* stream);
+int b2u_mse_finalize(const float* loss_partial, int32_t rows, int64_t P, float* loss, void* stream);
+/* sums[0..3] (device, double) += {sum (pred-target)^2, sum target, sum target^2, P}; partial: rows*3 doubles of scratch;
+ * ticket: one zero-initialised uint32.  Fixed-order combination (deterministic). */
+int b2u_regression_sums(const float* pred, int32_t ld, const float* target, int64_t P, double* partial, int32_t rows,
+                        double* sums, uint32_t* ticket, void* stream);
+/* ---- validation metric DiceMulti (train.py:196): counts (device, uint64 [3*C]) += per class {#(pred==c & y==c),
+ * #(pred==c), #(y==c)} with pred = argmax_c logits (first maximum wins); Dice_c = 2 I_c / (P_c + T_c). */
+int b2u_dice_counts(const float* logits, int32_t ld, const uint8_t* labels, int64_t P, int32_t C, uint64_t* counts,
                     void* stream);
 
 /* ---- optimizer ------------------------------------------------------------------------------------------------ */
@@ -320,6 +344,14 @@ int b2u_stitch_accumulate_q31(const float* logits, int32_t ld, int32_t C, int32_
                               uint8_t* cnt, int64_t Y, int64_t X, int64_t y_off, int64_t x_off, void* stream);
 int b2u_stitch_finalize_q31(const float* acc, const uint8_t* cnt, int32_t C, int64_t Y, int64_t X, uint8_t* mask,
                             void* stream);
+/* regression merge (predict.py:196-198, 300-316): the raw network output is summed (no softmax) ... */
+int b2u_stitch_accumulate_raw(const float* logits, int32_t ld, int32_t C, int32_t T, int32_t th, int32_t tw,
+                              const int32_t* y0, const int32_t* x0, const int32_t* sel, int32_t n_sel, float* acc,
+                              uint8_t* cnt, int64_t Y, int64_t X, int64_t y_off, int64_t x_off, void* stream);
+/* ... and out[c][y][x] = acc/cnt where tiles were placed, `nodata` elsewhere (regression: -9999, predict.py:313-316;
+ * also the averaged probabilities of the `all_classes` / `specific_class` merge, predict.py:326-337, nodata 0) */
+int b2u_stitch_finalize_mean(const float* acc, const uint8_t* cnt, int32_t C, int64_t Y, int64_t X, float nodata,
+                             float* out, void* stream);
 /* per-tile softmax probabilities (fp32 NCHW, what learn.predict returns, predict.py:193-203) and argmax */
 int b2u_softmax_nchw(const float* logits, int32_t ld, int32_t C, int64_t tiles, int32_t H, int32_t W, float* probs,
                      uint8_t* argmax, void* stream);

@@ -17,8 +17,9 @@ def softmax_probs(logits: np.ndarray) -> np.ndarray:
 
 
 def merge_tiles(preds: List[np.ndarray], geotrans: Sequence[Sequence[float]], large_file: bool = False,
-                all_classes: bool = False, specific_class=None):
-    """preds[i]: [C,h,w] float32 probabilities; geotrans[i] = [ulx, xsize, xres, uly, ysize, yres] (predict.py:222).
+                all_classes: bool = False, specific_class=None, regression: bool = False):
+    """preds[i]: [C,h,w] float32 probabilities (regression: [1,h,w] raw predictions, predict.py:196-198);
+    geotrans[i] = [ulx, xsize, xres, uly, ysize, yres] (predict.py:222).
     Returns (merged, (upleft_x, xres, upleft_y, yres))."""
     preds = [p.copy() for p in preds]
     if large_file:
@@ -45,6 +46,12 @@ def merge_tiles(preds: List[np.ndarray], geotrans: Sequence[Sequence[float]], la
         ly = round((g[3] + g[4] * g[5] - upleft_y_full) / g[5])
         merged[:, uy:ly, ux:lx] += pred
         counter[:, uy:ly, ux:lx] += np.ones_like(pred, dtype=np.int8)
+    if regression:
+        # predict.py:307-316: first channel, divide by the count, -9999 where no prediction was placed
+        merged, counter = merged[0], counter[0]
+        merged[counter > 0] /= counter[counter > 0]
+        merged[counter == 0] = -9999
+        return merged, (upleft_x_full, gt[0, 2], upleft_y_full, gt[0, 5])
     if large_file:
         mask = counter > 0
         merged[mask] //= counter[mask]
@@ -66,3 +73,13 @@ def merge_pixel_windows(preds: List[np.ndarray], windows: Sequence[Sequence[int]
     out, _ = merge_tiles(preds, gts)
     assert out.shape[-2:] == (height, width) or True
     return out
+
+
+def merge_pixel_windows_regression(preds: List[np.ndarray], windows: Sequence[Sequence[int]], height: int, width: int):
+    """regression merge (predict.py:307-316) driven by pixel windows: mean of the overlapping predictions, nodata -9999.
+    The reference sizes the mosaic by the tiles' extent; windows that do not reach (height, width) are padded with nodata."""
+    gts = [[float(x), float(w), 1.0, -float(y), float(h), -1.0] for (x, y, w, h) in windows]
+    out, _ = merge_tiles([np.asarray(p, dtype=np.float32) for p in preds], gts, regression=True)
+    full = np.full((height, width), -9999, dtype=np.float32)
+    full[:out.shape[0], :out.shape[1]] = out
+    return full

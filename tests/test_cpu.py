@@ -134,6 +134,40 @@ def test_bf16_emulation_tracks_oracle():
     assert all(q.grad is not None for q in m.parameters())
 
 
+def test_teacher_forced_emulation():
+    """Why the model-level gradient test teacher-forces the emulation (oracle/bf16_emulation.py `taps=`): a free-running
+    bf16 emulation is chaotic - perturbing the values in front of every rounding by 1e-6 relative (an accumulation-order
+    sized difference) moves deep-layer gradients by tens of percent - whereas with the forward activations pinned to
+    the perturbed run's own values every gradient agrees to a few percent, and a zeroed or sign-flipped tensor is
+    caught by the shared checker."""
+    import copy
+    from oracle.bf16_emulation import emulated_forward
+    from oracle.unet_oracle import make_oracle, weighted_ce
+    from parity_util import gradient_mismatches
+    from unet_b200.synth import aerial_like_tiles
+    o = make_oracle("xresnet18", 3, 2).train()
+    x_u8, y = aerial_like_tiles(4, 3, 64, 64, 2)
+    x, y, w = x_u8.float() / 255, y.long(), torch.full((2,), 0.5)
+
+    def run(**kw):
+        m = copy.deepcopy(o)
+        weighted_ce(emulated_forward(m, x, True, **kw), y, w).backward()
+        return {n: q.grad.clone() for n, q in m.named_parameters()}
+
+    torch.manual_seed(1)
+    rec = {}
+    g_plan = run(noise=1e-6, record=rec)          # stands in for the CUDA plan: same graph, other accumulation order
+    g_free, g_tf = run(), run(taps=rec)
+    assert len(gradient_mismatches(g_plan, g_free, 5e-2, 0.99)) > 20      # free running: no power on the deep layers
+    assert not gradient_mismatches(g_plan, g_tf, 5e-2, 0.999)             # teacher forced: everything agrees
+    broken = dict(g_plan)
+    name = "layers.0.7.1.convpath.1.0.weight"
+    broken[name] = torch.zeros_like(g_plan[name])
+    assert [b[0] for b in gradient_mismatches(broken, g_tf, 5e-2, 0.999)] == [name]
+    broken[name] = -g_plan[name]
+    assert [b[0] for b in gradient_mismatches(broken, g_tf, 5e-2, 0.999)] == [name]
+
+
 # ------------------------------------------------------------------------------------------------ layout / host logic
 @pytest.mark.parametrize("arch,n_in,n_out,size,params,mflops", [
     ("xresnet34", 4, 2, 256, 41244274, 63922.241536), ("xresnet18", 3, 2, 128, 31132240, 14652.801024),

@@ -283,12 +283,12 @@ def test_layout_casts_and_crop():
     N, Cc, H, W, ld = 2, 4, 16, 24, 16
     x8 = torch.randint(0, 256, (N, Cc, H, W), dtype=torch.uint8, device="cuda")
     y = torch.full((N, H, W, ld), 9.0, dtype=torch.bfloat16, device="cuda")
-    _lib.check(L.b2u_nchw_to_nhwc(p(x8), 1, p(y), N, Cc, H, W, ld, 0, ld, S()))
+    _lib.check(L.b2u_nchw_to_nhwc(p(x8), 1, 255.0, 1.0, p(y), N, Cc, H, W, ld, 0, ld, S()))
     torch.cuda.synchronize()
     ref = (x8.float() / 255).to(torch.bfloat16)
     assert torch.equal(y[..., :Cc].permute(0, 3, 1, 2), ref) and (y[..., Cc:] == 0).all()
     xf = torch.rand((N, Cc, H, W), device="cuda")
-    _lib.check(L.b2u_nchw_to_nhwc(p(xf), 0, p(y), N, Cc, H, W, ld, 0, ld, S()))
+    _lib.check(L.b2u_nchw_to_nhwc(p(xf), 0, 1.0, 1.0, p(y), N, Cc, H, W, ld, 0, ld, S()))
     back = torch.zeros((N, Cc, H, W), device="cuda")
     _lib.check(L.b2u_nhwc_to_nchw_f32(p(y), 0, ld, p(back), N, Cc, H, W, S()))
     torch.cuda.synchronize()
@@ -298,11 +298,127 @@ def test_layout_casts_and_crop():
     y0 = torch.tensor([0, 8, 24], dtype=torch.int32, device="cuda")
     x0 = torch.tensor([0, 34, 5], dtype=torch.int32, device="cuda")
     out = torch.zeros((3, 16, 16, ld), dtype=torch.bfloat16, device="cuda")
-    _lib.check(L.b2u_crop_tiles(p(raster), Cc, 40, 50, p(y0), p(x0), 3, 16, p(out), ld, S()))
+    _lib.check(L.b2u_crop_tiles(p(raster), 1, 255.0, 1.0, Cc, 40, 50, p(y0), p(x0), 3, 16, p(out), ld, S()))
     torch.cuda.synchronize()
     for t in range(3):
         ref = (raster[:, y0[t]:y0[t] + 16, x0[t]:x0[t] + 16].float() / 255).to(torch.bfloat16)
         assert torch.equal(out[t, ..., :Cc].permute(2, 0, 1), ref)
+
+
+@pytest.mark.parametrize("dtype,code", [(torch.uint16, 2), (torch.int16, 3)])
+def test_sixteen_bit_input_contract(dtype, code):
+    """A0 for 16-bit imagery: bands are read as int32 -> float32 (data.py:24), the 'int16' batch transform divides by 255
+    (utils.py:248-249, 288-289) and IntToFloatTensor by 255 again: two true fp32 divisions, then the bf16 cast.  The
+    8-bit-valued case (max < 257: get_datatype says 'int8', utils.py:72-89) sees one division only.  Bit-exact."""
+    L, _lib = lib()
+    N, Cc, H, W, ld = 2, 4, 16, 24, 16
+    g = torch.Generator().manual_seed(5)
+    lo, hi = (0, 65536) if dtype == torch.uint16 else (-2000, 32768)
+    xi = torch.randint(lo, hi, (N, Cc, H, W), generator=g, dtype=torch.int32)
+    x = xi.to(dtype).cuda()
+    y = torch.full((N, H, W, ld), 9.0, dtype=torch.bfloat16, device="cuda")
+    _lib.check(L.b2u_nchw_to_nhwc(p(x), code, 255.0, 255.0, p(y), N, Cc, H, W, ld, 0, ld, S()))
+    torch.cuda.synchronize()
+    ref = xi.cuda().float().div_(255).div_(255).to(torch.bfloat16)       # the reference's two in-place divisions
+    assert torch.equal(y[..., :Cc].permute(0, 3, 1, 2), ref) and (y[..., Cc:] == 0).all()
+    _lib.check(L.b2u_nchw_to_nhwc(p(x), code, 255.0, 1.0, p(y), N, Cc, H, W, ld, 0, ld, S()))
+    torch.cuda.synchronize()
+    assert torch.equal(y[..., :Cc].permute(0, 3, 1, 2), (xi.cuda().float() / 255).to(torch.bfloat16))
+    # crop from a 16-bit raster
+    ri = torch.randint(lo, hi, (Cc, 40, 50), generator=g, dtype=torch.int32)
+    raster = ri.to(dtype).cuda()
+    y0 = torch.tensor([0, 8, 24], dtype=torch.int32, device="cuda")
+    x0 = torch.tensor([0, 34, 5], dtype=torch.int32, device="cuda")
+    out = torch.zeros((3, 16, 16, ld), dtype=torch.bfloat16, device="cuda")
+    _lib.check(L.b2u_crop_tiles(p(raster), code, 255.0, 255.0, Cc, 40, 50, p(y0), p(x0), 3, 16, p(out), ld, S()))
+    torch.cuda.synchronize()
+    for t in range(3):
+        ref = ri[:, y0[t]:y0[t] + 16, x0[t]:x0[t] + 16].cuda().float().div_(255).div_(255).to(torch.bfloat16)
+        assert torch.equal(out[t, ..., :Cc].permute(2, 0, 1), ref)
+    with pytest.raises(_lib.B2UError):
+        _lib.check(L.b2u_nchw_to_nhwc(p(x), 7, 255.0, 1.0, p(y), N, Cc, H, W, ld, 0, ld, S()))
+
+
+def test_mse_loss_and_regression_sums():
+    """MSELossFlat(axis=1) fwd + bwd (train.py:189-192) against torch, and the sums behind fastai's rmse / R2Score."""
+    L, _lib = lib()
+    P_, ld, ldg, rows = 3 * 40 * 56, 8, 16, 37
+    g = torch.Generator(device="cuda").manual_seed(2)
+    pred = torch.randn((P_, ld), device="cuda", generator=g) * 3
+    tgt = torch.randn(P_, device="cuda", generator=g) * 2 + 1
+    dp = torch.full((P_, ldg), 7.0, dtype=torch.bfloat16, device="cuda")
+    part = torch.zeros(rows, device="cuda")
+    loss = torch.zeros(1, device="cuda")
+    _lib.check(L.b2u_mse_fwd_bwd(p(pred), ld, p(tgt), P_, p(dp), ldg, p(part), rows, 1.0, S()))
+    _lib.check(L.b2u_mse_finalize(p(part), rows, P_, p(loss), S()))
+    torch.cuda.synchronize()
+    z = pred[:, 0].clone().requires_grad_(True)
+    ref = torch.nn.functional.mse_loss(z, tgt)
+    ref.backward()
+    assert abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item())
+    assert rel(dp[:, 0].float(), z.grad) <= 2.0 ** -8 and (dp[:, 1:] == 0).all()
+    sums = torch.zeros(4, dtype=torch.float64, device="cuda")
+    partial = torch.zeros(rows * 3, dtype=torch.float64, device="cuda")
+    ticket = torch.zeros(1, dtype=torch.int32, device="cuda")
+    for _ in range(2):       # two validation batches accumulate
+        _lib.check(L.b2u_regression_sums(p(pred), ld, p(tgt), P_, p(partial), rows, p(sums), p(ticket), S()))
+    torch.cuda.synchronize()
+    d = (pred[:, 0].double() - tgt.double())
+    want = torch.stack([2 * (d * d).sum(), 2 * tgt.double().sum(), 2 * (tgt.double() ** 2).sum(),
+                        torch.tensor(2.0 * P_, dtype=torch.float64, device="cuda")])
+    assert torch.allclose(sums, want, rtol=1e-12)
+
+
+@pytest.mark.parametrize("C", [2, 8, 13])
+def test_dice_counts(C):
+    """DiceMulti counts (train.py:196) against the oracle's dice_multi: exact integers."""
+    from oracle.unet_oracle import dice_multi
+    L, _lib = lib()
+    P_, ld = 5 * 33 * 47, 8 if C <= 8 else 16
+    g = torch.Generator(device="cuda").manual_seed(C)
+    logits = torch.randn((P_, ld), device="cuda", generator=g)
+    logits[::7, 1] = logits[::7, 0]          # ties: the first maximum wins, as torch.argmax
+    labels = torch.randint(0, C, (P_,), device="cuda", generator=g, dtype=torch.int64).to(torch.uint8)
+    counts = torch.zeros(3 * C, dtype=torch.int64, device="cuda")
+    _lib.check(L.b2u_dice_counts(p(logits), ld, p(labels), P_, C, p(counts), S()))
+    _lib.check(L.b2u_dice_counts(p(logits), ld, p(labels), P_, C, p(counts), S()))    # accumulates over batches
+    torch.cuda.synchronize()
+    pred = logits[:, :C].argmax(1)
+    for c in range(C):
+        assert counts[c].item() == 2 * ((pred == c) & (labels == c)).sum().item()
+        assert counts[C + c].item() == 2 * (pred == c).sum().item()
+        assert counts[2 * C + c].item() == 2 * (labels == c).sum().item()
+    inter, ps, ts = counts[:C].double(), counts[C:2 * C].double(), counts[2 * C:].double()
+    dice = [(2 * inter[c] / (ps[c] + ts[c])).item() for c in range(C) if ps[c] + ts[c] > 0]
+    assert abs(sum(dice) / len(dice) - dice_multi(pred, labels.long(), C)) <= 1e-12
+
+
+def test_regression_stitch():
+    """regression merge (predict.py:300-316): raw predictions summed, divided by the count, -9999 where no tile was
+    placed - against the numpy restatement of the reference's merge."""
+    from oracle.stitch import merge_pixel_windows_regression
+    L, _lib = lib()
+    T, P_, ld, Y, X = 6, 16, 8, 40, 52
+    g = torch.Generator(device="cuda").manual_seed(9)
+    z = torch.randn((T, P_, P_, ld), device="cuda", generator=g)
+    wins = [(0, 0, P_, P_), (12, 0, P_, P_), (24, 0, P_, P_), (0, 12, P_, P_), (12, 12, P_, P_), (30, 20, P_, P_)]
+    from unet_b200.tiling import colour_classes
+    y0 = torch.tensor([w[1] for w in wins], dtype=torch.int32, device="cuda")
+    x0 = torch.tensor([w[0] for w in wins], dtype=torch.int32, device="cuda")
+    acc = torch.zeros((1, Y, X), device="cuda")
+    cnt = torch.zeros((Y, X), dtype=torch.uint8, device="cuda")
+    for cls in colour_classes(wins):
+        sel = torch.tensor(cls, dtype=torch.int32, device="cuda")
+        _lib.check(L.b2u_stitch_accumulate_raw(p(z), ld, 1, T, P_, P_, p(y0), p(x0), p(sel), len(cls), p(acc), p(cnt),
+                                               Y, X, 0, 0, S()))
+    out = torch.zeros((1, Y, X), device="cuda")
+    _lib.check(L.b2u_stitch_finalize_mean(p(acc), p(cnt), 1, Y, X, -9999.0, p(out), S()))
+    torch.cuda.synchronize()
+    ref = merge_pixel_windows_regression([z[t, :, :, 0].cpu().numpy()[None] for t in range(T)], wins, Y, X)
+    import numpy as np
+    got = out[0].cpu().numpy()
+    assert (got == -9999).sum() == (ref == -9999).sum() > 0
+    assert np.allclose(got, ref, rtol=1e-6, atol=1e-6)
 
 
 @pytest.mark.parametrize("Cout,Cin,ks", [(16, 12, 3), (100, 100, 3), (384, 96, 1), (40, 4, 3)])

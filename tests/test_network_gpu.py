@@ -10,11 +10,17 @@ Stated tolerances (bf16 storage, fp32 accumulation; errors are max|a-b| / max|b|
     rounding-boundary flips differ)
   * argmax masks: every disagreement with the fp32 oracle lies where the oracle's top-2 margin is below twice the
     measured logit error; >= 99.9 % agreement on pixels with a larger margin (north_star's 99.9 % bar)
-  * parameter gradients: for every tensor err(ours vs fp32) <= 1.6 * err(torch bf16 autocast vs fp32) + 2e-2
-    (tensors on which autocast itself is > 50 % off: <= 2 x its error + 0.25), and bit-identical on a re-run.
-    Random-init weights with noise labels make deep-layer gradients sums of cancelling terms, so ANY bf16 pipeline
-    shows O(1) max-norm errors there (tools/parity_probe.py); the calibrated bound still exposes wiring bugs, which
-    appear as an error far above the autocast profile at the offending tensor and everything upstream of it.
+  * parameter gradients, the check that pins the wiring: against the TEACHER-FORCED bf16 emulation
+    (oracle/bf16_emulation.py `taps=`: the emulation's forward values are pinned to the plan's stored activations, its
+    backward rounds where the plan stores bf16) every tensor agrees within GRAD_TOL (max-norm relative) with cosine
+    >= GRAD_COS; the same checker is then run on a copy with one weight gradient zeroed and must flag exactly that
+    tensor (the suite is known to be able to fail).  Under teacher forcing every stored forward activation must also
+    equal what the emulation computes from the plan's previous activations within 2 bf16 ulp of the tensor maximum
+    (a per-layer forward wiring check), and the logits within 1e-4.
+  * parameter gradients vs the fp32 oracle: err(ours) <= 1.6 * err(torch bf16 autocast vs fp32) + 2e-2 on every tensor
+    that stock autocast itself resolves to better than 50 %; the free-running comparison has no power beyond that
+    (the network is chaotic at random init: tests/test_cpu.py::test_teacher_forced_emulation), which is why the
+    teacher-forced check above exists.  Gradients are bit-identical on a re-run.
 """
 import copy
 import os
@@ -25,8 +31,47 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def rel(a, b):
-    return ((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-30)).item()
+from parity_util import gradient_mismatches, plan_taps, rel
+
+GRAD_TOL, GRAD_COS = 3e-2, 0.999      # plan vs teacher-forced emulation, every parameter tensor
+ACT_TOL = 2 * 2.0 ** -8               # stored activation vs the emulation's value from the plan's previous activations
+
+
+def teacher_forced_check(oracle, net, x, yl, w, logits):
+    """Gradients of the teacher-forced emulation vs the plan's, per-layer forward consistency, mutation self-test."""
+    from oracle.bf16_emulation import emulated_forward
+    from oracle.unet_oracle import weighted_ce
+    o_tf = copy.deepcopy(oracle)
+    o_tf.zero_grad()
+    taps, free = plan_taps(net), {}
+    l_tf = emulated_forward(o_tf, x, True, taps=taps, record=free)
+    weighted_ce(l_tf, yl, w).backward()
+    assert rel(logits, l_tf) <= 1e-4, rel(logits, l_tf)
+    assert len(free) >= 40
+    # (`layers.8.0.out` is not materialised when the final PixelShuffle is fused into its convolution: it is checked
+    # through `layers.10.cat`'s consumers instead)
+    mism = {k: rel(taps[k], v) for k, v in free.items() if k in taps}
+    assert len(mism) >= len(free) - 1
+    off = {k: e for k, e in mism.items() if e > ACT_TOL}
+    assert not off, sorted(off.items(), key=lambda kv: -kv[1])[:5]
+    ref = {n: p.grad for n, p in o_tf.named_parameters()}
+    grads = net.named_grads()
+    bad = gradient_mismatches(grads, ref, GRAD_TOL, GRAD_COS)
+    assert not bad, sorted(bad, key=lambda b: -b[1])[:10]
+    # the checker can fail: one zeroed / one sign-flipped weight gradient is flagged, and only that tensor
+    names = [n for n in ref if n.endswith("convpath.1.0.weight") and n.startswith("layers.0.7.")]
+    victim = names[-1]
+    broken = dict(grads)
+    broken[victim] = torch.zeros_like(grads[victim])
+    assert [b[0] for b in gradient_mismatches(broken, ref, GRAD_TOL, GRAD_COS)] == [victim]
+    broken[victim] = -grads[victim]
+    assert [b[0] for b in gradient_mismatches(broken, ref, GRAD_TOL, GRAD_COS)] == [victim]
+    worst = max(rel(grads[n], ref[n]) for n in ref)
+    if os.path.isdir("gpurun_out"):      # calibration record of the evidence runs (not part of the assertion)
+        with open("gpurun_out/tf_parity.txt", "a") as f:
+            f.write(f"{oracle.arch} {tuple(x.shape)}: worst grad err vs teacher-forced emulation {worst:.3e}, worst "
+                    f"activation mismatch {max(mism.values()):.3e}\n")
+    return worst
 
 
 def _setup(arch, n_in, n_out, size, batch, data):
@@ -103,15 +148,14 @@ def test_train_step_parity(arch, n_in, n_out, size, batch, data):
         shallow = k.startswith(("layers.0.0", "layers.0.1", "layers.0.2", "layers.0.4", "layers.0.5", "layers.6", "layers.7"))
         deep = arch == "xresnet50" and not shallow
         assert rel(b, sd[k]) <= (0.3 if deep else 5e-2), k
-    # gradients, calibrated against torch's own bf16 autocast
+    # gradients: (1) against the teacher-forced emulation - tight on every tensor, with a mutation self-test
+    teacher_forced_check(oracle, net, x, yl, w, logits)
+    # (2) against the fp32 oracle, calibrated with torch's own bf16 autocast, where autocast itself resolves the tensor
     grads, pa = net.named_grads(), dict(o_auto.named_parameters())
     bad = []
     for name, p in oracle.named_parameters():
         eo, ea = rel(grads[name], p.grad), rel(pa[name].grad, p.grad)
-        # ea > 0.5: stock bf16 autocast is itself > 50 % off on this tensor - no bf16 pipeline resolves it (cancelling
-        # sums), the two errors are independent noise draws; only a gross-error bound is meaningful there
-        bound = 1.6 * ea + 2e-2 if ea <= 0.5 else 2.0 * ea + 0.25
-        if eo > bound:
+        if ea <= 0.5 and eo > 1.6 * ea + 2e-2:
             bad.append((name, eo, ea))
     assert not bad, bad[:10]
     # determinism: a second forward/backward over the same inputs reproduces every gradient bit for bit (fixed-order
@@ -167,8 +211,7 @@ def test_self_attention_parity():
     bad = []
     for name, p in oracle.named_parameters():
         eo, ea = rel(grads[name], p.grad), rel(pa[name].grad, p.grad)
-        bound = 1.6 * ea + 2e-2 if ea <= 0.5 else 2.0 * ea + 0.25
-        if eo > bound:
+        if ea <= 0.5 and eo > 1.6 * ea + 2e-2:
             bad.append((name, eo, ea))
     assert not bad, bad[:10]
     sa_names = [n for n in grads if ".conv2.2." in n]

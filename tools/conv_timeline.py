@@ -34,6 +34,7 @@ if __name__ == "__main__":
     sys.argv = ["one_conv.py", case, "1"]
     ns = {}
     src = open(os.path.join(ROOT, "tools", "one_conv.py")).read()
+    ns["__file__"] = os.path.join(ROOT, "tools", "one_conv.py")
     exec(compile(src, "one_conv.py", "exec"), ns)          # builds the plan and runs it (warm-up + timed)
     plan = ns["plan"]
     lib = _lib.load()

@@ -17,6 +17,8 @@ EPI_RELU = 1
 EPI_STATS = 2
 EPI_OUT_F32 = 4
 
+DT_F32, DT_U8, DT_U16, DT_I16 = 0, 1, 2, 3     # b2u.h B2U_DT_*: element type of raw input tiles / rasters
+
 
 class B2UError(RuntimeError):
     pass
@@ -142,19 +144,25 @@ def _declare(lib):
         "b2u_attn_out": [vp, vp, vp, vp, i64, vp],
         "b2u_attn_out_bwd": [vp, vp, vp, vp, vp, vp, i64, vp],
         "b2u_pad_even_bwd": [vp, vp, i32, i32, i32, i32, i32, vp],
-        "b2u_nchw_to_nhwc": [vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp],
+        "b2u_nchw_to_nhwc": [vp, i32, f32, f32, vp, i32, i32, i32, i32, i32, i32, i32, vp],
         "b2u_pointwise_smallk": [vp, i32, i32, vp, i32, vp, i32, vp, i32, i64, i32, vp],
-        "b2u_crop_tiles": [u8p, i32, i64, i64, vp, vp, i32, i32, vp, i32, vp],
+        "b2u_crop_tiles": [vp, i32, f32, f32, i32, i64, i64, vp, vp, i32, i32, vp, i32, vp],
         "b2u_nhwc_to_nchw_f32": [vp, i32, i32, vp, i32, i32, i32, i32, vp],
         "b2u_ce_weight_sum": [u8p, i64, vp, i32, vp, i32, vp],
         "b2u_ce_fwd_bwd": [vp, i32, u8p, i64, i32, vp, vp, i32, vp, i32, vp, i32, f32, vp],
         "b2u_ce_finalize": [vp, i32, vp, i32, vp, vp],
+        "b2u_mse_fwd_bwd": [vp, i32, vp, i64, vp, i32, vp, i32, f32, vp],
+        "b2u_mse_finalize": [vp, i32, i64, vp, vp],
+        "b2u_regression_sums": [vp, i32, vp, i64, vp, i32, vp, vp, vp],
+        "b2u_dice_counts": [vp, i32, u8p, i64, i32, vp, vp],
         "b2u_sgd_step": [vp, vp, i64, f32, f32, vp],
         "b2u_adam_step": [vp, vp, vp, vp, i64, vp, vp, vp, i32, vp, vp],
         "b2u_stitch_accumulate": [vp, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp, u8p, i64, i64, i64, i64, vp],
         "b2u_stitch_finalize": [vp, u8p, i32, i64, i64, u8p, vp],
         "b2u_stitch_accumulate_q31": [vp, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp, u8p, i64, i64, i64, i64, vp],
         "b2u_stitch_finalize_q31": [vp, u8p, i32, i64, i64, u8p, vp],
+        "b2u_stitch_accumulate_raw": [vp, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp, u8p, i64, i64, i64, i64, vp],
+        "b2u_stitch_finalize_mean": [vp, u8p, i32, i64, i64, f32, vp, vp],
         "b2u_softmax_nchw": [vp, i32, i32, i64, i32, i32, vp, u8p, vp],
     }
     for name, args in sigs.items():

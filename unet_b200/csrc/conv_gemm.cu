@@ -111,6 +111,59 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane)
   return v[0];
 }
 
+// ---- lean MMA issue helpers (one thread).  NM = K=16 MMAs per 64-channel tap; descriptor low words advance by
+// immediates (+2 per K slice, +8 per pixel of the halo row, +b_step per tap); only the first MMA of a group takes a
+// run-time accumulate flag, the others accumulate unconditionally.
+template <bool kPair>
+__device__ __forceinline__ void mma_one(uint32_t d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc,
+                                        uint32_t accumulate) {
+  if (kPair) umma2_bf16_lohi(d, alo, ahi, blo, bhi, idesc, accumulate);
+  else umma_bf16_lohi(d, alo, ahi, blo, bhi, idesc, accumulate);
+}
+template <bool kPair>
+__device__ __forceinline__ void mma_acc(uint32_t d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc) {
+  if (kPair) umma2_bf16_lohi_acc(d, alo, ahi, blo, bhi, idesc);
+  else umma_bf16_lohi_acc(d, alo, ahi, blo, bhi, idesc);
+}
+template <int NM, bool kPair>
+__device__ __forceinline__ void issue_tap(uint32_t d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc,
+                                          uint32_t accumulate, bool first_runtime) {
+  if (first_runtime) mma_one<kPair>(d, alo, ahi, blo, bhi, idesc, accumulate);
+  else mma_acc<kPair>(d, alo, ahi, blo, bhi, idesc);
+#pragma unroll
+  for (int k = 1; k < NM; ++k) mma_acc<kPair>(d, alo + 2u * k, ahi, blo + 2u * k, bhi, idesc);
+}
+template <bool kPair>
+__device__ __forceinline__ void issue_tap_n(int nm, uint32_t d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi,
+                                            uint32_t idesc, uint32_t accumulate) {
+  switch (nm) {
+    case 4: issue_tap<4, kPair>(d, alo, ahi, blo, bhi, idesc, accumulate, true); break;
+    case 3: issue_tap<3, kPair>(d, alo, ahi, blo, bhi, idesc, accumulate, true); break;
+    case 2: issue_tap<2, kPair>(d, alo, ahi, blo, bhi, idesc, accumulate, true); break;
+    default: issue_tap<1, kPair>(d, alo, ahi, blo, bhi, idesc, accumulate, true); break;
+  }
+}
+// three taps of one filter row against one weight stage [3][rows][64]
+template <int NM, bool kPair>
+__device__ __forceinline__ void issue_row(uint32_t d, uint32_t a_row, uint32_t ahi, uint32_t b_lo, uint32_t bhi,
+                                          uint32_t b_step, uint32_t idesc, uint32_t accumulate) {
+  issue_tap<NM, kPair>(d, a_row, ahi, b_lo, bhi, idesc, accumulate, true);
+  issue_tap<NM, kPair>(d, a_row + 8u, ahi, b_lo + b_step, bhi, idesc, 1u, false);
+  issue_tap<NM, kPair>(d, a_row + 16u, ahi, b_lo + 2u * b_step, bhi, idesc, 1u, false);
+}
+// all nine taps of a 64-channel chunk against resident weights
+template <int NM, bool kPair>
+__device__ __forceinline__ void issue_3x3(uint32_t d, uint32_t a16, uint32_t ahi, uint32_t a_rstep, uint32_t b_lo,
+                                          uint32_t bhi, uint32_t b_step, uint32_t idesc, uint32_t accumulate) {
+  issue_row<NM, kPair>(d, a16, ahi, b_lo, bhi, b_step, idesc, accumulate);
+  issue_tap<NM, kPair>(d, a16 + a_rstep, ahi, b_lo + 3u * b_step, bhi, idesc, 1u, false);
+  issue_tap<NM, kPair>(d, a16 + a_rstep + 8u, ahi, b_lo + 4u * b_step, bhi, idesc, 1u, false);
+  issue_tap<NM, kPair>(d, a16 + a_rstep + 16u, ahi, b_lo + 5u * b_step, bhi, idesc, 1u, false);
+  issue_tap<NM, kPair>(d, a16 + 2u * a_rstep, ahi, b_lo + 6u * b_step, bhi, idesc, 1u, false);
+  issue_tap<NM, kPair>(d, a16 + 2u * a_rstep + 8u, ahi, b_lo + 7u * b_step, bhi, idesc, 1u, false);
+  issue_tap<NM, kPair>(d, a16 + 2u * a_rstep + 16u, ahi, b_lo + 8u * b_step, bhi, idesc, 1u, false);
+}
+
 // kAux: residual / mask operands in the epilogue; kStats: BatchNorm partial sums; kF32: fp32 logits output (head).
 // Compile-time switches: the epilogue is the critical path of the memory-/issue-bound layers, unused features must not
 // cost instructions there.
@@ -268,149 +321,128 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     }
   } else if (warp == 1 && rank == 0) {
     // ------------------------------------------------------------ MMA issuer (pair mode: the leader CTA only)
-    // The whole warp runs the loop convergently (waits included); only the leader lane's tcgen05 instructions execute.
-    const uint32_t leader = elect_one() ? 1u : 0u;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    const uint32_t lo_const = 1u << 16;  // LBO field (unused for K-major swizzled operands)
-    const uint32_t hiB = (uint32_t)(make_smem_desc(0, 0, 1024) >> 32);
-    auto mma = [&](uint32_t d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t accum) {
-      if (kPair) umma2_bf16_lohi_if(leader, d, alo, ahi, blo, bhi, p.idesc, accum);
-      else umma_bf16_lohi_if(leader, d, alo, ahi, blo, bhi, p.idesc, accum);
-    };
-    auto commit = [&](uint32_t bar) {
-      if (kPair) umma2_commit_if(leader, bar); else umma_commit_if(leader, bar);
-    };
-    [[maybe_unused]] int tl_n = 0, tl_c = 0;
-    if (p.halo) {
-      int sa = 0, sb = 0;
-      uint32_t pa = 0, pb = 0;
-      const uint32_t b_ring = smem_base + (uint32_t)p.SA * p.a_stage_bytes;
-      const uint32_t hiA = (uint32_t)(make_smem_desc(0, 0, (uint32_t)p.hw * 128u) >> 32);  // SBO = one halo row
-      if (p.wres && t_begin < t_end) {
-        mbar_wait_warp(fullB(0), 0);   // the resident weights have landed (both CTAs' halves in pair mode)
-        tc_fence_after();
-      }
-      for (int tt = t_begin; tt < t_end; tt += t_step) {
-        mbar_wait_warp(tempty_bar(acc), acc_phase ^ 1u);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccStride;
-        uint32_t accumulate = 0;
-        for (int kc = 0; kc < p.k_chunks; ++kc) {
-          mbar_wait_warp(fullA(sa), pa);
-          if (leader) TL_STAMP(1, tl_n);
-          const uint32_t a16 = lo_const | ((smem_base + (uint32_t)sa * p.a_stage_bytes) >> 4);
-          const int nm = (kc == p.k_chunks - 1) ? p.last_mmas : 4;
-          if (p.wres) {
-            // 9 taps x nm MMAs back to back against the resident weights: one wait and one commit per K chunk
-            tc_fence_after();
-            uint32_t a_rw = a16;
-            uint32_t b_lo = lo_const | ((b_ring + (uint32_t)(kc * 3) * bs_bytes) >> 4);
+    // ONE elected thread runs the issue loop.  A single thread retires a dependent instruction every ~4 clocks, so the
+    // loop must stay lean: an M=128 x N~112 MMA occupies the tensor pipe for ~60 clocks, and the earlier convergent /
+    // predicated form of this loop (22 instructions per MMA: vote, predicate and R2UR traffic) measured 85-99 clocks per
+    // MMA on the 100-channel layers (profiles/r02_conv_timeline.txt) - the issue thread, not the pipe, set the pace.
+    // Here every tap is straight-line code (template NM = MMAs per tap), descriptor words advance by immediates, and
+    // only the first MMA of a group carries a run-time accumulate flag.
+    if (elect_one()) {
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      const uint32_t lo_const = 1u << 16;  // LBO field (unused for K-major swizzled operands)
+      const uint32_t hiB = (uint32_t)(make_smem_desc(0, 0, 1024) >> 32);
+      const uint32_t idesc = p.idesc;
+      auto commit = [&](uint32_t bar) {
+        if (kPair) umma2_commit(bar); else umma_commit(bar);
+      };
+      [[maybe_unused]] int tl_n = 0, tl_c = 0;
+      if (p.halo) {
+        int sa = 0, sb = 0;
+        uint32_t pa = 0, pb = 0;
+        const uint32_t b_ring = smem_base + (uint32_t)p.SA * p.a_stage_bytes;
+        const uint32_t hiA = (uint32_t)(make_smem_desc(0, 0, (uint32_t)p.hw * 128u) >> 32);  // SBO = one halo row
+        const uint32_t b_step = b_bytes >> 4;           // one tap's weight block, in descriptor units
+        const uint32_t a_rstep = (uint32_t)p.hw * 8u;   // one halo row
+        if (p.wres && t_begin < t_end) {
+          mbar_wait(fullB(0), 0);   // the resident weights have landed (both CTAs' halves in pair mode)
+          tc_fence_after();
+        }
+        for (int tt = t_begin; tt < t_end; tt += t_step) {
+          mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccStride;
+          uint32_t accumulate = 0;
+          for (int kc = 0; kc < p.k_chunks; ++kc) {
+            mbar_wait(fullA(sa), pa);
+            TL_STAMP(1, tl_n);
+            const uint32_t a16 = lo_const | ((smem_base + (uint32_t)sa * p.a_stage_bytes) >> 4);
+            const int nm = (kc == p.k_chunks - 1) ? p.last_mmas : 4;
+            if (p.wres) {
+              // 9 taps x nm MMAs back to back against the resident weights: one wait and one commit per K chunk
+              tc_fence_after();
+              const uint32_t b_lo = lo_const | ((b_ring + (uint32_t)(kc * 3) * bs_bytes) >> 4);
+              switch (nm) {
+                case 4: issue_3x3<4, kPair>(d_tmem, a16, hiA, a_rstep, b_lo, hiB, b_step, idesc, accumulate); break;
+                case 3: issue_3x3<3, kPair>(d_tmem, a16, hiA, a_rstep, b_lo, hiB, b_step, idesc, accumulate); break;
+                case 2: issue_3x3<2, kPair>(d_tmem, a16, hiA, a_rstep, b_lo, hiB, b_step, idesc, accumulate); break;
+                default: issue_3x3<1, kPair>(d_tmem, a16, hiA, a_rstep, b_lo, hiB, b_step, idesc, accumulate); break;
+              }
+              accumulate = 1;
+              commit(emptyA(sa));
+              if (++sa == p.SA) { sa = 0; pa ^= 1u; }
+              continue;
+            }
+            // halo mode is always the 3x3 pattern: tap (r,s) reads the halo tile from pixel row r*(tw+2) + s
+            // (8 x 16-byte units per 128-byte pixel row): plain adds, no table lookups on the issue path
+            uint32_t a_row = a16;
 #pragma unroll 1
             for (int r = 0; r < 3; ++r) {
-              uint32_t a_lo = a_rw;
+              if (p.rowmode) {
+                // one barrier per filter row: 3 taps x nm MMAs between a wait and a commit
+                mbar_wait(fullB(sb), pb);
+                tc_fence_after();
+                const uint32_t b_lo = lo_const | ((b_ring + (uint32_t)sb * bs_bytes) >> 4);
+                switch (nm) {
+                  case 4: issue_row<4, kPair>(d_tmem, a_row, hiA, b_lo, hiB, b_step, idesc, accumulate); break;
+                  case 3: issue_row<3, kPair>(d_tmem, a_row, hiA, b_lo, hiB, b_step, idesc, accumulate); break;
+                  case 2: issue_row<2, kPair>(d_tmem, a_row, hiA, b_lo, hiB, b_step, idesc, accumulate); break;
+                  default: issue_row<1, kPair>(d_tmem, a_row, hiA, b_lo, hiB, b_step, idesc, accumulate); break;
+                }
+                accumulate = 1;
+                commit(emptyB(sb));
+                if (++sb == p.SB) { sb = 0; pb ^= 1u; }
+                a_row += a_rstep;
+                continue;
+              }
+              uint32_t a_lo = a_row;
 #pragma unroll 1
               for (int sx = 0; sx < 3; ++sx) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  if (k < nm) {
-                    mma(d_tmem, a_lo + 2u * k, hiA, b_lo + 2u * k, hiB, accumulate);
-                    accumulate = 1;
-                  }
-                }
+                mbar_wait(fullB(sb), pb);
+                tc_fence_after();
+                const uint32_t b_lo = lo_const | ((b_ring + (uint32_t)sb * b_bytes) >> 4);
+                // 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+                issue_tap_n<kPair>(nm, d_tmem, a_lo, hiA, b_lo, hiB, idesc, accumulate);
+                accumulate = 1;
+                commit(emptyB(sb));
+                if (++sb == p.SB) { sb = 0; pb ^= 1u; }
                 a_lo += 8u;
-                b_lo += b_bytes >> 4;
               }
-              a_rw += (uint32_t)p.hw * 8u;
+              a_row += a_rstep;
             }
             commit(emptyA(sa));
             if (++sa == p.SA) { sa = 0; pa ^= 1u; }
-            continue;
           }
-          // halo mode is always the 3x3 pattern: tap (r,s) reads the halo tile from pixel row r*(tw+2) + s
-          // (8 x 16-byte units per 128-byte pixel row): plain adds, no table lookups on the issue path
-          uint32_t a_row = a16;
-#pragma unroll 1
-          for (int r = 0; r < 3; ++r) {
-            uint32_t a_lo = a_row;
-            if (p.rowmode) {
-              // one barrier per filter row: 3 taps x nm MMAs between a wait and a commit
-              mbar_wait_warp(fullB(sb), pb);
-              tc_fence_after();
-              uint32_t b_lo = lo_const | ((b_ring + (uint32_t)sb * bs_bytes) >> 4);
-#pragma unroll 1
-              for (int sx = 0; sx < 3; ++sx) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  if (k < nm) {
-                    mma(d_tmem, a_lo + 2u * k, hiA, b_lo + 2u * k, hiB, accumulate);
-                    accumulate = 1;
-                  }
-                }
-                a_lo += 8u;
-                b_lo += b_bytes >> 4;
-              }
-              commit(emptyB(sb));
-              if (++sb == p.SB) { sb = 0; pb ^= 1u; }
-              a_row += (uint32_t)p.hw * 8u;
-              continue;
-            }
-#pragma unroll 1
-            for (int sx = 0; sx < 3; ++sx) {
-              mbar_wait_warp(fullB(sb), pb);
-              tc_fence_after();
-              const uint32_t b_lo = lo_const | ((b_ring + (uint32_t)sb * b_bytes) >> 4);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                if (k < nm) {
-                  // 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-                  mma(d_tmem, a_lo + 2u * k, hiA, b_lo + 2u * k, hiB, accumulate);
-                  accumulate = 1;
-                }
-              }
-              commit(emptyB(sb));
-              if (++sb == p.SB) { sb = 0; pb ^= 1u; }
-              a_lo += 8u;
-            }
-            a_row += (uint32_t)p.hw * 8u;
-          }
-          commit(emptyA(sa));
-          if (++sa == p.SA) { sa = 0; pa ^= 1u; }
+          commit(tfull_bar(acc));
+          TL_STAMP(2, tl_c);
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1u;
         }
-        commit(tfull_bar(acc));
-        if (leader) TL_STAMP(2, tl_c);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
-      }
-    } else {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tt = t_begin; tt < t_end; tt += t_step) {
-        mbar_wait_warp(tempty_bar(acc), acc_phase ^ 1u);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccStride;
-        uint32_t accumulate = 0;
-        for (int t = 0; t < p.num_taps; ++t) {
-          for (int kc = 0; kc < p.k_chunks; ++kc) {
-            mbar_wait_warp(full_bar(stage), phase);
-            tc_fence_after();
-            const uint32_t a_addr = smem_base + (uint32_t)stage * stage_bytes;
-            const uint32_t a_lo = lo_const | (a_addr >> 4), b_lo = lo_const | ((a_addr + kABytes) >> 4);
-            const int nm = (kc == p.k_chunks - 1) ? p.last_mmas : 4;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (k < nm) {
-                mma(d_tmem, a_lo + 2u * k, hiB, b_lo + 2u * k, hiB, accumulate);
-                accumulate = 1;
-              }
+      } else {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tt = t_begin; tt < t_end; tt += t_step) {
+          mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccStride;
+          uint32_t accumulate = 0;
+          for (int t = 0; t < p.num_taps; ++t) {
+            for (int kc = 0; kc < p.k_chunks; ++kc) {
+              mbar_wait(full_bar(stage), phase);
+              tc_fence_after();
+              const uint32_t a_addr = smem_base + (uint32_t)stage * stage_bytes;
+              const uint32_t a_lo = lo_const | (a_addr >> 4), b_lo = lo_const | ((a_addr + kABytes) >> 4);
+              const int nm = (kc == p.k_chunks - 1) ? p.last_mmas : 4;
+              issue_tap_n<kPair>(nm, d_tmem, a_lo, hiB, b_lo, hiB, idesc, accumulate);
+              accumulate = 1;
+              commit(empty_bar(stage));
+              if (++stage == S) { stage = 0; phase ^= 1u; }
             }
-            commit(empty_bar(stage));
-            if (++stage == S) { stage = 0; phase ^= 1u; }
           }
+          commit(tfull_bar(acc));
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1u;
         }
-        commit(tfull_bar(acc));
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
       }
     }
   } else if (warp >= 4) {

@@ -409,10 +409,24 @@ __global__ void pointwise_smallk_kernel(const __nv_bfloat16* __restrict__ a, int
 }
 
 // ------------------------------------------------------------------------------------------------ layout casts
-// NCHW (fp32, or uint8 divided by 255) -> NHWC bf16 with pitch ld at channel offset ch_off; remaining lanes of the
-// 8-channel group(s) touched are zeroed when zero_pad is set.
-__global__ void nchw_to_nhwc_kernel(const void* __restrict__ x, int is_u8, __nv_bfloat16* __restrict__ y, int N, int C,
-                                    int H, int W, int ld, int ch_off, int Cw) {
+// raw band value -> the network's input value: the reference reads every GeoTIFF dtype as int32 -> float32
+// (data.py:24), divides 16-bit datasets by 255 inside its batch transform (utils.py:248-249, 288-289) and by 255 again
+// in fastai's IntToFloatTensor; 8-bit datasets see the second division only.  Two true fp32 divisions, as torch does.
+__device__ __forceinline__ float load_raw(const void* __restrict__ x, int dtype, long long i, float div, float div2) {
+  float v;
+  switch (dtype) {
+    case B2U_DT_U8: v = (float)reinterpret_cast<const uint8_t*>(x)[i]; break;
+    case B2U_DT_U16: v = (float)reinterpret_cast<const uint16_t*>(x)[i]; break;
+    case B2U_DT_I16: v = (float)reinterpret_cast<const int16_t*>(x)[i]; break;
+    default: v = reinterpret_cast<const float*>(x)[i]; break;
+  }
+  return (v / div) / div2;
+}
+
+// NCHW (fp32 / uint8 / uint16 / int16, divided by div and div2) -> NHWC bf16 with pitch ld at channel offset ch_off;
+// remaining lanes of the 8-channel group(s) touched are zeroed when zero_pad is set.
+__global__ void nchw_to_nhwc_kernel(const void* __restrict__ x, int dtype, float div, float div2,
+                                    __nv_bfloat16* __restrict__ y, int N, int C, int H, int W, int ld, int ch_off, int Cw) {
   pdl_enter();
   const long long HW = (long long)H * W;
   const long long total = (long long)N * HW;
@@ -427,8 +441,7 @@ __global__ void nchw_to_nhwc_kernel(const void* __restrict__ x, int is_u8, __nv_
         v[k] = 0.f;
         if (c < C) {
           const long long src = (n * C + c) * HW + hw;
-          v[k] = is_u8 ? (float)reinterpret_cast<const uint8_t*>(x)[src] / 255.f
-                       : reinterpret_cast<const float*>(x)[src];
+          v[k] = load_raw(x, dtype, src, div, div2);
         }
       }
       if (c0 + 8 <= Cw && (((ch_off + c0) & 7) == 0)) {
@@ -443,8 +456,8 @@ __global__ void nchw_to_nhwc_kernel(const void* __restrict__ x, int is_u8, __nv_
   }
 }
 
-// tile t = raster[:, y0[t]:y0[t]+P, x0[t]:x0[t]+P] / 255 -> bf16 NHWC [T,P,P,ld] (crop + IntToFloatTensor + layout cast)
-__global__ void crop_tiles_kernel(const uint8_t* __restrict__ raster, int C, long long Y, long long X,
+// tile t = raster[:, y0[t]:y0[t]+P, x0[t]:x0[t]+P] / div / div2 -> bf16 NHWC [T,P,P,ld] (crop + input contract + layout cast)
+__global__ void crop_tiles_kernel(const void* __restrict__ raster, int dtype, float div, float div2, int C, long long Y, long long X,
                                   const int* __restrict__ ty0, const int* __restrict__ tx0, int T, int P,
                                   __nv_bfloat16* __restrict__ out, int ld) {
   pdl_enter();
@@ -458,7 +471,7 @@ __global__ void crop_tiles_kernel(const uint8_t* __restrict__ raster, int C, lon
     __nv_bfloat16* dst = out + i * ld;
     for (int c = 0; c < ld; ++c) {
       float v = 0.f;
-      if (c < C && inb) v = (float)raster[((long long)c * Y + gy) * X + gx] / 255.f;
+      if (c < C && inb) v = load_raw(raster, dtype, ((long long)c * Y + gy) * X + gx, div, div2);
       dst[c] = __float2bfloat16_rn(v);
     }
   }
@@ -586,6 +599,112 @@ __global__ void ce_finalize_kernel(const float* loss_partial, int rows, const fl
   }
 }
 
+// MSELossFlat(axis=1) of the regression variant (train.py:189-192): loss = mean_p (pred_p - target_p)^2 over the
+// flattened batch; dpred = grad_scale * 2 (pred - target) / P.  pred is lane 0 of the fp32 head output.
+__global__ void mse_fwd_bwd_kernel(const float* __restrict__ pred, int ld, const float* __restrict__ target, long long P,
+                                   __nv_bfloat16* __restrict__ dpred, int ldg, float* __restrict__ loss_partial,
+                                   float grad_scale) {
+  pdl_enter();
+  __shared__ float sh[32];
+  float acc = 0.f;
+  const float gs = grad_scale * 2.f / (float)P;
+  const long long per = (P + gridDim.x - 1) / gridDim.x;
+  const long long p0 = (long long)blockIdx.x * per, p1 = min(P, p0 + per);
+  for (long long p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
+    const float d = pred[p * ld] - target[p];
+    acc += d * d;
+    if (dpred) {
+      uint4 u = make_uint4(pack_bf16x2(gs * d, 0.f), 0u, 0u, 0u);
+      for (int c0 = 0; c0 < ldg; c0 += 8) {
+        *reinterpret_cast<uint4*>(dpred + p * ldg + c0) = u;
+        u.x = 0u;
+      }
+    }
+  }
+  const float r = block_sum(acc, sh);
+  if (threadIdx.x == 0) loss_partial[blockIdx.x] = r;
+}
+
+__global__ void mse_finalize_kernel(const float* loss_partial, int rows, long long P, float* loss) {
+  pdl_enter();
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double l = 0;
+    for (int i = 0; i < rows; ++i) l += loss_partial[i];
+    loss[0] = (float)(l / (double)P);
+  }
+}
+
+// validation sums of the regression metrics (fastai rmse, R2Score; train.py:190): sums[0..3] += {sum (p-t)^2, sum t,
+// sum t^2, n} in double.  Block partials are combined by the last block in block order (fixed order: deterministic).
+__global__ void regression_sums_kernel(const float* __restrict__ pred, int ld, const float* __restrict__ target,
+                                       long long P, double* __restrict__ partial, double* __restrict__ sums,
+                                       unsigned int* __restrict__ ticket) {
+  pdl_enter();
+  __shared__ double sh[3][8];
+  __shared__ bool last;
+  double a = 0, b = 0, c = 0;
+  const long long per = (P + gridDim.x - 1) / gridDim.x;
+  const long long p0 = (long long)blockIdx.x * per, p1 = min(P, p0 + per);
+  for (long long p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
+    const double t = target[p], d = (double)pred[p * ld] - t;
+    a += d * d; b += t; c += t * t;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); c += __shfl_xor_sync(0xffffffffu, c, o);
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { sh[0][w] = a; sh[1][w] = b; sh[2][w] = c; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ra = 0, rb = 0, rc = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { ra += sh[0][i]; rb += sh[1][i]; rc += sh[2][i]; }
+    partial[blockIdx.x * 3 + 0] = ra; partial[blockIdx.x * 3 + 1] = rb; partial[blockIdx.x * 3 + 2] = rc;
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    if (last) {
+      __threadfence();
+      double s0 = 0, s1 = 0, s2 = 0;
+      for (unsigned i = 0; i < gridDim.x; ++i) {
+        s0 += __ldcg(partial + i * 3); s1 += __ldcg(partial + i * 3 + 1); s2 += __ldcg(partial + i * 3 + 2);
+      }
+      sums[0] += s0; sums[1] += s1; sums[2] += s2; sums[3] += (double)P;
+      *ticket = 0u;
+    }
+  }
+}
+
+// DiceMulti counts (fastai metrics.py, reached from train.py:196): prediction = argmax_c logits (first maximum wins, as
+// torch.argmax); counts[c] += #(pred == c & target == c), counts[C + c] += #(pred == c), counts[2C + c] += #(target == c).
+// Integer atomics: the result does not depend on scheduling.
+template <int MAXC>
+__global__ void dice_counts_kernel(const float* __restrict__ logits, int ld, const uint8_t* __restrict__ labels,
+                                   long long P, int C, unsigned long long* __restrict__ counts) {
+  pdl_enter();
+  __shared__ unsigned int sc[3 * MAXC];
+  for (int i = threadIdx.x; i < 3 * MAXC; i += blockDim.x) sc[i] = 0u;
+  __syncthreads();
+  // a block handles at most 2^31 pixels between flushes: 32-bit shared counters cannot overflow
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+    const float* z = logits + p * ld;
+    int best = 0;
+    float bv = z[0];
+#pragma unroll
+    for (int c = 1; c < MAXC; ++c)
+      if (c < C) { const float v = z[c]; if (v > bv) { bv = v; best = c; } }
+    const int y = labels[p];
+    atomicAdd(&sc[MAXC + best], 1u);
+    if (y < C) {
+      atomicAdd(&sc[2 * MAXC + y], 1u);
+      if (y == best) atomicAdd(&sc[y], 1u);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * MAXC; i += blockDim.x) {
+    const int k = i / MAXC, c = i - k * MAXC;
+    if (c < C && sc[i]) atomicAdd(&counts[k * C + c], (unsigned long long)sc[i]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ optimizers
 __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, long long n, float lr, float gs) {
   pdl_enter();
@@ -626,7 +745,7 @@ __global__ void stitch_accumulate_kernel(const float* __restrict__ logits, int l
                                          const int* __restrict__ ty0, const int* __restrict__ tx0,
                                          const int* __restrict__ sel, int n_sel, float* __restrict__ acc,
                                          uint8_t* __restrict__ cnt, long long Y, long long X, long long y_off,
-                                         long long x_off, float quant) {
+                                         long long x_off, float quant, int raw) {
   pdl_enter();
   const long long per_tile = (long long)th * tw;
   const int nt = sel ? n_sel : T;
@@ -639,6 +758,13 @@ __global__ void stitch_accumulate_kernel(const float* __restrict__ logits, int l
     const long long gy = (long long)ty0[t] + yy - y_off, gx = (long long)tx0[t] + xx - x_off;
     if (gy < 0 || gy >= Y || gx < 0 || gx >= X) continue;
     const float* z = logits + ((long long)t * per_tile + r) * ld;
+    const long long o = gy * X + gx;
+    if (raw) {
+      // regression merge (predict.py:196-198, 300-302): the network output itself is summed, no softmax
+      for (int c = 0; c < C; ++c) acc[(long long)c * Y * X + o] += z[c];
+      cnt[o] += 1;
+      continue;
+    }
     float e[MAXC];
     float m = -INFINITY;
 #pragma unroll
@@ -653,7 +779,6 @@ __global__ void stitch_accumulate_kernel(const float* __restrict__ logits, int l
       se += e[c];
     }
     const float inv = 1.f / se;
-    const long long o = gy * X + gx;
 #pragma unroll
     for (int c = 0; c < MAXC; ++c)
       if (c < C) {
@@ -681,6 +806,17 @@ __global__ void stitch_finalize_kernel(const float* __restrict__ acc, const uint
       }
     }
     mask[i] = (uint8_t)best;
+  }
+}
+
+// averaged values of the merge: out[c][i] = acc[c][i] / cnt[i] where tiles were placed, else `nodata` (regression:
+// predict.py:307-316 with nodata -9999; averaged class probabilities of `all_classes` / `specific_class`: nodata 0)
+__global__ void stitch_finalize_mean_kernel(const float* __restrict__ acc, const uint8_t* __restrict__ cnt, int C,
+                                            long long YX, float nodata, float* __restrict__ out) {
+  pdl_enter();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < YX; i += (long long)gridDim.x * blockDim.x) {
+    const int n = cnt[i];
+    for (int c = 0; c < C; ++c) out[(long long)c * YX + i] = n > 0 ? acc[(long long)c * YX + i] / (float)n : nodata;
   }
 }
 
@@ -860,21 +996,27 @@ extern "C" int b2u_pointwise_smallk(const void* a, int32_t lda, int32_t K, const
   return B2U_OK;
 }
 
-extern "C" int b2u_nchw_to_nhwc(const void* x, int32_t x_is_u8, void* y, int32_t N, int32_t C, int32_t H, int32_t W,
-                                int32_t ld, int32_t ch_off, int32_t write_c, void* stream) {
+extern "C" int b2u_nchw_to_nhwc(const void* x, int32_t x_dtype, float div, float div2, void* y, int32_t N, int32_t C,
+                                int32_t H, int32_t W, int32_t ld, int32_t ch_off, int32_t write_c, void* stream) {
   B2U_CHECK_ARG(x && y && C > 0 && write_c >= C && ch_off + write_c <= ld, "nchw_to_nhwc: bad argument");
+  B2U_CHECK_ARG(x_dtype >= B2U_DT_F32 && x_dtype <= B2U_DT_I16 && div != 0.f && div2 != 0.f,
+                "nchw_to_nhwc: x_dtype=%d (0 f32, 1 u8, 2 u16, 3 i16) / divisors invalid", x_dtype);
   const long long items = (long long)N * H * W;
-  launch_k(nchw_to_nhwc_kernel, dim3(grid_for(items, 256)), dim3(256), 0, (cudaStream_t)stream, x, x_is_u8, (bf)y, N, C, H, W, ld, ch_off,
-                                                                            write_c);
+  launch_k(nchw_to_nhwc_kernel, dim3(grid_for(items, 256)), dim3(256), 0, (cudaStream_t)stream, x, x_dtype, div, div2, (bf)y, N, C, H, W,
+           ld, ch_off, write_c);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }
 
-extern "C" int b2u_crop_tiles(const uint8_t* raster, int32_t C, int64_t Y, int64_t X, const int32_t* y0,
-                              const int32_t* x0, int32_t T, int32_t P, void* out, int32_t ld, void* stream) {
+extern "C" int b2u_crop_tiles(const void* raster, int32_t r_dtype, float div, float div2, int32_t C, int64_t Y, int64_t X,
+                              const int32_t* y0, const int32_t* x0, int32_t T, int32_t P, void* out, int32_t ld,
+                              void* stream) {
   B2U_CHECK_ARG(raster && y0 && x0 && out && C > 0 && C <= ld && T > 0 && P > 0, "crop_tiles: bad argument");
+  B2U_CHECK_ARG(r_dtype >= B2U_DT_F32 && r_dtype <= B2U_DT_I16 && div != 0.f && div2 != 0.f,
+                "crop_tiles: r_dtype=%d (0 f32, 1 u8, 2 u16, 3 i16) / divisors invalid", r_dtype);
   const long long items = (long long)T * P * P;
-  launch_k(crop_tiles_kernel, dim3(grid_for(items, 256)), dim3(256), 0, (cudaStream_t)stream, raster, C, Y, X, y0, x0, T, P, (bf)out, ld);
+  launch_k(crop_tiles_kernel, dim3(grid_for(items, 256)), dim3(256), 0, (cudaStream_t)stream, raster, r_dtype, div, div2, C, Y, X, y0,
+           x0, T, P, (bf)out, ld);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }
@@ -921,6 +1063,46 @@ extern "C" int b2u_ce_finalize(const float* loss_partial, int32_t rows, const fl
   return B2U_OK;
 }
 
+extern "C" int b2u_mse_fwd_bwd(const float* pred, int32_t ld, const float* target, int64_t P, void* dpred, int32_t ldg,
+                               float* loss_partial, int32_t rows, float grad_scale, void* stream) {
+  B2U_CHECK_ARG(pred && target && loss_partial && rows > 0 && P > 0 && ld >= 1, "mse_fwd_bwd: bad argument");
+  B2U_CHECK_ARG(!dpred || (ldg >= 8 && ldg % 8 == 0), "mse_fwd_bwd: ldg=%d must be a positive multiple of 8", ldg);
+  launch_k(mse_fwd_bwd_kernel, dim3(rows), dim3(256), 0, (cudaStream_t)stream, pred, ld, target, (long long)P, (bf)dpred, ldg,
+           loss_partial, grad_scale);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" int b2u_mse_finalize(const float* loss_partial, int32_t rows, int64_t P, float* loss, void* stream) {
+  B2U_CHECK_ARG(loss_partial && loss && rows > 0 && P > 0, "mse_finalize: bad argument");
+  launch_k(mse_finalize_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, loss_partial, rows, (long long)P, loss);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" int b2u_regression_sums(const float* pred, int32_t ld, const float* target, int64_t P, double* partial,
+                                   int32_t rows, double* sums, uint32_t* ticket, void* stream) {
+  B2U_CHECK_ARG(pred && target && partial && sums && ticket && rows > 0 && P > 0 && ld >= 1, "regression_sums: bad argument");
+  launch_k(regression_sums_kernel, dim3(rows), dim3(256), 0, (cudaStream_t)stream, pred, ld, target, (long long)P, partial, sums,
+           ticket);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" int b2u_dice_counts(const float* logits, int32_t ld, const uint8_t* labels, int64_t P, int32_t C,
+                               uint64_t* counts, void* stream) {
+  B2U_CHECK_ARG(logits && labels && counts && P > 0 && C >= 1 && C <= 32 && C <= ld, "dice_counts: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C <= 8)
+    launch_k(dice_counts_kernel<8>, dim3(grid_for(P, 256)), dim3(256), 0, st, logits, ld, labels, (long long)P, C,
+             (unsigned long long*)counts);
+  else
+    launch_k(dice_counts_kernel<32>, dim3(grid_for(P, 256)), dim3(256), 0, st, logits, ld, labels, (long long)P, C,
+             (unsigned long long*)counts);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
 extern "C" int b2u_sgd_step(float* p, const float* g, int64_t n, float lr, float grad_scale, void* stream) {
   B2U_CHECK_ARG(p && g && n > 0, "sgd_step: bad argument");
   launch_k(sgd_kernel, dim3(grid_for(n, 256)), dim3(256), 0, (cudaStream_t)stream, p, g, n, lr, grad_scale);
@@ -942,7 +1124,7 @@ extern "C" int b2u_adam_step(float* p, const float* g, float* m, float* v, int64
 static int stitch_accumulate_impl(const float* logits, int32_t ld, int32_t C, int32_t T, int32_t th, int32_t tw,
                                   const int32_t* y0, const int32_t* x0, const int32_t* sel, int32_t n_sel, float* acc,
                                   uint8_t* cnt, int64_t Y, int64_t X, int64_t y_off, int64_t x_off, float quant,
-                                  void* stream) {
+                                  int raw, void* stream) {
   B2U_CHECK_ARG(logits && y0 && x0 && acc && cnt && C >= 1 && C <= 32 && C <= ld, "stitch_accumulate: bad argument");
   const int nt = sel ? n_sel : T;
   if (nt <= 0) return B2U_OK;
@@ -950,10 +1132,10 @@ static int stitch_accumulate_impl(const float* logits, int32_t ld, int32_t C, in
   cudaStream_t st = (cudaStream_t)stream;
   if (C <= 8)
     launch_k(stitch_accumulate_kernel<8>, dim3(grid_for(items, 256)), dim3(256), 0, st, logits, ld, C, T, th, tw, y0, x0,
-             sel, n_sel, acc, cnt, Y, X, y_off, x_off, quant);
+             sel, n_sel, acc, cnt, Y, X, y_off, x_off, quant, raw);
   else
     launch_k(stitch_accumulate_kernel<32>, dim3(grid_for(items, 256)), dim3(256), 0, st, logits, ld, C, T, th, tw, y0, x0,
-             sel, n_sel, acc, cnt, Y, X, y_off, x_off, quant);
+             sel, n_sel, acc, cnt, Y, X, y_off, x_off, quant, raw);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }
@@ -962,14 +1144,30 @@ extern "C" int b2u_stitch_accumulate(const float* logits, int32_t ld, int32_t C,
                                      const int32_t* y0, const int32_t* x0, const int32_t* sel, int32_t n_sel,
                                      float* acc, uint8_t* cnt, int64_t Y, int64_t X, int64_t y_off, int64_t x_off,
                                      void* stream) {
-  return stitch_accumulate_impl(logits, ld, C, T, th, tw, y0, x0, sel, n_sel, acc, cnt, Y, X, y_off, x_off, 0.f, stream);
+  return stitch_accumulate_impl(logits, ld, C, T, th, tw, y0, x0, sel, n_sel, acc, cnt, Y, X, y_off, x_off, 0.f, 0, stream);
+}
+
+extern "C" int b2u_stitch_accumulate_raw(const float* logits, int32_t ld, int32_t C, int32_t T, int32_t th, int32_t tw,
+                                         const int32_t* y0, const int32_t* x0, const int32_t* sel, int32_t n_sel,
+                                         float* acc, uint8_t* cnt, int64_t Y, int64_t X, int64_t y_off, int64_t x_off,
+                                         void* stream) {
+  return stitch_accumulate_impl(logits, ld, C, T, th, tw, y0, x0, sel, n_sel, acc, cnt, Y, X, y_off, x_off, 0.f, 1, stream);
+}
+
+extern "C" int b2u_stitch_finalize_mean(const float* acc, const uint8_t* cnt, int32_t C, int64_t Y, int64_t X,
+                                        float nodata, float* out, void* stream) {
+  B2U_CHECK_ARG(acc && cnt && out && C >= 1, "stitch_finalize_mean: bad argument");
+  launch_k(stitch_finalize_mean_kernel, dim3(grid_for(Y * X, 256)), dim3(256), 0, (cudaStream_t)stream, acc, cnt, C, (long long)(Y * X),
+           nodata, out);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
 }
 
 extern "C" int b2u_stitch_accumulate_q31(const float* logits, int32_t ld, int32_t C, int32_t T, int32_t th, int32_t tw,
                                          const int32_t* y0, const int32_t* x0, const int32_t* sel, int32_t n_sel,
                                          float* acc, uint8_t* cnt, int64_t Y, int64_t X, int64_t y_off, int64_t x_off,
                                          void* stream) {
-  return stitch_accumulate_impl(logits, ld, C, T, th, tw, y0, x0, sel, n_sel, acc, cnt, Y, X, y_off, x_off, 31.f, stream);
+  return stitch_accumulate_impl(logits, ld, C, T, th, tw, y0, x0, sel, n_sel, acc, cnt, Y, X, y_off, x_off, 31.f, 0, stream);
 }
 
 extern "C" int b2u_stitch_finalize(const float* acc, const uint8_t* cnt, int32_t C, int64_t Y, int64_t X, uint8_t* mask,

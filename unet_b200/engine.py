@@ -32,14 +32,15 @@ def one_cycle(pct: float, lr_max: float, div: float = 25.0, div_final: float = 1
 
 class Trainer:
     def __init__(self, net: UNetB200, optimizer: str = "sgd", lr: float = 1e-3, wd: float = 0.01,
-                 encoder_factor: float = 10.0, use_graph: bool = True, bucket_mb: float = 32.0):
+                 encoder_factor: float = 10.0, use_graph: bool = True, bucket_mb: float = 32.0,
+                 input_dtype: torch.dtype = torch.uint8):
         assert net.training
         self.net, self.lr, self.optimizer = net, lr, optimizer.lower()
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.use_graph = use_graph
         dev = net.device
         N, C, H, W = net.N, net.n_in, net.H, net.W
-        self.x_static = torch.zeros((N, C, H, W), dtype=torch.uint8, device=dev)
+        self.x_static = torch.zeros((N, C, H, W), dtype=input_dtype, device=dev)   # raw band values (A0 input contract)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self._copy_stream: Optional[torch.cuda.Stream] = None
         self._prefetched = None
@@ -195,7 +196,8 @@ class Trainer:
             self._stage_free.record(st)          # the staging buffers may be overwritten once these copies are done
         else:
             self.x_static.copy_(x, non_blocking=True)
-            self.net.labels.copy_(y if y.dtype == torch.uint8 else y.to(torch.uint8), non_blocking=True)
+            ld = self.net.labels.dtype
+            self.net.labels.copy_(y if y.dtype == ld else y.to(ld), non_blocking=True)
         self._prefetched = None
 
     def _prefetch(self, x: torch.Tensor, y: torch.Tensor) -> None:
@@ -209,14 +211,15 @@ class Trainer:
             cs.wait_event(self._stage_free)      # NOT the compute stream as a whole: the copy must overlap this step
         with torch.cuda.stream(cs):
             self._x_stage.copy_(x, non_blocking=True)
-            self._y_stage.copy_(y if y.dtype == torch.uint8 else y.to(torch.uint8), non_blocking=True)
+            self._y_stage.copy_(y if y.dtype == self._y_stage.dtype else y.to(self._y_stage.dtype), non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(cs)
         self._prefetched = (x, y, ev)
 
     def step(self, x: torch.Tensor, y: torch.Tensor,
              prefetch: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> torch.Tensor:
-        """x: uint8 [N,C,H,W] (host pinned or device), y: uint8/int64 [N,H,W]. Returns the device loss scalar of this
+        """x: raw band values [N,C,H,W] of the trainer's `input_dtype` (uint8; uint16 / int16 for 16-bit imagery), host
+        pinned or device; y: uint8/int64 class ids [N,H,W] (float32 targets for the regression variant). Returns the device loss scalar of this
         step (mean over the local batch, before the parameter update).  `prefetch=(x_next, y_next)` starts the
         host-to-device copy of the next batch behind this step's kernels; pass the same tensor objects to the next call."""
         if self.use_graph and self.graph is None:

@@ -31,6 +31,30 @@ BN_MOMENTUM = 0.1
 STATS_ROWS = 592  # block partial rows of the standalone reductions (4 per SM)
 
 
+_RAW_DTYPES = {torch.float32: _lib.DT_F32, torch.uint8: _lib.DT_U8, torch.uint16: _lib.DT_U16, torch.int16: _lib.DT_I16}
+
+
+def input_contract(dtype: torch.dtype, input_div: Tuple[float, float]) -> Tuple[int, float, float]:
+    """(b2u dtype code, div, div2) of the reference's input contract: every GeoTIFF dtype is read
+    as int32 -> float32 (data.py:24); a dataset whose values exceed 8 bits ('int16', utils.py:72-89) is divided by 255
+    inside the reference's batch transform (utils.py:248-249, 288-289) and fastai's IntToFloatTensor divides by 255
+    once more (MaskBlock, data.py:100); the regression variant has no IntToFloatTensor (RegressionBlock, data.py:98).
+    `input_div` is the plan's (div, div2) for RAW integer tiles; fp32 input is taken as already scaled."""
+    if dtype not in _RAW_DTYPES:
+        raise TypeError(f"tiles must be float32, uint8, uint16 or int16, got {dtype}")
+    if dtype == torch.float32:
+        return _lib.DT_F32, 1.0, 1.0
+    return _RAW_DTYPES[dtype], float(input_div[0]), float(input_div[1])
+
+
+def input_divisors(sixteen_bit: bool, regression: bool = False) -> Tuple[float, float]:
+    """the (div, div2) pair of a dataset: 8-bit classification 255 / 1, 16-bit classification 255 / 255, regression
+    1 / 1 (8-bit) or 255 / 1 (16-bit: only the batch transform's division remains)"""
+    if regression:
+        return (255.0, 1.0) if sixteen_bit else (1.0, 1.0)
+    return (255.0, 255.0) if sixteen_bit else (255.0, 1.0)
+
+
 class Act:
     """An NHWC bf16 activation and (lazily) its gradient."""
 
@@ -77,13 +101,18 @@ class UNetB200:
 
     def __init__(self, arch: str = "xresnet34", n_in: int = 4, n_out: int = 2, size: Tuple[int, int] = (256, 256),
                  batch: int = 8, training: bool = True, device: Optional[torch.device] = None,
-                 class_weights: Optional[Sequence[float]] = None, self_attention: bool = False):
+                 class_weights: Optional[Sequence[float]] = None, self_attention: bool = False,
+                 input_div: Tuple[float, float] = (255.0, 1.0), regression: bool = False):
         if not torch.cuda.is_available():
             raise _lib.B2UError("UNetB200 needs a CUDA device (sm_100a); there is no CPU path")
         self.lib = _lib.load()
         _lib.check(self.lib.b2u_device_check(), "b2u_device_check")
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.self_attention = bool(self_attention)
+        self.input_div = (float(input_div[0]), float(input_div[1]))
+        self.regression = bool(regression)
+        if self.regression and n_out != 1:
+            raise ValueError("the regression variant has n_out = 1 (train.py:137-138)")
         self.spec: NetSpec = build_spec(arch, n_in, n_out, self.self_attention)
         self.layout = ParamLayout(self.spec)
         self.N, (self.H, self.W) = batch, size
@@ -151,40 +180,78 @@ class UNetB200:
         self.weights_changed()
 
     def init_parameters(self, seed: int = 0, randomize_bn: bool = True) -> None:
-        """Random initialisation on the device (no checkpoint is reachable offline): kaiming-normal conv weights as
-        fastai's init_cnn / apply_init do, biases 0.  With randomize_bn the BN affine parameters and running statistics
-        are drawn away from their defaults — stock fastai sets gamma = 0 on the last BN of every ResBlock, which would
-        switch the conv paths off and make throughput and parity measurements vacuous."""
+        """Random initialisation on the device (no checkpoint is reachable offline).
+
+        randomize_bn=False is fastai's own start (what `unet_learner_MS` hands to `fit_one_cycle`, train.py:128-144):
+        encoder convs kaiming-normal (xresnet init_cnn), the replaced first conv with torch's default Conv2d init
+        (train.py:130-135); BatchNorm gamma 1, beta 1e-3, and gamma 0 on the last BatchNorm of every ResBlock convpath
+        (NormType.BatchZero: each block starts as the identity); decoder ConvLayers kaiming-uniform with bias
+        N(0, 0.01) (ConvLayer / init_linear defaults), PixelShuffle convs ICNR (every 4 consecutive output channels
+        share one kernel), middle conv and final ResBlock kaiming-normal with bias 0 (DynamicUnet's apply_init), head
+        and the spectral-normed attention convs torch's default conv init, attention gamma 0.
+        randomize_bn=True (benchmarks and parity tests) draws kaiming-normal convs and moves every BatchNorm affine
+        parameter and running statistic away from its default - with gamma = 0 the conv paths are switched off and
+        throughput / parity measurements would be vacuous."""
         g = torch.Generator(device=self.device).manual_seed(seed)
+        dev = self.device
+        zero_bn = set()
+        if not randomize_bn:
+            for st in self.spec.stages:
+                for b in st:
+                    zero_bn.add(b.convpath[-1].bn_prefix + ".weight")
+        fastai = not randomize_bn
+        first = self.spec.stem[0].wname
+        zero_bias = {cs.bname for cs in list(self.spec.middle) + list(self.spec.final_res)}
+        shuf = {cs.wname for cs in [u.shuf for u in self.spec.unet] + [self.spec.final_shuf]}
+        default_init = {first, self.spec.head.wname}
+        kaiming_normal_w = {cs.wname for cs in list(self.spec.middle) + list(self.spec.final_res)}
         with torch.no_grad():
             for e in self.layout.entries:
                 p = self.param(e.name)
                 if len(e.shape) == 4:
                     fan_in = e.shape[1] * e.shape[2] * e.shape[3]
-                    p.copy_(torch.randn(e.shape, generator=g, device=self.device) * (2.0 / fan_in) ** 0.5)
+                    decoder = e.group == 2
+                    if fastai and e.name in default_init:       # nn.Conv2d default: kaiming_uniform(a=sqrt(5))
+                        b = 1.0 / fan_in ** 0.5
+                        p.copy_((torch.rand(e.shape, generator=g, device=dev) * 2 - 1) * b)
+                    elif fastai and e.name in shuf:             # icnr_init: one kaiming-normal kernel per 4 outputs
+                        k = torch.randn((e.shape[0] // 4,) + tuple(e.shape[1:]), generator=g, device=dev) * (2.0 / fan_in) ** 0.5
+                        p.copy_(k.repeat_interleave(4, dim=0))
+                    elif fastai and decoder and e.name not in kaiming_normal_w:   # ReLU ConvLayer: kaiming_uniform
+                        b = (6.0 / fan_in) ** 0.5
+                        p.copy_((torch.rand(e.shape, generator=g, device=dev) * 2 - 1) * b)
+                    else:
+                        p.copy_(torch.randn(e.shape, generator=g, device=dev) * (2.0 / fan_in) ** 0.5)
                 elif len(e.shape) == 3:              # spectral-normed Conv1d weight_orig of SelfAttention
-                    p.copy_(torch.randn(e.shape, generator=g, device=self.device) * (2.0 / e.shape[1]) ** 0.5)
+                    if fastai:
+                        b = 1.0 / e.shape[1] ** 0.5
+                        p.copy_((torch.rand(e.shape, generator=g, device=dev) * 2 - 1) * b)
+                    else:
+                        p.copy_(torch.randn(e.shape, generator=g, device=dev) * (2.0 / e.shape[1]) ** 0.5)
                 elif e.name.endswith(".gamma"):      # fastai: 0 (the block starts as the identity)
                     p.fill_(0.5 if randomize_bn else 0.0)
                 elif e.name.endswith(".0.bias"):
-                    p.zero_()
+                    if fastai and e.name not in zero_bias:
+                        p.copy_(torch.randn(e.shape, generator=g, device=dev) * 0.01)
+                    else:
+                        p.zero_()
                 elif e.name.endswith(".weight"):   # BN gamma
                     if randomize_bn:
-                        p.copy_(torch.rand(e.shape, generator=g, device=self.device) + 0.5)
+                        p.copy_(torch.rand(e.shape, generator=g, device=dev) + 0.5)
                     else:
-                        p.fill_(1.0)
+                        p.fill_(0.0 if e.name in zero_bn else 1.0)
                 else:                              # BN beta
                     if randomize_bn:
-                        p.copy_(torch.randn(e.shape, generator=g, device=self.device) * 0.1)
+                        p.copy_(torch.randn(e.shape, generator=g, device=dev) * 0.1)
                     else:
                         p.fill_(1e-3)
             for k, b in self.buffers.items():
                 if k.endswith(("weight_u", "weight_v")):
                     continue
                 if k.endswith("running_mean"):
-                    b.copy_(torch.randn(b.shape, generator=g, device=self.device) * 0.1 if randomize_bn else torch.zeros_like(b))
+                    b.copy_(torch.randn(b.shape, generator=g, device=dev) * 0.1 if randomize_bn else torch.zeros_like(b))
                 else:
-                    b.copy_(torch.rand(b.shape, generator=g, device=self.device) + 0.5 if randomize_bn else torch.ones_like(b))
+                    b.copy_(torch.rand(b.shape, generator=g, device=dev) + 0.5 if randomize_bn else torch.ones_like(b))
         self.weights_changed()
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
@@ -773,7 +840,8 @@ class UNetB200:
         if train:
             # loss buffers
             P_ = N * H * W
-            self.labels = torch.zeros((N, H, W), dtype=torch.uint8, device=dev)
+            # class ids (uint8) - or the continuous target of the regression variant (RegressionBlock, data.py:98)
+            self.labels = torch.zeros((N, H, W), dtype=torch.float32 if self.regression else torch.uint8, device=dev)
             self.dlogits = torch.zeros((N, H, W, padc(spec.n_out)), dtype=torch.bfloat16, device=dev)
             self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
             self._ce_rows = 592
@@ -839,18 +907,18 @@ class UNetB200:
 
     # ------------------------------------------------------------------------------------------------ execution
     def set_input(self, x: torch.Tensor, stream: Optional[int] = None) -> None:
-        """x: [N, n_in, H, W] on the device — fp32 already scaled to [0,1] (the reference's x = raw/255, data.py:24 +
-        IntToFloatTensor) or raw uint8 (divided by 255 in the kernel)."""
+        """x: [N, n_in, H, W] on the device — fp32 already scaled (the reference's x = raw/255, data.py:24 +
+        IntToFloatTensor) or raw uint8 / uint16 / int16 band values, divided in the kernel as `input_contract` says."""
         assert x.is_cuda and x.is_contiguous() and tuple(x.shape) == (self.N, self.n_in, self.H, self.W), x.shape
-        assert x.dtype in (torch.float32, torch.uint8)
+        dt, div, div2 = input_contract(x.dtype, self.input_div)
         s = stream if stream is not None else ops.stream_ptr()
-        _lib.check(self.lib.b2u_nchw_to_nhwc(x.data_ptr(), int(x.dtype == torch.uint8), self.x_in.t.data_ptr(), self.N,
+        _lib.check(self.lib.b2u_nchw_to_nhwc(x.data_ptr(), dt, div, div2, self.x_in.t.data_ptr(), self.N,
                                              self.n_in, self.H, self.W, self.x_in.ld, 0, self.x_in.ld, s),
                    "b2u_nchw_to_nhwc")
 
     def set_labels(self, y: torch.Tensor) -> None:
         assert self.training and tuple(y.shape) == (self.N, self.H, self.W)
-        self.labels.copy_(y.to(torch.uint8) if y.dtype != torch.uint8 else y, non_blocking=True)
+        self.labels.copy_(y if y.dtype == self.labels.dtype else y.to(self.labels.dtype), non_blocking=True)
 
     def forward(self, stream: Optional[int] = None) -> torch.Tensor:
         """Runs the forward plan; returns the fp32 NHWC logits buffer [N,H,W,ld] (first n_out lanes valid)."""
@@ -863,6 +931,14 @@ class UNetB200:
         s = stream if stream is not None else ops.stream_ptr()
         lib, P_ = self.lib, self.N * self.H * self.W
         ld = self.logits.shape[-1]
+        if self.regression:
+            # MSELossFlat(axis=1) (train.py:189-192): mean squared error over the flattened batch
+            _lib.check(lib.b2u_mse_fwd_bwd(self.logits.data_ptr(), ld, self.labels.data_ptr(), P_, self.dlogits.data_ptr(),
+                                           self.dlogits.shape[-1], self._loss_part.data_ptr(), self._ce_rows, grad_scale,
+                                           s), "b2u_mse_fwd_bwd")
+            _lib.check(lib.b2u_mse_finalize(self._loss_part.data_ptr(), self._ce_rows, P_, self.loss.data_ptr(), s),
+                       "b2u_mse_finalize")
+            return self.loss
         _lib.check(lib.b2u_ce_weight_sum(self.labels.data_ptr(), P_, _p(self.class_weights), self.n_out,
                                          self._wsum_part.data_ptr(), self._ce_rows, s), "b2u_ce_weight_sum")
         _lib.check(lib.b2u_ce_fwd_bwd(self.logits.data_ptr(), ld, self.labels.data_ptr(), P_, self.n_out,

@@ -12,7 +12,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib, ops
-from .network import UNetB200
+from .network import UNetB200, input_contract
 from .tiling import Window, colour_classes, compute_windows, shard_windows_by_columns
 
 
@@ -49,11 +49,12 @@ class TiledPredictor:
 
     def predict_raster(self, raster: torch.Tensor, patch_overlap: float, rank: int = 0, world: int = 1,
                        return_probs: bool = False, large_file: bool = False):
-        """raster: uint8 [C, Y, X] on the device. Returns (mask uint8 [Y, x_end-x_begin], x_begin, x_end) for the
+        """raster: uint8 / uint16 / int16 [C, Y, X] on the device (raw band values, scaled by the plan's input contract). Returns (mask uint8 [Y, x_end-x_begin], x_begin, x_end) for the
         column strip this rank owns (the whole raster when world == 1).  `large_file`: the reference's int8 merge
         (predict.py:217-219, 318-323).  `return_probs` also returns the accumulators (sum of probabilities, counts)."""
         net, lib, dev, P, B = self.net, self.lib, self.dev, self.P, self.B
-        assert raster.is_cuda and raster.dtype == torch.uint8 and raster.dim() == 3 and raster.is_contiguous()
+        assert raster.is_cuda and raster.dim() == 3 and raster.is_contiguous()
+        r_dt, r_div, r_div2 = input_contract(raster.dtype, net.input_div)
         Cc, Y, X = raster.shape
         assert Cc == net.n_in and Y >= P and X >= P, "raster smaller than one tile is not supported"
         windows = compute_windows(Y, X, P, patch_overlap)
@@ -89,8 +90,8 @@ class TiledPredictor:
         accumulate = lib.b2u_stitch_accumulate_q31 if large_file else lib.b2u_stitch_accumulate
         for oy, ox, classes in plan:
             y0, x0 = base + 4 * oy, base + 4 * ox
-            _lib.check(lib.b2u_crop_tiles(raster.data_ptr(), Cc, Y, X, y0, x0, B, P, net.x_in.t.data_ptr(), net.x_in.ld, s),
-                       "b2u_crop_tiles")
+            _lib.check(lib.b2u_crop_tiles(raster.data_ptr(), r_dt, r_div, r_div2, Cc, Y, X, y0, x0, B, P,
+                                          net.x_in.t.data_ptr(), net.x_in.ld, s), "b2u_crop_tiles")
             net.forward(s)
             for osel, nsel in classes:
                 _lib.check(accumulate(net.logits.data_ptr(), ld, net.n_out, B, P, P, y0, x0, base + 4 * osel, nsel,
