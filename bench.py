@@ -153,15 +153,59 @@ def _guard_stdout():
 
 
 def load_traffic():
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/r01_traffic.json)."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (newest profiles/rNN_traffic.json;
+    ncu cannot run inside the timed bench, so this one field is read from the evidence file of the same code)."""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        path = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(path):
+            with open(path) as f:
+                d = json.load(f)
+            d["file"] = "profiles/" + name
+            return d
+    return None
+
+
+def load_secondary_bar():
+    """stock torch + cuDNN (bf16 autocast, channels_last) on the same B200, same network / batch: tools/torch_baseline.py,
+    recorded in profiles/ (the oracle module may not run inside this file outside the cpu_baseline leg)."""
+    path = os.path.join(ROOT, "profiles", "r02_torch_cudnn_baseline.json")
     if os.path.exists(path):
         with open(path) as f:
             return json.load(f)
     return None
 
 
-def predict_section(dev, rank, world, side, batch, max_over_ranks, barrier):
+def profile_step(net, trainer, x, y):
+    """One eager training step with a CUDA-event pair around EVERY op (real order, warm caches).  Returns
+    [(kind, algorithmic bytes, ms)] of the memory-bound ops (network.py registers kind / bytes per op)."""
+    from unet_b200 import ops
+    st = torch.cuda.current_stream()
+    s = ops.stream_ptr()
+    trainer.x_static.copy_(x)
+    net.labels.copy_(y)
+    evs = []
+
+    def timed(fn, meta):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(st)
+        fn()
+        b.record(st)
+        evs.append((meta, a, b))
+
+    timed(lambda: net.set_input(trainer.x_static, s), ("nchw_to_nhwc", net.N * net.H * net.W * (net.n_in + net.x_in.ld * 2)))
+    for op, meta in zip(net.fwd_ops, net.fwd_meta):
+        timed(lambda op=op: op(s), meta)
+    P_ = net.N * net.H * net.W
+    timed(lambda: net.loss_and_grad(s), ("ce_weight_sum+ce_fwd_bwd+ce_finalize",
+                                         P_ * (net.logits.shape[-1] * 4 + 2 + net.dlogits.shape[-1] * 2)))
+    for op, meta in zip(net.bwd_ops, net.bwd_meta):
+        timed(lambda op=op: op(s), meta)
+    timed(lambda: net.sgd_step(1e-3, s), ("sgd+stage_weights", net.layout.total * 12 + net.layout.total * 4))
+    torch.cuda.synchronize()
+    return [(m[0], m[1], a.elapsed_time(b)) for m, a, b in evs if m[0]]
+
+
+def predict_section(dev, rank, world, side, batch, max_over_ranks, barrier, peaks):
     """The other half of BASELINE's metric: tiled prediction (256x256 tiles, 32-px overlap, overlap-average + argmax) of
     a synthetic 4-band raster, tiles sharded over the ranks by output column strips.  `value`: raster resident in HBM;
     `e2e`: the raster strip comes from pinned host memory and the uint8 mask strip is read back, inside the timed region."""
@@ -174,14 +218,18 @@ def predict_section(dev, rank, world, side, batch, max_over_ranks, barrier):
     g = torch.Generator(device=dev).manual_seed(1234)
     raster = torch.randint(0, 256, (N_IN, side, side), dtype=torch.uint8, device=dev, generator=g)
     pred.predict_raster(raster[:, :1024, :1024].contiguous(), 0.125)   # warm-up
+    from unet_b200.predict_engine import gather_mask_strips
+    pred.predict_raster(raster, 0.125, rank, world)                    # second warm-up at full size (allocator, caches)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     mask, xb, xe = pred.predict_raster(raster, 0.125, rank, world)
+    full = gather_mask_strips(mask, side, rank, world) if world > 1 else mask     # the path's only collective (NCCL)
     e1.record()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
     n_tiles = len(compute_windows(side, side, SIZE, 0.125))
+    stitch = pred.last_stitch_profile
     # e2e: this rank's input strip (the tile columns it runs) from pinned host memory, mask strip back to the host
     windows = compute_windows(side, side, SIZE, 0.125)
     idx, xb, xe = shard_windows_by_columns(windows, side, rank, world)
@@ -205,12 +253,119 @@ def predict_section(dev, rank, world, side, batch, max_over_ranks, barrier):
     same = bool(torch.equal(m2, mask))
     flops = n_tiles * net.flops_fwd_per_tile
     return {"metric": "predict tiles/sec (256x256x4-band xresnet34-DynamicUnet, bf16, tiled predict + stitch + argmax)",
-            "workload": f"{side}x{side} 4-band raster, 256-px tiles, 32-px overlap: {n_tiles} tiles (BASELINE configs[2] is 20000x20000 = 8100 tiles: tools/predict_bench.py, profiles/r01_predict_20000.jsonl)",
+            "workload": f"BASELINE configs[2]: {side}x{side} 4-band raster, 256-px tiles, 32-px overlap: {n_tiles} tiles, "
+                        f"owner-computes column strips over {world} GPU(s), final uint8 mask gather inside the timed region",
             "value": n_tiles / (ms * 1e-3), "unit": UNIT, "seconds": ms * 1e-3, "tiles": n_tiles,
             "tiles_run_rank0": len(idx), "fwd_gflop_per_tile": net.flops_fwd_per_tile / 1e9,
             "algorithmic_tflops_per_gpu": flops / (ms * 1e-3) / 1e12 / world,
+            "tensor_core_frac_of_burst_peak": flops / (ms * 1e-3) / 1e12 / world / peaks["tf_burst"],
+            "stitch_kernels": stitch,
             "e2e": {"value": n_tiles / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes": host.numel() * world,
                     "d2h_bytes": host_mask.numel() * world, "strip_mask_equals_sharded_mask": same}}
+
+
+def plan_bytes(plan) -> int:
+    """algorithmic bytes of one implicit-GEMM launch: activations in (every view once), weights, residual / mask
+    operands, output - all bf16 at their unpadded channel counts (fp32 for the head's logits)"""
+    d = plan.desc
+    px_out = d.out.N * d.out.H * d.out.W
+    b = 0
+    for i in range(d.num_a):
+        b += d.a[i].N * d.a[i].H * d.a[i].W * d.w_cin * 2
+    b += d.w_rows * d.num_taps * d.w_cin * 2
+    for v in (d.res, d.res_mask, d.zmask):
+        if v.ptr:
+            b += px_out * d.out.C * 2
+    b += px_out * d.out.C * (4 if d.out_f32 else 2)
+    return b
+
+
+def extra_configs(dev, rank, world, args, peaks, max_over_ranks, barrier):
+    """BASELINE configs[3] and configs[4] as sub-records of the one JSON line (every rank runs its own replica of the
+    per-GPU workload; values are whole-job aggregates): xresnet50-DynamicUnet 4-band 512x512, 8 classes, bf16 training
+    with batch statistics (fwd + CE + bwd + SGD, CUDA graph), and xresnet18-DynamicUnet 3-band 128x128 inference at
+    batch 512 per GPU (eval plan, BN folded) - the memory-bound kernel stress."""
+    from unet_b200.engine import Trainer
+    from unet_b200.network import UNetB200
+    from unet_b200.synth import uniform_tiles
+    out = {}
+    # ---- configs[3]: R50 / 512 / 8 classes, training
+    try:
+        B = args.r50_batch
+        net = UNetB200("xresnet50", 4, 8, (512, 512), B, training=True, device=dev)
+        net.init_parameters(seed=0)
+        tr = Trainer(net, optimizer="sgd", lr=1e-3, use_graph=True)
+        x, y = uniform_tiles(B, 4, 512, 512, 8, seed=99 + rank)
+        x, y = x.to(dev), y.to(dev)
+        for _ in range(3):
+            tr.step(x, y)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        steps = 5
+        e0.record()
+        for _ in range(steps):
+            tr.step(x, y)
+        e1.record()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+        tf = 3 * net.flops_fwd_per_tile * B / (ms * 1e-3) / 1e12
+        out["config4_xresnet50_512_train"] = {
+            "workload": "BASELINE configs[3]: xresnet50-DynamicUnet 4-band 512x512, 8 classes, train-mode BN, bf16, "
+                        f"batch {B}/GPU, fwd+CE+bwd+SGD (CUDA graph)", "value": B * world / (ms * 1e-3), "unit": UNIT,
+            "ms_per_step": ms, "steps": steps, "warmup": 3, "batch_per_gpu": B,
+            "train_gflop_per_tile": 3 * net.flops_fwd_per_tile / 1e9, "algorithmic_tflops_per_gpu": tf,
+            "tensor_core_frac_of_burst_peak": tf / peaks["tf_burst"], "final_loss": float(net.loss.item()),
+            "gpu_launches_per_step": net.launches_per_train_step}
+        del tr, net, x, y
+    except Exception as ex:   # e.g. out of memory on a smaller part: reported, never hidden
+        out["config4_xresnet50_512_train"] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+    torch.cuda.empty_cache()
+    # ---- configs[4]: R18 / 128 / 3-band, batch 512 inference
+    try:
+        B = 512
+        net = UNetB200("xresnet18", 3, 2, (128, 128), B, training=False, device=dev)
+        net.init_parameters(seed=0)
+        x, _ = uniform_tiles(B, 3, 128, 128, 2, seed=7 + rank)
+        x = x.to(dev)
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            net.set_input(x)
+            net.forward()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g, stream=side):
+            net.set_input(x)
+            net.forward()
+        for _ in range(3):
+            g.replay()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        iters = 20
+        e0.record()
+        for _ in range(iters):
+            g.replay()
+        e1.record()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1)) / iters
+        tf = net.flops_fwd_per_tile * B / (ms * 1e-3) / 1e12
+        act_bytes = sum(a.t.numel() * 2 for a in net.acts)          # every stored activation written once (+ read once)
+        out["config5_xresnet18_128_infer"] = {
+            "workload": "BASELINE configs[4]: xresnet18-DynamicUnet 3-band 128x128, batch 512/GPU, inference "
+                        "(eval plan, BN folded into the conv epilogues, uint8 tiles in, fp32 logits out, CUDA graph)",
+            "value": B * world / (ms * 1e-3), "unit": UNIT, "ms_per_batch": ms, "iters": iters, "warmup": 3,
+            "fwd_gflop_per_tile": net.flops_fwd_per_tile / 1e9, "algorithmic_tflops_per_gpu": tf,
+            "tensor_core_frac_of_burst_peak": tf / peaks["tf_burst"],
+            "activation_bytes_written_per_batch": act_bytes,
+            "activation_write_plus_read_gbs": 2 * act_bytes / (ms * 1e-3) / 1e9,
+            "hbm_frac_of_measured_peak": 2 * act_bytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+            "gpu_launches_per_batch": net.launches_fwd + 1}
+        del g, net, x
+    except Exception as ex:
+        out["config5_xresnet18_128_infer"] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -224,7 +379,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-predict", action="store_true")
-    ap.add_argument("--predict-side", type=int, default=10240, help="side of the synthetic raster of the predict section")
+    ap.add_argument("--predict-side", type=int, default=20000, help="side of the synthetic raster of the predict section "
+                    "(BASELINE configs[2]: 20000)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the BASELINE configs[3] / configs[4] sub-records")
+    ap.add_argument("--r50-batch", type=int, default=16, help="tiles per GPU per step of the xresnet50 / 512-px line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b2u" else args.warmup
 
@@ -316,6 +474,7 @@ def main():
     # ---- roofline of the dominant kernel (implicit-GEMM conv: fprop + dgrad launches), measured live with CUDA events
     kernels = {}
     roofline = None
+    roofline_mem = None
     if not args.no_profile:
         ops.PROFILE = []
         trainer.use_graph = False
@@ -333,28 +492,53 @@ def main():
                              "share_of_step": ms / (dev_ms / args.steps)}
         c = kernels["conv"]
         tr_ncu = load_traffic()
+        conv_plans = [p for k, p, a, b in prof if k == "conv"]
+        # algorithmic bytes of a conv launch: every operand once (input views, weights, residual / masks) + the output
+        alg_bytes = sum(plan_bytes(p) for p in conv_plans) / max(1, len(conv_plans))
         roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel (fprop+dgrad launches)",
                     "achieved": c["tflops"], "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                     "frac": c["tflops"] / peaks["tf_sustained"],
+                    "frac_burst": c["tflops"] / peaks["tf_burst"], "peak_burst": peaks["tf_burst"],
                     "traffic": tr_ncu["conv_gemm_kernel"]["dram_bytes_per_launch"] if tr_ncu else None,
-                    "traffic_source": tr_ncu["source"] if tr_ncu else None,
-                    "algorithmic_flops_per_launch": sum(p.flops for k, p, a, b in prof if k == "conv") / max(1, c["launches"]),
+                    "traffic_source": (tr_ncu.get("file", "") + ": " + tr_ncu["source"]) if tr_ncu else None,
+                    "algorithmic_flops_per_launch": sum(p.flops for p in conv_plans) / max(1, c["launches"]),
+                    "algorithmic_bytes_per_launch": alg_bytes,
                     "avg_launch_ms": c["ms"] / max(1, c["launches"]), "launches_per_step": c["launches"],
-                    "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)"}
+                    "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step); frac_burst uses the burst figure BASELINE.md's 50 % target is defined on"}
+        kernels["wgrad"]["frac_burst"] = kernels["wgrad"]["tflops"] / peaks["tf_burst"]
+        # HBM roofline of the memory-bound kernels: algorithmic bytes (inputs once + outputs once) / event time, per kind
+        agg = {}
+        trainer.use_graph = False
+        for kind, nbytes, ms in profile_step(net, trainer, dev_x[0], dev_y[0]):
+            a = agg.setdefault(kind, [0, 0, 0.0])
+            a[0] += 1; a[1] += nbytes; a[2] += ms
+        trainer.use_graph = True
+        roofline_mem = [{"kernel": k, "launches": a[0], "algorithmic_bytes": a[1], "ms": a[2],
+                         "achieved_gbs": a[1] / (a[2] * 1e-3) / 1e9, "peak_gbs": peaks["hbm_gbs"],
+                         "frac": a[1] / (a[2] * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+                        for k, a in sorted(agg.items(), key=lambda t: -t[1][2]) if a[2] > 0]
 
     # ---- whole-step tensor-core fraction from algorithmic FLOPs (fwd + dgrad + wgrad = 3x fwd conv FLOPs)
+    launches_per_step = net.launches_per_train_step
     train_flops_per_tile = 3 * net.flops_fwd_per_tile
     step_tflops = value * train_flops_per_tile / 1e12 / world
 
+    # free the training plan before the other workloads (each builds its own static plan)
+    del trainer, net
+    torch.cuda.empty_cache()
     predict = None
     if not args.no_predict:
-        predict = predict_section(dev, rank, world, args.predict_side, B, max_over_ranks, barrier)
+        predict = predict_section(dev, rank, world, args.predict_side, B, max_over_ranks, barrier, peaks)
+        torch.cuda.empty_cache()
+    extra = None
+    if not args.no_extra:
+        extra = extra_configs(dev, rank, world, args, peaks, max_over_ranks, barrier)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        t_step, cores, _ = cpu_oracle_step_time(8, 2, 1)
+        t_step, cores, _ = cpu_oracle_step_time(8, 5, 1)
         cpu_baseline = {"value": 8 / t_step, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": "BASELINE config 1: batch 8, fwd+CE+bwd+SGD, fp32 torch oracle, 2 timed steps after 1 warm-up"}
+                        "sample": "BASELINE config 1: batch 8, fwd+CE+bwd+SGD, fp32 torch oracle, 5 timed steps after 1 warm-up"}
 
     if rank == 0:
         line = {
@@ -366,16 +550,17 @@ def main():
                        "global_batch": B * world, "optimizer": "sgd", "parallelism": f"dp{world}",
                        "l2": "per-step working set (activations+gradients, several GB) far exceeds the 126 MB L2; no flush needed",
                        "cuda_graph": True},
-            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "roofline": roofline, "roofline_mem": roofline_mem, "cpu_baseline": cpu_baseline,
+            "secondary_bar": load_secondary_bar(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": net.launches_per_train_step * args.steps + args.steps,
+            "gpu_launches": launches_per_step * args.steps + args.steps,
             "clocks": clocks, "kernels": kernels,
             "tensor_core_frac_step": {"algorithmic_tflops_per_gpu": step_tflops,
                                       "of_burst_peak": step_tflops / peaks["tf_burst"],
                                       "of_sustained_peak": step_tflops / peaks["tf_sustained"],
                                       "train_gflop_per_tile": train_flops_per_tile / 1e9},
-            "final_loss": loss_val, "predict": predict,
+            "final_loss": loss_val, "predict": predict, "extra": extra,
         }
         print(json.dumps(line), file=out, flush=True)
     if world > 1:

@@ -81,6 +81,7 @@ class _Ctx:
     """per-call state of emulated_forward: teacher-forcing taps, recording dict, noise level (sensitivity probe)"""
     taps = None
     record = None
+    mismatch = None
     noise = 0.0
 
 
@@ -92,9 +93,13 @@ def q(x, name=None):
         if _Ctx.taps is not None and name in _Ctx.taps:
             t = _Ctx.taps[name].to(y.dtype)
             assert t.shape == y.shape, (name, tuple(t.shape), tuple(y.shape))
+            if _Ctx.mismatch is not None:     # what THIS graph computes from the previous taps vs the tap itself
+                _Ctx.mismatch[name] = ((t - y.detach()).abs().max() / t.abs().max().clamp_min(1e-30)).item()
             y = y + (t - y).detach()          # forward value: the tap; gradient: through this graph
         if _Ctx.record is not None:
-            _Ctx.record[name] = y.detach()
+            if y.requires_grad:
+                y.retain_grad()           # after backward: the (unrounded) gradient arriving at this stored activation
+            _Ctx.record[name] = y
     return y
 
 
@@ -154,15 +159,16 @@ def _conv_bias(x, layer, relu=True, res=None, name=None):
 
 
 def emulated_forward(model: DynamicUnetOracle, x: torch.Tensor, training: bool = True, taps=None, record=None,
-                     noise: float = 0.0) -> torch.Tensor:
-    """taps / record: see the module docstring (teacher forcing).  noise: relative Gaussian perturbation applied in
-    front of every rounding (forward and backward) - a probe of the conditioning, standing in for the difference
-    between two fp32 accumulation orders."""
-    _Ctx.taps, _Ctx.record, _Ctx.noise = taps, record, noise
+                     noise: float = 0.0, mismatch=None) -> torch.Tensor:
+    """taps / record: see the module docstring (teacher forcing).  mismatch (dict, with taps): per tapped rounding point
+    the max-norm relative difference between the tap and what this graph computes from the PREVIOUS taps - a per-layer
+    forward check.  noise: relative Gaussian perturbation applied in front of every rounding (forward and backward) - a
+    probe of the conditioning, standing in for the difference between two fp32 accumulation orders."""
+    _Ctx.taps, _Ctx.record, _Ctx.noise, _Ctx.mismatch = taps, record, noise, mismatch
     try:
         return _emulated_forward(model, x, training)
     finally:
-        _Ctx.taps, _Ctx.record, _Ctx.noise = None, None, 0.0
+        _Ctx.taps, _Ctx.record, _Ctx.noise, _Ctx.mismatch = None, None, 0.0, None
 
 
 def _emulated_forward(model: DynamicUnetOracle, x: torch.Tensor, training: bool) -> torch.Tensor:

@@ -34,6 +34,14 @@ def gradient_mismatches(grads: Dict[str, torch.Tensor], ref: Dict[str, torch.Ten
 
 
 def plan_taps(net) -> Dict[str, torch.Tensor]:
-    """the CUDA plan's stored activations as NCHW fp32 tensors, keyed by the plan's activation names (the rounding
-    point names of oracle/bf16_emulation.py)"""
-    return {name: a.t[..., :a.C].permute(0, 3, 1, 2).float().contiguous() for name, a in net.named_acts.items()}
+    """the CUDA plan's stored activations as NCHW fp32 tensors in torch channel order, keyed by the plan's activation
+    names (the rounding point names of oracle/bf16_emulation.py).  The 1x1 convolutions of PixelShuffle_ICNR keep their
+    output channels in (i, j, c) order in the plan (GEMM row (2i+j)*c + c_ holds torch channel 4 c_ + 2i + j)."""
+    from unet_b200.layout import shuffle_row_of_co
+    out = {}
+    for name, a in net.named_acts.items():
+        t = a.t[..., :a.C].permute(0, 3, 1, 2).float().contiguous()
+        if name.endswith(".shuf.0.out") or name == "layers.8.0.out":
+            t = t[:, torch.tensor(shuffle_row_of_co(a.C), device=t.device)].contiguous()
+        out[name] = t
+    return out

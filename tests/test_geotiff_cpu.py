@@ -94,6 +94,9 @@ def test_tile_helpers_and_class_zero(tmp_path):
     assert np.array_equal(open_tile(fn), img)                      # uint8 stays raw (divided by 255 on the device)
     assert np.array_equal(open_mask(fn), msk)                      # utils.py:51-55 get_y: band 1 of mask_tiles/<name>
     write_geotiff(fn, img.astype(np.uint16) * 3, GEO)
+    x = open_tile(fn, chnls=[0, 2])                                # 16-bit tiles stay raw too (A0 input contract on the device)
+    assert x.dtype == np.uint16 and np.array_equal(x, img[[0, 2]].astype(np.uint16) * 3)
+    write_geotiff(fn, img.astype(np.float32) * 3, GEO)
     x = open_tile(fn, chnls=[0, 2])
     assert x.dtype == np.float32 and np.allclose(x, img[[0, 2]].astype(np.float32) * 3 / 255.0)
     # predict.py:34-36: class 0 -> nodata, other classes decremented

@@ -57,5 +57,7 @@ if __name__ == "__main__":
     print("first 12 tiles (clk since start): accumulator committed", [int(x) for x in per_tile_mma[:12]])
     ep = t[3][t[3] > 0] - t0
     print("first 24 epilogue stamps:", [int(x) for x in ep[:24]])
+    print("epilogue stamps 200..260 (deltas):", [int(ep[i + 1] - ep[i]) for i in range(200, min(260, len(ep) - 1))])
+    print("plan: SA", plan.info.stages, "info", [(n, getattr(plan.info, n)) for n, _ in plan.info._fields_])
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     torch.save(t, os.path.join(ROOT, "gpurun_out", f"conv_timeline_{case}.pt"))

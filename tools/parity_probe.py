@@ -35,6 +35,13 @@ def run(arch, n_in, n_out, size, batch, data='uniform'):
     p3 = dict(o3.named_parameters())
     net.set_input(x_u8); net.set_labels(y); net.forward(); loss = net.loss_and_grad(); net.backward()
     torch.cuda.synchronize()
+    # teacher-forced emulation: forward values pinned to the plan's stored activations
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+    from parity_util import plan_taps, cosine
+    o4 = copy.deepcopy(oracle); o4.zero_grad()
+    free = {}
+    l4 = emulated_forward(o4, x, True, taps=plan_taps(net), record=free); weighted_ce(l4, y, w).backward()
+    p4 = dict(o4.named_parameters())
     lg = net.logits_nchw()
     lines = [f"{arch} size {size} batch {batch} data {data}",
              f"vs EMULATION: logits {rel(lg, l3):.3e} loss ours {loss.item():.6f} emu {loss3.item():.6f} argmax agree {(lg.argmax(1) == l3.argmax(1)).float().mean().item():.5f}",
@@ -46,7 +53,8 @@ def run(arch, n_in, n_out, size, batch, data='uniform'):
     for name, p in oracle.named_parameters():
         eo, ea, ee = rel(grads[name], p.grad), rel(p2[name].grad, p.grad), rel(grads[name], p3[name].grad)
         wo, wa, we = max(wo, eo), max(wa, ea), max(we, ee)
-        lines.append(f"{eo:.3e} {ea:.3e} {ee:.3e} {name}")
+        et = rel(grads[name], p4[name].grad)
+        lines.append(f"{eo:.3e} {ea:.3e} {ee:.3e} TF {et:.3e} cos {cosine(grads[name], p4[name].grad):.5f} {name}")
     lines.insert(4, f"worst grad rel: ours-vs-fp32 {wo:.3e} autocast-vs-fp32 {wa:.3e} ours-vs-emulation {we:.3e}")
     os.makedirs("gpurun_out", exist_ok=True)
     open(f"gpurun_out/probe_{arch}_{size}_{batch}_{data}.txt", "w").write("\n".join(lines))

@@ -426,13 +426,13 @@ def write_geotiff(path: Union[str, Path], array: np.ndarray, geo: Optional[GeoIn
 
 # ------------------------------------------------------------------------------------------ reference-shaped helpers
 def open_tile(fn: Union[str, Path], chnls: Optional[Sequence[int]] = None) -> np.ndarray:
-    """`open_npy` (data.py:18-28): `[bands, H, W]` of an image tile.  uint8 tiles stay uint8 (the kernels divide by 255
-    on the device, which is what MaskBlock's IntToFloatTensor(div=255) does after the int32 -> float32 cast of
-    data.py:24); any other sample type is returned as float32 already divided by 255."""
+    """`open_npy` (data.py:18-28): `[bands, H, W]` of an image tile.  uint8 / uint16 / int16 tiles keep their raw band
+    values (the device kernels apply the int32 -> float32 cast of data.py:24 and the divisions by 255 of the reference's
+    batch transforms, `unet_b200.network.input_contract`); any other sample type is returned as float32 divided by 255."""
     a, _ = read_geotiff(fn)
     if chnls is not None:
         a = a[list(chnls)]
-    if a.dtype == np.uint8:
+    if a.dtype in (np.uint8, np.uint16, np.int16):
         return a
     return a.astype(np.int32).astype(np.float32) / 255.0 if a.dtype.kind in "ui" else a.astype(np.float32) / 255.0
 

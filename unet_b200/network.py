@@ -145,6 +145,8 @@ class UNetB200:
         self.named_acts: Dict[str, Act] = {}
         self.fwd_ops: List[Callable[[int], None]] = []
         self.bwd_ops: List[Callable[[int], None]] = []
+        self.fwd_meta: List[Tuple[str, int]] = []      # (kernel kind, algorithmic bytes) per op, "" for the GEMMs
+        self.bwd_meta: List[Tuple[str, int]] = []
         self.bwd_side: List[bool] = []   # weight-gradient launches: independent of the dgrad chain -> second stream
         self._side_stream: Optional[torch.cuda.Stream] = None
         self._bwd_builders: List[Callable[[], None]] = []
@@ -353,15 +355,19 @@ class UNetB200:
             return views, ops.taps_conv3_s2()
         return [view_nhwc(x.t, x.C)], ops.taps_conv(cs.ks)
 
-    def _fwd(self, fn: Callable[[int], None], n: int = 1) -> None:
+    def _fwd(self, fn: Callable[[int], None], n: int = 1, kind: str = "", nbytes: int = 0) -> None:
+        """kind / nbytes: kernel name and ALGORITHMIC bytes (inputs read once + outputs written once) of a memory-bound
+        op - what bench.py's `roofline_mem` divides by the measured time."""
         self.fwd_ops.append(fn)
         self.op_tags.append(("fwd", sys._getframe(1).f_code.co_name, sys._getframe(1).f_lineno))
+        self.fwd_meta.append((kind, int(nbytes)))
         self.launches_fwd += n
 
-    def _bwd(self, fn: Callable[[int], None], n: int = 1, side: bool = False) -> None:
+    def _bwd(self, fn: Callable[[int], None], n: int = 1, side: bool = False, kind: str = "", nbytes: int = 0) -> None:
         self.bwd_ops.append(fn)
         self.bwd_side.append(side)
         self.op_tags.append(("bwd", sys._getframe(1).f_code.co_name, sys._getframe(1).f_lineno))
+        self.bwd_meta.append((kind, int(nbytes)))
         self.launches_bwd += n
 
     def _conv_fwd(self, cs: ConvSpec, x: Act, y: Act, *, out_C: Optional[int] = None, scale=None, shift=None,
@@ -373,7 +379,10 @@ class UNetB200:
                         res=view_nhwc(res.t, cs.nf) if res is not None else None, relu=relu, stats=stats,
                         out_f32=out_f32, fin=fin)
         self._keep.append(plan)
-        self._fwd(plan.run)
+        # convolutions over a handful of input or output channels are HBM-bound: input once + output once
+        small = cs.ni <= 8 or cs.nf <= 8
+        nb = x.pixels * x.ld * 2 + (y.pixels * 4 * out_f32.shape[-1] if out_f32 is not None else y.pixels * y.ld * 2)
+        self._fwd(plan.run, kind=("conv_gemm(stem)" if cs.ni <= 8 else "conv_gemm(head)") if small else "", nbytes=nb if small else 0)
         return plan
 
     def _bn_finalize_op(self, bn: BNState, partial: torch.Tensor, count: float, train_stats: bool = True):
@@ -496,7 +505,8 @@ class UNetB200:
                                             rows, ld, float(pixels), _p(bn.dgamma), _p(bn.dbeta), _p(bn.mean_g),
                                             _p(bn.mean_gx), sync.data_ptr(), s), "b2u_bn_bwd_fused")
         self._keep.append(partial)
-        self._bwd(run, 1)
+        # algorithmic bytes: dz, x (and the block output that carries the ReLU mask) read once, dx written once
+        self._bwd(run, 1, kind="bn_bwd_fused", nbytes=pixels * 2 * (lddz + ldx + (ldy if y is not None else 0) + lddx))
 
     def _wgrad(self, cs: ConvSpec, dy: torch.Tensor, x: Act):
         """dW (and db) of conv `cs` from dy (bf16 NHWC tensor [N,Ho,Wo,padc(nf)]) and its input activation x."""
@@ -576,7 +586,8 @@ class UNetB200:
                 Z = None
                 if apply:
                     Z = self._act(h, w_, cs.nf, cs.name + ".out")
-                    self._fwd(self._bn_apply_op(R.t, R.ld, bn, Z.t, Z.ld, R.pixels, cs.act))
+                    self._fwd(self._bn_apply_op(R.t, R.ld, bn, Z.t, Z.ld, R.pixels, cs.act), kind="bn_apply",
+                              nbytes=R.pixels * (R.ld + Z.ld) * 2)
                 return R, Z, bn
             Z = self._act(h, w_, cs.nf, cs.name + ".out")
             if apply:
@@ -609,14 +620,16 @@ class UNetB200:
         mp = self._act(h, w_, mp_in.C, "maxpool")
         idx = torch.zeros((N, h, w_, mp.ld), dtype=torch.uint8, device=dev) if train else None
         self._fwd(lambda s, a=mp_in, b=mp, idx=idx: _lib.check(
-            lib.b2u_maxpool_fwd(a.t.data_ptr(), b.t.data_ptr(), _p(idx), N, a.H, a.W, a.C, a.ld, s), "b2u_maxpool_fwd"))
+            lib.b2u_maxpool_fwd(a.t.data_ptr(), b.t.data_ptr(), _p(idx), N, a.H, a.W, a.C, a.ld, s), "b2u_maxpool_fwd"),
+            kind="maxpool_fwd", nbytes=mp_in.pixels * mp_in.ld * 2 + mp.pixels * mp.ld * (3 if train else 2))
         if train:
             def mp_bwd():
                 g = mp_in.ensure_grad()
                 acc = int(mp_in.grad_written)
                 self._bwd(lambda s: _lib.check(lib.b2u_maxpool_bwd(mp.grad.data_ptr(), idx.data_ptr(), g.data_ptr(), acc,
                                                                    N, mp_in.H, mp_in.W, mp_in.C, mp_in.ld, s),
-                                               "b2u_maxpool_bwd"))
+                                               "b2u_maxpool_bwd"), kind="maxpool_bwd",
+                          nbytes=mp.pixels * mp.ld * 3 + mp_in.pixels * mp_in.ld * (4 if acc else 2))
                 mp_in.grad_written = True
             bwd_layers.append(mp_bwd)
         x = mp
@@ -651,9 +664,10 @@ class UNetB200:
                 if train:
                     if idrec is not None:
                         self._fwd(self._bn_apply_op(Rl.t, Rl.ld, bnl, out.t, out.ld, out.pixels, True, idrec[1].t,
-                                                    idrec[1].ld, idrec[2]))
+                                                    idrec[1].ld, idrec[2]), kind="bn_apply", nbytes=out.pixels * out.ld * 6)
                     else:
-                        self._fwd(self._bn_apply_op(Rl.t, Rl.ld, bnl, out.t, out.ld, out.pixels, True, xin.t, xin.ld))
+                        self._fwd(self._bn_apply_op(Rl.t, Rl.ld, bnl, out.t, out.ld, out.pixels, True, xin.t, xin.ld),
+                                  kind="bn_apply", nbytes=out.pixels * out.ld * 6)
                 else:
                     # eval: BN folded into the conv epilogues; the block tail is one fused launch
                     if idrec is not None:
@@ -766,7 +780,8 @@ class UNetB200:
             self._fwd(lambda s, P=P, S=S, cat=cat, bnS=bnS, cu=ub.cu: _lib.check(
                 lib.b2u_shuffle_cat_fwd_crop(P.t.data_ptr(), P.ld, cu, 1, S.t.data_ptr(), S.ld, S.C, _p(bnS.scale),
                                              _p(bnS.shift), 1, cat.t.data_ptr(), cat.ld, N, P.H, P.W, cat.H, cat.W, s),
-                "b2u_shuffle_cat_fwd"))
+                "b2u_shuffle_cat_fwd"), kind="shuffle_cat_fwd",
+                nbytes=(P.pixels * P.ld + S.pixels * S.ld + cat.pixels * cat.ld) * 2)
             c1 = conv_bias(ub.conv1, cat, h, w_)
             c2 = conv_bias(ub.conv2, c1, h, w_)
             sa_bwd = None
@@ -783,7 +798,8 @@ class UNetB200:
                     dcat = cat.grad
                     self._bwd(lambda s: _lib.check(lib.b2u_shuffle_bwd_crop(dcat.data_ptr(), cat.ld, P.t.data_ptr(),
                                                                             dP.data_ptr(), P.ld, ub.cu, 1, N, P.H, P.W,
-                                                                            cat.H, cat.W, s), "b2u_shuffle_bwd"))
+                                                                            cat.H, cat.W, s), "b2u_shuffle_bwd"),
+                              kind="shuffle_bwd", nbytes=(cat.pixels * ub.cu + 2 * P.pixels * P.ld) * 2)
                     P.grad_written = True
                     dS = S.ensure_grad()
                     self._bn_bwd(bnS, dcat[..., ub.cu:], cat.ld, S.t, S.ld, None, 0, False, dS, S.ld, S.pixels,
@@ -823,7 +839,7 @@ class UNetB200:
             lanes = min(xin.ld, cat.ld - cu)
             self._fwd(lambda s: _lib.check(
                 lib.b2u_copy_lanes(xin.t.data_ptr(), xin.ld, 0, cat.t.data_ptr(), cat.ld, cu, lanes, cat.pixels, s),
-                "b2u_copy_lanes"))
+                "b2u_copy_lanes"), kind="copy_lanes", nbytes=cat.pixels * lanes * 4)
         else:
             self._fwd(lambda s: _lib.check(
                 lib.b2u_shuffle_cat_fwd_crop(P8.t.data_ptr(), P8.ld, cu, 0, xin.t.data_ptr(), xin.ld, xin.C, None, None, 0,
@@ -857,7 +873,8 @@ class UNetB200:
                     wd = self._w[hd.name]["wd"]
                     self._bwd(lambda s: _lib.check(lib.b2u_pointwise_smallk(
                         dL.data_ptr(), dL.shape[-1], hd.nf, wd.data_ptr(), wd.shape[-1], A2.t.data_ptr(), A2.ld,
-                        dA2.data_ptr(), A2.ld, A2.pixels, A2.C, s), "b2u_pointwise_smallk"))
+                        dA2.data_ptr(), A2.ld, A2.pixels, A2.C, s), "b2u_pointwise_smallk"), kind="pointwise_smallk",
+                        nbytes=A2.pixels * (dL.shape[-1] + 2 * A2.ld) * 2)
                 else:
                     self._dgrad(hd, dL, A2, zmask=True)
                 A2.grad_written = True
@@ -872,7 +889,8 @@ class UNetB200:
                     # the ReLU mask of the shuffle conv is read from cat itself (cat[..., :cu] = relu(conv) shuffled)
                     self._bwd(lambda s: _lib.check(lib.b2u_shuffle_bwd_from_cat(
                         cat.grad.data_ptr(), cat.t.data_ptr(), cat.ld, dP8.data_ptr(), dP8.shape[-1], cu, N, hs, ws, s),
-                        "b2u_shuffle_bwd_from_cat"))
+                        "b2u_shuffle_bwd_from_cat"), kind="shuffle_bwd(final)",
+                        nbytes=(2 * cat.pixels * cu + N * hs * ws * dP8.shape[-1]) * 2)
                     self._wgrad(fs, dP8, U)
                     self._dgrad(fs, dP8, U, zmask=U.pre_relu_grad)
                 else:

@@ -32,6 +32,10 @@ def _timed(kind, plan, fn):
     PROFILE.append((kind, plan, a, b))
 
 
+import os as _os
+_PITCH16 = _os.environ.get("B2U_PITCH16") is not None    # A/B switch: plain 16-lane pitch everywhere
+
+
 def padc(c: int) -> int:
     """channel pitch of NHWC activations / GEMM weights: whole 32-byte sectors (16 bf16).  TMA throughput halves when
     the innermost extent ends inside a sector (measured: Cin=104 -> 3.1 ms, Cin=112 -> 1.25 ms for the same launch)."""
@@ -40,7 +44,7 @@ def padc(c: int) -> int:
     # that costs <= 1/3 more lanes: the GEMM K loop then runs on whole 64-channel chunks (no partial TMA boxes, and the
     # 3x3 convolutions qualify for row-mode weight stages) - measured 0.91 ms vs 1.12 ms for the 100->100 3x3 launch
     c64 = (c + 63) // 64 * 64
-    if c > 64 and c64 != c16 and (c64 - c) * 3 <= c:
+    if c > 64 and c64 != c16 and (c64 - c) * 3 <= c and not _PITCH16:
         return c64
     return c16
 

@@ -10,7 +10,10 @@ Deliberately not replicated: the `pathlib.PosixPath = pathlib.WindowsPath` monke
 from __future__ import annotations
 
 import json
+import os
+import subprocess
 import sys
+import tempfile
 import time
 import warnings
 from typing import Any, Dict, Optional, Union
@@ -32,6 +35,8 @@ DEFAULTS: Dict[str, Any] = {
     "enable_extra_parameters": False, "self_attention": True, "ENCODER_FACTOR": 10, "LR_FINDER": None,
     "VALID_SCENES": ["vali"], "loss_func": None, "monitor": "dice_multi", "all_classes": False, "specific_class": None,
     "large_file": False, "max_empty": 0.9, "ARCHITECTURE": "xresnet34",
+    # not in the reference (single GPU): data-parallel training / sharded prediction over the GPUs of one box
+    "N_GPUS": 1,
 }
 
 # what main() forces when enable_extra_parameters is off (params_and_main.py:134-147)
@@ -65,6 +70,20 @@ def main(params: Union[str, Dict[str, Any], None] = None) -> Dict[str, Any]:
     p = resolve(params)
     out: Dict[str, Any] = {}
     t0 = time.time()
+    n_gpus = int(p.get("N_GPUS") or 1)
+    if n_gpus > 1 and "RANK" not in os.environ and (p["Train"] or p["Predict"]):
+        # one process per GPU: tile creation runs here once, then Train / Predict are re-entered under torch.distributed.run
+        # (NCCL over NVLink); every rank trains on its share of the batches and rank 0 writes the files
+        if p["Create_tiles"]:
+            main({**p, "Train": False, "Predict": False, "N_GPUS": 1, "enable_extra_parameters": True})
+        with tempfile.NamedTemporaryFile("w", suffix=".json", delete=False) as f:
+            json.dump({**p, "Create_tiles": False, "enable_extra_parameters": True}, f)
+        port = 29500 + os.getpid() % 2000
+        subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n_gpus}",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), "-m", "unet_b200.params_and_main",
+                        f.name], check=True)
+        os.unlink(f.name)
+        return out
     if p["Create_tiles"]:
         from .create_tiles import split_raster
         out["tiles"] = split_raster(path_to_raster=p["image_path"], path_to_mask=p["mask_path"], patch_size=p["patch_size"],

@@ -102,6 +102,21 @@ class TiledPredictor:
             return mask, xb, xe, acc, cnt
         return mask, xb, xe
 
+    def _forward_tiles(self, tiles: torch.Tensor) -> int:
+        T = tiles.shape[0]
+        assert T <= self.B
+        x = tiles
+        if T < self.B:
+            x = torch.cat([tiles, tiles[:1].expand(self.B - T, -1, -1, -1)], 0).contiguous()
+        self.net.set_input(x)
+        self.net.forward()
+        return T
+
+    def predict_tiles_raw(self, tiles: torch.Tensor) -> torch.Tensor:
+        """the regression variant's `Learner_adjust.predict` (train.py:87-95): the network output itself, [T,1,H,W] fp32"""
+        T = self._forward_tiles(tiles)
+        return self.net.logits_nchw()[:T]
+
     def predict_tiles(self, tiles_u8: torch.Tensor):
         """what `learn.predict` returns per tile (predict.py:193-203): softmax probabilities [T,C,H,W] fp32 and the
         argmax [T,H,W] uint8, for a batch of uint8 tiles [T<=B, C, P, P] on the device."""
