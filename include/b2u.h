@@ -106,6 +106,12 @@ typedef struct b2u_conv_desc {
    * `out` still gives the GEMM geometry (N,H,W) and the total channel count. */
   int32_t num_out;
   b2u_view out_nt[4];
+  /* w_batch_rows > 0: BATCHED weights - image n of the GEMM space multiplies rows [n * w_batch_rows, n * w_batch_rows +
+   * w_rows) of `w` (which then holds out.N * w_batch_rows rows): out[n,p,r] = sum_c a[n,p,c] * w[n * w_batch_rows + r][c].
+   * This is torch.bmm(A, B^T) on the implicit-GEMM kernel - the batched products of fastai's SelfAttention
+   * (`bmm(f^T, g)`, `bmm(h, beta)` and their backward; reference train.py:142, params_and_main.py:83).  Pixel tiles never
+   * cross an image and CTA pairs are off in this mode.  Needs a 1x1 tap table. */
+  int32_t w_batch_rows;
 } b2u_conv_desc;
 
 typedef struct b2u_conv_info {
@@ -317,6 +323,11 @@ int b2u_dice_counts(const float* logits, int32_t ld, const uint8_t* labels, int6
                     void* stream);
 
 /* ---- optimizer ------------------------------------------------------------------------------------------------ */
+/* ---- data-parallel gradient exchange: the fp32 gradient range is cast to bf16 for the NCCL all-reduce (half the bytes
+ * over NVLink) and back before the optimizer.  x / y: fp32 ranges 16-byte aligned, bf16 ranges 8-byte aligned. */
+int b2u_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream);
+int b2u_cast_bf16_f32(const void* x, float* y, int64_t n, void* stream);
+
 /* p -= lr * grad_scale * g over one flat fp32 buffer (BASELINE config 1: plain SGD) */
 int b2u_sgd_step(float* p, const float* g, int64_t n, float lr, float grad_scale, void* stream);
 /* fastai Adam (train.py:218): decoupled wd, per-segment lr / wd via device tables (seg_end = exclusive end offsets);
@@ -344,6 +355,13 @@ int b2u_stitch_accumulate_q31(const float* logits, int32_t ld, int32_t C, int32_
                               uint8_t* cnt, int64_t Y, int64_t X, int64_t y_off, int64_t x_off, void* stream);
 int b2u_stitch_finalize_q31(const float* acc, const uint8_t* cnt, int32_t C, int64_t Y, int64_t X, uint8_t* mask,
                             void* stream);
+/* the same accumulate with the selection count on the device (`*n_sel_dev` <= max_sel tiles of `sel` are processed), so
+ * that a whole batch - crop, forward, accumulate of each colour class - replays as ONE captured CUDA graph while the
+ * per-batch tile origins / class lists are swapped underneath it.  mode: 0 softmax, 1 `large_file` (x31), 2 raw. */
+int b2u_stitch_accumulate_dev(const float* logits, int32_t ld, int32_t C, int32_t T, int32_t th, int32_t tw,
+                              const int32_t* y0, const int32_t* x0, const int32_t* sel, const int32_t* n_sel_dev,
+                              int32_t max_sel, int32_t mode, float* acc, uint8_t* cnt, int64_t Y, int64_t X,
+                              int64_t y_off, int64_t x_off, void* stream);
 /* regression merge (predict.py:196-198, 300-316): the raw network output is summed (no softmax) ... */
 int b2u_stitch_accumulate_raw(const float* logits, int32_t ld, int32_t C, int32_t T, int32_t th, int32_t tw,
                               const int32_t* y0, const int32_t* x0, const int32_t* sel, int32_t n_sel, float* acc,
@@ -366,10 +384,15 @@ int b2u_spectral_norm(const float* W, int32_t Co, int32_t Ci, float* u, float* v
 /* gradient through W_sn = W / sigma(W) with u, v constant: dW <- (dW - sum(dW * W_sn) u v^T) / sigma, in place */
 int b2u_spectral_norm_bwd(float* dW, const float* W, int32_t Co, int32_t Ci, const float* u, const float* v,
                           const float* sigma, void* stream);
-/* beta[b][i][j] = softmax over i of S[b][i][j] (F.softmax(..., dim=1)), bf16 [B][n][n] */
-int b2u_softmax_dim1(const void* S, void* beta, int32_t B, int32_t n, void* stream);
-/* dS = beta * (dbeta - sum_i beta * dbeta), column-wise; dS may alias dbeta */
-int b2u_softmax_dim1_bwd(const void* beta, const void* dbeta, void* dS, int32_t B, int32_t n, void* stream);
+/* batched transpose of an NHWC-style bf16 tensor: y[b][c][i] = x[b][i][c] for i < n, c < C (x rows of pitch ldx, y rows of
+ * pitch ldy >= n; pad lanes of y are zeroed) - puts the contraction index of a batched product innermost */
+int b2u_transpose_bnc(const void* x, int32_t ldx, void* y, int32_t ldy, int32_t B, int32_t n, int32_t C, void* stream);
+/* beta[b][i][j] = softmax over i of S[b][i][j] (F.softmax(..., dim=1)), bf16 [B][n] rows of pitch ld >= n; betaT
+ * (nullable, same shape) also receives the transpose betaT[b][j][i] */
+int b2u_softmax_dim1(const void* S, void* beta, void* betaT, int32_t B, int32_t n, int32_t ld, void* stream);
+/* dS = beta * (dbeta - sum_i beta * dbeta), column-wise; dS may alias dbeta; dST (nullable) receives the transpose */
+int b2u_softmax_dim1_bwd(const void* beta, const void* dbeta, void* dS, void* dST, int32_t B, int32_t n, int32_t ld,
+                         void* stream);
 /* out = gamma[0] * o + x over `elems` bf16 elements (multiple of 8) */
 int b2u_attn_out(const void* o, const void* x, const float* gamma, void* out, int64_t elems, void* stream);
 /* d_o = gamma[0] * dout (bf16) and dgamma[0] = sum(dout * o) (fp32, fixed-order two-stage reduction;

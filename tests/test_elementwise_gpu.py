@@ -499,3 +499,36 @@ def test_pointwise_smallk_head_dgrad():
     torch.cuda.synchronize()
     assert rel(out[:, :Cc], ref) <= 1e-2
     assert (out[:, Cc:] == 0).all()
+
+
+@pytest.mark.parametrize("n,C", [(256, 48), (1024, 384), (625, 40), (64, 384)])
+def test_softmax_dim1_transposes_and_batched_transpose(n, C):
+    """softmax over the QUERY axis with its transposed copy (fastai SelfAttention: F.softmax(bmm(f^T, g), dim=1)), its
+    backward with the transposed dS, and the batched [n, C] -> [C, n] transpose that puts contraction indices innermost."""
+    from unet_b200.ops import padc
+    L, _lib = lib()
+    B, ld = 3, padc(n)
+    g = torch.Generator(device="cuda").manual_seed(n)
+    Sm = torch.zeros((B, n, ld), dtype=torch.bfloat16, device="cuda")
+    Sm[..., :n] = (torch.randn((B, n, n), device="cuda", generator=g) * 2).to(torch.bfloat16)
+    beta, betaT = torch.zeros_like(Sm), torch.zeros_like(Sm)
+    _lib.check(L.b2u_softmax_dim1(p(Sm), p(beta), p(betaT), B, n, ld, S()))
+    torch.cuda.synchronize()
+    ref = torch.softmax(Sm[..., :n].float(), dim=1)
+    assert rel(beta[..., :n], ref) <= 2.0 ** -8
+    assert torch.equal(betaT[..., :n], beta[..., :n].transpose(1, 2))
+    db = torch.zeros_like(Sm)
+    db[..., :n] = torch.randn((B, n, n), device="cuda", generator=g).to(torch.bfloat16)
+    dS, dST = torch.zeros_like(Sm), torch.zeros_like(Sm)
+    _lib.check(L.b2u_softmax_dim1_bwd(p(beta), p(db), p(dS), p(dST), B, n, ld, S()))
+    torch.cuda.synchronize()
+    bf, dbf = beta[..., :n].float(), db[..., :n].float()
+    ref_ds = bf * (dbf - (bf * dbf).sum(1, keepdim=True))
+    assert rel(dS[..., :n], ref_ds) <= 1e-2
+    assert torch.equal(dST[..., :n], dS[..., :n].transpose(1, 2))
+    x = torch.zeros((B, n, padc(C)), dtype=torch.bfloat16, device="cuda")
+    x[..., :C] = torch.randn((B, n, C), device="cuda", generator=g).to(torch.bfloat16)
+    y = torch.full((B, C, ld), 5.0, dtype=torch.bfloat16, device="cuda")
+    _lib.check(L.b2u_transpose_bnc(p(x), padc(C), p(y), ld, B, n, C, S()))
+    torch.cuda.synchronize()
+    assert torch.equal(y[..., :n], x[..., :C].transpose(1, 2)) and (y[..., n:] == 0).all()

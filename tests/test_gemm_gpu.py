@@ -360,3 +360,27 @@ def test_conv_pixel_shuffle_store(N, Cin, cu, H, W):
                                           ops.stream_ptr()), "b2u_shuffle_bwd_from_cat")
     torch.cuda.synchronize()
     assert torch.equal(d1, d2)
+
+
+@pytest.mark.parametrize("N,h,w,Cin,rows", [(3, 16, 16, 48, 256), (2, 32, 32, 1024, 384), (4, 8, 8, 64, 48),
+                                             (2, 25, 25, 48, 625), (3, 16, 16, 256, 48)])
+def test_conv_batched_weights_is_bmm(N, h, w, Cin, rows):
+    """b2u_conv_desc.w_batch_rows: out[img] = A[img] @ W[img]^T - torch.bmm on the implicit-GEMM kernel (the batched
+    products of fastai's SelfAttention, forward and backward shapes; one image smaller than a 128-pixel tile)."""
+    from unet_b200 import ops
+    n = h * w
+    a = rnd(N, n, Cin, seed=5, scale=Cin ** -0.5)
+    wt = rnd(N, rows, Cin, seed=6)
+    ref = torch.bmm(a, wt.transpose(1, 2))                                   # [N, n, rows]
+    ld_a, ld_o = ops.padc(Cin), ops.padc(rows)
+    at = torch.zeros((N, h, w, ld_a), dtype=torch.bfloat16, device="cuda")
+    at[..., :Cin] = a.view(N, h, w, Cin).to(torch.bfloat16)
+    wb = torch.zeros((N * rows, 1, ld_a), dtype=torch.bfloat16, device="cuda")
+    wb[:, 0, :Cin] = wt.reshape(N * rows, Cin).to(torch.bfloat16)
+    out = torch.full((N, h, w, ld_o), 3.0, dtype=torch.bfloat16, device="cuda")
+    plan = ops.ConvPlan([ops.view_nhwc(at, Cin)], ops.view_nhwc(out, rows), wb, Cin, ops.taps_conv(1), w_batch_rows=rows)
+    assert plan.info.tile_n == 1
+    plan.run()
+    torch.cuda.synchronize()
+    e = rel_err(out.view(N, n, ld_o)[..., :rows], ref)
+    assert e <= 1e-2, (e, [(k, getattr(plan.info, k)) for k, _ in plan.info._fields_])

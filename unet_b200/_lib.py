@@ -49,6 +49,7 @@ class ConvDesc(C.Structure):
         ("out_f32", C.c_void_p), ("out_f32_ld", C.c_int32),
         ("fin", BNFin),
         ("num_out", C.c_int32), ("out_nt", View * 4),
+        ("w_batch_rows", C.c_int32),
     ]
 
 
@@ -139,8 +140,9 @@ def _declare(lib):
         "b2u_pad_even_fwd": [vp, vp, i32, i32, i32, i32, vp],
         "b2u_spectral_norm": [vp, i32, i32, vp, vp, i32, vp, vp],
         "b2u_spectral_norm_bwd": [vp, vp, i32, i32, vp, vp, vp, vp],
-        "b2u_softmax_dim1": [vp, vp, i32, i32, vp],
-        "b2u_softmax_dim1_bwd": [vp, vp, vp, i32, i32, vp],
+        "b2u_softmax_dim1": [vp, vp, vp, i32, i32, i32, vp],
+        "b2u_softmax_dim1_bwd": [vp, vp, vp, vp, i32, i32, i32, vp],
+        "b2u_transpose_bnc": [vp, i32, vp, i32, i32, i32, i32, vp],
         "b2u_attn_out": [vp, vp, vp, vp, i64, vp],
         "b2u_attn_out_bwd": [vp, vp, vp, vp, vp, vp, i64, vp],
         "b2u_pad_even_bwd": [vp, vp, i32, i32, i32, i32, i32, vp],
@@ -155,12 +157,15 @@ def _declare(lib):
         "b2u_mse_finalize": [vp, i32, i64, vp, vp],
         "b2u_regression_sums": [vp, i32, vp, i64, vp, i32, vp, vp, vp],
         "b2u_dice_counts": [vp, i32, u8p, i64, i32, vp, vp],
+        "b2u_cast_f32_bf16": [vp, vp, i64, vp],
+        "b2u_cast_bf16_f32": [vp, vp, i64, vp],
         "b2u_sgd_step": [vp, vp, i64, f32, f32, vp],
         "b2u_adam_step": [vp, vp, vp, vp, i64, vp, vp, vp, i32, vp, vp],
         "b2u_stitch_accumulate": [vp, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp, u8p, i64, i64, i64, i64, vp],
         "b2u_stitch_finalize": [vp, u8p, i32, i64, i64, u8p, vp],
         "b2u_stitch_accumulate_q31": [vp, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp, u8p, i64, i64, i64, i64, vp],
         "b2u_stitch_finalize_q31": [vp, u8p, i32, i64, i64, u8p, vp],
+        "b2u_stitch_accumulate_dev": [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, i32, i32, vp, u8p, i64, i64, i64, i64, vp],
         "b2u_stitch_accumulate_raw": [vp, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp, u8p, i64, i64, i64, i64, vp],
         "b2u_stitch_finalize_mean": [vp, u8p, i32, i64, i64, f32, vp, vp],
         "b2u_softmax_nchw": [vp, i32, i32, i64, i32, i32, vp, u8p, vp],

@@ -3,7 +3,9 @@
 // spectral normalisation of the query / key / value weights (torch.nn.utils.spectral_norm: one power iteration per
 // training forward), the softmax over the QUERY axis (F.softmax(bmm(f^T, g), dim=1)), the gamma residual, and their
 // backward passes.  The 1x1 convolutions run on the implicit-GEMM kernel; the two batched attention products
-// (n x n x C/8 and n x C x n per image, ~0.1 % of the step's FLOPs) are plain library GEMMs issued by the host layer.
+// (n x n x C/8 and n x C x n per image and their four backward products, ~1.4 % of the forward FLOPs at 256-px tiles) run
+// on the same kernel with BATCHED weights (b2u_conv_desc.w_batch_rows): the softmax kernels also emit the transposed
+// matrices and b2u_transpose_bnc the transposed operands, so that every product has its contraction index innermost.
 #include "host_util.h"
 #include "ptx.cuh"
 #include "stream.cuh"
@@ -94,18 +96,21 @@ __global__ void __launch_bounds__(1024) spectral_norm_bwd_kernel(float* __restri
   }
 }
 
-// Column softmax of S[b] (n x n, row-major, bf16): block = 32 columns x 8 row lanes.
+// Column softmax of S[b] (n x n, rows of pitch ld, bf16): block = 32 columns x 8 row lanes.  betaT (nullable) receives
+// the transpose (betaT[b][j][i] = beta[b][i][j]) through a 32 x 32 shared-memory tile, so both writes are coalesced.
 __global__ void __launch_bounds__(256) softmax_dim1_kernel(const __nv_bfloat16* __restrict__ S,
-                                                          __nv_bfloat16* __restrict__ beta, int n) {
+                                                          __nv_bfloat16* __restrict__ beta,
+                                                          __nv_bfloat16* __restrict__ betaT, int n, int ld) {
   pdl_enter();
   __shared__ float sh[8][33];
+  __shared__ __nv_bfloat16 tile[32][34];
   const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
-  const int j = blockIdx.x * 32 + cl;
-  const size_t base = (size_t)blockIdx.y * n * n;
+  const int j0 = blockIdx.x * 32, j = j0 + cl;
+  const size_t base = (size_t)blockIdx.y * n * ld;
   const bool ok = j < n;
   float m = -INFINITY;
   if (ok)
-    for (int i = rl; i < n; i += 8) m = fmaxf(m, __bfloat162float(S[base + (size_t)i * n + j]));
+    for (int i = rl; i < n; i += 8) m = fmaxf(m, __bfloat162float(S[base + (size_t)i * ld + j]));
   sh[rl][cl] = m;
   __syncthreads();
   m = sh[0][cl];
@@ -114,32 +119,51 @@ __global__ void __launch_bounds__(256) softmax_dim1_kernel(const __nv_bfloat16* 
   __syncthreads();
   float s = 0.f;
   if (ok)
-    for (int i = rl; i < n; i += 8) s += expf(__bfloat162float(S[base + (size_t)i * n + j]) - m);
+    for (int i = rl; i < n; i += 8) s += expf(__bfloat162float(S[base + (size_t)i * ld + j]) - m);
   sh[rl][cl] = s;
   __syncthreads();
   s = 0.f;
 #pragma unroll
   for (int q = 0; q < 8; ++q) s += sh[q][cl];
   const float inv = 1.f / s;
-  if (ok)
-    for (int i = rl; i < n; i += 8) {
-      const size_t o = base + (size_t)i * n + j;
-      beta[o] = __float2bfloat16_rn(expf(__bfloat162float(S[o]) - m) * inv);
+  for (int i0 = 0; i0 < n; i0 += 32) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = i0 + rl + 8 * k;
+      __nv_bfloat16 v = __float2bfloat16_rn(0.f);
+      if (ok && i < n) {
+        const size_t o = base + (size_t)i * ld + j;
+        v = __float2bfloat16_rn(expf(__bfloat162float(S[o]) - m) * inv);
+        beta[o] = v;
+      }
+      tile[rl + 8 * k][cl] = v;
     }
+    if (betaT) {
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int jj = j0 + rl + 8 * k, i = i0 + cl;        // row jj of the transpose, 32 consecutive i
+        if (jj < n && i < n) betaT[base + (size_t)jj * ld + i] = tile[cl][rl + 8 * k];
+      }
+      __syncthreads();
+    }
+  }
 }
 
 __global__ void __launch_bounds__(256) softmax_dim1_bwd_kernel(const __nv_bfloat16* __restrict__ beta,
-                                                              const __nv_bfloat16* dbeta, __nv_bfloat16* dS, int n) {
+                                                              const __nv_bfloat16* dbeta, __nv_bfloat16* dS,
+                                                              __nv_bfloat16* __restrict__ dST, int n, int ld) {
   pdl_enter();
   __shared__ float sh[8][33];
+  __shared__ __nv_bfloat16 tile[32][34];
   const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
-  const int j = blockIdx.x * 32 + cl;
-  const size_t base = (size_t)blockIdx.y * n * n;
+  const int j0 = blockIdx.x * 32, j = j0 + cl;
+  const size_t base = (size_t)blockIdx.y * n * ld;
   const bool ok = j < n;
   float t = 0.f;
   if (ok)
     for (int i = rl; i < n; i += 8) {
-      const size_t o = base + (size_t)i * n + j;
+      const size_t o = base + (size_t)i * ld + j;
       t += __bfloat162float(beta[o]) * __bfloat162float(dbeta[o]);
     }
   sh[rl][cl] = t;
@@ -147,11 +171,50 @@ __global__ void __launch_bounds__(256) softmax_dim1_bwd_kernel(const __nv_bfloat
   t = 0.f;
 #pragma unroll
   for (int q = 0; q < 8; ++q) t += sh[q][cl];
-  if (ok)
-    for (int i = rl; i < n; i += 8) {
-      const size_t o = base + (size_t)i * n + j;
-      dS[o] = __float2bfloat16_rn(__bfloat162float(beta[o]) * (__bfloat162float(dbeta[o]) - t));
+  for (int i0 = 0; i0 < n; i0 += 32) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = i0 + rl + 8 * k;
+      __nv_bfloat16 v = __float2bfloat16_rn(0.f);
+      if (ok && i < n) {
+        const size_t o = base + (size_t)i * ld + j;
+        v = __float2bfloat16_rn(__bfloat162float(beta[o]) * (__bfloat162float(dbeta[o]) - t));
+        dS[o] = v;
+      }
+      tile[rl + 8 * k][cl] = v;
     }
+    if (dST) {
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int jj = j0 + rl + 8 * k, i = i0 + cl;
+        if (jj < n && i < n) dST[base + (size_t)jj * ld + i] = tile[cl][rl + 8 * k];
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// y[b][c][i] = x[b][i][c] (bf16): 32 x 32 tiles through shared memory, coalesced on both sides; pad lanes of y zeroed
+__global__ void __launch_bounds__(256) transpose_bnc_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
+                                                           __nv_bfloat16* __restrict__ y, int ldy, int n, int C) {
+  pdl_enter();
+  __shared__ __nv_bfloat16 tile[32][34];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int i0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const __nv_bfloat16* xb = x + (size_t)blockIdx.z * n * ldx;
+  __nv_bfloat16* yb = y + (size_t)blockIdx.z * C * ldy;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = i0 + rl + 8 * k, c = c0 + cl;
+    tile[rl + 8 * k][cl] = (i < n && c < C) ? xb[(size_t)i * ldx + c] : __float2bfloat16_rn(0.f);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = c0 + rl + 8 * k, i = i0 + cl;
+    if (c < C && i < ldy) yb[(size_t)c * ldy + i] = tile[cl][rl + 8 * k];
+  }
 }
 
 __global__ void __launch_bounds__(256) attn_out_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ x,
@@ -236,17 +299,27 @@ extern "C" int b2u_spectral_norm_bwd(float* dW, const float* W, int32_t Co, int3
   return B2U_OK;
 }
 
-extern "C" int b2u_softmax_dim1(const void* S, void* beta, int32_t B, int32_t n, void* stream) {
-  B2U_CHECK_ARG(S && beta && B > 0 && n > 0 && B <= 65535, "softmax_dim1: bad argument");
-  launch_k(softmax_dim1_kernel, dim3(ceil_div(n, 32), B), dim3(256), 0, (cudaStream_t)stream, (cbf)S, (bf)beta, n);
+extern "C" int b2u_softmax_dim1(const void* S, void* beta, void* betaT, int32_t B, int32_t n, int32_t ld, void* stream) {
+  B2U_CHECK_ARG(S && beta && B > 0 && n > 0 && ld >= n && B <= 65535, "softmax_dim1: bad argument");
+  launch_k(softmax_dim1_kernel, dim3(ceil_div(n, 32), B), dim3(256), 0, (cudaStream_t)stream, (cbf)S, (bf)beta, (bf)betaT, n, ld);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }
 
-extern "C" int b2u_softmax_dim1_bwd(const void* beta, const void* dbeta, void* dS, int32_t B, int32_t n, void* stream) {
-  B2U_CHECK_ARG(beta && dbeta && dS && B > 0 && n > 0 && B <= 65535, "softmax_dim1_bwd: bad argument");
+extern "C" int b2u_softmax_dim1_bwd(const void* beta, const void* dbeta, void* dS, void* dST, int32_t B, int32_t n,
+                                    int32_t ld, void* stream) {
+  B2U_CHECK_ARG(beta && dbeta && dS && B > 0 && n > 0 && ld >= n && B <= 65535, "softmax_dim1_bwd: bad argument");
   launch_k(softmax_dim1_bwd_kernel, dim3(ceil_div(n, 32), B), dim3(256), 0, (cudaStream_t)stream, (cbf)beta, (cbf)dbeta,
-           (bf)dS, n);
+           (bf)dS, (bf)dST, n, ld);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" int b2u_transpose_bnc(const void* x, int32_t ldx, void* y, int32_t ldy, int32_t B, int32_t n, int32_t C,
+                                 void* stream) {
+  B2U_CHECK_ARG(x && y && B > 0 && B <= 65535 && n > 0 && C > 0 && ldx >= C && ldy >= n, "transpose_bnc: bad argument");
+  launch_k(transpose_bnc_kernel, dim3(ceil_div(ldy, 32), ceil_div(C, 32), B), dim3(256), 0, (cudaStream_t)stream, (cbf)x, ldx,
+           (bf)y, ldy, n, C);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }

@@ -51,6 +51,7 @@ struct ConvParams {
   float* out_f32;
   int out_f32_ld;
   b2u_bn_fin fin;   // counter != nullptr: the last CTA to retire finalizes the BatchNorm statistics
+  int w_batch_rows; // > 0: batched weights, image n uses weight rows n * w_batch_rows + ... (tn == 1, no CTA pairs)
   int multi_out;    // N tile nt is stored through tm_out_nt[nt] at channel 0 (PixelShuffle phases -> parity planes)
   CUtensorMap tm_out_nt[4];
 #ifdef B2U_TIMELINE
@@ -76,6 +77,7 @@ struct ConvParams {
 static constexpr int kThreads = 384;   // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 epilogue
 static constexpr uint32_t kABytes = 128 * 128;       // 128 pixels x 64 bf16
 static constexpr uint32_t kStagingBytes = 128 * 128; // 128 pixels x 64 bf16, one output chunk
+static constexpr uint32_t kAuxRing = 3;               // operand buffers in flight / in use per 64-channel chunk
 static constexpr uint32_t kTmemCols = 512;
 static constexpr uint32_t kAccStride = 256;
 
@@ -183,8 +185,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   const uint32_t ring_bytes = p.halo ? ((uint32_t)p.SA * p.a_stage_bytes + (uint32_t)p.SB * bs_bytes) : (uint32_t)S * stage_bytes;
   const int n_ring_bars = p.halo ? 2 * (p.SA + p.SB) : 2 * S;
   const uint32_t stg_base = smem_base + ring_bytes;
-  const uint32_t aux_base = stg_base + (uint32_t)p.stg_bufs * kStagingBytes;  // n_aux x 2 x 16 KB, double buffered per output chunk
-  const uint32_t bar_base = aux_base + (uint32_t)p.n_aux * 2 * kStagingBytes;
+  // with residual / mask operands (kAux) there is no separate staging: a ring of kAuxRing buffers, each n_aux x 16 KB, receives
+  // the operands of a 64-channel output chunk by TMA two chunks ahead; the result is computed IN PLACE over operand 0
+  // and stored from there (stg_bufs == 0).  Without operands: stg_bufs plain staging buffers.
+  const uint32_t aux_base = stg_base + (uint32_t)p.stg_bufs * kStagingBytes;
+  const uint32_t epi_bufs = (uint32_t)p.stg_bufs + (uint32_t)p.n_aux * kAuxRing;
+  const uint32_t bar_base = stg_base + epi_bufs * kStagingBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(S + s); };
   // halo-mode ring barriers: fullA[SA] emptyA[SA] fullB[SB] emptyB[SB]
@@ -195,11 +201,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   auto tfull_bar = [&](int a) { return bar_base + 8u * (uint32_t)(n_ring_bars + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (uint32_t)(n_ring_bars + 2 + a); };
   auto aux_bar = [&](int b) { return bar_base + 8u * (uint32_t)(n_ring_bars + 4 + b); };
-  const uint32_t tmem_slot = bar_base + 8u * (uint32_t)(n_ring_bars + 6);
+  const uint32_t tmem_slot = bar_base + 8u * (uint32_t)(n_ring_bars + 7);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
-      smem + (size_t)ring_bytes + (size_t)(p.stg_bufs + 2 * p.n_aux) * kStagingBytes + 8 * (n_ring_bars + 6));
+      smem + (size_t)ring_bytes + (size_t)epi_bufs * kStagingBytes + 8 * (n_ring_bars + 7));
 
-  float* s_stats = reinterpret_cast<float*>(smem + (size_t)ring_bytes + (size_t)(p.stg_bufs + 2 * p.n_aux) * kStagingBytes + 512);
+  float* s_stats = reinterpret_cast<float*>(smem + (size_t)ring_bytes + (size_t)epi_bufs * kStagingBytes + 512);
   for (int i = threadIdx.x; i < 8 * p.stats_cols; i += kThreads) s_stats[i] = 0.f;
   if (threadIdx.x == 0) {
     if (smem_base & 1023u) {
@@ -210,8 +216,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), kPair ? 257 : 256);   // pair: + one remote arrive from the peer's epilogue
-      mbar_init(aux_bar(a), 1);
     }
+    for (int a = 0; a < (int)kAuxRing; ++a) mbar_init(aux_bar(a), 1);
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) {
@@ -313,7 +319,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             const uint32_t a_dst = smem_base + (uint32_t)stage * stage_bytes;
             if (rank == 0) mbar_expect_tx(full_bar(stage), tx_mult * stage_bytes);
             load4(a_dst, ma, full_bar(stage), kc * 64, xx, yy, n0);
-            load3(a_dst + kABytes, &p.tm_b, full_bar(stage), kc * 64, wt, nt * p.BN + b_row0);
+            load3(a_dst + kABytes, &p.tm_b, full_bar(stage), kc * 64, wt, nt * p.BN + b_row0 + n0 * p.w_batch_rows);
             if (++stage == S) { stage = 0; phase ^= 1u; }
           }
         }
@@ -471,10 +477,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       const int by2 = rem2 / p.tiles_x, bx2 = rem2 - by2 * p.tiles_x;
       mbar_expect_tx(aux_bar(buf), (uint32_t)p.n_aux * kStagingBytes);
       for (int i = 0; i < p.n_aux; ++i)
-        tma_load_4d(aux_base + (uint32_t)i * 2 * kStagingBytes + buf * kStagingBytes, &p.tm_aux[i], aux_bar(buf),
+        tma_load_4d(aux_base + (buf * (uint32_t)p.n_aux + (uint32_t)i) * kStagingBytes, &p.tm_aux[i], aux_bar(buf),
                     nt2 * p.BN + chunk * 64, bx2 * p.tw, by2 * p.th, bn2 * p.tn);
     };
-    if (kAux && e == 0 && t_begin < t_end) issue_aux(t_begin, 0, 0);
+    // prefetch cursor of the operand loads: (tile, chunk) of the next chunk to fetch; two chunks run ahead
+    int pf_t = t_begin, pf_j = 0;
+    uint32_t pf_ctr = 0;
+    auto prefetch_aux = [&]() {
+      if (pf_t < t_end) {
+        issue_aux(pf_t, pf_j, pf_ctr % kAuxRing);
+        ++pf_ctr;
+        if (++pf_j == n_chunks) { pf_j = 0; pf_t += t_step; }
+      }
+    };
+    if (kAux && e == 0) { prefetch_aux(); prefetch_aux(); }
     for (int tt = t_begin; tt < t_end; tt += t_step) {
       const int m = tile_m(tt), nt = tile_nt(tt);
       const int bn = m / tiles_xy, rem = m - bn * tiles_xy;
@@ -494,15 +510,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       for (int j = 0; j < n_chunks; ++j) {
         const int g = 2 * j + hsel;
         const bool active = g < n_groups;   // warp-uniform
-        if (kAux) {
-          // residual / mask tiles arrive through TMA (coalesced, asynchronous), one 64-channel chunk ahead
-          if (e == 0) {
-            int t2 = tt, j2 = j + 1;
-            if (j2 >= n_chunks) { t2 = tt + t_step; j2 = 0; }
-            if (t2 < t_end) issue_aux(t2, j2, (chunk_ctr + 1u) & 1u);
-          }
-          mbar_wait(aux_bar(chunk_ctr & 1u), (chunk_ctr >> 1) & 1u);
-        }
+        const uint32_t abuf = chunk_ctr % kAuxRing;
+        // residual / mask tiles arrive through TMA (coalesced, asynchronous), two 64-channel chunks ahead
+        if (kAux) mbar_wait(aux_bar(abuf), (chunk_ctr / kAuxRing) & 1u);
         uint32_t r[32];
         if (active) {
           tmem_ld32(taddr + (uint32_t)(g * 32), r);
@@ -535,7 +545,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             }
           }
           if (kAux) {
-            const uint32_t abase = aux_base + (chunk_ctr & 1u) * kStagingBytes + (uint32_t)row * 128u;
+            const uint32_t abase = aux_base + abuf * (uint32_t)p.n_aux * kStagingBytes + (uint32_t)row * 128u;
             if (has_res) {
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
@@ -544,7 +554,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 unpack8(ld_shared_v4(abase + off), rv);
                 if (has_rm) {
                   float mv[8];
-                  unpack8(ld_shared_v4(abase + (uint32_t)slot_rm * 2 * kStagingBytes + off), mv);
+                  unpack8(ld_shared_v4(abase + (uint32_t)slot_rm * kStagingBytes + off), mv);
 #pragma unroll
                   for (int i = 0; i < 8; ++i) v[q * 8 + i] += (mv[i] > 0.f) ? rv[i] : 0.f;
                 } else {
@@ -560,8 +570,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           }
           if (kAux) {
             if (has_zm) {
-              const uint32_t abase = aux_base + (chunk_ctr & 1u) * kStagingBytes + (uint32_t)row * 128u +
-                                     (uint32_t)slot_zm * 2 * kStagingBytes;
+              const uint32_t abase = aux_base + abuf * (uint32_t)p.n_aux * kStagingBytes + (uint32_t)row * 128u +
+                                     (uint32_t)slot_zm * kStagingBytes;
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 const uint32_t off = (((uint32_t)(hsel * 4 + q)) ^ ((uint32_t)row & 7u)) << 4;
@@ -590,10 +600,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         } else {
           // bf16 pack -> swizzled staging (SWIZZLE_128B: 16-byte chunk j of row r lands at chunk j ^ (r & 7))
           const uint32_t buf = p.stg_bufs == 2 ? (chunk_ctr & 1u) : 0u;
-          // the store that last used this staging buffer has finished reading it
-          if (e == 0) { if (p.stg_bufs == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
-          named_bar_sync(1, 256);
-          const uint32_t row_addr = stg_base + buf * kStagingBytes + (uint32_t)row * 128u;
+          // kAux: the result overwrites operand 0 of this chunk in place (every thread reads and writes its own 64 bytes of
+          // its own pixel row only), and the buffer's previous store was drained before the operand load was issued
+          const uint32_t out_buf = kAux ? aux_base + abuf * (uint32_t)p.n_aux * kStagingBytes : stg_base + buf * kStagingBytes;
+          if (!kAux) {
+            // the store that last used this staging buffer has finished reading it
+            if (e == 0) { if (p.stg_bufs == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
+            named_bar_sync(1, 256);
+          }
+          const uint32_t row_addr = out_buf + (uint32_t)row * 128u;
           if (active) {
             uint32_t pk[16];
 #pragma unroll
@@ -626,9 +641,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           named_bar_sync(1, 256);
           if (e == 0) {
             if (kPair && rank != 0 && j == n_chunks - 1) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
-            if (p.multi_out) tma_store_4d(&p.tm_out_nt[nt], stg_base + buf * kStagingBytes, j * 64, x0, y0, n0);
-            else tma_store_4d(&p.tm_out, stg_base + buf * kStagingBytes, nt * p.BN + j * 64, x0, y0, n0);
+            if (p.multi_out) tma_store_4d(&p.tm_out_nt[nt], out_buf, j * 64, x0, y0, n0);
+            else tma_store_4d(&p.tm_out, out_buf, nt * p.BN + j * 64, x0, y0, n0);
             tma_store_commit();
+            if (kAux) {
+              // the buffer of the PREVIOUS chunk is free once its store has read it (one chunk ago: normally done): the
+              // operands of chunk + 2 go there, so two loads are in flight while this chunk's store drains
+              tma_store_wait_read<1>();
+              prefetch_aux();
+            }
             TL_STAMP(3, tl_e);
           }
         }
@@ -687,8 +708,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 
   // ---------------------------------------------------------------- fused BatchNorm finalize (last CTA to retire)
   if (p.fin.counter != nullptr) {
-    volatile int* s_last = reinterpret_cast<volatile int*>(
-        smem + (size_t)ring_bytes + (size_t)(p.stg_bufs + 2 * p.n_aux) * kStagingBytes + 504);
+    volatile int* s_last = reinterpret_cast<volatile int*>(smem + (size_t)ring_bytes + (size_t)epi_bufs * kStagingBytes + 504);
     if (threadIdx.x == 0) {
       __threadfence();
       const unsigned int ticket = atomicAdd(p.fin.counter, 1u);
@@ -840,9 +860,25 @@ static int conv_plan_fill(const b2u_conv_desc* d, b2u_conv_plan* plan, bool enco
   }
   int tw, th, tn, tx, ty, tb;
   pick_m_tile(d->out.N, d->out.H, d->out.W, &tw, &th, &tn, &tx, &ty, &tb);
+  const bool batched_w = d->w_batch_rows > 0;
+  if (batched_w) {
+    B2U_CHECK_ARG(d->w_batch_rows >= d->w_rows && !multi_out && !out_f32, "conv: w_batch_rows=%d < w_rows=%d (or an unsupported epilogue)",
+                  d->w_batch_rows, d->w_rows);
+    // one image per pixel tile (its weights differ from the neighbour's): the widest power-of-two box of <= 128 pixels
+    // inside an image; images smaller than 128 pixels leave the upper accumulator rows unused (never stored)
+    long long best = -1;
+    for (int w = 128; w >= 1; w >>= 1)
+      for (int h = 128 / w; h >= 1; h >>= 1) {
+        const long long cost = (long long)ceil_div(d->out.W, w) * ceil_div(d->out.H, h) * 128 - (long long)0;
+        const long long waste = cost * 1000 + (128 - w * h);      // fewest tiles first, then the fullest tile
+        if (best < 0 || waste < best) { best = waste; tw = w; th = h; }
+      }
+    tn = 1;
+    tx = ceil_div(d->out.W, tw); ty = ceil_div(d->out.H, th); tb = d->out.N;
+  }
   // halo mode: 3x3 stride-1 tap table over a single view (fprop and dgrad of the 3x3 convolutions), images >= 16 x 8
   static const bool halo_disabled = getenv("B2U_CONV_NO_HALO") != nullptr;  // A/B switch for profiling
-  bool halo = !halo_disabled && d->num_taps == 9 && d->num_a == 1 && d->out.H >= 16 && d->out.W >= 8;
+  bool halo = !halo_disabled && !batched_w && d->num_taps == 9 && d->num_a == 1 && d->out.H >= 16 && d->out.W >= 8;
   for (int t = 0; halo && t < 9; ++t) halo = d->tap_a[t] == 0 && d->tap_dy[t] == t / 3 - 1 && d->tap_dx[t] == t % 3 - 1;
   if (halo) {
     tw = 8; th = 16; tn = 1;
@@ -855,7 +891,7 @@ static int conv_plan_fill(const b2u_conv_desc* d, b2u_conv_plan* plan, bool enco
   // CTA-pair mode: two pixel tiles share every weight stage (each SM holds half of its rows) and one M = 256 MMA stream
   static const bool pair_disabled = getenv("B2U_CONV_NO_PAIR") != nullptr;  // A/B switch for profiling
   // (tiles with little MMA work - 1x1 convolutions over few channels - are epilogue/store-bound: pairing only adds sync)
-  const bool pair = !pair_disabled && !out_f32 && !multi_out && BN % 16 == 0 && p.m_tiles >= 2 &&
+  const bool pair = !pair_disabled && !out_f32 && !multi_out && !batched_w && BN % 16 == 0 && p.m_tiles >= 2 &&
                     (halo || d->num_taps * ceil_div(Cin, 64) >= 8);
   plan->pair = pair;
   const int b_rows = pair ? BN / 2 : BN;   // weight rows per CTA and tap
@@ -874,9 +910,12 @@ static int conv_plan_fill(const b2u_conv_desc* d, b2u_conv_plan* plan, bool enco
   p.n_aux = n_aux;
   const uint32_t stage_bytes = kABytes + (uint32_t)b_rows * 128u;
   p.stats_cols = ((d->flags & B2U_EPI_STATS) && n_tiles * BN <= 512) ? n_tiles * BN : 0;
-  p.stg_bufs = 2;
+  // epilogue buffers: with residual / mask operands a ring of kAuxRing x n_aux operand buffers that doubles as staging
+  // (results are computed in place), otherwise 2 staging buffers (1 next to resident weights)
+  p.stg_bufs = n_aux > 0 ? 0 : 2;
   p.rowmode = 0;
-  uint32_t fixed = (2 + 2 * (uint32_t)n_aux) * kStagingBytes + 512 + (uint32_t)p.stats_cols * 32u;
+  const uint32_t aux_bytes = (uint32_t)n_aux * kAuxRing * kStagingBytes;
+  uint32_t fixed = (uint32_t)p.stg_bufs * kStagingBytes + aux_bytes + 512 + (uint32_t)p.stats_cols * 32u;
   int stages;
   if (halo) {
     p.a_tx_bytes = (uint32_t)((tw + 2) * (th + 2)) * 128u;
@@ -896,9 +935,10 @@ static int conv_plan_fill(const b2u_conv_desc* d, b2u_conv_plan* plan, bool enco
       const uint32_t wbytes = (uint32_t)p.k_chunks * 9u * bb;
       const int try_sa[3] = {3, 2, 2}, try_stg[3] = {1, 2, 1};
       for (int i = 0; i < 3 && !p.wres; ++i) {
-        const uint32_t fx = fixed - (2u - (uint32_t)try_stg[i]) * kStagingBytes;
+        const int stg = n_aux > 0 ? 0 : try_stg[i];
+        const uint32_t fx = fixed - (uint32_t)(p.stg_bufs - stg) * kStagingBytes;
         if ((uint32_t)try_sa[i] * p.a_stage_bytes + wbytes + fx <= 232448u) {
-          p.wres = 1; p.rowmode = 1; p.SA = try_sa[i]; p.SB = 3 * p.k_chunks; p.stg_bufs = try_stg[i];
+          p.wres = 1; p.rowmode = 1; p.SA = try_sa[i]; p.SB = 3 * p.k_chunks; p.stg_bufs = stg;
           fixed = fx;
           bb *= 3;
         }
@@ -906,10 +946,10 @@ static int conv_plan_fill(const b2u_conv_desc* d, b2u_conv_plan* plan, bool enco
     }
     // (measured: a partial last K chunk, e.g. Cin = 100, makes row mode slower than per-tap stages, so it is excluded)
     if (!p.wres && !row_disabled && BN <= 128 && tapw_ok && d->w_taps == 9 && Cin % 64 == 0) {
-      const uint32_t fixed1 = fixed - kStagingBytes;
+      const uint32_t fixed1 = n_aux > 0 ? fixed : fixed - kStagingBytes;
       const int sb3 = (int)((232448u - fixed1 - 2u * p.a_stage_bytes) / (3u * bb));
       if (sb3 >= 3) {
-        p.rowmode = 1; p.stg_bufs = 1; fixed = fixed1; p.SA = 2; p.SB = sb3 > 4 ? 4 : sb3;
+        p.rowmode = 1; p.stg_bufs = n_aux > 0 ? 0 : 1; fixed = fixed1; p.SA = 2; p.SB = sb3 > 4 ? 4 : sb3;
         bb *= 3;
       }
     }
@@ -940,6 +980,7 @@ static int conv_plan_fill(const b2u_conv_desc* d, b2u_conv_plan* plan, bool enco
   p.res = ev(d->res); p.res_mask = ev(d->res_mask); p.zmask = ev(d->zmask);
   p.flags = d->flags; p.stats = d->stats; p.stats_ld = d->stats_ld;
   p.multi_out = multi_out ? d->num_out : 0;
+  p.w_batch_rows = batched_w ? d->w_batch_rows : 0;
 #ifdef B2U_TIMELINE
   p.timeline = nullptr;
 #endif
@@ -986,7 +1027,8 @@ static int conv_plan_fill(const b2u_conv_desc* d, b2u_conv_plan* plan, bool enco
     }
     {
       const int cin_ext = round_up(Cin, 16) <= d->w_cinp ? round_up(Cin, 16) : (round_up(Cin, 8) <= d->w_cinp ? round_up(Cin, 8) : Cin);
-      uint64_t dims[3] = {(uint64_t)cin_ext, (uint64_t)d->w_taps, (uint64_t)d->w_rows};
+      const uint64_t rows_total = batched_w ? (uint64_t)(d->out.N - 1) * d->w_batch_rows + d->w_rows : (uint64_t)d->w_rows;
+      uint64_t dims[3] = {(uint64_t)cin_ext, (uint64_t)d->w_taps, rows_total};
       uint64_t str[3] = {2, (uint64_t)d->w_cinp * 2, (uint64_t)d->w_cinp * 2 * (uint64_t)d->w_taps};
       uint32_t box[3] = {64, 1, (uint32_t)b_rows};
       int rc = encode_tmap_bf16(&p.tm_b, d->w, 3, dims, str, box);

@@ -469,10 +469,18 @@ __global__ void crop_tiles_kernel(const void* __restrict__ raster, int dtype, fl
     const long long gy = (long long)ty0[t] + yy, gx = (long long)tx0[t] + xx;
     const bool inb = gy >= 0 && gy < Y && gx >= 0 && gx < X;
     __nv_bfloat16* dst = out + i * ld;
-    for (int c = 0; c < ld; ++c) {
-      float v = 0.f;
-      if (c < C && inb) v = load_raw(raster, dtype, ((long long)c * Y + gy) * X + gx, div, div2);
-      dst[c] = __float2bfloat16_rn(v);
+    // ld is a multiple of 8 (checked on the host): whole 16-byte stores, zeros in the pad lanes
+    for (int c0 = 0; c0 < ld; c0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int c = c0 + k;
+        v[k] = (c < C && inb) ? load_raw(raster, dtype, ((long long)c * Y + gy) * X + gx, div, div2) : 0.f;
+      }
+      uint4 u;
+      u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+      u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+      *reinterpret_cast<uint4*>(dst + c0) = u;
     }
   }
 }
@@ -705,6 +713,28 @@ __global__ void dice_counts_kernel(const float* __restrict__ logits, int ld, con
   }
 }
 
+// fp32 <-> bf16 casts of a gradient range (the bf16 copy is what travels over NVLink in the data-parallel all-reduce)
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+  pdl_enter();
+  const long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    uint2 u;
+    u.x = pack_bf16x2(v.x, v.y); u.y = pack_bf16x2(v.z, v.w);
+    reinterpret_cast<uint2*>(y)[i] = u;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) y[(n4 << 2) + threadIdx.x] = __float2bfloat16_rn(x[(n4 << 2) + threadIdx.x]);
+}
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, long long n) {
+  pdl_enter();
+  const long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const uint2 u = reinterpret_cast<const uint2*>(x)[i];
+    reinterpret_cast<float4*>(y)[i] = make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) y[(n4 << 2) + threadIdx.x] = __bfloat162float(x[(n4 << 2) + threadIdx.x]);
+}
+
 // ------------------------------------------------------------------------------------------------ optimizers
 __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, long long n, float lr, float gs) {
   pdl_enter();
@@ -745,10 +775,12 @@ __global__ void stitch_accumulate_kernel(const float* __restrict__ logits, int l
                                          const int* __restrict__ ty0, const int* __restrict__ tx0,
                                          const int* __restrict__ sel, int n_sel, float* __restrict__ acc,
                                          uint8_t* __restrict__ cnt, long long Y, long long X, long long y_off,
-                                         long long x_off, float quant, int raw) {
+                                         long long x_off, float quant, int raw, const int* __restrict__ n_sel_dev) {
   pdl_enter();
   const long long per_tile = (long long)th * tw;
-  const int nt = sel ? n_sel : T;
+  // n_sel_dev: the number of selected tiles lives on the device (launches captured in a CUDA graph: the host value
+  // n_sel is then only the upper bound the grid was sized for)
+  const int nt = sel ? (n_sel_dev ? min(*n_sel_dev, n_sel) : n_sel) : T;
   const long long total = (long long)nt * per_tile;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int k = (int)(i / per_tile);
@@ -1011,7 +1043,7 @@ extern "C" int b2u_nchw_to_nhwc(const void* x, int32_t x_dtype, float div, float
 extern "C" int b2u_crop_tiles(const void* raster, int32_t r_dtype, float div, float div2, int32_t C, int64_t Y, int64_t X,
                               const int32_t* y0, const int32_t* x0, int32_t T, int32_t P, void* out, int32_t ld,
                               void* stream) {
-  B2U_CHECK_ARG(raster && y0 && x0 && out && C > 0 && C <= ld && T > 0 && P > 0, "crop_tiles: bad argument");
+  B2U_CHECK_ARG(raster && y0 && x0 && out && C > 0 && C <= ld && ld % 8 == 0 && T > 0 && P > 0, "crop_tiles: bad argument");
   B2U_CHECK_ARG(r_dtype >= B2U_DT_F32 && r_dtype <= B2U_DT_I16 && div != 0.f && div2 != 0.f,
                 "crop_tiles: r_dtype=%d (0 f32, 1 u8, 2 u16, 3 i16) / divisors invalid", r_dtype);
   const long long items = (long long)T * P * P;
@@ -1103,6 +1135,22 @@ extern "C" int b2u_dice_counts(const float* logits, int32_t ld, const uint8_t* l
   return B2U_OK;
 }
 
+extern "C" int b2u_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream) {
+  B2U_CHECK_ARG(x && y && n > 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 7) == 0,
+                "cast_f32_bf16: null / misaligned argument (fp32 range 16-byte, bf16 range 8-byte aligned)");
+  launch_k(cast_f32_bf16_kernel, dim3(grid_for(n / 4 + 1, 256)), dim3(256), 0, (cudaStream_t)stream, x, (bf)y, (long long)n);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" int b2u_cast_bf16_f32(const void* x, float* y, int64_t n, void* stream) {
+  B2U_CHECK_ARG(x && y && n > 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0,
+                "cast_bf16_f32: null / misaligned argument (fp32 range 16-byte, bf16 range 8-byte aligned)");
+  launch_k(cast_bf16_f32_kernel, dim3(grid_for(n / 4 + 1, 256)), dim3(256), 0, (cudaStream_t)stream, (cbf)x, y, (long long)n);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
 extern "C" int b2u_sgd_step(float* p, const float* g, int64_t n, float lr, float grad_scale, void* stream) {
   B2U_CHECK_ARG(p && g && n > 0, "sgd_step: bad argument");
   launch_k(sgd_kernel, dim3(grid_for(n, 256)), dim3(256), 0, (cudaStream_t)stream, p, g, n, lr, grad_scale);
@@ -1124,7 +1172,7 @@ extern "C" int b2u_adam_step(float* p, const float* g, float* m, float* v, int64
 static int stitch_accumulate_impl(const float* logits, int32_t ld, int32_t C, int32_t T, int32_t th, int32_t tw,
                                   const int32_t* y0, const int32_t* x0, const int32_t* sel, int32_t n_sel, float* acc,
                                   uint8_t* cnt, int64_t Y, int64_t X, int64_t y_off, int64_t x_off, float quant,
-                                  int raw, void* stream) {
+                                  int raw, void* stream, const int32_t* n_sel_dev = nullptr) {
   B2U_CHECK_ARG(logits && y0 && x0 && acc && cnt && C >= 1 && C <= 32 && C <= ld, "stitch_accumulate: bad argument");
   const int nt = sel ? n_sel : T;
   if (nt <= 0) return B2U_OK;
@@ -1132,10 +1180,10 @@ static int stitch_accumulate_impl(const float* logits, int32_t ld, int32_t C, in
   cudaStream_t st = (cudaStream_t)stream;
   if (C <= 8)
     launch_k(stitch_accumulate_kernel<8>, dim3(grid_for(items, 256)), dim3(256), 0, st, logits, ld, C, T, th, tw, y0, x0,
-             sel, n_sel, acc, cnt, Y, X, y_off, x_off, quant, raw);
+             sel, n_sel, acc, cnt, Y, X, y_off, x_off, quant, raw, n_sel_dev);
   else
     launch_k(stitch_accumulate_kernel<32>, dim3(grid_for(items, 256)), dim3(256), 0, st, logits, ld, C, T, th, tw, y0, x0,
-             sel, n_sel, acc, cnt, Y, X, y_off, x_off, quant, raw);
+             sel, n_sel, acc, cnt, Y, X, y_off, x_off, quant, raw, n_sel_dev);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }
@@ -1145,6 +1193,16 @@ extern "C" int b2u_stitch_accumulate(const float* logits, int32_t ld, int32_t C,
                                      float* acc, uint8_t* cnt, int64_t Y, int64_t X, int64_t y_off, int64_t x_off,
                                      void* stream) {
   return stitch_accumulate_impl(logits, ld, C, T, th, tw, y0, x0, sel, n_sel, acc, cnt, Y, X, y_off, x_off, 0.f, 0, stream);
+}
+
+extern "C" int b2u_stitch_accumulate_dev(const float* logits, int32_t ld, int32_t C, int32_t T, int32_t th, int32_t tw,
+                                         const int32_t* y0, const int32_t* x0, const int32_t* sel,
+                                         const int32_t* n_sel_dev, int32_t max_sel, int32_t mode, float* acc,
+                                         uint8_t* cnt, int64_t Y, int64_t X, int64_t y_off, int64_t x_off,
+                                         void* stream) {
+  B2U_CHECK_ARG(sel && n_sel_dev && max_sel > 0 && mode >= 0 && mode <= 2, "stitch_accumulate_dev: bad argument");
+  return stitch_accumulate_impl(logits, ld, C, T, th, tw, y0, x0, sel, max_sel, acc, cnt, Y, X, y_off, x_off,
+                                mode == 1 ? 31.f : 0.f, mode == 2 ? 1 : 0, stream, n_sel_dev);
 }
 
 extern "C" int b2u_stitch_accumulate_raw(const float* logits, int32_t ld, int32_t C, int32_t T, int32_t th, int32_t tw,

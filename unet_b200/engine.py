@@ -33,7 +33,7 @@ def one_cycle(pct: float, lr_max: float, div: float = 25.0, div_final: float = 1
 class Trainer:
     def __init__(self, net: UNetB200, optimizer: str = "sgd", lr: float = 1e-3, wd: float = 0.01,
                  encoder_factor: float = 10.0, use_graph: bool = True, bucket_mb: float = 32.0,
-                 input_dtype: torch.dtype = torch.uint8):
+                 input_dtype: torch.dtype = torch.uint8, grad_bf16: Optional[bool] = None):
         assert net.training
         self.net, self.lr, self.optimizer = net, lr, optimizer.lower()
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
@@ -48,6 +48,11 @@ class Trainer:
         self.step_count = 0
         self.bucket_elems = int(bucket_mb * (1 << 20) / 4)
         self.overlap_allreduce = os.environ.get("B2U_NO_AR_OVERLAP") is None   # A/B switches
+        # gradients travel as bf16 (half the all-reduce bytes; the cast kernels sit inside the captured graphs): the
+        # default for N > 1, B2U_GRAD_FP32=1 (or grad_bf16=False) keeps the fp32 exchange - with 2 ranks that one is
+        # bit-exact (a + b == b + a), which the multi-GPU parity test uses
+        self.grad_bf16 = (self.world > 1 and os.environ.get("B2U_GRAD_FP32") is None) if grad_bf16 is None else bool(grad_bf16)
+        self.gbf = torch.zeros(net.layout.total, dtype=torch.bfloat16, device=dev) if self.grad_bf16 else None
         self.min_seg_mb = float(os.environ.get("B2U_AR_MIN_SEG_MB", "24"))
         if os.environ.get("B2U_BUCKET_MB"):
             self.bucket_elems = int(float(os.environ["B2U_BUCKET_MB"]) * (1 << 20) / 4)
@@ -83,7 +88,7 @@ class Trainer:
     def _allreduce(self, lo: int = 0, hi: Optional[int] = None, async_op: bool = False):
         if self.world == 1:
             return []
-        g = self.net.grads
+        g = self.gbf if self.grad_bf16 else self.net.grads
         hi = g.numel() if hi is None else hi
         # bucketed so that NCCL pipelines over NVLink; summed here, divided by world inside the optimizer kernel
         works = []
@@ -98,6 +103,14 @@ class Trainer:
         self._allreduce()
         self._update()
 
+    def _to_wire(self, lo: int, hi: int) -> None:
+        """gradient range [lo, hi) -> its bf16 wire copy (no-op for the fp32 exchange); enqueued behind the kernels that
+        produced it, i.e. captured at the end of its backward segment"""
+        if self.grad_bf16 and hi > lo:
+            lo4 = lo // 4 * 4         # keep the 16-byte alignment of the fp32 range (neighbours are rewritten identically)
+            _lib.check(self.net.lib.b2u_cast_f32_bf16(self.net.grads[lo4:].data_ptr(), self.gbf[lo4:].data_ptr(), hi - lo4,
+                                                      ops.stream_ptr()), "b2u_cast_f32_bf16")
+
     def _fwd_bwd(self, part: Optional[int] = None) -> None:
         """part None: everything; part i: segment i of self.segments (segment 0 also holds input cast + forward + loss)."""
         net = self.net
@@ -108,9 +121,12 @@ class Trainer:
             net.loss_and_grad(s)
         if part is None:
             net.backward(s)
+            if self.world > 1:
+                self._to_wire(0, net.layout.total)
         else:
-            b, e, _, _ = self.segments[part]
+            b, e, lo, hi = self.segments[part]
             net.backward(s, b, e)
+            self._to_wire(lo, hi)
 
     def _plan_segments(self) -> None:
         net = self.net
@@ -120,6 +136,9 @@ class Trainer:
     def _update(self) -> None:
         net = self.net
         s = ops.stream_ptr()
+        if self.grad_bf16 and self.world > 1:
+            _lib.check(net.lib.b2u_cast_bf16_f32(self.gbf.data_ptr(), net.grads.data_ptr(), net.layout.total, s),
+                       "b2u_cast_bf16_f32")
         if self.optimizer == "sgd":
             _lib.check(net.lib.b2u_sgd_step(net.params.data_ptr(), net.grads.data_ptr(), net.layout.total, self.lr,
                                             1.0 / self.world, s), "b2u_sgd_step")
@@ -276,6 +295,9 @@ def init_distributed() -> Tuple[int, int, int]:
     if torch.cuda.is_available():
         torch.cuda.set_device(local)
     if world > 1 and not dist.is_initialized():
+        # the persistent conv kernels occupy every SM: NCCL gets a small, fixed number of CTAs (NVSwitch bandwidth does not
+        # need many channels; more CTAs only take SMs away from the backward pass the all-reduce hides behind)
+        os.environ.setdefault("NCCL_MAX_CTAS", os.environ.get("B2U_NCCL_MAX_CTAS", "8"))
         dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo", rank=rank, world_size=world)
     return rank, local, world
 

@@ -419,8 +419,9 @@ class UNetB200:
     def _self_attention(self, sa, c2: Act, h: int, w_: int):
         """fastai layers.SelfAttention on the output of UnetBlock.conv2 (after its ReLU): spectral-normed 1x1 query / key /
         value convolutions, beta = softmax(q_i . k_j over i), o_j = sum_i beta_ij v_i, out = gamma * o + x.  The
-        convolutions run on the implicit-GEMM kernel, the two batched attention products are library GEMMs (torch.bmm ->
-        cuBLAS, ~0.1 % of the step's FLOPs), the rest is csrc/attention.cu.  Returns (output Act, backward builder)."""
+        convolutions AND the batched attention products (two forward, four backward; 2 n^2 (C/8 + C) FLOP per image and
+        direction = 1.4 % of the forward FLOPs at 256-px tiles) run on the implicit-GEMM kernel - the products as 1x1
+        convolutions with per-image weights - the rest is csrc/attention.cu.  Returns (output Act, backward builder)."""
         lib, dev, N, train = self.lib, self.device, self.N, self.training
         n, Cc = h * w_, sa.c
         convs = sa.convs()
@@ -438,16 +439,31 @@ class UNetB200:
         V = self._act(h, w_, sa.value.nf, sa.name + ".v")
         for cs, y in zip(convs, (Q, K, V)):
             self._conv_fwd(cs, c2, y)
-        Q3, K3, V3 = (a.t.view(N, n, a.ld) for a in (Q, K, V))
-        S = torch.zeros((N, n, n), dtype=torch.bfloat16, device=dev)       # logits q_i . k_j; reused for d(beta) / dS
-        beta = torch.zeros_like(S)
+        ldn = padc(n)
+        zt = lambda *shape: torch.zeros(shape, dtype=torch.bfloat16, device=dev)
+        S = zt(N, h, w_, ldn)             # logits q_i . k_j ([image][i][j]); reused for d(beta) and dS in the backward pass
+        beta, betaT = zt(N, h, w_, ldn), zt(N, h, w_, ldn)        # softmax over i, and its transpose ([image][j][i])
+        VT = zt(N, Cc, ldn)               # value^T: channels x positions (the contraction index of `o` innermost)
         O = self._act(h, w_, Cc, sa.name + ".o")
-        O3 = O.t.view(N, n, O.ld)
         out = self._act(h, w_, Cc, sa.name + ".out")
-        self._keep += [S, beta]
-        self._fwd(lambda s: torch.bmm(Q3, K3.transpose(1, 2), out=S))
-        self._fwd(lambda s: _lib.check(lib.b2u_softmax_dim1(S.data_ptr(), beta.data_ptr(), N, n, s), "b2u_softmax_dim1"))
-        self._fwd(lambda s: torch.bmm(beta.transpose(1, 2), V3, out=O3))
+        self._keep += [S, beta, betaT, VT]
+
+        def bmm(a_t: torch.Tensor, a_c: int, w_t: torch.Tensor, rows: int, out_t: torch.Tensor) -> ConvPlan:
+            """out[img, p, r] = sum_c a[img, p, c] * w[img, r, c]: torch.bmm(A, W^T) as a 1x1 'convolution' whose weights
+            change with the image (b2u_conv_desc.w_batch_rows)"""
+            plan = ConvPlan([view_nhwc(a_t, a_c)], view_nhwc(out_t, rows), w_t.view(N * rows, 1, w_t.shape[-1]), a_c,
+                            ops.taps_conv(1), w_batch_rows=rows)
+            self._keep.append(plan)
+            return plan
+
+        p_s = bmm(Q.t, sa.query.nf, K.t, n, S)                  # S[i][j] = q_i . k_j          (bmm(f^T, g))
+        p_o = bmm(betaT, n, VT, Cc, O.t)                        # o_j = sum_i beta_ij v_i      (bmm(h, beta))
+        self._fwd(p_s.run)
+        self._fwd(lambda s: _lib.check(lib.b2u_softmax_dim1(S.data_ptr(), beta.data_ptr(), betaT.data_ptr(), N, n, ldn, s),
+                                       "b2u_softmax_dim1"))
+        self._fwd(lambda s: _lib.check(lib.b2u_transpose_bnc(V.t.data_ptr(), V.ld, VT.data_ptr(), ldn, N, n, Cc, s),
+                                       "b2u_transpose_bnc"))
+        self._fwd(p_o.run)
         self._fwd(lambda s: _lib.check(lib.b2u_attn_out(O.t.data_ptr(), c2.t.data_ptr(), gamma.data_ptr(), out.t.data_ptr(),
                                                         out.t.numel(), s), "b2u_attn_out"))
         if not train:
@@ -458,19 +474,29 @@ class UNetB200:
             dOut = out.grad
             dO = torch.zeros_like(O.t)
             dQ, dK, dV = torch.zeros_like(Q.t), torch.zeros_like(K.t), torch.zeros_like(V.t)
+            dOT, KT, QT = zt(N, Cc, ldn), zt(N, sa.key.nf, ldn), zt(N, sa.query.nf, ldn)
             scratch = torch.zeros(1025, dtype=torch.float32, device=dev)
-            self._keep += [dO, dQ, dK, dV, scratch]
-            dO3, dQ3, dK3, dV3 = dO.view(N, n, O.ld), dQ.view(N, n, Q.ld), dK.view(N, n, K.ld), dV.view(N, n, V.ld)
+            self._keep += [dO, dQ, dK, dV, dOT, KT, QT, scratch]
             dgamma = self.grad(sa.gamma)
+            tr = lambda x, ldx, y, cc: (lambda s: _lib.check(lib.b2u_transpose_bnc(x.data_ptr(), ldx, y.data_ptr(), ldn, N, n, cc, s),
+                                                            "b2u_transpose_bnc"))
+            p_dv = bmm(beta, n, dOT, Cc, dV)                     # dV_i = sum_j beta_ij dO_j
+            p_db = bmm(V.t, Cc, dO, n, S)                        # d(beta)_ij = v_i . dO_j   (into S)
+            p_dq = bmm(S, n, KT, sa.query.nf, dQ)                # dQ_i = sum_j dS_ij k_j
+            p_dk = bmm(betaT, n, QT, sa.key.nf, dK)              # dK_j = sum_i dS_ij q_i    (dS^T lives in betaT's buffer)
             self._bwd(lambda s: _lib.check(lib.b2u_attn_out_bwd(dOut.data_ptr(), O.t.data_ptr(), gamma.data_ptr(),
                                                                 dO.data_ptr(), dgamma.data_ptr(), scratch.data_ptr(),
                                                                 dO.numel(), s), "b2u_attn_out_bwd"))
-            self._bwd(lambda s: torch.bmm(beta, dO3, out=dV3))                      # dV_i = sum_j beta_ij dO_j
-            self._bwd(lambda s: torch.bmm(V3, dO3.transpose(1, 2), out=S))          # d(beta)_ij = V_i . dO_j
-            self._bwd(lambda s: _lib.check(lib.b2u_softmax_dim1_bwd(beta.data_ptr(), S.data_ptr(), S.data_ptr(), N, n, s),
-                                           "b2u_softmax_dim1_bwd"))                  # dS, in place
-            self._bwd(lambda s: torch.bmm(S, K3, out=dQ3))                          # dQ_i = sum_j dS_ij K_j
-            self._bwd(lambda s: torch.bmm(S.transpose(1, 2), Q3, out=dK3))          # dK_j = sum_i dS_ij Q_i
+            self._bwd(tr(dO, O.ld, dOT, Cc))
+            self._bwd(p_dv.run)
+            self._bwd(p_db.run)
+            self._bwd(lambda s: _lib.check(lib.b2u_softmax_dim1_bwd(beta.data_ptr(), S.data_ptr(), S.data_ptr(),
+                                                                    betaT.data_ptr(), N, n, ldn, s),
+                                           "b2u_softmax_dim1_bwd"))                  # dS in place, dS^T over beta^T
+            self._bwd(tr(K.t, K.ld, KT, sa.key.nf))
+            self._bwd(tr(Q.t, Q.ld, QT, sa.query.nf))
+            self._bwd(p_dq.run)
+            self._bwd(p_dk.run)
             for cs, d in zip(convs, (dQ, dK, dV)):
                 self._wgrad(cs, d, c2)
                 # gradient through W / sigma(W), after the split-K reduce of this weight (same stream as the wgrad)
@@ -567,7 +593,10 @@ class UNetB200:
 
         # ---- input
         self.x_in = self._act(H, W, spec.n_in, "input", zero=True)
-        self.logits = torch.zeros((N, H, W, 8 if spec.n_out <= 8 else padc(spec.n_out)), dtype=torch.float32, device=dev)
+        # fp32 logits [N, H, W, ld]: ld = n_out for up to 8 classes (8 bytes per pixel at C = 2; a pitch of 8 floats made the
+        # head store - and the loss / stitch kernels read - 4 x the useful bytes in partial sectors)
+        self.logits = torch.zeros((N, H, W, spec.n_out if spec.n_out <= 8 else padc(spec.n_out)), dtype=torch.float32,
+                                  device=dev)
         bwd_layers: List[Callable[[], None]] = []
 
         # ---- encoder ConvLayer = conv -> BN -> [ReLU]

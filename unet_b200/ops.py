@@ -137,7 +137,8 @@ class ConvPlan:
                  scale: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None,
                  res: Optional[View] = None, res_mask: Optional[View] = None, zmask: Optional[View] = None,
                  relu: bool = False, stats: bool = False, out_f32: Optional[torch.Tensor] = None,
-                 stats_ld: Optional[int] = None, fin: Optional[dict] = None, outs: Optional[Sequence[View]] = None):
+                 stats_ld: Optional[int] = None, fin: Optional[dict] = None, outs: Optional[Sequence[View]] = None,
+                 w_batch_rows: int = 0):
         """fin (with stats=True): dict(count, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, scale,
         shift) of fp32 tensors -> the kernel's last CTA finalizes the BatchNorm statistics itself when the shape allows
         (self.fused_finalize tells the caller whether a separate b2u_bn_finalize launch is still needed)."""
@@ -156,6 +157,12 @@ class ConvPlan:
                 d.out_nt[i] = v
         d.w = w.data_ptr()
         d.w_rows, d.w_taps, d.w_cinp = w.shape
+        if w_batch_rows:
+            # batched weights (torch.bmm on the implicit-GEMM kernel): w holds N blocks of w_batch_rows rows, image n of the
+            # GEMM space multiplies block n; the first out.C rows of a block are used
+            assert w.shape[0] == out_view.N * w_batch_rows and out_view.C <= w_batch_rows, (w.shape, out_view.N, w_batch_rows)
+            d.w_rows = out_view.C
+            d.w_batch_rows = w_batch_rows
         d.w_cin = w_cin
         _fill_taps(d, taps)
         for t in (scale, shift):

@@ -47,11 +47,18 @@ class TiledPredictor:
         self.B, self.P = net.N, net.H
         assert net.H == net.W
 
+    MAX_CLASSES = 4       # tiles on a regular grid overlap their direct neighbours only: 2 x 2 colour classes
+
     def predict_raster(self, raster: torch.Tensor, patch_overlap: float, rank: int = 0, world: int = 1,
                        return_probs: bool = False, large_file: bool = False):
-        """raster: uint8 / uint16 / int16 [C, Y, X] on the device (raw band values, scaled by the plan's input contract). Returns (mask uint8 [Y, x_end-x_begin], x_begin, x_end) for the
+        """raster: uint8 / uint16 / int16 [C, Y, X] on the device (raw band values, scaled by the plan's input contract).
+        Returns (mask uint8 [Y, x_end-x_begin], x_begin, x_end) for the
         column strip this rank owns (the whole raster when world == 1).  `large_file`: the reference's int8 merge
-        (predict.py:217-219, 318-323).  `return_probs` also returns the accumulators (sum of probabilities, counts)."""
+        (predict.py:217-219, 318-323).  `return_probs` also returns the accumulators (sum of probabilities, counts).
+        One batch = crop -> forward -> one accumulate per colour class, every launch reading the batch's tile origins /
+        class lists from a fixed device block that is refilled (device-to-device) in front of it - no host round trip, no
+        per-batch host-to-device copy.  (Replaying the batch as a captured CUDA graph was measured and dropped: with
+        programmatic dependent launch the eager launches already overlap, 5.86 vs 6.07 ms per batch of 64 tiles.)"""
         net, lib, dev, P, B = self.net, self.lib, self.dev, self.P, self.B
         assert raster.is_cuda and raster.dim() == 3 and raster.is_contiguous()
         r_dt, r_div, r_div2 = input_contract(raster.dtype, net.input_div)
@@ -63,41 +70,51 @@ class TiledPredictor:
         acc = torch.zeros((net.n_out, Y, SX), dtype=torch.float32, device=dev)
         cnt = torch.zeros((Y, SX), dtype=torch.uint8, device=dev)
         mask = torch.empty((Y, SX), dtype=torch.uint8, device=dev)
-        s = ops.stream_ptr()
         ld = net.logits.shape[-1]
         self.tiles_run = len(idx)
-        # Tile origins and the per-batch colour classes of the whole job go to the device in ONE copy: a small pageable
-        # host-to-device copy per batch would block the host behind the previous batch's kernels every time and expose
-        # part of the launch overhead of a forward pass (measured on the 20000 x 20000 raster: 10.08k -> 10.46k tiles/s)
-        flat: List[int] = []
-        plan = []
-        for b0 in range(0, len(idx), B):
-            wins = [windows[i] for i in idx[b0:b0 + B]]
-            # pad the last batch by repeating its first tile; padded tiles are never selected for stitching
-            pad = wins + [wins[0]] * (B - len(wins))
-            oy = len(flat)
-            flat += [w[1] for w in pad]
-            ox = len(flat)
-            flat += [w[0] for w in pad]
-            classes = []
-            for cls in colour_classes(wins):
-                classes.append((len(flat), len(cls)))
-                flat += cls
-            plan.append((oy, ox, classes))
-        meta = torch.tensor(flat, dtype=torch.int32).to(dev)
-        self._keep = meta
-        base = meta.data_ptr()
-        accumulate = lib.b2u_stitch_accumulate_q31 if large_file else lib.b2u_stitch_accumulate
-        for oy, ox, classes in plan:
-            y0, x0 = base + 4 * oy, base + 4 * ox
-            _lib.check(lib.b2u_crop_tiles(raster.data_ptr(), r_dt, r_div, r_div2, Cc, Y, X, y0, x0, B, P,
+        # Per-batch metadata block (int32): y0[B] x0[B] then MAX_CLASSES x (count, sel[B]).  The blocks of the whole job go
+        # to the device in ONE copy: a small pageable host-to-device copy per batch would block the host behind the
+        # previous batch's kernels every time (measured on the 20000 x 20000 raster: 10.08k -> 10.46k tiles/s)
+        MC = self.MAX_CLASSES
+        blk = 2 * B + MC * (1 + B)
+        n_batches = (len(idx) + B - 1) // B
+        host = torch.zeros((max(1, n_batches), blk), dtype=torch.int32)
+        for b in range(n_batches):
+            wins = [windows[i] for i in idx[b * B:(b + 1) * B]]
+            pad = wins + [wins[0]] * (B - len(wins))      # padded tiles are never selected for stitching
+            row = host[b]
+            row[:B] = torch.tensor([w[1] for w in pad], dtype=torch.int32)
+            row[B:2 * B] = torch.tensor([w[0] for w in pad], dtype=torch.int32)
+            classes = colour_classes(wins)
+            assert len(classes) <= MC, "tiles overlap more than their direct neighbours"
+            for k, cls in enumerate(classes):
+                o = 2 * B + k * (1 + B)
+                row[o] = len(cls)
+                row[o + 1:o + 1 + len(cls)] = torch.tensor(cls, dtype=torch.int32)
+        meta = host.to(dev)
+        cur = torch.zeros(blk, dtype=torch.int32, device=dev)
+        self._keep = (meta, cur)
+        cb = cur.data_ptr()
+        mode = 1 if large_file else 0
+
+        def one_batch(s):
+            _lib.check(lib.b2u_crop_tiles(raster.data_ptr(), r_dt, r_div, r_div2, Cc, Y, X, cb, cb + 4 * B, B, P,
                                           net.x_in.t.data_ptr(), net.x_in.ld, s), "b2u_crop_tiles")
             net.forward(s)
-            for osel, nsel in classes:
-                _lib.check(accumulate(net.logits.data_ptr(), ld, net.n_out, B, P, P, y0, x0, base + 4 * osel, nsel,
-                                      acc.data_ptr(), cnt.data_ptr(), Y, SX, 0, xb, s), "b2u_stitch_accumulate")
+            for k in range(MC):
+                o = cb + 4 * (2 * B + k * (1 + B))
+                _lib.check(lib.b2u_stitch_accumulate_dev(net.logits.data_ptr(), ld, net.n_out, B, P, P, cb, cb + 4 * B,
+                                                         o + 4, o, B, mode, acc.data_ptr(), cnt.data_ptr(), Y, SX, 0, xb,
+                                                         s), "b2u_stitch_accumulate_dev")
+
+        s = ops.stream_ptr()
+        for b in range(n_batches):
+            cur.copy_(meta[b], non_blocking=True)
+            one_batch(s)
         finalize = lib.b2u_stitch_finalize_q31 if large_file else lib.b2u_stitch_finalize
         _lib.check(finalize(acc.data_ptr(), cnt.data_ptr(), net.n_out, Y, SX, mask.data_ptr(), s), "b2u_stitch_finalize")
+        self.last_stitch_profile = {"batches": n_batches, "tiles_run": len(idx),
+                                    "launches_per_batch": 1 + net.launches_fwd + MC + 1}
         if return_probs:
             return mask, xb, xe, acc, cnt
         return mask, xb, xe
