@@ -50,7 +50,13 @@ typedef struct b2u_view {
 enum {
   B2U_EPI_RELU = 1,    /* max(v, 0) */
   B2U_EPI_STATS = 2,   /* emit per-channel sum / sum-of-squares partials of the stored values */
-  B2U_EPI_OUT_F32 = 4  /* store fp32 to out_f32 (dense NHWC with pitch out_f32_ld) instead of bf16 through `out` */
+  B2U_EPI_OUT_F32 = 4, /* store fp32 to out_f32 (dense NHWC with pitch out_f32_ld) instead of bf16 through `out` */
+  /* fused 1x1 head (layers.12 of the DynamicUnet, ConvLayer(ni, n_out, ks=1, act_cls=None)): on top of the normal bf16
+   * output the epilogue writes out_f32[pixel][k] = head_b[k] + sum_c head_w[k][c] * bf16(out[pixel][c]) for k < head_n
+   * (<= 8), head_w being the head's staged bf16 weights [head_n][head_ld].  One pass instead of re-reading the largest
+   * activation of the network.  Needs Cout <= 256 (one N tile). */
+  B2U_EPI_HEAD = 8,
+  B2U_EPI_HEAD_ONLY = 16 /* with B2U_EPI_HEAD: skip the bf16 output altogether (inference: nothing else reads it) */
 };
 
 /* Optional fused BatchNorm finalize of a B2U_EPI_STATS convolution (training-mode nn.BatchNorm2d statistics, what
@@ -112,6 +118,10 @@ typedef struct b2u_conv_desc {
    * (`bmm(f^T, g)`, `bmm(h, beta)` and their backward; reference train.py:142, params_and_main.py:83).  Pixel tiles never
    * cross an image and CTA pairs are off in this mode.  Needs a 1x1 tap table. */
   int32_t w_batch_rows;
+  /* B2U_EPI_HEAD */
+  const void* head_w;   /* bf16 [head_n][head_ld], channel order of this convolution's output */
+  const float* head_b;  /* fp32 [head_n], nullable */
+  int32_t head_n, head_ld;
 } b2u_conv_desc;
 
 typedef struct b2u_conv_info {

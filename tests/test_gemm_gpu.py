@@ -384,3 +384,34 @@ def test_conv_batched_weights_is_bmm(N, h, w, Cin, rows):
     torch.cuda.synchronize()
     e = rel_err(out.view(N, n, ld_o)[..., :rows], ref)
     assert e <= 1e-2, (e, [(k, getattr(plan.info, k)) for k, _ in plan.info._fields_])
+
+
+@pytest.mark.parametrize("N,C,H,W,n_out,only,res", [(2, 100, 64, 64, 2, False, True), (1, 99, 32, 48, 2, True, True),
+                                                     (2, 64, 16, 16, 8, False, False), (1, 128, 32, 32, 1, True, False)])
+def test_conv_fused_head(N, C, H, W, n_out, only, res):
+    """B2U_EPI_HEAD: the 1x1 head (layers.12) in the epilogue of the preceding 3x3 convolution: logits == head(bf16(out));
+    with B2U_EPI_HEAD_ONLY the bf16 output is not written at all."""
+    from unet_b200 import ops
+    x = rnd(N, C, H, W, seed=1)
+    w = rnd(C, C, 3, 3, seed=2, scale=(C * 9) ** -0.5)
+    b = rnd(C, seed=3)
+    hw_ = rnd(n_out, C, 1, 1, seed=4, scale=C ** -0.5)
+    hb = rnd(n_out, seed=5)
+    y_ref = F.conv2d(x, w, b, padding=1)
+    if res:
+        y_ref = y_ref + x
+    y_ref = F.relu(y_ref).to(torch.bfloat16).float()
+    logits_ref = F.conv2d(y_ref, hw_, hb)
+    xa = to_nhwc(x)
+    ya = torch.full((N, H, W, ops.padc(C)), 7.0, dtype=torch.bfloat16, device="cuda")
+    lg = torch.full((N, H, W, n_out), 9.0, dtype=torch.float32, device="cuda")
+    plan = ops.ConvPlan([ops.view_nhwc(xa, C)], ops.view_nhwc(ya, C), gemm_weights(w), C, ops.taps_conv(3),
+                        shift=padvec(b), relu=True, res=ops.view_nhwc(xa, C) if res else None,
+                        head=dict(w=gemm_weights(hw_), b=padvec(hb), out=lg, only=only))
+    plan.run()
+    torch.cuda.synchronize()
+    assert rel_err(lg.permute(0, 3, 1, 2), logits_ref) <= 5e-3      # (a rounding-boundary flip of one bf16 output moves a logit by ~1e-3)
+    if only:
+        assert (ya == 7.0).all()
+    else:
+        assert rel_err(ya[..., :C].permute(0, 3, 1, 2), y_ref) <= 1e-2

@@ -16,6 +16,8 @@ MAX_VIEWS = 4
 EPI_RELU = 1
 EPI_STATS = 2
 EPI_OUT_F32 = 4
+EPI_HEAD = 8
+EPI_HEAD_ONLY = 16
 
 DT_F32, DT_U8, DT_U16, DT_I16 = 0, 1, 2, 3     # b2u.h B2U_DT_*: element type of raw input tiles / rasters
 
@@ -50,6 +52,7 @@ class ConvDesc(C.Structure):
         ("fin", BNFin),
         ("num_out", C.c_int32), ("out_nt", View * 4),
         ("w_batch_rows", C.c_int32),
+        ("head_w", C.c_void_p), ("head_b", C.c_void_p), ("head_n", C.c_int32), ("head_ld", C.c_int32),
     ]
 
 

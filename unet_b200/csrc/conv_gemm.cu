@@ -51,6 +51,9 @@ struct ConvParams {
   float* out_f32;
   int out_f32_ld;
   b2u_bn_fin fin;   // counter != nullptr: the last CTA to retire finalizes the BatchNorm statistics
+  const __nv_bfloat16* head_w;   // B2U_EPI_HEAD: fused 1x1 head, bf16 [head_n][head_ld]
+  const float* head_b;
+  int head_n, head_ld;
   int w_batch_rows; // > 0: batched weights, image n uses weight rows n * w_batch_rows + ... (tn == 1, no CTA pairs)
   int multi_out;    // N tile nt is stored through tm_out_nt[nt] at channel 0 (PixelShuffle phases -> parity planes)
   CUtensorMap tm_out_nt[4];
@@ -171,7 +174,8 @@ __device__ __forceinline__ void issue_3x3(uint32_t d, uint32_t a16, uint32_t ahi
 // cost instructions there.
 // kPair: CTA-pair mode (cluster of 2, tcgen05 cta_group::2): CTA rank r of a pair owns pixel tile 2*pm + r and HALF of the
 // weight rows of every stage; the leader's MMA thread issues M = 256 instructions that drive both SMs' tensor cores.
-template <bool kAux, bool kStats, bool kF32, bool kPair>
+// kHead: the fused 1x1 head (B2U_EPI_HEAD) - a compile-time switch like the others, its accumulators cost registers.
+template <bool kAux, bool kStats, bool kF32, bool kPair, bool kHead = false>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
@@ -471,6 +475,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const bool has_res = kAux && p.res.ptr != nullptr, has_rm = kAux && p.res_mask.ptr != nullptr,
                has_zm = kAux && p.zmask.ptr != nullptr;
     const int slot_rm = has_res ? 1 : 0, slot_zm = (has_res ? 1 : 0) + (has_rm ? 1 : 0);
+    constexpr bool has_head = kHead;
+    const bool head_only = has_head && (p.flags & B2U_EPI_HEAD_ONLY) != 0;
+    float* s_head = s_stats + 8 * p.stats_cols;       // 2 x 128 x 8 floats behind the statistics accumulators
+    uint32_t tile_ctr = 0;
     auto issue_aux = [&](int t, int chunk, uint32_t buf) {
       const int m2 = tile_m(t), nt2 = tile_nt(t);
       const int bn2 = m2 / tiles_xy, rem2 = m2 - bn2 * tiles_xy;
@@ -505,6 +513,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       if (e == 0) TL_STAMP(3, tl_e);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)acc * kAccStride + ((uint32_t)(q4 * 32) << 16);
+      float hl[8];      // fused head: this thread's share (its 32-channel groups) of the pixel's head_n logits
+#pragma unroll
+      for (int k = 0; k < 8; ++k) hl[k] = 0.f;
 
 #pragma unroll 1
       for (int j = 0; j < n_chunks; ++j) {
@@ -598,18 +609,45 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
               if (c0 + i < p.Cout) op[i] = v[i];
           }
         } else {
+          if (has_head && active) {
+            // logits of the fused 1x1 head from the bf16-rounded outputs (what a separate head convolution would read)
+            float vb[32];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const uint32_t pk2 = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+              vb[2 * i] = bf16_lo(pk2);
+              vb[2 * i + 1] = bf16_hi(pk2);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              if (k < p.head_n) {
+                const uint4* wp = reinterpret_cast<const uint4*>(p.head_w + (size_t)k * p.head_ld + c0);
+                float a = 0.f;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  float wv[8];
+                  unpack8(__ldg(wp + q), wv);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) a += vb[q * 8 + i] * wv[i];
+                }
+                hl[k] += a;
+              }
+            }
+          }
           // bf16 pack -> swizzled staging (SWIZZLE_128B: 16-byte chunk j of row r lands at chunk j ^ (r & 7))
           const uint32_t buf = p.stg_bufs == 2 ? (chunk_ctr & 1u) : 0u;
           // kAux: the result overwrites operand 0 of this chunk in place (every thread reads and writes its own 64 bytes of
           // its own pixel row only), and the buffer's previous store was drained before the operand load was issued
           const uint32_t out_buf = kAux ? aux_base + abuf * (uint32_t)p.n_aux * kStagingBytes : stg_base + buf * kStagingBytes;
-          if (!kAux) {
+          if (!kAux && !head_only) {
             // the store that last used this staging buffer has finished reading it
             if (e == 0) { if (p.stg_bufs == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
             named_bar_sync(1, 256);
           }
           const uint32_t row_addr = out_buf + (uint32_t)row * 128u;
-          if (active) {
+          if (head_only) {
+            // nothing is staged or stored (inference with the fused head): only the hand-overs of the chunk remain
+          } else if (active) {
             uint32_t pk[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
@@ -637,13 +675,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
               asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0u) : "memory");
             }
           }
-          fence_proxy_async_smem();
+          if (!head_only) fence_proxy_async_smem();
           named_bar_sync(1, 256);
           if (e == 0) {
             if (kPair && rank != 0 && j == n_chunks - 1) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
-            if (p.multi_out) tma_store_4d(&p.tm_out_nt[nt], out_buf, j * 64, x0, y0, n0);
-            else tma_store_4d(&p.tm_out, out_buf, nt * p.BN + j * 64, x0, y0, n0);
-            tma_store_commit();
+            if (!head_only) {
+              if (p.multi_out) tma_store_4d(&p.tm_out_nt[nt], out_buf, j * 64, x0, y0, n0);
+              else tma_store_4d(&p.tm_out, out_buf, nt * p.BN + j * 64, x0, y0, n0);
+              tma_store_commit();
+            }
             if (kAux) {
               // the buffer of the PREVIOUS chunk is free once its store has read it (one chunk ago: normally done): the
               // operands of chunk + 2 go there, so two loads are in flight while this chunk's store drains
@@ -676,6 +716,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             sp[p.stats_ld + c] = sq;
           }
         }
+      }
+      if (has_head) {
+        // the two warps of a lane quarter hold the even / odd 32-channel groups of the same 32 pixels: the odd one hands
+        // its partial logits over through shared memory (double buffered by tile), the even one adds the bias and writes
+        float* hx = s_head + (size_t)(tile_ctr & 1u) * 128 * 8 + (size_t)row * 8;
+        if (hsel == 1) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) hx[k] = hl[k];
+        }
+        named_bar_sync(1, 256);
+        if (hsel == 0 && valid) {
+          float* op = p.out_f32 + ((long long)(pn * p.Ho + py) * p.Wo + px) * p.out_f32_ld;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (k < p.head_n) op[k] = hl[k] + hx[k] + (p.head_b ? __ldg(p.head_b + k) : 0.f);
+        }
+        ++tile_ctr;
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
@@ -915,7 +972,17 @@ static int conv_plan_fill(const b2u_conv_desc* d, b2u_conv_plan* plan, bool enco
   p.stg_bufs = n_aux > 0 ? 0 : 2;
   p.rowmode = 0;
   const uint32_t aux_bytes = (uint32_t)n_aux * kAuxRing * kStagingBytes;
-  uint32_t fixed = (uint32_t)p.stg_bufs * kStagingBytes + aux_bytes + 512 + (uint32_t)p.stats_cols * 32u;
+  const bool has_head = (d->flags & B2U_EPI_HEAD) != 0;
+  if (has_head) {
+    B2U_CHECK_ARG(n_tiles == 1 && !out_f32 && !(d->flags & B2U_EPI_STATS) && !multi_out && d->head_w && d->out_f32 &&
+                  d->head_n >= 1 && d->head_n <= 8 && d->out_f32_ld >= d->head_n && d->head_ld % 8 == 0 &&
+                  d->head_ld >= round_up(Cout, 32) && (reinterpret_cast<uintptr_t>(d->head_w) & 15) == 0,
+                  "conv: fused head needs one N tile (Cout <= 256), bf16 weights [head_n <= 8][head_ld >= round_up(Cout, 32), "
+                  "multiple of 8] 16-byte aligned, and an fp32 output with pitch >= head_n");
+  } else {
+    B2U_CHECK_ARG(!(d->flags & B2U_EPI_HEAD_ONLY), "conv: B2U_EPI_HEAD_ONLY without B2U_EPI_HEAD");
+  }
+  uint32_t fixed = (uint32_t)p.stg_bufs * kStagingBytes + aux_bytes + 512 + (uint32_t)p.stats_cols * 32u + (has_head ? 8192u : 0u);
   int stages;
   if (halo) {
     p.a_tx_bytes = (uint32_t)((tw + 2) * (th + 2)) * 128u;
@@ -981,6 +1048,7 @@ static int conv_plan_fill(const b2u_conv_desc* d, b2u_conv_plan* plan, bool enco
   p.flags = d->flags; p.stats = d->stats; p.stats_ld = d->stats_ld;
   p.multi_out = multi_out ? d->num_out : 0;
   p.w_batch_rows = batched_w ? d->w_batch_rows : 0;
+  p.head_w = (const __nv_bfloat16*)d->head_w; p.head_b = d->head_b; p.head_n = d->head_n; p.head_ld = d->head_ld;
 #ifdef B2U_TIMELINE
   p.timeline = nullptr;
 #endif
@@ -1093,7 +1161,9 @@ extern "C" int b2u_conv_plan_create(const b2u_conv_desc* d, b2u_conv_plan** out)
         (const void*)conv_gemm_kernel<true, false, false, false>,  (const void*)conv_gemm_kernel<true, true, false, false>,
         (const void*)conv_gemm_kernel<false, false, true, false>,
         (const void*)conv_gemm_kernel<false, false, false, true>,  (const void*)conv_gemm_kernel<false, true, false, true>,
-        (const void*)conv_gemm_kernel<true, false, false, true>,   (const void*)conv_gemm_kernel<true, true, false, true>};
+        (const void*)conv_gemm_kernel<true, false, false, true>,   (const void*)conv_gemm_kernel<true, true, false, true>,
+        (const void*)conv_gemm_kernel<true, false, false, true, true>, (const void*)conv_gemm_kernel<true, false, false, false, true>,
+        (const void*)conv_gemm_kernel<false, false, false, true, true>, (const void*)conv_gemm_kernel<false, false, false, false, true>};
     for (const void* f : variants) {
       cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
       if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(conv_gemm_kernel): %s", cudaGetErrorString(e)); delete plan; return B2U_ERR_CUDA; }
@@ -1115,7 +1185,11 @@ extern "C" int b2u_conv_run(const b2u_conv_plan* plan, void* stream) {
   const ConvParams& p = plan->p;
   const bool aux = p.n_aux > 0, stats = (p.flags & B2U_EPI_STATS) != 0, f32 = (p.flags & B2U_EPI_OUT_F32) != 0;
   void (*kern)(const ConvParams) = nullptr;
-  if (f32) kern = conv_gemm_kernel<false, false, true, false>;
+  const bool head = (p.flags & B2U_EPI_HEAD) != 0;
+  if (head) {
+    if (plan->pair) kern = aux ? conv_gemm_kernel<true, false, false, true, true> : conv_gemm_kernel<false, false, false, true, true>;
+    else kern = aux ? conv_gemm_kernel<true, false, false, false, true> : conv_gemm_kernel<false, false, false, false, true>;
+  } else if (f32) kern = conv_gemm_kernel<false, false, true, false>;
   else if (plan->pair) {
     if (aux && stats) kern = conv_gemm_kernel<true, true, false, true>;
     else if (aux) kern = conv_gemm_kernel<true, false, false, true>;

@@ -138,7 +138,7 @@ class ConvPlan:
                  res: Optional[View] = None, res_mask: Optional[View] = None, zmask: Optional[View] = None,
                  relu: bool = False, stats: bool = False, out_f32: Optional[torch.Tensor] = None,
                  stats_ld: Optional[int] = None, fin: Optional[dict] = None, outs: Optional[Sequence[View]] = None,
-                 w_batch_rows: int = 0):
+                 w_batch_rows: int = 0, head: Optional[dict] = None):
         """fin (with stats=True): dict(count, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, scale,
         shift) of fp32 tensors -> the kernel's last CTA finalizes the BatchNorm statistics itself when the shape allows
         (self.fused_finalize tells the caller whether a separate b2u_bn_finalize launch is still needed)."""
@@ -186,6 +186,16 @@ class ConvPlan:
             flags |= _lib.EPI_OUT_F32
             d.out_f32 = out_f32.data_ptr()
             d.out_f32_ld = out_f32.shape[-1]
+        if head is not None:
+            # fused 1x1 head: dict(w = staged bf16 head weights [n_out, 1, ld], b = fp32 bias or None, out = fp32 logits
+            # [N, H, W, ld_out], only = skip the bf16 output of this convolution)
+            hw, hb, ho = head["w"], head.get("b"), head["out"]
+            assert hw.dtype == torch.bfloat16 and hw.is_contiguous() and ho.dtype == torch.float32 and ho.is_contiguous()
+            flags |= _lib.EPI_HEAD | (_lib.EPI_HEAD_ONLY if head.get("only") else 0)
+            d.head_w, d.head_n, d.head_ld = hw.data_ptr(), hw.shape[0], hw.shape[-1]
+            d.head_b = hb.data_ptr() if hb is not None else None
+            d.out_f32, d.out_f32_ld = ho.data_ptr(), ho.shape[-1]
+            self._keep += [hw, hb, ho]
         d.flags = flags
         self.stats = None
         self.fused_finalize = False
