@@ -261,42 +261,65 @@ def test_network_requires_cuda():
 
 
 # ------------------------------------------------------------------------------------------------ gloo, world_size 2
-def _ddp_worker(rank, world, port, out):
+def _ddp_worker(rank, world, port, data_dir, out):
+    """The host side of the data-parallel step on a gloo group: the product's batch dealing (`reference_api._tile_batches`
+    with rank / world) and the product's segment + bucket schedule of the gradient all-reduce (`engine.plan_segments`,
+    `engine.bucket_ranges`) driving real collectives."""
     import torch.distributed as dist
+    from pathlib import Path
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from unet_b200.engine import shard_range
-    torch.manual_seed(0)
-    model = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3, padding=1), torch.nn.ReLU(), torch.nn.Conv2d(4, 2, 1))
-    x = torch.randn(8, 3, 8, 8, generator=torch.Generator().manual_seed(1))
-    y = torch.randint(0, 2, (8, 8, 8), generator=torch.Generator().manual_seed(2))
-    a, b = shard_range(8, rank, world)
-    loss = torch.nn.functional.cross_entropy(model(x[a:b]), y[a:b])
-    loss.backward()
-    flat = torch.cat([p.grad.flatten() for p in model.parameters()])
-    # the engine's scheme: bucketed SUM all-reduce over one flat buffer, 1/world applied by the optimizer kernel
-    bucket = 37
-    for s in range(0, flat.numel(), bucket):
-        dist.all_reduce(flat[s:s + bucket], op=dist.ReduceOp.SUM)
-    flat /= world
+    from unet_b200.engine import bucket_ranges, plan_segments
+    from unet_b200.reference_api import _tile_batches
+    files = sorted((Path(data_dir) / "trai" / "img_tiles").glob("*.tif"))
+    gen = _tile_batches(files, 2, 2, False, shuffle_seed=3, drop_last=True, rank=rank, world=world)
+    seen = []
+    for epoch in range(2):
+        ids = []
+        for x, y, n in gen():
+            assert n == 2 and x.shape == (2, 1, 4, 4) and y.dtype == torch.uint8
+            ids += [int(v) for v in x[:, 0, 0, 0]]          # every tile carries its id in its pixels
+        seen.append(ids)
+    everyone = [None] * world
+    dist.all_gather_object(everyone, (gen.n_batches, seen))
+    # gradient exchange: rank r contributes r + 1 everywhere; segments x buckets must touch every element exactly once
+    total, n_ops = 1003, 40
+    marks = [(10, 700), (22, 420), (31, 90)]
+    flat = torch.full((total,), float(rank + 1))
+    ranges = []
+    for b, e, lo, hi in plan_segments(marks, total, n_ops, min_seg_elems=200):
+        for a, z in bucket_ranges(lo, hi, 97):
+            dist.all_reduce(flat[a:z], op=dist.ReduceOp.SUM)
+            ranges.append((a, z))
     if rank == 0:
-        torch.save(flat, out)
+        torch.save({"everyone": everyone, "flat": flat, "ranges": ranges}, out)
     dist.destroy_process_group()
 
 
-def test_data_parallel_gradient_average_gloo(tmp_path):
+def test_data_parallel_host_logic_gloo(tmp_path):
     import torch.multiprocessing as mp
+    from unet_b200.geotiff import GeoInfo, write_geotiff
+    for sub in ("img_tiles", "mask_tiles"):
+        (tmp_path / "trai" / sub).mkdir(parents=True)
+    for i in range(11):
+        write_geotiff(tmp_path / "trai" / "img_tiles" / f"t{i:02d}.tif", np.full((1, 4, 4), i, dtype=np.uint8), GeoInfo())
+        write_geotiff(tmp_path / "trai" / "mask_tiles" / f"t{i:02d}.tif", np.full((4, 4), i % 2, dtype=np.uint8), GeoInfo())
     out = str(tmp_path / "g.pt")
     port = 29500 + (os.getpid() % 500)
-    mp.spawn(_ddp_worker, args=(2, port, out), nprocs=2, join=True)
-    got = torch.load(out)
-    torch.manual_seed(0)
-    model = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3, padding=1), torch.nn.ReLU(), torch.nn.Conv2d(4, 2, 1))
-    x = torch.randn(8, 3, 8, 8, generator=torch.Generator().manual_seed(1))
-    y = torch.randint(0, 2, (8, 8, 8), generator=torch.Generator().manual_seed(2))
-    torch.nn.functional.cross_entropy(model(x), y).backward()
-    ref = torch.cat([p.grad.flatten() for p in model.parameters()])
-    assert torch.allclose(got, ref, atol=1e-6)       # equal shards: mean of shard means == full-batch mean
+    mp.spawn(_ddp_worker, args=(2, port, str(tmp_path), out), nprocs=2, join=True)
+    got = torch.load(out, weights_only=False)
+    (nb0, seen0), (nb1, seen1) = got["everyone"]
+    assert nb0 == nb1 == 2                      # 11 tiles, batch 2, 2 ranks: 5 global batches -> 2 per rank, equal step counts
+    for ep in range(2):
+        a, b = seen0[ep], seen1[ep]
+        assert len(a) == len(b) == 4 and not set(a) & set(b)       # disjoint shares of the same shuffled order
+        order = list(range(11))
+        np.random.default_rng(3 + ep).shuffle(order)
+        assert a == order[0:2] + order[4:6] and b == order[2:4] + order[6:8]   # global batches dealt round-robin
+    assert seen0[0] != seen0[1]                                     # reshuffled every epoch
+    assert torch.equal(got["flat"], torch.full((1003,), 3.0))       # every gradient element reduced exactly once
+    cover = sorted(got["ranges"])
+    assert cover[0][0] == 0 and cover[-1][1] == 1003 and all(cover[i][1] == cover[i + 1][0] for i in range(len(cover) - 1))
 
 
 def test_allreduce_segments_tile_ops_and_gradients():

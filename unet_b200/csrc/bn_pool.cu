@@ -4,6 +4,8 @@
 //
 // Replaces nn.BatchNorm2d / nn.MaxPool2d forward+backward (cudnnBatchNormalization*, ATen max_pool2d) as reached from
 // fastai's ConvLayer / XResNet / UnetBlock.bn (reference train.py:128,141).
+#include <stdlib.h>
+
 #include "host_util.h"
 #include "ptx.cuh"
 #include "stream.cuh"
@@ -724,7 +726,10 @@ extern "C" int b2u_bn_bwd_fused(const void* dz, int32_t lddz, const void* x, int
     max_blocks = per_sm * sm_count();
   }
   int grid = rows < max_blocks ? rows : max_blocks;
-  const long long by_work = (pixels * ((C + 7) / 8) + 1023) / 1024;   // >= ~4 (pixel, 8-channel group) items per thread
+  // >= ~4 (pixel, 8-channel group) items per thread; B2U_BN_BWD_ITEMS overrides the items per block (A/B switch: fewer,
+  // fatter blocks make the two grid barriers of the small layers cheaper)
+  static const long long per_block = getenv("B2U_BN_BWD_ITEMS") ? atoll(getenv("B2U_BN_BWD_ITEMS")) : 1024;
+  const long long by_work = (pixels * ((C + 7) / 8) + per_block - 1) / per_block;
   if (grid > by_work) grid = (int)by_work;
   if (grid < 1) grid = 1;
   launch_k(bn_bwd_fused_kernel, dim3(grid), dim3(threads), smem, (cudaStream_t)stream, 

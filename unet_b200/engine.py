@@ -92,8 +92,8 @@ class Trainer:
         hi = g.numel() if hi is None else hi
         # bucketed so that NCCL pipelines over NVLink; summed here, divided by world inside the optimizer kernel
         works = []
-        for start in range(lo, hi, self.bucket_elems):
-            w = dist.all_reduce(g[start:min(hi, start + self.bucket_elems)], op=dist.ReduceOp.SUM, async_op=async_op)
+        for a, b in bucket_ranges(lo, hi, self.bucket_elems):
+            w = dist.all_reduce(g[a:b], op=dist.ReduceOp.SUM, async_op=async_op)
             if async_op:
                 works.append(w)
         return works
@@ -268,6 +268,11 @@ class Trainer:
             self._prefetch(*prefetch)
         self.step_count += 1
         return self.net.loss
+
+
+def bucket_ranges(lo: int, hi: int, bucket_elems: int) -> List[Tuple[int, int]]:
+    """[lo, hi) of the flat gradient buffer cut into all-reduce buckets of at most `bucket_elems` elements"""
+    return [(a, min(hi, a + bucket_elems)) for a in range(lo, hi, max(1, bucket_elems))]
 
 
 def plan_segments(marks: Sequence[Tuple[int, int]], total: int, n_ops: int,

@@ -517,7 +517,7 @@ class UNetB200:
                 ldy: int, relu: bool, dx: torch.Tensor, lddx: int, pixels: int, accumulate: bool):
         """reduce -> finalize -> apply in one launch (grid barrier inside); dgamma/dbeta land in the flat gradient
         buffer."""
-        rows = max(1, min(STATS_ROWS, pixels * ((bn.C + 7) // 8) // 1024))   # >= ~4 (pixel, 8-channel) items per thread
+        rows = max(1, min(STATS_ROWS, pixels * ((bn.C + 7) // 8) // int(os.environ.get("B2U_BN_BWD_ITEMS", "1024"))))   # >= ~4 (pixel, 8-channel) items per thread
         partial = torch.zeros((rows, 2, padc(bn.C)), dtype=torch.float32, device=self.device)
         lib = self.lib
         ld = padc(bn.C)
