@@ -210,42 +210,40 @@ def predict_section(dev, rank, world, side, batch, max_over_ranks, barrier, peak
     a synthetic 4-band raster, tiles sharded over the ranks by output column strips.  `value`: raster resident in HBM;
     `e2e`: the raster strip comes from pinned host memory and the uint8 mask strip is read back, inside the timed region."""
     from unet_b200.network import UNetB200
-    from unet_b200.predict_engine import TiledPredictor
-    from unet_b200.tiling import compute_windows, shard_windows_by_columns
+    from unet_b200.predict_engine import TiledPredictor, gather_mask_cells
+    from unet_b200.tiling import compute_windows, shard_grid, shard_windows_2d
     net = UNetB200(ARCH, N_IN, N_OUT, (SIZE, SIZE), batch, training=False, device=dev)
     net.init_parameters(seed=0)
     pred = TiledPredictor(net)
     g = torch.Generator(device=dev).manual_seed(1234)
     raster = torch.randint(0, 256, (N_IN, side, side), dtype=torch.uint8, device=dev, generator=g)
+    windows = compute_windows(side, side, SIZE, 0.125)
+    n_tiles = len(windows)
+    grid = shard_grid(windows, side, side, world)          # ownership grid of the output: strips up to 4 ranks, 4 x 2 at 8
     pred.predict_raster(raster[:, :1024, :1024].contiguous(), 0.125)   # warm-up
-    from unet_b200.predict_engine import gather_mask_strips
-    pred.predict_raster(raster, 0.125, rank, world)                    # second warm-up at full size (allocator, caches)
+    pred.predict_raster(raster, 0.125, rank, world, grid=grid)         # second warm-up at full size (allocator, caches)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    mask, xb, xe = pred.predict_raster(raster, 0.125, rank, world)
-    full = gather_mask_strips(mask, side, rank, world) if world > 1 else mask     # the path's only collective (NCCL)
+    mask, rect = pred.predict_raster(raster, 0.125, rank, world, grid=grid)
+    full = gather_mask_cells(mask, side, side, grid, rank, world)       # the path's only collective (NCCL all-gather)
     e1.record()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
-    n_tiles = len(compute_windows(side, side, SIZE, 0.125))
     stitch = pred.last_stitch_profile
-    # e2e: this rank's input strip (the tile columns it runs) from pinned host memory, mask strip back to the host
-    windows = compute_windows(side, side, SIZE, 0.125)
-    idx, xb, xe = shard_windows_by_columns(windows, side, rank, world)
-    xs0 = min(windows[i][0] for i in idx)
-    xs1 = max(windows[i][0] + windows[i][2] for i in idx)
-    host = raster[:, :, xs0:xs1].contiguous().cpu().pin_memory()
-    host_mask = torch.empty((side, xe - xb), dtype=torch.uint8).pin_memory()
+    tiles_max = int(max_over_ranks(float(stitch["tiles_run"])))
+    # e2e: this rank's part of the raster (the tiles it runs) from pinned host memory, its mask cell back to the host
+    idx, (xb, xe, yb, ye) = shard_windows_2d(windows, side, side, rank, world, grid)
+    xs0, xs1 = min(windows[i][0] for i in idx), max(windows[i][0] + windows[i][2] for i in idx)
+    ys0, ys1 = min(windows[i][1] for i in idx), max(windows[i][1] + windows[i][3] for i in idx)
+    host = raster[:, ys0:ys1, xs0:xs1].contiguous().cpu().pin_memory()
+    host_mask = torch.empty((ye - yb, xe - xb), dtype=torch.uint8).pin_memory()
     barrier()
     t0 = time.perf_counter()
-    strip = host.to(dev, non_blocking=True)
-    if world == 1:
-        m2, _, _ = pred.predict_raster(strip, 0.125, 0, 1)
-    else:
-        # the strip holds exactly this rank's tile columns: a 1-rank prediction of the strip, cropped to the owned columns
-        m2, _, _ = pred.predict_raster(strip, 0.125, 0, 1)
-        m2 = m2[:, xb - xs0:xe - xs0]
+    part = host.to(dev, non_blocking=True)
+    # the part holds exactly this rank's tiles: a 1-rank prediction of it, cropped to the owned cell
+    m2, _, _ = pred.predict_raster(part, 0.125, 0, 1)
+    m2 = m2[yb - ys0:ye - ys0, xb - xs0:xe - xs0]
     host_mask.copy_(m2, non_blocking=True)
     torch.cuda.synchronize()
     barrier()
@@ -254,14 +252,15 @@ def predict_section(dev, rank, world, side, batch, max_over_ranks, barrier, peak
     flops = n_tiles * net.flops_fwd_per_tile
     return {"metric": "predict tiles/sec (256x256x4-band xresnet34-DynamicUnet, bf16, tiled predict + stitch + argmax)",
             "workload": f"BASELINE configs[2]: {side}x{side} 4-band raster, 256-px tiles, 32-px overlap: {n_tiles} tiles, "
-                        f"owner-computes column strips over {world} GPU(s), final uint8 mask gather inside the timed region",
+                        f"owner-computes {grid[0]} x {grid[1]} grid of output cells over {world} GPU(s) (tiles on a cell border run "
+                        f"on both sides: {tiles_max} tiles on the fullest rank), final uint8 mask all-gather inside the timed region",
             "value": n_tiles / (ms * 1e-3), "unit": UNIT, "seconds": ms * 1e-3, "tiles": n_tiles,
-            "tiles_run_rank0": len(idx), "fwd_gflop_per_tile": net.flops_fwd_per_tile / 1e9,
+            "tiles_run_max_rank": tiles_max, "ownership_grid": list(grid), "fwd_gflop_per_tile": net.flops_fwd_per_tile / 1e9,
             "algorithmic_tflops_per_gpu": flops / (ms * 1e-3) / 1e12 / world,
             "tensor_core_frac_of_burst_peak": flops / (ms * 1e-3) / 1e12 / world / peaks["tf_burst"],
             "stitch_kernels": stitch,
             "e2e": {"value": n_tiles / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes": host.numel() * world,
-                    "d2h_bytes": host_mask.numel() * world, "strip_mask_equals_sharded_mask": same}}
+                    "d2h_bytes": host_mask.numel() * world, "part_mask_equals_sharded_mask": same}}
 
 
 def plan_bytes(plan) -> int:

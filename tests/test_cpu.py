@@ -348,10 +348,15 @@ def _gather_worker(rank, world, port, out):
     wins = compute_windows(Y, X, 32, 0.25)
     idx, xb, xe = shard_windows_by_columns(wins, X, rank, world)
     got = gather_mask_strips(full[:, xb:xe].contiguous(), X, rank, world)
+    # the 2-D ownership grid (here forced to 1 x 2: one column, two row cells) gathers the same way
+    from unet_b200.predict_engine import gather_mask_cells
+    from unet_b200.tiling import shard_windows_2d
+    _, (cxb, cxe, cyb, cye) = shard_windows_2d(wins, X, Y, rank, world, (1, 2))
+    got2 = gather_mask_cells(full[cyb:cye, cxb:cxe].contiguous(), Y, X, (1, 2), rank, world)
     if rank == 0:
-        torch.save(got, out)
+        torch.save((got, got2), out)
     else:
-        assert got is None
+        assert got is None and got2 is None
     dist.destroy_process_group()
 
 
@@ -365,11 +370,34 @@ def test_prediction_strip_gather_gloo(tmp_path):
     mp.spawn(_gather_worker, args=(2, port, out), nprocs=2, join=True)
     Y, X = 37, 101
     full = (torch.arange(Y * X, dtype=torch.int64).reshape(Y, X) % 251).to(torch.uint8)
-    assert torch.equal(torch.load(out), full)
+    g1, g2 = torch.load(out)
+    assert torch.equal(g1, full) and torch.equal(g2, full)
     wins = compute_windows(Y, X, 32, 0.25)
     i0, b0, e0 = shard_windows_by_columns(wins, X, 0, 2)
     i1, b1, e1 = shard_windows_by_columns(wins, X, 1, 2)
     assert (b0, e0, b1, e1) == (0, 51, 51, 101) and set(i0) | set(i1) == set(range(len(wins))) and set(i0) & set(i1)
+
+
+def test_ownership_grid_covers_every_pixel_with_all_its_tiles():
+    """tiling.shard_windows_2d: every output pixel belongs to exactly one cell, and the cell's rank runs EVERY tile covering
+    that pixel (so sums / counts / argmax are local); the grid chosen for BASELINE configs[2] at 8 ranks is 4 x 2 with
+    1104 tiles on the fullest rank (column strips: 1170)."""
+    from unet_b200.tiling import compute_windows, shard_grid, shard_windows_2d, shard_windows_by_columns
+    Y, X, P = 150, 230, 64
+    wins = compute_windows(Y, X, P, 0.25)
+    for world, grid in ((4, (2, 2)), (6, (3, 2)), (3, (1, 3))):
+        owner = np.full((Y, X), -1)
+        for r in range(world):
+            idx, (xb, xe, yb, ye) = shard_windows_2d(wins, X, Y, r, world, grid)
+            assert (owner[yb:ye, xb:xe] == -1).all()
+            owner[yb:ye, xb:xe] = r
+            need = {i for i, (x, y, w, h) in enumerate(wins) if x < xe and x + w > xb and y < ye and y + h > yb}
+            assert set(idx) == need
+        assert (owner >= 0).all()
+    big = compute_windows(20000, 20000, 256, 0.125)
+    assert shard_grid(big, 20000, 20000, 8) == (4, 2) and shard_grid(big, 20000, 20000, 2) == (2, 1)
+    assert max(len(shard_windows_2d(big, 20000, 20000, r, 8, (4, 2))[0]) for r in range(8)) == 1104
+    assert max(len(shard_windows_by_columns(big, 20000, r, 8)[0]) for r in range(8)) == 1170
 
 
 def test_ctypes_signatures_match_the_header():

@@ -310,6 +310,10 @@ def test_predict_raster_matches_reference_merge():
         parts.append(m)
     torch.cuda.synchronize()
     assert torch.equal(torch.cat(parts, dim=1), mask)
+    # 2 x 2 ownership grid (what 8 GPUs use as 4 x 2): every cell equals the same window of the 1-GPU mask
+    for r in range(4):
+        m, (xb, xe, yb, ye) = pred.predict_raster(raster, ov, rank=r, world=4, grid=(2, 2))
+        assert torch.equal(m, mask[yb:ye, xb:xe])
 
 
 def test_against_committed_golden_fixture():

@@ -73,8 +73,12 @@ raster = raster[0].to(dev).contiguous()
 strip, xb, xe = pred.predict_raster(raster, 0.125, rank, world)
 full = gather_mask_strips(strip, raster.shape[2], rank, world)
 one, _, _ = pred.predict_raster(raster, 0.125, 0, 1)
+from unet_b200.predict_engine import gather_mask_cells
+grid = (1, world)          # row cells: the other axis of the 2-D ownership grid
+cell, rect = pred.predict_raster(raster, 0.125, rank, world, grid=grid)
+full2 = gather_mask_cells(cell, raster.shape[1], raster.shape[2], grid, rank, world)
 if rank == 0:
-    same = torch.equal(full, one)
+    same = torch.equal(full, one) and torch.equal(full2, one)
     ok = ok and same
     print(f"ddp_check predict world={world}: gathered mask == one-GPU mask: {same} -> {'OK' if same else 'FAIL'}", flush=True)
 flag = torch.tensor([1 if ok else 0], device=dev)

@@ -99,6 +99,13 @@ int sm_count() {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 148;
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  // B2U_SM_LIMIT: size every persistent grid for fewer SMs than the device has - the data-parallel engine leaves a few
+  // SMs to NCCL's all-reduce CTAs, which cannot co-reside with a persistent convolution CTA (it owns the SM's whole
+  // shared memory and TMEM)
+  if (const char* lim = getenv("B2U_SM_LIMIT")) {
+    const int v = atoi(lim);
+    if (v >= 8 && v < n) n = v - (v & 1);     // even: CTA pairs
+  }
   return n;
 }
 

@@ -13,7 +13,7 @@ import torch
 
 from . import _lib, ops
 from .network import UNetB200, input_contract
-from .tiling import Window, colour_classes, compute_windows, shard_windows_by_columns
+from .tiling import Window, _split, colour_classes, compute_windows, shard_grid, shard_windows_2d, shard_windows_by_columns
 
 
 def gather_mask_strips(strip: torch.Tensor, width: int, rank: int, world: int, dst: int = 0) -> Optional[torch.Tensor]:
@@ -40,6 +40,30 @@ def gather_mask_strips(strip: torch.Tensor, width: int, rank: int, world: int, d
     return torch.cat(cols, 0).t().contiguous()
 
 
+def gather_mask_cells(cell: torch.Tensor, height: int, width: int, grid: Tuple[int, int], rank: int, world: int,
+                      dst: int = 0) -> Optional[torch.Tensor]:
+    """the 2-D counterpart of `gather_mask_strips`: the uint8 cells of a gx x gy ownership grid (`tiling.shard_windows_2d`)
+    are all-gathered (padded to the largest cell) and assembled into the full [height, width] mask on rank `dst`"""
+    import torch.distributed as dist
+    if world == 1:
+        return cell
+    gx, gy = grid
+    hmax = max(_split(height, gy, k)[1] - _split(height, gy, k)[0] for k in range(gy))
+    wmax = max(_split(width, gx, k)[1] - _split(width, gx, k)[0] for k in range(gx))
+    buf = torch.zeros((hmax, wmax), dtype=cell.dtype, device=cell.device)
+    buf[:cell.shape[0], :cell.shape[1]] = cell
+    parts = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(parts, buf)
+    if rank != dst:
+        return None
+    full = torch.empty((height, width), dtype=cell.dtype, device=cell.device)
+    for r in range(world):
+        xb, xe = _split(width, gx, r % gx)
+        yb, ye = _split(height, gy, r // gx)
+        full[yb:ye, xb:xe] = parts[r][:ye - yb, :xe - xb]
+    return full
+
+
 class TiledPredictor:
     def __init__(self, net: UNetB200):
         assert not net.training, "prediction uses the eval plan (running BN statistics folded into the convolutions)"
@@ -50,11 +74,13 @@ class TiledPredictor:
     MAX_CLASSES = 4       # tiles on a regular grid overlap their direct neighbours only: 2 x 2 colour classes
 
     def predict_raster(self, raster: torch.Tensor, patch_overlap: float, rank: int = 0, world: int = 1,
-                       return_probs: bool = False, large_file: bool = False):
+                       return_probs: bool = False, large_file: bool = False, grid: Optional[Tuple[int, int]] = None):
         """raster: uint8 / uint16 / int16 [C, Y, X] on the device (raw band values, scaled by the plan's input contract).
         Returns (mask uint8 [Y, x_end-x_begin], x_begin, x_end) for the
-        column strip this rank owns (the whole raster when world == 1).  `large_file`: the reference's int8 merge
-        (predict.py:217-219, 318-323).  `return_probs` also returns the accumulators (sum of probabilities, counts).
+        column strip this rank owns (the whole raster when world == 1).  With `grid=(gx, gy)` the rank owns cell
+        (rank % gx, rank // gx) of a gx x gy grid instead (`tiling.shard_windows_2d`; fewer duplicated tiles at 8 ranks) and
+        the return value is (mask [y_end-y_begin, x_end-x_begin], (x_begin, x_end, y_begin, y_end)).  `large_file`: the
+        reference's int8 merge (predict.py:217-219, 318-323).  `return_probs` also returns the accumulators.
         One batch = crop -> forward -> one accumulate per colour class, every launch reading the batch's tile origins /
         class lists from a fixed device block that is refilled (device-to-device) in front of it - no host round trip, no
         per-batch host-to-device copy.  (Replaying the batch as a captured CUDA graph was measured and dropped: with
@@ -65,11 +91,15 @@ class TiledPredictor:
         Cc, Y, X = raster.shape
         assert Cc == net.n_in and Y >= P and X >= P, "raster smaller than one tile is not supported"
         windows = compute_windows(Y, X, P, patch_overlap)
-        idx, xb, xe = shard_windows_by_columns(windows, X, rank, world)
-        SX = xe - xb
-        acc = torch.zeros((net.n_out, Y, SX), dtype=torch.float32, device=dev)
-        cnt = torch.zeros((Y, SX), dtype=torch.uint8, device=dev)
-        mask = torch.empty((Y, SX), dtype=torch.uint8, device=dev)
+        if grid is None:
+            idx, xb, xe = shard_windows_by_columns(windows, X, rank, world)
+            yb, ye = 0, Y
+        else:
+            idx, (xb, xe, yb, ye) = shard_windows_2d(windows, X, Y, rank, world, grid)
+        SX, SY = xe - xb, ye - yb
+        acc = torch.zeros((net.n_out, SY, SX), dtype=torch.float32, device=dev)
+        cnt = torch.zeros((SY, SX), dtype=torch.uint8, device=dev)
+        mask = torch.empty((SY, SX), dtype=torch.uint8, device=dev)
         ld = net.logits.shape[-1]
         self.tiles_run = len(idx)
         # Per-batch metadata block (int32): y0[B] x0[B] then MAX_CLASSES x (count, sel[B]).  The blocks of the whole job go
@@ -104,7 +134,7 @@ class TiledPredictor:
             for k in range(MC):
                 o = cb + 4 * (2 * B + k * (1 + B))
                 _lib.check(lib.b2u_stitch_accumulate_dev(net.logits.data_ptr(), ld, net.n_out, B, P, P, cb, cb + 4 * B,
-                                                         o + 4, o, B, mode, acc.data_ptr(), cnt.data_ptr(), Y, SX, 0, xb,
+                                                         o + 4, o, B, mode, acc.data_ptr(), cnt.data_ptr(), SY, SX, yb, xb,
                                                          s), "b2u_stitch_accumulate_dev")
 
         s = ops.stream_ptr()
@@ -112,9 +142,11 @@ class TiledPredictor:
             cur.copy_(meta[b], non_blocking=True)
             one_batch(s)
         finalize = lib.b2u_stitch_finalize_q31 if large_file else lib.b2u_stitch_finalize
-        _lib.check(finalize(acc.data_ptr(), cnt.data_ptr(), net.n_out, Y, SX, mask.data_ptr(), s), "b2u_stitch_finalize")
+        _lib.check(finalize(acc.data_ptr(), cnt.data_ptr(), net.n_out, SY, SX, mask.data_ptr(), s), "b2u_stitch_finalize")
         self.last_stitch_profile = {"batches": n_batches, "tiles_run": len(idx),
                                     "launches_per_batch": 1 + net.launches_fwd + MC + 1}
+        if grid is not None:
+            return (mask, (xb, xe, yb, ye), acc, cnt) if return_probs else (mask, (xb, xe, yb, ye))
         if return_probs:
             return mask, xb, xe, acc, cnt
         return mask, xb, xe
