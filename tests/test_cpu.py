@@ -447,3 +447,39 @@ def test_every_kernel_waits_for_its_predecessor():
             assert "pdl_enter()" in src[m.end():i], f"{fn}: kernel {m.group(1)} never calls pdl_enter()"
             kernels += 1
     assert kernels >= 35
+
+
+def test_augmentation_is_a_dihedral_transform_of_image_and_mask_together(tmp_path):
+    """reference_api.augmented (transforms=True): ceil(B * n_transform_imgs) tiles of every batch get one of the eight flips /
+    90-degree rotations, image and mask with the SAME transform, raw integer values untouched (utils.py:196-295 applies its
+    pipeline to image and mask together); share 0 changes nothing, a share outside [0, 1] raises as utils.py:236 does."""
+    from unet_b200.geotiff import GeoInfo, write_geotiff
+    from unet_b200.reference_api import _tile_batches, augmented
+    for sub in ("img_tiles", "mask_tiles"):
+        (tmp_path / "trai" / sub).mkdir(parents=True)
+    rng = np.random.default_rng(0)
+    for i in range(8):
+        img = rng.integers(0, 256, size=(3, 8, 8), dtype=np.uint8)
+        write_geotiff(tmp_path / "trai" / "img_tiles" / f"t{i}.tif", img, GeoInfo())
+        write_geotiff(tmp_path / "trai" / "mask_tiles" / f"t{i}.tif", (img[0] > 127).astype(np.uint8), GeoInfo())
+    files = sorted((tmp_path / "trai" / "img_tiles").glob("*.tif"))
+    plain = list(_tile_batches(files, 4, 2, False, None, False)())
+    aug = augmented(_tile_batches(files, 4, 2, False, None, False), 0.5, seed=1)
+    assert aug.n_batches == 2
+    changed = 0
+    for (x0, y0, n0), (x1, y1, n1) in zip(plain, aug()):
+        assert n0 == n1 and x1.dtype == torch.uint8
+        for i in range(4):
+            ok = False
+            for op in range(8):
+                xi, yi = (x0[i].flip(-1), y0[i].flip(-1)) if op & 4 else (x0[i], y0[i])
+                xi, yi = torch.rot90(xi, op & 3, (-2, -1)), torch.rot90(yi, op & 3, (-2, -1))
+                ok = ok or (torch.equal(xi, x1[i]) and torch.equal(yi, y1[i]))
+            assert ok                                                  # a dihedral transform, mask moved with the image
+            assert torch.equal((x1[i][0] > 127).to(torch.uint8), y1[i])    # pixel values untouched, mask still matches
+            changed += int(not torch.equal(x0[i], x1[i]))
+    assert 1 <= changed <= 4                                           # 2 of 4 tiles per batch were selected (identity allowed)
+    same = list(augmented(_tile_batches(files, 4, 2, False, None, False), 0.0)())
+    assert all(torch.equal(a[0], b[0]) for a, b in zip(plain, same))
+    with pytest.raises(ValueError):
+        augmented(_tile_batches(files, 4, 2, False, None, False), 1.5)

@@ -19,11 +19,23 @@ CASES = {
     "c112_112": (64, 256, 256, 112, 112, 3, True, False, False, True),
     "c96_96": (64, 128, 128, 96, 96, 3, True, False, False, True),
     "c128_128s": (64, 128, 128, 128, 128, 3, True, False, False, True),
+    # encoder shapes; suffix s = BN statistics in the epilogue, f = statistics + fused finalize (11th field: 0 / 1 / 2)
+    "e64": (64, 64, 64, 64, 64, 3, False, False, False, False, 0),
+    "e64s": (64, 64, 64, 64, 64, 3, False, False, False, False, 1),
+    "e64f": (64, 64, 64, 64, 64, 3, False, False, False, False, 2),
+    "e128": (64, 32, 32, 128, 128, 3, False, False, False, False, 0),
+    "e128f": (64, 32, 32, 128, 128, 3, False, False, False, False, 2),
+    "e256": (64, 16, 16, 256, 256, 3, False, False, False, False, 0),
+    "e256s": (64, 16, 16, 256, 256, 3, False, False, False, False, 1),
+    "e256f": (64, 16, 16, 256, 256, 3, False, False, False, False, 2),
+    "e512": (64, 8, 8, 512, 512, 3, False, False, False, False, 0),
+    "e512f": (64, 8, 8, 512, 512, 3, False, False, False, False, 2),
 }
 case = sys.argv[1]
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 pitch = int(sys.argv[3]) if len(sys.argv) > 3 else 0
-N, H, W, Cin, Cout, ks, relu, zm, res, bias = CASES[case]
+N, H, W, Cin, Cout, ks, relu, zm, res, bias = CASES[case][:10]
+st = CASES[case][10] if len(CASES[case]) > 10 else 0
 g = torch.Generator(device="cuda").manual_seed(0)
 pi = max(pitch, ops.padc(Cin)); po = max(pitch, ops.padc(Cout))
 x = torch.randn((N, H, W, pi), generator=g, device="cuda").to(torch.bfloat16)
@@ -33,7 +45,10 @@ z = torch.randn((N, H, W, po), generator=g, device="cuda").to(torch.bfloat16)
 b = torch.randn(ops.pad32(Cout), generator=g, device="cuda")
 plan = ops.ConvPlan([ops.view_nhwc(x, Cin)], ops.view_nhwc(y, Cout), w, Cin, ops.taps_conv(ks),
                     shift=b if bias else None, relu=relu, zmask=ops.view_nhwc(z, Cout) if zm else None,
-                    res=ops.view_nhwc(z, Cout) if res else None)
+                    res=ops.view_nhwc(z, Cout) if res else None, stats=st > 0,
+                    fin=dict(count=N * H * W, eps=1e-5, momentum=0.1,
+                             **{k: torch.ones(po, device="cuda") for k in ("gamma", "beta", "running_mean", "running_var", "mean",
+                                                                           "invstd", "scale", "shift")}) if st == 2 else None)
 for _ in range(2):
     plan.run()
 torch.cuda.synchronize()

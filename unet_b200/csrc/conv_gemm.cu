@@ -941,6 +941,14 @@ static int conv_plan_fill(const b2u_conv_desc* d, b2u_conv_plan* plan, bool enco
     tw = 8; th = 16; tn = 1;
     tx = ceil_div(d->out.W, tw); ty = ceil_div(d->out.H, th); tb = d->out.N;
   }
+  // under-filled grids (the 8 x 8 stages: 32 pixel tiles): halve the channel tile while that doubles the CTAs that get
+  // work - a 128-wide tile streams half of the weight rows and issues MMAs of half the duration, so the launch's critical
+  // path (one tile per CTA) halves; the activations it re-reads are a few MB in L2
+  static const bool nsplit_disabled = getenv("B2U_CONV_NO_NSPLIT") != nullptr;  // A/B switch for profiling
+  if (!nsplit_disabled && !multi_out && !batched_w && !out_f32 && !(d->flags & B2U_EPI_HEAD)) {
+    const int sms = encode ? sm_count() : 148;
+    while (BN >= 128 && BN % 32 == 0 && Cout % (BN / 2) == 0 && 2 * n_tiles * tx * ty * tb <= sms) { BN /= 2; n_tiles *= 2; }
+  }
   p.halo = halo ? 1 : 0;
   p.hw = tw + 2;
   p.tw = tw; p.th = th; p.tn = tn; p.tiles_x = tx; p.tiles_y = ty;
