@@ -296,6 +296,13 @@ int b2u_pointwise_smallk(const void* a, int32_t lda, int32_t K, const void* w, i
 /* x NCHW of x_dtype -> bf16 NHWC pitch ld, channels [ch_off, ch_off+write_c) written (lanes >= C zeroed) */
 int b2u_nchw_to_nhwc(const void* x, int32_t x_dtype, float div, float div2, void* y, int32_t N, int32_t C, int32_t H,
                      int32_t W, int32_t ld, int32_t ch_off, int32_t write_c, void* stream);
+/* im2col of an NHWC bf16 tensor with few channels: y[n,oy,ox, c*ks*ks + ky*ks + kx] = x[n, oy*stride+ky-pad, ox*stride+kx-pad, c]
+ * (zeros outside the image and in lanes C*ks*ks .. ldy; the channel order of torch.nn.functional.unfold and of a conv
+ * weight [Cout][Cin][kh][kw] read as rows of Cin*kh*kw).  Used for the first stem convolution (xresnet.py stem: 3x3
+ * stride 2 over the n_in image bands, reached from train.py:98-160 `unet_learner_MS`): over the 36 im2col lanes it is a
+ * 1x1 convolution with whole-sector rows, and so is its weight gradient. */
+int b2u_im2col(const void* x, int32_t ldx, int32_t C, int32_t N, int32_t H, int32_t W, int32_t ks, int32_t stride,
+               int32_t pad, void* y, int32_t ldy, void* stream);
 /* tile t = raster[:, y0[t]:y0[t]+P, x0[t]:x0[t]+P] / div / div2 -> bf16 NHWC [T,P,P,ld]: the crop of
  * create_tiles_unet.py:410 fused with the input contract above and the layout cast; raster is [C][Y][X] of r_dtype on
  * the device */

@@ -24,7 +24,7 @@ the tap (the CUDA plan's stored activation) while gradients still flow through t
 linear map with exactly the plan's coefficients (same ReLU masks, same BatchNorm inputs), rounding-flip noise is no
 longer amplified, and every parameter gradient must agree tightly.  `record=` collects the rounding points of a run.
 Names are the plan's activation names (unet_b200/network.py `_act(..., name)`): `<conv>.raw`, `<conv>.out`,
-`<block>.out`, `enc.bnrelu`, `layers.N.cat`, `input`.
+`<block>.out`, `enc.bnrelu`, `layers.N.cat`, `input`, and `layers.5.conv2.2.{q,k,v,beta,o,out}` of the SelfAttention block.
 """
 from __future__ import annotations
 
@@ -43,6 +43,8 @@ class _Q(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
+        if _Ctx.noise:                    # sensitivity probe: perturb in front of the gradient's rounding as well
+            g = g * (1 + _Ctx.noise * torch.randn_like(g))
         return g.to(torch.bfloat16).to(torch.float32)
 
 
@@ -158,6 +160,39 @@ def _conv_bias(x, layer, relu=True, res=None, name=None):
     return q(F.relu(y), name and name + ".out") if relu else y
 
 
+def _self_attention(x, sa, name, training):
+    """fastai SelfAttention behind UnetBlock.conv2 with the plan's rounding points (unet_b200/network.py
+    `_self_attention`): spectral-normed 1x1 query / key / value convolutions (one power iteration in training mode,
+    sigma = u^T W v differentiated through W as torch.nn.utils.spectral_norm does), stored q / k / v, the logits
+    S[i][j] = q_i . k_j (stored, but overwritten by the backward pass: not a tap), beta = softmax over i (stored; tap
+    layout [N, j, i_h, i_w] = the plan's [image][i][j] tensor read as NHWC), o = sum_i beta_ij v_i, out = gamma o + x.
+    The plan's backward writes x's gradient as (d out + W_q^T dQ) first, then adds W_k^T dK and W_v^T dV to the stored
+    value: three consumers in that order."""
+    N, C, H, W = x.shape
+    n = H * W
+    xa, xb, xc = fork(x, 3)
+
+    def sn(layer):
+        conv = layer[0]
+        Wo = conv.weight_orig
+        Wm = Wo.flatten(1)
+        u, v = conv.weight_u.detach().clone(), conv.weight_v.detach().clone()
+        if training:
+            with torch.no_grad():
+                v = F.normalize(Wm.t() @ u, dim=0, eps=1e-12)
+                u = F.normalize(Wm @ v, dim=0, eps=1e-12)
+        sigma = torch.dot(u, Wm @ v)
+        return wq(Wo / sigma)
+
+    proj = lambda t, layer, nm: q(F.conv1d(t.flatten(2), sn(layer)).view(N, -1, H, W), nm).flatten(2)
+    f, g, h = proj(xa, sa.query, name + ".q"), proj(xb, sa.key, name + ".k"), proj(xc, sa.value, name + ".v")
+    S = q(torch.bmm(f.transpose(1, 2), g))                                  # [N, i, j]
+    beta = q(F.softmax(S, dim=1).permute(0, 2, 1).reshape(N, n, H, W), name + ".beta")
+    beta = beta.reshape(N, n, n).permute(0, 2, 1)                           # back to [N, i, j]
+    o = q(torch.bmm(h, beta).view(N, C, H, W), name + ".o")
+    return q(sa.gamma * o + xa, name + ".out")
+
+
 def emulated_forward(model: DynamicUnetOracle, x: torch.Tensor, training: bool = True, taps=None, record=None,
                      noise: float = 0.0, mismatch=None) -> torch.Tensor:
     """taps / record: see the module docstring (teacher forcing).  mismatch (dict, with taps): per tapped rounding point
@@ -205,6 +240,8 @@ def _emulated_forward(model: DynamicUnetOracle, x: torch.Tensor, training: bool)
             up = F.interpolate(up, s.shape[-2:], mode="nearest")
         cat = q(F.relu(torch.cat([up, _bn(s, ub.bn, training)], dim=1)), f"layers.{4 + j}.cat")
         h = _conv_bias(_conv_bias(cat, ub.conv1, name=f"layers.{4 + j}.conv1"), ub.conv2, name=f"layers.{4 + j}.conv2")
+        if len(ub.conv2) > 2:                  # ConvLayer(..., xtra=SelfAttention): module "2" behind conv + ReLU
+            h = _self_attention(h, ub.conv2[2], f"layers.{4 + j}.conv2.2", training)
     p8 = _conv_bias(h, L[8][0], name="layers.8.0")
     up8 = L[8][1](p8)
     if up8.shape[-2:] != x0.shape[-2:]:

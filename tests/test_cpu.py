@@ -134,7 +134,8 @@ def test_bf16_emulation_tracks_oracle():
     assert all(q.grad is not None for q in m.parameters())
 
 
-def test_teacher_forced_emulation():
+@pytest.mark.parametrize("self_attention", [False, True])
+def test_teacher_forced_emulation(self_attention):
     """Why the model-level gradient test teacher-forces the emulation (oracle/bf16_emulation.py `taps=`): a free-running
     bf16 emulation is chaotic - perturbing the values in front of every rounding by 1e-6 relative (an accumulation-order
     sized difference) moves deep-layer gradients by tens of percent - whereas with the forward activations pinned to
@@ -145,7 +146,7 @@ def test_teacher_forced_emulation():
     from oracle.unet_oracle import make_oracle, weighted_ce
     from parity_util import gradient_mismatches
     from unet_b200.synth import aerial_like_tiles
-    o = make_oracle("xresnet18", 3, 2).train()
+    o = make_oracle("xresnet18", 3, 2, self_attention=self_attention).train()
     x_u8, y = aerial_like_tiles(4, 3, 64, 64, 2)
     x, y, w = x_u8.float() / 255, y.long(), torch.full((2,), 0.5)
 

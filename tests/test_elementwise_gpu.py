@@ -532,3 +532,23 @@ def test_softmax_dim1_transposes_and_batched_transpose(n, C):
     _lib.check(L.b2u_transpose_bnc(p(x), padc(C), p(y), ld, B, n, C, S()))
     torch.cuda.synchronize()
     assert torch.equal(y[..., :n], x[..., :C].transpose(1, 2)) and (y[..., n:] == 0).all()
+
+
+@pytest.mark.parametrize("N,Cc,H,W,ks,stride,pad,ldy", [(3, 4, 32, 32, 3, 2, 1, 48), (2, 3, 17, 23, 3, 2, 1, 32),
+                                                          (2, 7, 16, 16, 3, 1, 1, 64), (1, 4, 8, 8, 1, 1, 0, 8)])
+def test_im2col_is_unfold(N, Cc, H, W, ks, stride, pad, ldy):
+    """b2u_im2col == torch.nn.functional.unfold (lane = c*ks*ks + ky*ks + kx, zeros outside the image and in the pad lanes):
+    a pure gather, bit-exact; with the weight [Cout][Cin][kh][kw] read as rows of Cin*kh*kw the 1x1 product over these lanes
+    is the convolution itself (the im2col stem of UNetB200)."""
+    L, _lib = lib()
+    x = rnd(N, Cc, H, W, seed=3)
+    xn = nhwc(x)
+    Ho, Wo = (H + 2 * pad - ks) // stride + 1, (W + 2 * pad - ks) // stride + 1
+    y = torch.full((N, Ho, Wo, ldy), 7.0, dtype=torch.bfloat16, device="cuda")
+    _lib.check(L.b2u_im2col(xn.data_ptr(), xn.shape[-1], Cc, N, H, W, ks, stride, pad, y.data_ptr(), ldy, None), "b2u_im2col")
+    ref = F.unfold(x, ks, padding=pad, stride=stride).view(N, Cc * ks * ks, Ho, Wo).permute(0, 2, 3, 1)
+    assert torch.equal(y[..., :Cc * ks * ks].float(), ref)
+    assert (y[..., Cc * ks * ks:] == 0).all()
+    w = rnd(5, Cc, ks, ks, seed=4)
+    conv = F.conv2d(x, w, stride=stride, padding=pad).permute(0, 2, 3, 1)
+    assert rel(y[..., :Cc * ks * ks].float() @ w.view(5, -1).t(), conv) < 1e-5

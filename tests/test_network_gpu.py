@@ -6,15 +6,19 @@ Stated tolerances (bf16 storage, fp32 accumulation; errors are max|a-b| / max|b|
     for xresnet50 <= max(3e-2, 1.25 x the autocast error measured in the same test) - autocast reads 5.6-5.8e-2 there
     and this pipeline 5.3-6.2e-2 (tools/parity_probe.py xresnet50 4 8 64 2)
   * loss vs the fp32 oracle              <= 5e-3
-  * logits vs the bf16-storage emulation <= 2e-2 and loss <= 2e-4 (same rounding points: only accumulation order and
+  * logits vs the bf16-storage emulation <= 2e-2 and loss <= 2e-4 (5e-4 for xresnet50; same rounding points: only accumulation order and
     rounding-boundary flips differ)
   * argmax masks: every disagreement with the fp32 oracle lies where the oracle's top-2 margin is below twice the
     measured logit error; >= 99.9 % agreement on pixels with a larger margin (north_star's 99.9 % bar)
   * parameter gradients, the check that pins the wiring: against the TEACHER-FORCED bf16 emulation
     (oracle/bf16_emulation.py `taps=`: the emulation's forward values are pinned to the plan's stored activations, its
-    backward rounds where the plan stores bf16) every tensor agrees within GRAD_TOL (max-norm relative) with cosine
-    >= GRAD_COS; the same checker is then run on a copy with one weight gradient zeroed and must flag exactly that
-    tensor (the suite is known to be able to fail).  Under teacher forcing every stored forward activation must also
+    backward rounds where the plan stores bf16) every tensor agrees within GRAD_TOL in the relative L2 norm (measured:
+    1.0-1.8e-2; GRAD_TOL_DEEP for xresnet50: 2.7e-2), with cosine >= GRAD_COS and no element off by more than GRAD_TOL_MAX of the tensor maximum (measured
+    1.2-6.7e-2: the max-norm follows single rounding flips, whose realisation changes with any change of summation
+    order in the forward pass); tensors of fewer than 16 elements (SelfAttention gamma: one cancelling sum) pass up to
+    4 x their own measured sensitivity to sub-ulp perturbations of the stored gradients.  The same checker is then run
+    on copies with one weight gradient zeroed, sign-flipped and scaled by 1.05 and must flag exactly that tensor (the
+    suite is known to be able to fail).  Under teacher forcing every stored forward activation must also
     equal what the emulation computes from the plan's previous activations within 2 bf16 ulp of the tensor maximum
     (a per-layer forward wiring check), and the logits within 1e-4.
   * parameter gradients vs the fp32 oracle: err(ours) <= 1.6 * err(torch bf16 autocast vs fp32) + 2e-2 on every tensor
@@ -33,8 +37,9 @@ pytestmark = pytest.mark.gpu
 
 from parity_util import gradient_mismatches, plan_taps, rel
 
-GRAD_TOL, GRAD_COS = 3e-2, 0.999      # plan vs teacher-forced emulation, every parameter tensor (measured worst: 1.2-2.3e-2;
-GRAD_TOL_DEEP = 5e-2                  # xresnet50, 50+ stored tensors per path: 3.3e-2); a zeroed tensor reads 1.0 / cos 0
+GRAD_TOL, GRAD_COS = 3e-2, 0.999      # plan vs teacher-forced emulation, every parameter tensor: relative L2 error, cosine
+GRAD_TOL_DEEP = 4e-2                  # xresnet50 / 101 (50+ stored tensors per path; measured 2.7e-2)
+GRAD_TOL_MAX = 1e-1                   # ... and the largest single-element error relative to the tensor maximum
 ACT_TOL = 2 * 2.0 ** -8               # stored activation vs the emulation's value from the plan's previous activations
 
 
@@ -56,22 +61,35 @@ def teacher_forced_check(oracle, net, x, yl, w, logits):
     assert not off, sorted(off.items(), key=lambda kv: -kv[1])[:5]
     ref = {n: p.grad for n, p in o_tf.named_parameters()}
     grads = net.named_grads()
+    # tensors that are ONE cancelling sum: how far the reference itself moves under a 2^-9 relative perturbation in front
+    # of every backward rounding (forward values stay pinned by the taps)
+    tiny = [n for n in ref if ref[n].numel() < 16]
+    floors = {}
+    if tiny:
+        o_n = copy.deepcopy(oracle)
+        o_n.zero_grad()
+        torch.manual_seed(1234)
+        weighted_ce(emulated_forward(o_n, x, True, taps=taps, noise=2.0 ** -9), yl, w).backward()
+        g_n = {n: p.grad for n, p in o_n.named_parameters()}
+        floors = {n: rel(g_n[n], ref[n]) for n in tiny}
     tol = GRAD_TOL_DEEP if oracle.arch in ("xresnet50", "xresnet101") else GRAD_TOL
-    bad = gradient_mismatches(grads, ref, tol, GRAD_COS)
-    assert not bad, sorted(bad, key=lambda b: -b[1])[:10]
-    # the checker can fail: one zeroed / one sign-flipped weight gradient is flagged, and only that tensor
+    check = lambda g: gradient_mismatches(g, ref, tol, GRAD_COS, GRAD_TOL_MAX, floors)
+    bad = check(grads)
+    assert not bad, (sorted(bad, key=lambda b: -b[1])[:10], floors)
+    # the checker can fail: one zeroed / sign-flipped / 5 %-scaled weight gradient is flagged, and only that tensor
     names = [n for n in ref if n.endswith("convpath.1.0.weight") and n.startswith("layers.0.7.")]
     victim = names[-1]
-    broken = dict(grads)
-    broken[victim] = torch.zeros_like(grads[victim])
-    assert [b[0] for b in gradient_mismatches(broken, ref, tol, GRAD_COS)] == [victim]
-    broken[victim] = -grads[victim]
-    assert [b[0] for b in gradient_mismatches(broken, ref, tol, GRAD_COS)] == [victim]
-    worst = max(rel(grads[n], ref[n]) for n in ref)
+    for mutate in (torch.zeros_like, lambda g: -g, lambda g: 1.05 * g):
+        broken = dict(grads)
+        broken[victim] = mutate(grads[victim])
+        assert [b[0] for b in check(broken)] == [victim]
+    from parity_util import rel_l2
+    worst = max(rel(grads[n], ref[n]) for n in ref if n not in floors)
+    worst2 = max(rel_l2(grads[n], ref[n]) for n in ref if n not in floors)
     if os.path.isdir("gpurun_out"):      # calibration record of the evidence runs (not part of the assertion)
         with open("gpurun_out/tf_parity.txt", "a") as f:
-            f.write(f"{oracle.arch} {tuple(x.shape)}: worst grad err vs teacher-forced emulation {worst:.3e}, worst "
-                    f"activation mismatch {max(mism.values()):.3e}\n")
+            f.write(f"{oracle.arch} {tuple(x.shape)}: worst grad err vs teacher-forced emulation L2 {worst2:.3e} max-norm "
+                    f"{worst:.3e}, worst activation mismatch {max(mism.values()):.3e}, floors {floors}\n")
     return worst
 
 
@@ -131,7 +149,9 @@ def test_train_step_parity(arch, n_in, n_out, size, batch, data):
     assert e_logits <= max(3e-2, 1.25 * e_auto), (e_logits, e_auto)
     assert abs(loss.item() - loss_ref.item()) / abs(loss_ref.item()) <= 5e-3
     assert rel(logits, l_emu) <= (3e-2 if arch == "xresnet50" else 2e-2)
-    assert abs(loss.item() - loss_emu.item()) / abs(loss_emu.item()) <= 2e-4
+    # (xresnet50 at batch 2 / 64 px normalises over 8 values in its last stage: the fp32 summation order of the batch
+    # statistics alone moves the loss by 1-3e-4 there - measured with two orders of the same sums)
+    assert abs(loss.item() - loss_emu.item()) / abs(loss_emu.item()) <= (5e-4 if arch == "xresnet50" else 2e-4)
     # argmax: disagreements only inside the error band
     top2 = logits_ref.topk(2, dim=1).values
     margin = top2[:, 0] - top2[:, 1]
@@ -180,6 +200,7 @@ def test_self_attention_parity():
     torch.backends.cuda.matmul.allow_tf32 = False
     arch, n_in, n_out, size, batch = "xresnet18", 4, 2, 128, 4
     oracle = make_oracle(arch, n_in, n_out, seed=0, self_attention=True).cuda().train()
+    o_init = copy.deepcopy(oracle)        # (a training-mode forward advances the power-iteration vectors in place)
     net = UNetB200(arch, n_in, n_out, (size, size), batch, training=True, self_attention=True)
     sd0 = copy.deepcopy(oracle.state_dict())
     net.load_state_dict(sd0)
@@ -212,11 +233,16 @@ def test_self_attention_parity():
     bad = []
     for name, p in oracle.named_parameters():
         eo, ea = rel(grads[name], p.grad), rel(pa[name].grad, p.grad)
-        if ea <= 0.5 and eo > 1.6 * ea + 2e-2:
+        # (tensors that stock autocast itself misses by more than 10 % - the scalar gamma, one cancelling sum, reads 17 %
+        # there - say nothing either way in a free-running comparison)
+        if ea <= 0.1 and eo > 1.6 * ea + 2e-2:
             bad.append((name, eo, ea))
     assert not bad, bad[:10]
     sa_names = [n for n in grads if ".conv2.2." in n]
     assert len(sa_names) == 4 and all(grads[n].abs().max() > 0 for n in sa_names)
+    # the wiring of the block (gamma, the weight_orig tensors behind sigma, the order in which the four consumers of
+    # conv2's output accumulate their gradients) against the teacher-forced emulation of the same graph
+    teacher_forced_check(o_init, net, x, yl, w, logits)
     # eval mode: sigma from the stored u / v, no power iteration
     oracle.eval()
     ev = UNetB200(arch, n_in, n_out, (size, size), batch, training=False, self_attention=True)

@@ -30,6 +30,11 @@ CASES = {
     "e256f": (64, 16, 16, 256, 256, 3, False, False, False, False, 2),
     "e512": (64, 8, 8, 512, 512, 3, False, False, False, False, 0),
     "e512f": (64, 8, 8, 512, 512, 3, False, False, False, False, 2),
+    "s32": (64, 128, 128, 32, 32, 3, False, False, False, False, 0),
+    "s32f": (64, 128, 128, 32, 32, 3, False, False, False, False, 2),
+    "s32_64": (64, 128, 128, 32, 64, 3, False, False, False, False, 0),
+    "s32_64f": (64, 128, 128, 32, 64, 3, False, False, False, False, 2),
+    "s64_32": (64, 128, 128, 64, 32, 3, False, False, False, False, 0),
 }
 case = sys.argv[1]
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3

@@ -36,7 +36,7 @@ struct ConvParams {
   int wres;          // halo mode with ALL weights of the (single) N tile resident in shared memory for the whole launch:
                      // SB = 3*k_chunks filter-row blocks loaded once; only the activation halo tiles stream per tile
   int rowmode;       // halo mode with one weight stage per FILTER ROW (3 taps, one barrier): amortises the issue-side cost
-  int stg_bufs;      // output staging buffers (2, or 1 in row mode to make room for the larger weight stages)
+  int stg_bufs;      // output staging ring: 1..4 buffers (whatever shared memory is left), 0 with residual / mask operands
   CUtensorMap tm_b3; // weights viewed as (Cin, Cout, tap): a box of 3 taps lands as [3][BN][64] in smem
   uint32_t a_stage_bytes, a_tx_bytes;
   CUtensorMap tm_ah;
@@ -93,6 +93,11 @@ __device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&o)[8]) {
 __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
 __device__ __forceinline__ void unpack8(const uint4& u, float (&o)[8]) {
@@ -210,7 +215,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       smem + (size_t)ring_bytes + (size_t)epi_bufs * kStagingBytes + 8 * (n_ring_bars + 7));
 
   float* s_stats = reinterpret_cast<float*>(smem + (size_t)ring_bytes + (size_t)epi_bufs * kStagingBytes + 512);
-  for (int i = threadIdx.x; i < 8 * p.stats_cols; i += kThreads) s_stats[i] = 0.f;
+  for (int i = threadIdx.x; i < 16 * p.stats_cols; i += kThreads) s_stats[i] = 0.f;
   if (threadIdx.x == 0) {
     if (smem_base & 1023u) {
       printf("b2u: dynamic smem base 0x%x not 1024-byte aligned\n", smem_base);
@@ -467,6 +472,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t chunk_ctr = 0;
+    uint32_t stg_buf = 0;        // staging ring position (chunk_ctr % stg_bufs)
     [[maybe_unused]] int tl_e = 0;
     const int n_groups = (p.BN + 31) >> 5;
     const int n_chunks = (n_groups + 1) >> 1;
@@ -477,7 +483,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const int slot_rm = has_res ? 1 : 0, slot_zm = (has_res ? 1 : 0) + (has_rm ? 1 : 0);
     constexpr bool has_head = kHead;
     const bool head_only = has_head && (p.flags & B2U_EPI_HEAD_ONLY) != 0;
-    float* s_head = s_stats + 8 * p.stats_cols;       // 2 x 128 x 8 floats behind the statistics accumulators
+    float* s_head = s_stats + 16 * p.stats_cols;      // 2 x 128 x 8 floats behind the statistics accumulators
     uint32_t tile_ctr = 0;
     auto issue_aux = [&](int t, int chunk, uint32_t buf) {
       const int m2 = tile_m(t), nt2 = tile_nt(t);
@@ -599,6 +605,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             for (int i = 0; i < 32; ++i)
               if (c0 + i >= p.Cout) v[i] = 0.f;
           }
+          if (kStats && !valid) {
+            // rows outside the image are clipped by the TMA store; staged as zeros they drop out of the column sums
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+          }
         }
 
         if (kF32) {
@@ -635,13 +646,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             }
           }
           // bf16 pack -> swizzled staging (SWIZZLE_128B: 16-byte chunk j of row r lands at chunk j ^ (r & 7))
-          const uint32_t buf = p.stg_bufs == 2 ? (chunk_ctr & 1u) : 0u;
+          const uint32_t buf = stg_buf;
           // kAux: the result overwrites operand 0 of this chunk in place (every thread reads and writes its own 64 bytes of
           // its own pixel row only), and the buffer's previous store was drained before the operand load was issued
           const uint32_t out_buf = kAux ? aux_base + abuf * (uint32_t)p.n_aux * kStagingBytes : stg_base + buf * kStagingBytes;
-          if (!kAux && !head_only) {
-            // the store that last used this staging buffer has finished reading it
-            if (e == 0) { if (p.stg_bufs == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
+          if (!kAux && !head_only && p.stg_bufs == 1) {
+            // single staging buffer: the store of the previous chunk has finished reading it
+            if (e == 0) tma_store_wait_read<0>();
             named_bar_sync(1, 256);
           }
           const uint32_t row_addr = out_buf + (uint32_t)row * 128u;
@@ -658,7 +669,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                            "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
                            : "memory");
             }
-            if (kStats) {
+            if (kStats && p.stats_cols == 0) {
               // statistics of what is actually stored (bf16-rounded), so that BN forward/backward are self-consistent
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
@@ -676,6 +687,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             }
           }
           if (!head_only) fence_proxy_async_smem();
+          if (!kAux && !head_only && p.stg_bufs >= 2 && e == 0) {
+            // staging ring: before the barrier that publishes this chunk, the issuing thread makes sure that the buffer of
+            // the NEXT chunk is free (its store, stg_bufs - 1 chunks ago, has read it) - one CTA-wide barrier per chunk
+            switch (p.stg_bufs) {
+              case 4: tma_store_wait_read<2>(); break;
+              case 3: tma_store_wait_read<1>(); break;
+              default: tma_store_wait_read<0>(); break;
+            }
+          }
           named_bar_sync(1, 256);
           if (e == 0) {
             if (kPair && rank != 0 && j == n_chunks - 1) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
@@ -694,28 +714,47 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           }
         }
         ++chunk_ctr;
-        if (kStats && active) {
-          float s1[32], s2[32];
+        if (kStats && p.stats_cols > 0) {
+          // Column sums of the STAGED chunk (the bf16 values the store writes: BN forward / backward stay self-consistent;
+          // clipped rows and pad lanes were staged as zeros).  Warp ew reads rows 16*ew .. 16*ew+15, lane l the 32-bit word
+          // l of every row (channels 2l, 2l+1 of the chunk; the 128-byte swizzle permutes whole 16-byte units inside a row,
+          // so the 32 lanes always hit 32 different banks) and keeps private accumulators in shared memory - no shuffles.
+          const uint32_t sbase = (kAux ? aux_base + abuf * (uint32_t)p.n_aux * kStagingBytes : stg_base + stg_buf * kStagingBytes) +
+                                 (uint32_t)ew * 2048u + (uint32_t)(lane & 3) * 4u;
+          const uint32_t u = (uint32_t)lane >> 2;
+          float sa = 0.f, sb = 0.f, qa = 0.f, qb = 0.f;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float q = (valid && (c0 + i < p.Cout)) ? v[i] : 0.f;
-            s1[i] = q;
-            s2[i] = q * q;
+          for (int i = 0; i < 16; ++i) {
+            const uint32_t w = ld_shared_u32(sbase + (uint32_t)i * 128u + ((u ^ (uint32_t)(i & 7)) << 4));
+            const float a = bf16_lo(w), b = bf16_hi(w);
+            sa += a; sb += b;
+            qa = fmaf(a, a, qa); qb = fmaf(b, b, qb);
           }
+          const int c = nt * p.BN + j * 64 + 2 * lane;
+          if (j * 64 + 2 * lane < p.BN && c < p.stats_cols) {    // BN is even: both channels of the word are inside
+            float2* s1 = reinterpret_cast<float2*>(s_stats + (size_t)(ew * 2 + 0) * p.stats_cols + c);
+            float2* s2 = reinterpret_cast<float2*>(s_stats + (size_t)(ew * 2 + 1) * p.stats_cols + c);
+            float2 t1 = *s1, t2 = *s2;
+            t1.x += sa; t1.y += sb; t2.x += qa; t2.y += qb;
+            *s1 = t1; *s2 = t2;
+          }
+        } else if (kStats && active) {
+          // (rows outside the image and lanes past Cout were zeroed above)
+          float s1[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) s1[i] = v[i];
           const float sum = warp_transpose_reduce(s1, lane);
-          const float sq = warp_transpose_reduce(s2, lane);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) s1[i] = v[i] * v[i];
+          const float sq = warp_transpose_reduce(s1, lane);
           const int c = c0 + lane;
-          if (p.stats_cols > 0) {
-            if (c < p.stats_cols) {   // this lane quarter's private accumulators (column groups are disjoint): no race
-              s_stats[(q4 * 2 + 0) * p.stats_cols + c] += sum;
-              s_stats[(q4 * 2 + 1) * p.stats_cols + c] += sq;
-            }
-          } else if (c < p.stats_ld && m < p.m_tiles) {
+          if (c < p.stats_ld && m < p.m_tiles) {
             float* sp = p.stats + (size_t)(m * 4 + q4) * 2 * p.stats_ld;
             sp[c] = sum;
             sp[p.stats_ld + c] = sq;
           }
         }
+        if (++stg_buf >= (uint32_t)p.stg_bufs) stg_buf = 0;
       }
       if (has_head) {
         // the two warps of a lane quarter hold the even / odd 32-channel groups of the same 32 pixels: the odd one hands
@@ -739,13 +778,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     }
     if (e == 0 && !kF32) tma_store_wait_all<0>();
     if (kStats && p.stats_cols > 0) {
-      // one partial row per CTA: the four lane quarters' accumulators are combined in a fixed order
+      // one partial row per CTA: the eight warps' accumulators are combined in a fixed order
       named_bar_sync(1, 256);
       float* sp = p.stats + (size_t)blockIdx.x * 2 * p.stats_ld;
       for (int c = e; c < p.stats_cols && c < p.stats_ld; c += 256) {
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
+        for (int w = 0; w < 8; ++w) {
           s1 += s_stats[(w * 2 + 0) * p.stats_cols + c];
           s2 += s_stats[(w * 2 + 1) * p.stats_cols + c];
         }
@@ -941,14 +980,6 @@ static int conv_plan_fill(const b2u_conv_desc* d, b2u_conv_plan* plan, bool enco
     tw = 8; th = 16; tn = 1;
     tx = ceil_div(d->out.W, tw); ty = ceil_div(d->out.H, th); tb = d->out.N;
   }
-  // under-filled grids (the 8 x 8 stages: 32 pixel tiles): halve the channel tile while that doubles the CTAs that get
-  // work - a 128-wide tile streams half of the weight rows and issues MMAs of half the duration, so the launch's critical
-  // path (one tile per CTA) halves; the activations it re-reads are a few MB in L2
-  static const bool nsplit_disabled = getenv("B2U_CONV_NO_NSPLIT") != nullptr;  // A/B switch for profiling
-  if (!nsplit_disabled && !multi_out && !batched_w && !out_f32 && !(d->flags & B2U_EPI_HEAD)) {
-    const int sms = encode ? sm_count() : 148;
-    while (BN >= 128 && BN % 32 == 0 && Cout % (BN / 2) == 0 && 2 * n_tiles * tx * ty * tb <= sms) { BN /= 2; n_tiles *= 2; }
-  }
   p.halo = halo ? 1 : 0;
   p.hw = tw + 2;
   p.tw = tw; p.th = th; p.tn = tn; p.tiles_x = tx; p.tiles_y = ty;
@@ -956,8 +987,24 @@ static int conv_plan_fill(const b2u_conv_desc* d, b2u_conv_plan* plan, bool enco
   // CTA-pair mode: two pixel tiles share every weight stage (each SM holds half of its rows) and one M = 256 MMA stream
   static const bool pair_disabled = getenv("B2U_CONV_NO_PAIR") != nullptr;  // A/B switch for profiling
   // (tiles with little MMA work - 1x1 convolutions over few channels - are epilogue/store-bound: pairing only adds sync)
+  // ... unless ALL weight rows of a 3x3 layer fit in one CTA's shared memory next to three halo stages (<= 64 output
+  // channels at <= 64 input channels): nothing is streamed per tile that a pair could share, and the M = 256 MMAs of a
+  // pair run slower than two independent M = 128 streams at these widths (measured: 32->32 @128^2 0.101 -> 0.060 ms,
+  // 64->64 @64^2 0.030 -> 0.025 ms without pairs)
+  bool solo_resident = false;
+  if (halo && n_tiles == 1 && d->w_taps == 9 && getenv("B2U_CONV_NO_WRES") == nullptr) {
+    bool tw_ok = true;
+    for (int t = 0; t < 9; ++t) tw_ok = tw_ok && d->tap_w[t] == t;
+    const uint32_t a_st = ((uint32_t)((tw + 2) * (th + 2)) * 128u + 1023u) & ~1023u;
+    const uint32_t w_full = (uint32_t)ceil_div(Cin, 64) * 9u * (uint32_t)BN * 128u;
+    const int aux = (d->res.ptr ? 1 : 0) + (d->res_mask.ptr ? 1 : 0) + (d->zmask.ptr ? 1 : 0);
+    const uint32_t fx = (aux > 0 ? (uint32_t)aux * kAuxRing : 1u) * kStagingBytes + 512u +
+                        ((d->flags & B2U_EPI_STATS) ? (uint32_t)BN * 64u : 0u) + ((d->flags & B2U_EPI_HEAD) ? 8192u : 0u);
+    solo_resident = tw_ok && 3u * a_st + w_full + fx <= 232448u;
+  }
+  static const bool solo_disabled = getenv("B2U_CONV_NO_SOLO") != nullptr;  // A/B switch for profiling
   const bool pair = !pair_disabled && !out_f32 && !multi_out && !batched_w && BN % 16 == 0 && p.m_tiles >= 2 &&
-                    (halo || d->num_taps * ceil_div(Cin, 64) >= 8);
+                    (halo || d->num_taps * ceil_div(Cin, 64) >= 8) && !(solo_resident && !solo_disabled);
   plan->pair = pair;
   const int b_rows = pair ? BN / 2 : BN;   // weight rows per CTA and tap
   p.num_taps = d->num_taps;
@@ -990,7 +1037,7 @@ static int conv_plan_fill(const b2u_conv_desc* d, b2u_conv_plan* plan, bool enco
   } else {
     B2U_CHECK_ARG(!(d->flags & B2U_EPI_HEAD_ONLY), "conv: B2U_EPI_HEAD_ONLY without B2U_EPI_HEAD");
   }
-  uint32_t fixed = (uint32_t)p.stg_bufs * kStagingBytes + aux_bytes + 512 + (uint32_t)p.stats_cols * 32u + (has_head ? 8192u : 0u);
+  uint32_t fixed = (uint32_t)p.stg_bufs * kStagingBytes + aux_bytes + 512 + (uint32_t)p.stats_cols * 64u + (has_head ? 8192u : 0u);
   int stages;
   if (halo) {
     p.a_tx_bytes = (uint32_t)((tw + 2) * (th + 2)) * 128u;
@@ -1046,6 +1093,13 @@ static int conv_plan_fill(const b2u_conv_desc* d, b2u_conv_plan* plan, bool enco
     plan->smem_bytes = (size_t)stages * stage_bytes + fixed;
   }
   p.stages = stages;
+  // spare shared memory goes to the output staging ring (up to 4 buffers): a TMA store takes 700-1400 clocks to read its
+  // buffer, so the layers whose tiles carry little MMA work (<= 64 channels) are paced by how many stores may be in flight
+  static const int max_stg = getenv("B2U_CONV_MAX_STG") ? atoi(getenv("B2U_CONV_MAX_STG")) : 4;   // A/B switch for profiling
+  while (n_aux == 0 && !out_f32 && p.stg_bufs >= 1 && p.stg_bufs < max_stg && plan->smem_bytes + kStagingBytes <= 232448u) {
+    ++p.stg_bufs;
+    plan->smem_bytes += kStagingBytes;
+  }
   // at least half of the SM's shared memory, so that exactly one CTA (and its 512 TMEM columns) lives on an SM
   if (plan->smem_bytes < 120 * 1024) plan->smem_bytes = 120 * 1024;
   p.idesc = make_idesc_bf16(pair ? 256 : 128, BN, 0, 0);

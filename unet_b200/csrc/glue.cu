@@ -456,6 +456,59 @@ __global__ void nchw_to_nhwc_kernel(const void* __restrict__ x, int dtype, float
   }
 }
 
+// im2col of a small-channel NHWC bf16 tensor: y[n, oy, ox, c * ks*ks + ky*ks + kx] = x[n, oy*stride + ky - pad, ox*stride + kx - pad, c]
+// (zero outside the image and in the pad lanes up to ldy) - torch.nn.functional.unfold's channel order, which is also the
+// order of a conv weight [Cout][Cin][kh][kw] read as [Cout][Cin*kh*kw]: the stem's 3x3 stride-2 convolution over 4 bands
+// becomes a 1x1 convolution over 36 "channels" whose rows are whole 32-byte sectors for TMA (the 8-byte pixels of the
+// 4-band image were one TMA request each).  A warp owns 32 consecutive output pixels: every lane gathers its pixel's
+// taps (one 16-byte load per tap when the input pitch allows) into a row of a shared-memory tile, then the warp copies
+// the tile - contiguous in shared AND in global memory - with 16-byte accesses.
+__global__ void __launch_bounds__(256) im2col_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int C, int H, int W,
+                                                     __nv_bfloat16* __restrict__ y, int ldy, int Ho, int Wo, int ks, int stride,
+                                                     int pad, long long total_pix) {
+  pdl_enter();
+  extern __shared__ __align__(16) unsigned short im2col_sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, KK = ks * ks;
+  unsigned short* tile = im2col_sm + (size_t)warp * 32 * ldy;
+  unsigned short* row = tile + (size_t)lane * ldy;
+  const unsigned short* xs = reinterpret_cast<const unsigned short*>(x);
+  const bool vec = (ldx & 7) == 0 && C <= 8;
+  const int units = ldy >> 3;
+  for (long long base = ((long long)blockIdx.x * 8 + warp) * 32; base < total_pix; base += (long long)gridDim.x * 256) {
+    const long long pix = base + lane;
+    for (int u = 0; u < units; ++u) reinterpret_cast<uint4*>(row)[u] = make_uint4(0u, 0u, 0u, 0u);
+    if (pix < total_pix) {
+      const long long n = pix / ((long long)Ho * Wo);
+      const int r = (int)(pix - n * Ho * Wo), oy = r / Wo, ox = r - oy * Wo;
+      int t = 0;
+      for (int ky = 0; ky < ks; ++ky) {
+        const int iy = oy * stride + ky - pad;
+        for (int kx = 0; kx < ks; ++kx, ++t) {
+          const int ix = ox * stride + kx - pad;
+          if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+          const unsigned short* src = xs + ((n * H + iy) * W + ix) * ldx;
+          if (vec) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(src));
+            const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              if (c < C) row[c * KK + t] = (unsigned short)(w4[c >> 1] >> ((c & 1) * 16));
+          } else {
+            for (int c = 0; c < C; ++c) row[c * KK + t] = __ldg(src + c);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    const long long left = total_pix - base;
+    const int n16 = (int)(left < 32 ? left : 32) * units;
+    uint4* dst = reinterpret_cast<uint4*>(y + base * ldy);
+    const uint4* srcv = reinterpret_cast<const uint4*>(tile);
+    for (int i = lane; i < n16; i += 32) dst[i] = srcv[i];
+    __syncwarp();
+  }
+}
+
 // tile t = raster[:, y0[t]:y0[t]+P, x0[t]:x0[t]+P] / div / div2 -> bf16 NHWC [T,P,P,ld] (crop + input contract + layout cast)
 __global__ void crop_tiles_kernel(const void* __restrict__ raster, int dtype, float div, float div2, int C, long long Y, long long X,
                                   const int* __restrict__ ty0, const int* __restrict__ tx0, int T, int P,
@@ -1036,6 +1089,21 @@ extern "C" int b2u_nchw_to_nhwc(const void* x, int32_t x_dtype, float div, float
   const long long items = (long long)N * H * W;
   launch_k(nchw_to_nhwc_kernel, dim3(grid_for(items, 256)), dim3(256), 0, (cudaStream_t)stream, x, x_dtype, div, div2, (bf)y, N, C, H, W,
            ld, ch_off, write_c);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" int b2u_im2col(const void* x, int32_t ldx, int32_t C, int32_t N, int32_t H, int32_t W, int32_t ks, int32_t stride,
+                          int32_t pad, void* y, int32_t ldy, void* stream) {
+  B2U_CHECK_ARG(x && y && C > 0 && C <= ldx && N > 0 && H > 0 && W > 0 && ks >= 1 && stride >= 1 && pad >= 0, "im2col: bad argument");
+  B2U_CHECK_ARG(ldy % 8 == 0 && ldy >= C * ks * ks, "im2col: ldy=%d must be a multiple of 8 and hold C*ks*ks=%d lanes", ldy, C * ks * ks);
+  const int Ho = (H + 2 * pad - ks) / stride + 1, Wo = (W + 2 * pad - ks) / stride + 1;
+  B2U_CHECK_ARG(Ho > 0 && Wo > 0, "im2col: empty output");
+  const long long pixels = (long long)N * Ho * Wo;
+  const size_t smem = (size_t)256 * ldy * 2;
+  B2U_CHECK_ARG(smem <= 48 * 1024, "im2col: ldy=%d too wide for the shared-memory tile", ldy);
+  launch_k(im2col_kernel, dim3(grid_for(pixels, 256)), dim3(256), smem, (cudaStream_t)stream, (const __nv_bfloat16*)x, ldx, C, H, W,
+           (bf)y, ldy, Ho, Wo, ks, stride, pad, pixels);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }

@@ -394,7 +394,10 @@ static int wgrad_fill(const b2u_wgrad_desc* d, b2u_wgrad_plan* plan, bool encode
   B2U_CHECK_ARG(d->num_taps >= 1 && d->num_taps <= B2U_MAX_TAPS, "wgrad: num_taps out of range");
   B2U_CHECK_ARG(d->Cout > 0 && d->Cin > 0, "wgrad: bad channel counts");
   B2U_CHECK_ARG(d->dy.C == d->Cout, "wgrad: dy.C=%d != Cout=%d", d->dy.C, d->Cout);
-  for (int i = 0; i < d->num_a; ++i) B2U_CHECK_ARG(d->a[i].C == d->Cin, "wgrad: a[%d].C != Cin", i);
+  // a view may expose the zero pad lanes up to the next multiple of 16 channels (whole 32-byte sectors for TMA): their
+  // products land in accumulator columns >= Cin that the reduction never reads
+  for (int i = 0; i < d->num_a; ++i)
+    B2U_CHECK_ARG(d->a[i].C >= d->Cin && d->a[i].C <= round_up(d->Cin, 16), "wgrad: a[%d].C=%d does not match Cin=%d", i, d->a[i].C, d->Cin);
   WgradParams& p = plan->p;
   memset(&p, 0, sizeof(p));
   p.num_taps = d->num_taps;

@@ -13,6 +13,7 @@ batched kernel.
 from __future__ import annotations
 
 import ctypes as C
+import dataclasses
 import sys
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
@@ -28,6 +29,7 @@ BN_EPS = 1e-5
 SIDE_STREAM_WGRAD = os.environ.get("B2U_NO_SIDE_STREAM") is None   # A/B switches for profiling
 FUSED_FINAL_SHUFFLE = os.environ.get("B2U_NO_FUSED_SHUFFLE") is None
 FUSED_HEAD = os.environ.get("B2U_NO_FUSED_HEAD") is None
+STEM_IM2COL = os.environ.get("B2U_NO_STEM_IM2COL") is None      # A/B switch for profiling
 BN_MOMENTUM = 0.1
 STATS_ROWS = 592  # block partial rows of the standalone reductions (4 per SM)
 
@@ -290,8 +292,9 @@ class UNetB200:
         self._bn[prefix] = st
         return st
 
-    def _weights(self, cs: ConvSpec, need_dgrad: bool) -> Dict[str, torch.Tensor]:
-        """bf16 GEMM copies of one conv's weights + staging item for the batched cast kernel."""
+    def _weights(self, cs: ConvSpec, need_dgrad: bool, master_cin: Optional[int] = None) -> Dict[str, torch.Tensor]:
+        """bf16 GEMM copies of one conv's weights + staging item for the batched cast kernel.  master_cin: row length of
+        the fp32 master when the GEMM sees zero pad lanes behind it (the im2col stem: 36 of 48 lanes)."""
         dev = self.device
         kk = cs.ks * cs.ks
         wf = torch.zeros((cs.nf, kk, padc(cs.ni)), dtype=torch.bfloat16, device=dev)
@@ -311,7 +314,7 @@ class UNetB200:
         it.bias = self.param(cs.bname).data_ptr() if cs.bname else None
         it.row_of_co = _p(w["row_of_co"])
         it.wf, it.wd, it.bias_rows = wf.data_ptr(), _p(wd), _p(w["bias_rows"])
-        it.Cout, it.Cin, it.kk, it.wf_cinp, it.wd_coutp = cs.nf, cs.ni, kk, padc(cs.ni), padc(cs.nf)
+        it.Cout, it.Cin, it.kk, it.wf_cinp, it.wd_coutp = cs.nf, master_cin or cs.ni, kk, padc(cs.ni), padc(cs.nf)
         it.scale = 0.25 if cs.pool else 1.0
         if cs.sn:
             sig = torch.ones(2, dtype=torch.float32, device=dev)      # {sigma, 1/sigma}, written by b2u_spectral_norm
@@ -443,7 +446,8 @@ class UNetB200:
         ldn = padc(n)
         zt = lambda *shape: torch.zeros(shape, dtype=torch.bfloat16, device=dev)
         S = zt(N, h, w_, ldn)             # logits q_i . k_j ([image][i][j]); reused for d(beta) and dS in the backward pass
-        beta, betaT = zt(N, h, w_, ldn), zt(N, h, w_, ldn)        # softmax over i, and its transpose ([image][j][i])
+        # softmax over i (a named activation: the parity tests pin it), and its transpose ([image][j][i])
+        beta, betaT = self._act(h, w_, n, sa.name + ".beta", zero=True).t, zt(N, h, w_, ldn)
         VT = zt(N, Cc, ldn)               # value^T: channels x positions (the contraction index of `o` innermost)
         O = self._act(h, w_, Cc, sa.name + ".o")
         out = self._act(h, w_, Cc, sa.name + ".out")
@@ -543,7 +547,9 @@ class UNetB200:
         spec = dict(cs=cs, dy_view=view_nhwc(dy, cs.nf), views=views, taps=taps, kidx=kidx,
                     dw=self.grad(cs.wname), db=self.grad(cs.bname) if cs.bname else None, row_perm=w["row_perm"],
                     alpha=0.25 if cs.pool else 1.0, keep=(dy, x))
-        info = WgradPlan.query(spec["dy_view"], views, taps, cs.nf, cs.ni, spec["db"] is not None)
+        # (im2col stem: the views expose 48 lanes, the master weight - and its gradient - has n_in*9 = 36 columns)
+        spec["cin"] = self.spec.stem[0].ni * 9 if cs is self._cs0_col else cs.ni
+        info = WgradPlan.query(spec["dy_view"], views, taps, cs.nf, spec["cin"], spec["db"] is not None)
         spec["bytes"] = info.partial_bytes
         self._wgrad_specs.append(spec)
         slot = len(self._wgrad_specs) - 1
@@ -588,8 +594,18 @@ class UNetB200:
         spec, N, H, W, dev, lib = self.spec, self.N, self.H, self.W, self.device, self.lib
         train = self.training
         # weights for every conv (first stem conv never needs a dgrad copy: the image has no gradient)
+        # im2col stem: the first convolution (3x3, stride 2, n_in bands) runs as a 1x1 convolution over the n_in*9 im2col
+        # lanes written by b2u_im2col (zero padded to whole 32-byte sectors) - its weight [nf][n_in][3][3] read as rows of
+        # n_in*9 IS the 1x1 weight, and so is its gradient
+        cs0 = spec.stem[0]
+        self.stem_im2col = STEM_IM2COL and cs0.ks == 3 and cs0.stride == 2 and cs0.ni * 9 <= 64 and not cs0.pool
+        self._cs0_col = dataclasses.replace(cs0, ni=(cs0.ni * 9 + 15) // 16 * 16, ks=1, stride=1) if self.stem_im2col else None
         for i, cs in enumerate(spec.convs()):
-            self._weights(cs, need_dgrad=train and i != 0)
+            if i == 0 and self.stem_im2col:
+                assert cs is cs0
+                self._weights(self._cs0_col, need_dgrad=False, master_cin=cs0.ni * 9)
+            else:
+                self._weights(cs, need_dgrad=train and i != 0)
         self._finish_wstage()
 
         # ---- input
@@ -639,6 +655,12 @@ class UNetB200:
         h, w_ = up2(H), up2(W)
         feats: Dict[int, Act] = {}
         for i, cs in enumerate(spec.stem):
+            if i == 0 and self.stem_im2col:
+                xc = self._act(h, w_, self._cs0_col.ni, "input.im2col", zero=True)
+                self._fwd(lambda s, a=x, b=xc, c0=cs: _lib.check(
+                    lib.b2u_im2col(a.t.data_ptr(), a.ld, c0.ni, N, a.H, a.W, c0.ks, c0.stride, c0.ks // 2, b.t.data_ptr(), b.ld, s),
+                    "b2u_im2col"), kind="im2col", nbytes=x.pixels * x.ld * 2 + xc.pixels * xc.ld * 2)
+                cs, x = self._cs0_col, xc
             R, Z, bn = conv_bn(cs, x, h, w_, apply=True)
             if train:
                 bwd_layers.append(conv_bn_bwd(cs, x, R, Z, bn, need_dx=i != 0))
@@ -958,7 +980,7 @@ class UNetB200:
             self._wgrad_plans = []
             for sp in self._wgrad_specs:
                 cs = sp["cs"]
-                self._wgrad_plans.append(WgradPlan(sp["dy_view"], sp["views"], sp["taps"], cs.nf, cs.ni, cs.ks * cs.ks,
+                self._wgrad_plans.append(WgradPlan(sp["dy_view"], sp["views"], sp["taps"], cs.nf, sp["cin"], cs.ks * cs.ks,
                                                    sp["kidx"], sp["dw"].reshape(-1), sp["db"], sp["row_perm"],
                                                    sp["alpha"], self._wgrad_ws))
         self.feats = feats
