@@ -72,7 +72,7 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
+        sm, mx, reasons, pw = [], None, set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ts, ln in self.lines:
             if ts < t0 or ts > t1 + 0.15:   # only samples taken DURING the timed region
@@ -85,12 +85,17 @@ class ClockSampler:
                 mx = float(parts[1])
             except ValueError:
                 continue
+            try:
+                pw.append(float(parts[2]))
+            except ValueError:
+                pass
             for n, v in zip(names, parts[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         sm.sort()
+        pw.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w": pw[len(pw) // 2] if pw else None}
 
 
 def cpu_oracle_step_time(batch: int, steps: int, warmup: int):
@@ -429,7 +434,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    sampler = ClockSampler(local)
+    vis = [v for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip().isdigit()]
+    sampler = ClockSampler(int(vis[local]) if local < len(vis) else local)    # nvidia-smi counts physical GPUs
     if rank == 0:
         sampler.start()   # started early (nvidia-smi needs ~1 s to produce its first sample); filtered by time below
     # ---- warm-up (includes graph capture)

@@ -14,7 +14,7 @@ timeout 200 python tools/predict_profile.py 8192 64 > gpurun_out/${R}_predict_pr
 timeout 300 python tools/torch_baseline.py 64 > gpurun_out/${R}_torch_baseline.txt 2>&1
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 1200 -c 800 --csv --log-file gpurun_out/${R}_launches_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-profile --no-predict --no-extra > gpurun_out/ncu_bench.log 2>&1
 timeout 500 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed --clock-control none -k regex:"conv_gemm|wgrad_gemm" --launch-skip 368 -c 184 --csv --log-file gpurun_out/${R}_gemm_kernel_metrics.csv python tools/step_eager.py 3 64 > gpurun_out/ncu_step.log 2>&1
-timeout 500 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"bn_|shuffle|maxpool|ce_|pointwise|copy_lanes|nchw|sgd|stage_weights|wgrad_reduce" --launch-skip 1000 -c 500 --csv --log-file gpurun_out/${R}_mem_kernel_metrics.csv python tools/step_eager.py 3 64 > gpurun_out/ncu_step_mem.log 2>&1
+timeout 500 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"bn_|shuffle|maxpool|ce_|pointwise|copy_lanes|nchw|im2col|sgd|stage_weights|wgrad_reduce" --launch-skip 340 -c 170 --csv --log-file gpurun_out/${R}_mem_kernel_metrics.csv python tools/step_eager.py 3 64 > gpurun_out/ncu_step_mem.log 2>&1
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:conv_gemm --launch-skip 2 -c 1 -f -o gpurun_out/${R}_conv_res100 python tools/one_conv.py res100 3 > gpurun_out/ncu_conv.log 2>&1
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:conv_gemm --launch-skip 2 -c 1 -f -o gpurun_out/${R}_conv_c100 python tools/one_conv.py c100_100 3 > gpurun_out/ncu_conv2.log 2>&1
 for f in gpurun_out/ncu_step.log gpurun_out/ncu_conv.log gpurun_out/ncu_step_mem.log; do tail -n 2 $f; done

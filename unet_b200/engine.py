@@ -30,6 +30,11 @@ def one_cycle(pct: float, lr_max: float, div: float = 25.0, div_final: float = 1
     return cos(lr_max, lr_max / div_final, q), cos(moms[1], moms[2], q)
 
 
+# DIAGNOSTIC ONLY (bench A/B at N > 1): B2U_DIAG_SKIP_ALLREDUCE=1 leaves the gradients un-reduced, i.e. N independent
+# replicas that still meet at the step barrier - what the slowest of N ranks costs without any collective.  Training
+# with it is wrong by construction; Learner / train_func refuse to run with it set.
+_SKIP_ALLREDUCE = os.environ.get("B2U_DIAG_SKIP_ALLREDUCE") is not None
+
 class Trainer:
     def __init__(self, net: UNetB200, optimizer: str = "sgd", lr: float = 1e-3, wd: float = 0.01,
                  encoder_factor: float = 10.0, use_graph: bool = True, bucket_mb: float = 32.0,
@@ -86,7 +91,7 @@ class Trainer:
 
     # ------------------------------------------------------------------------------------------------ device step
     def _allreduce(self, lo: int = 0, hi: Optional[int] = None, async_op: bool = False):
-        if self.world == 1:
+        if self.world == 1 or _SKIP_ALLREDUCE:
             return []
         g = self.gbf if self.grad_bf16 else self.net.grads
         hi = g.numel() if hi is None else hi

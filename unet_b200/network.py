@@ -598,7 +598,9 @@ class UNetB200:
         # lanes written by b2u_im2col (zero padded to whole 32-byte sectors) - its weight [nf][n_in][3][3] read as rows of
         # n_in*9 IS the 1x1 weight, and so is its gradient
         cs0 = spec.stem[0]
-        self.stem_im2col = STEM_IM2COL and cs0.ks == 3 and cs0.stride == 2 and cs0.ni * 9 <= 64 and not cs0.pool
+        # (training only: the win is the weight gradient - 0.167 -> 0.04 ms, the 8-byte pixels of the 4-band image are one
+        # TMA request each; for the inference forward the extra im2col pass costs more than the 1x1 form saves)
+        self.stem_im2col = STEM_IM2COL and train and cs0.ks == 3 and cs0.stride == 2 and cs0.ni * 9 <= 64 and not cs0.pool
         self._cs0_col = dataclasses.replace(cs0, ni=(cs0.ni * 9 + 15) // 16 * 16, ks=1, stride=1) if self.stem_im2col else None
         for i, cs in enumerate(spec.convs()):
             if i == 0 and self.stem_im2col:

@@ -95,6 +95,8 @@ class Learner:
         AvgSmoothLoss (debiased exponential average, beta 0.98, running across epochs); SaveModelCallback keeps the best
         epoch by `monitor` and reloads it after the fit (train.py:198-209).  Batches are (x, y) or (x, y, n_real)."""
         assert train_batches is not None, "train_batches: callable returning an iterable of (x_raw, y) batches"
+        if os.environ.get("B2U_DIAG_SKIP_ALLREDUCE") is not None:
+            raise RuntimeError("B2U_DIAG_SKIP_ALLREDUCE is a bench diagnostic (un-reduced gradients): unset it to train")
         lr_max = self.lr if lr_max is None else lr_max
         monitor = monitor or ("r2_score" if self.regression else "dice_multi")      # train.py:198-201
         n_per_epoch = getattr(train_batches, "n_batches", None)
