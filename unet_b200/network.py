@@ -383,10 +383,13 @@ class UNetB200:
                         res=view_nhwc(res.t, cs.nf) if res is not None else None, relu=relu, stats=stats,
                         out_f32=out_f32, fin=fin, head=head)
         self._keep.append(plan)
+        if cs is self._cs0_col:
+            plan.alg_cin = self.spec.stem[0].ni * 9      # 36 real lanes of the 48 the GEMM sees (ConvPlan.flops)
         # convolutions over a handful of input or output channels are HBM-bound: input once + output once
-        small = cs.ni <= 8 or cs.nf <= 8
+        stem = cs.ni <= 8 or cs is self._cs0_col        # (the im2col form of the stem: 36 lanes in, 32 channels out - still HBM-bound)
+        small = stem or cs.nf <= 8
         nb = x.pixels * x.ld * 2 + (y.pixels * 4 * out_f32.shape[-1] if out_f32 is not None else y.pixels * y.ld * 2)
-        self._fwd(plan.run, kind=("conv_gemm(stem)" if cs.ni <= 8 else "conv_gemm(head)") if small else "", nbytes=nb if small else 0)
+        self._fwd(plan.run, kind=("conv_gemm(stem)" if stem else "conv_gemm(head)") if small else "", nbytes=nb if small else 0)
         return plan
 
     def _bn_finalize_op(self, bn: BNState, partial: torch.Tensor, count: float, train_stats: bool = True):

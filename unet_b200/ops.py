@@ -236,7 +236,7 @@ class ConvPlan:
     def flops(self) -> int:
         """algorithmic FLOPs of this launch: 2 * pixels * Cout * Cin * taps (unpadded channels)"""
         d = self.desc
-        return 2 * d.out.N * d.out.H * d.out.W * d.out.C * d.w_cin * d.num_taps
+        return 2 * d.out.N * d.out.H * d.out.W * d.out.C * getattr(self, "alg_cin", d.w_cin) * d.num_taps
 
     def __del__(self):
         h = getattr(self, "handle", None)
