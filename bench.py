@@ -120,7 +120,7 @@ def cpu_oracle_step_time(batch: int, steps: int, warmup: int):
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
-    return sum(times) / len(times), cores, float(loss)
+    return sum(times) / len(times), cores, float(loss.detach())
 
 
 def run_reference(args, rank: int, out):

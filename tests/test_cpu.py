@@ -484,3 +484,28 @@ def test_augmentation_is_a_dihedral_transform_of_image_and_mask_together(tmp_pat
     assert all(torch.equal(a[0], b[0]) for a, b in zip(plain, same))
     with pytest.raises(ValueError):
         augmented(_tile_batches(files, 4, 2, False, None, False), 1.5)
+
+
+def test_gradient_checker_flags_what_it_should():
+    """tests/parity_util.gradient_mismatches on synthetic tensors: rounding-sized noise passes; a zeroed, a sign-flipped and a
+    5 %-scaled tensor, one corrupted element of a large tensor and a rotated direction are each flagged - and only them."""
+    from parity_util import gradient_mismatches
+    g = torch.Generator().manual_seed(0)
+    ref = {f"t{i}": torch.randn(64, 32, 3, 3, generator=g) for i in range(6)}
+    ref["bn"] = torch.randn(64, generator=g)
+    noisy = {k: v * (1 + 2.0 ** -8 * torch.randn(v.shape, generator=g)) for k, v in ref.items()}      # ~1 bf16 ulp per element
+    check = lambda gr: [b[0] for b in gradient_mismatches(gr, ref, 3e-2, 0.999, 0.1)]
+    assert check(noisy) == []
+    for name, mutate in (("t0", torch.zeros_like), ("t1", lambda t: -t), ("t2", lambda t: 1.05 * t),
+                         ("bn", lambda t: t.roll(1))):
+        broken = dict(noisy)
+        broken[name] = mutate(noisy[name])
+        assert check(broken) == [name], name
+    broken = dict(noisy)
+    broken["t3"] = noisy["t3"].clone()
+    broken["t3"].view(-1)[7] += 0.5 * ref["t3"].abs().max()             # one wrong element: invisible to the L2 norm alone
+    assert check(broken) == ["t3"]
+    # a tensor that is one cancelling sum passes up to 4 x its measured floor, and not beyond
+    ref1, got1 = {"gamma": torch.tensor([1.0])}, {"gamma": torch.tensor([1.2])}
+    assert gradient_mismatches(got1, ref1, 3e-2, 0.999, 0.1, floors={"gamma": 0.06}) == []
+    assert [b[0] for b in gradient_mismatches(got1, ref1, 3e-2, 0.999, 0.1, floors={"gamma": 0.04})] == ["gamma"]

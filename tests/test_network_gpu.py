@@ -13,7 +13,7 @@ Stated tolerances (bf16 storage, fp32 accumulation; errors are max|a-b| / max|b|
   * parameter gradients, the check that pins the wiring: against the TEACHER-FORCED bf16 emulation
     (oracle/bf16_emulation.py `taps=`: the emulation's forward values are pinned to the plan's stored activations, its
     backward rounds where the plan stores bf16) every tensor agrees within GRAD_TOL in the relative L2 norm (measured:
-    1.0-1.8e-2; GRAD_TOL_DEEP for xresnet50: 2.7e-2), with cosine >= GRAD_COS and no element off by more than GRAD_TOL_MAX of the tensor maximum (measured
+    1.0-2.1e-2; GRAD_TOL_DEEP for xresnet50: 3.0e-2), with cosine >= GRAD_COS and no element off by more than GRAD_TOL_MAX of the tensor maximum (measured
     1.2-6.7e-2: the max-norm follows single rounding flips, whose realisation changes with any change of summation
     order in the forward pass); tensors of fewer than 16 elements (SelfAttention gamma: one cancelling sum) pass up to
     4 x their own measured sensitivity to sub-ulp perturbations of the stored gradients.  The same checker is then run
@@ -38,7 +38,7 @@ pytestmark = pytest.mark.gpu
 from parity_util import gradient_mismatches, plan_taps, rel
 
 GRAD_TOL, GRAD_COS = 3e-2, 0.999      # plan vs teacher-forced emulation, every parameter tensor: relative L2 error, cosine
-GRAD_TOL_DEEP = 4e-2                  # xresnet50 / 101 (50+ stored tensors per path; measured 2.7e-2)
+GRAD_TOL_DEEP = 4e-2                  # xresnet50 / 101 (50+ stored tensors per path; measured 2.7-3.0e-2)
 GRAD_TOL_MAX = 1e-1                   # ... and the largest single-element error relative to the tensor maximum
 ACT_TOL = 2 * 2.0 ** -8               # stored activation vs the emulation's value from the plan's previous activations
 

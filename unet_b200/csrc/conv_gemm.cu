@@ -31,7 +31,8 @@ struct ConvParams {
   // tap (dy,dx) is the same smem tile addressed from row (dy+1)*(tw+2) + dx+1 with SBO = (tw+2)*128 (tiles are 8 wide, so
   // every 8-row group of the M dimension is one image row).  The UMMA swizzle phase follows the absolute smem address
   // (profiles/r01_swizzle_offset_probe.txt).  A and B have separate rings: SA halo stages, SB weight stages.
-  int stats_cols;  // > 0: BN partial sums are accumulated per warp in smem over all tiles of the CTA (4*grid rows)
+  int stats_cols;  // > 0: BN column sums are accumulated per epilogue warp in smem over all tiles of the CTA, one partial row per
+                   // CTA leaves the kernel (0: Cout > 512, one partial row per (tile, lane quarter) straight to global memory)
   int halo, SA, SB, hw;
   int wres;          // halo mode with ALL weights of the (single) N tile resident in shared memory for the whole launch:
                      // SB = 3*k_chunks filter-row blocks loaded once; only the activation halo tiles stream per tile
