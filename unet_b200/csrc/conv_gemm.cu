@@ -1122,7 +1122,7 @@ static int conv_plan_fill(const b2u_conv_desc* d, b2u_conv_plan* plan, bool enco
   info.m_tiles = p.m_tiles; info.n_tiles = n_tiles; info.block_n = BN; info.tile_w = tw; info.tile_h = th; info.tile_n = tn;
   info.stages = stages; info.k_chunks = p.k_chunks;
   const int total = p.m_tiles * n_tiles;
-  const int sms = encode ? sm_count() : 148;
+  const int sms = sm_count();   // (148 without a device: query and plan creation must agree on the split / grid sizes)
   if (pair) {
     const int pair_tiles = ((p.m_tiles + 1) / 2) * n_tiles;
     info.grid = 2 * (pair_tiles < sms / 2 ? pair_tiles : sms / 2);

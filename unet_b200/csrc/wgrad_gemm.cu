@@ -453,7 +453,7 @@ static int wgrad_fill(const b2u_wgrad_desc* d, b2u_wgrad_plan* plan, bool encode
   p.b_box_tx = (uint32_t)(p.hw * p.th * p.tn) * 128u;
   p.b_box_bytes = (p.b_box_tx + 1023u) & ~1023u;
   const int base_units = p.n_co * p.inner;
-  const int sms = encode ? sm_count() : 148;
+  const int sms = sm_count();   // (148 without a device: query and plan creation must agree on the split / grid sizes)
   // Split count from a small cost model (microseconds): a CTA runs its units back to back (one accumulator set, so the
   // epilogue is not overlapped), every split adds one partial tile set that is written here and read by the reduce.
   //   wave cost  = steps * t_step + t_epi,   t_step ~ T taps x 4 MMAs of 128 x BN x 16 (measured ~1.8x the MMA floor)
