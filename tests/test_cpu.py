@@ -509,3 +509,23 @@ def test_gradient_checker_flags_what_it_should():
     ref1, got1 = {"gamma": torch.tensor([1.0])}, {"gamma": torch.tensor([1.2])}
     assert gradient_mismatches(got1, ref1, 3e-2, 0.999, 0.1, floors={"gamma": 0.06}) == []
     assert [b[0] for b in gradient_mismatches(got1, ref1, 3e-2, 0.999, 0.1, floors={"gamma": 0.04})] == ["gamma"]
+
+
+def test_im2col_stem_identity():
+    """The identity behind the im2col stem of the training plan (network.py `stem_im2col`, csrc/glue.cu `im2col_kernel`):
+    with lanes ordered c * 9 + ky * 3 + kx (torch `unfold`), the 3x3 stride-2 convolution equals a 1x1 product with the
+    weight tensor [Cout][Cin][3][3] READ AS rows of Cin*9 - no re-layout of the master weight - and the gradient of that
+    1x1 weight, reshaped, is the convolution's weight gradient."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 4, 18, 22, generator=g)
+    w = torch.randn(32, 4, 3, 3, generator=g, requires_grad=True)
+    y = F.conv2d(x, w, stride=2, padding=1)
+    cols = F.unfold(x, 3, padding=1, stride=2)                      # [N, 36, Ho*Wo]
+    w2 = w.detach().reshape(32, 36).clone().requires_grad_(True)
+    y2 = (w2 @ cols).view(2, 32, y.shape[2], y.shape[3])
+    assert torch.allclose(y, y2, atol=1e-5)
+    dy = torch.randn(y.shape, generator=g)
+    y.backward(dy)
+    y2.backward(dy)
+    assert torch.allclose(w.grad.reshape(32, 36), w2.grad, atol=1e-4)
