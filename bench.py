@@ -449,8 +449,11 @@ def main():
     barrier()
     t_wall0 = time.time()
     e0.record(st)
+    sync_each = os.environ.get("B2U_BENCH_SYNC_EACH_STEP") is not None     # A/B switch: host waits for every step
     for i in range(args.steps):
         trainer.step(dev_x[i % n_pool], dev_y[i % n_pool])
+        if sync_each:
+            st.synchronize()
     e1.record(st)
     barrier()
     t_wall1 = time.time()
