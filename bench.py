@@ -324,6 +324,36 @@ def extra_configs(dev, rank, world, args, peaks, max_over_ranks, barrier):
     except Exception as ex:   # e.g. out of memory on a smaller part: reported, never hidden
         out["config4_xresnet50_512_train"] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
     torch.cuda.empty_cache()
+    # ---- the reference's DEFAULT model (params_and_main.py:83 self_attention=True): BASELINE configs[1] with fastai's
+    # SelfAttention block on UnetBlock #1 (1 024 positions at 256-px tiles), training, same batch
+    try:
+        B = args.batch
+        net = UNetB200(ARCH, N_IN, N_OUT, (SIZE, SIZE), B, training=True, self_attention=True, device=dev)
+        net.init_parameters(seed=0)
+        tr = Trainer(net, optimizer="sgd", lr=1e-3, use_graph=True)
+        x, y = uniform_tiles(B, N_IN, SIZE, SIZE, N_OUT, seed=199 + rank)
+        x, y = x.to(dev), y.to(dev)
+        for _ in range(3):
+            tr.step(x, y)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        steps = 10
+        e0.record()
+        for _ in range(steps):
+            tr.step(x, y)
+        e1.record()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+        out["config2_self_attention_train"] = {
+            "workload": f"BASELINE configs[1] with self_attention=True (the reference's default): {ARCH}-DynamicUnet "
+                        f"{N_IN}-band {SIZE}x{SIZE}, bf16, batch {B}/GPU, fwd+CE+bwd+SGD (CUDA graph); attention products "
+                        "on the implicit-GEMM kernel", "value": B * world / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+            "steps": steps, "warmup": 3, "batch_per_gpu": B, "final_loss": float(net.loss.item()),
+            "gpu_launches_per_step": net.launches_per_train_step}
+        del tr, net, x, y
+    except Exception as ex:
+        out["config2_self_attention_train"] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+    torch.cuda.empty_cache()
     # ---- configs[4]: R18 / 128 / 3-band, batch 512 inference
     try:
         B = 512
