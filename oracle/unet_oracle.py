@@ -18,6 +18,10 @@ fastai/layers.py) for exactly the flags the reference passes, anchored on the re
 Module and parameter names follow fastai's so that `state_dict()` keys are the ones a reference-trained checkpoint has
 (`layers.0.4.0.convpath.0.0.weight`, `layers.4.shuf.0.0.bias`, ...; SURVEY.md 8(a) key map).
 
+Pieces that DO have an independent implementation in this image are pinned against it (tests/test_cpu.py): the residual
+stages against torchvision's ResNet stages (numerically, same weights), fastai_adam_step against torch.optim.AdamW,
+dice_multi against scikit-learn's macro F1.  The fastai-specific wiring stays unpinned.
+
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module.
 """
 from __future__ import annotations

@@ -529,3 +529,69 @@ def test_im2col_stem_identity():
     y.backward(dy)
     y2.backward(dy)
     assert torch.allclose(w.grad.reshape(32, 36), w2.grad, atol=1e-4)
+
+
+@pytest.mark.parametrize("arch,tv_name", [("xresnet18", "resnet18"), ("xresnet34", "resnet34"), ("xresnet50", "resnet50")])
+def test_oracle_residual_stages_equal_torchvision(arch, tv_name):
+    """An independent pin of the oracle's encoder (the reference's fastai xresnet cannot be imported): every residual stage
+    of the restated body computes exactly what torchvision's ResNet stage computes with the same weights - block order
+    conv -> BN -> ReLU, no conv bias next to BN, stride on the 3x3 of a bottleneck, residual add before the last ReLU -
+    once torchvision's strided 1x1 shortcut is replaced by the ResNet-D shortcut xresnet uses (AvgPool2d(2, ceil_mode) ->
+    1x1 conv -> BN, fastai layers.ResBlock pool_first).  And the parameter totals differ from torchvision's body by the
+    stem alone (three 3x3 convolutions + BN vs one 7x7 + BN): SURVEY.md 8(c) sanity check (i)."""
+    import torchvision
+    from oracle.unet_oracle import xresnet_body
+    torch.manual_seed(0)
+    body = xresnet_body(arch, 4)
+    tv = getattr(torchvision.models, tv_name)(weights=None)
+    count = lambda mods: sum(p.numel() for m in mods for p in m.parameters())
+    ours_stages, tv_stages = list(body.children())[4:], [tv.layer1, tv.layer2, tv.layer3, tv.layer4]
+    assert count(ours_stages) == count(tv_stages)
+    stem_ours, stem_tv = count(list(body.children())[:3]), count([tv.conv1, tv.bn1])
+    assert count(body.children()) - count([tv.conv1, tv.bn1] + tv_stages) == stem_ours - stem_tv
+    x = torch.randn(2, 64, 20, 20)
+    for so, st in zip(ours_stages, tv_stages):
+        for bo, bt in zip(so, st):
+            for m in bo.modules():                      # non-trivial BatchNorm everywhere (BatchZero gamma would hide the path)
+                if isinstance(m, torch.nn.BatchNorm2d):
+                    m.weight.data.uniform_(0.5, 1.5); m.bias.data.normal_(0, 0.1)
+                    m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.5, 1.5)
+            convs = [l[0] for l in bo.convpath]
+            bns = [l[1] for l in bo.convpath]
+            for i, (c, b) in enumerate(zip(convs, bns), start=1):
+                assert c.bias is None
+                getattr(bt, f"conv{i}").load_state_dict(c.state_dict())
+                getattr(bt, f"bn{i}").load_state_dict(b.state_dict())
+                assert getattr(bt, f"conv{i}").stride == c.stride and getattr(bt, f"conv{i}").kernel_size == c.kernel_size
+            bt.downsample = bo.idpath if len(bo.idpath) else None      # ResNet-D shortcut (identity when empty)
+        for mode in (True, False):
+            so.train(mode); st.train(mode)
+            with torch.no_grad():
+                yo, yt = so(x), st(x)
+            assert yo.shape == yt.shape and torch.allclose(yo, yt, atol=1e-5, rtol=1e-5), (arch, mode)
+        so.eval()
+        with torch.no_grad():
+            x = so(x)
+
+
+def test_oracle_adam_and_dice_equal_independent_implementations():
+    """Two more independent pins of the oracle: fastai's Adam with decoupled weight decay as restated in
+    oracle.fastai_adam_step (train.py:218 `opt_func=Adam`; eps 1e-5, wd 0.01) is torch.optim.AdamW step for step, and
+    oracle.dice_multi (train.py:196 `DiceMulti`) is scikit-learn's macro F1 when every class occurs."""
+    from sklearn.metrics import f1_score
+    from oracle.unet_oracle import dice_multi, fastai_adam_step
+    g = torch.Generator().manual_seed(0)
+    p0 = torch.randn(257, generator=g)
+    p, m, v = p0.clone(), torch.zeros(257), torch.zeros(257)
+    q = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([q], lr=3e-3, betas=(0.9, 0.99), eps=1e-5, weight_decay=0.01)
+    for step in range(1, 8):
+        grad = torch.randn(257, generator=g)
+        fastai_adam_step(p, grad, m, v, step, lr=3e-3, mom=0.9, sqr_mom=0.99, eps=1e-5, wd=0.01)
+        q.grad = grad.clone()
+        opt.step()
+        assert torch.allclose(p, q.detach(), atol=1e-6, rtol=1e-5), step
+    pred = torch.randint(0, 4, (3, 50, 50), generator=g)
+    tgt = torch.randint(0, 4, (3, 50, 50), generator=g)
+    ref = f1_score(tgt.flatten().numpy(), pred.flatten().numpy(), average="macro")
+    assert abs(dice_multi(pred, tgt, 4) - ref) < 1e-12
