@@ -595,3 +595,29 @@ def test_oracle_adam_and_dice_equal_independent_implementations():
     tgt = torch.randint(0, 4, (3, 50, 50), generator=g)
     ref = f1_score(tgt.flatten().numpy(), pred.flatten().numpy(), average="macro")
     assert abs(dice_multi(pred, tgt, 4) - ref) < 1e-12
+
+
+def test_oracle_merge_equals_fold_on_a_regular_grid():
+    """Independent cross-check of the oracle's overlap merge (predict.py:284-326 restated in oracle/stitch.py): where the
+    sliding windows form a regular grid, summing overlapping tiles is torch.nn.functional.fold (col2im) and the count is
+    the fold of ones - the averaged probabilities and the argmax mask must agree exactly."""
+    import torch.nn.functional as F
+    from oracle.stitch import merge_pixel_windows, merge_tiles
+    from oracle.windows import compute_windows
+    P, ov, C = 32, 0.25, 3
+    stride = P - int(P * ov)
+    H, W = P + 4 * stride, P + 6 * stride                          # (H - P) % stride == 0: no border-snapped window
+    wins = compute_windows(H, W, P, ov)
+    ys, xs = sorted({w[1] for w in wins}), sorted({w[0] for w in wins})
+    assert ys == list(range(0, H - P + 1, stride)) and xs == list(range(0, W - P + 1, stride))
+    rng = np.random.default_rng(0)
+    preds = [rng.random((C, P, P), dtype=np.float32) for _ in wins]
+    mask = merge_pixel_windows(preds, wins, H, W)
+    avg, _ = merge_tiles(preds, [[float(x), float(w), 1.0, -float(y), float(h), -1.0] for (x, y, w, h) in wins], all_classes=True)
+    order = {(w[1], w[0]): i for i, w in enumerate(wins)}           # fold walks blocks row-major (y outer, x inner)
+    cols = torch.stack([torch.from_numpy(preds[order[(y, x)]]).reshape(-1) for y in ys for x in xs], dim=1)[None]
+    num = F.fold(cols, (H, W), kernel_size=P, stride=stride)[0]
+    cnt = F.fold(torch.ones_like(cols), (H, W), kernel_size=P, stride=stride)[0]
+    ref = (num / cnt).numpy()
+    assert np.allclose(avg, ref, atol=1e-6)
+    assert (mask == ref.argmax(0)).mean() > 0.9999                  # (ties between float sums in another order aside)
